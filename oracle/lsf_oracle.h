@@ -1,0 +1,85 @@
+/*
+ * lsf_oracle.h -- C-ABI of the CPU ORACLE.
+ *
+ * TEST INFRASTRUCTURE ONLY. This is a from-scratch CPU restatement of the reference's
+ * (Algomorph/LevelSetFusion-Python + cpp/ submodule) non-rigid warp-field optimisation path.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load it. The product (levelsetfusion-python_b200/) never links, imports or calls it.
+ *
+ * Conventions (all arrays float32, C-contiguous, numpy index semantics):
+ *   2D scalar field  f[H][W]        (row = y = axis 0, col = x = axis 1)
+ *   2D vector field  v[H][W][2]     component 0 = u/x (displaces along columns, axis 1),
+ *                                   component 1 = v/y (displaces along rows,    axis 0)
+ *   3D scalar field  f[X][Y][Z]     numpy [i][j][k] == Eigen tensor(i,j,k)
+ *   3D vector field  v[X][Y][Z][3]  component c displaces along numpy axis c
+ * (reference: cpp/src/nonrigid_optimization/field_warping.tpp:29-43,80-89,159-168,
+ *  cpp/src/python_export/eigen_numpy_tensor.cpp:168-187)
+ *
+ * Build: g++ -O3 -fopenmp -ffp-contract=off (no FMA contraction: the reference CI build is plain
+ * SSE2 float32, cpp/CMakeLists.txt:65-73).
+ */
+#pragma once
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+	int tikhonov_term_enabled;
+	int gradient_kernel_enabled;
+	int maximum_chunk_size;
+	float rate;
+	int maximum_iteration_count;
+	float maximum_warp_update_threshold;
+	float data_term_amplifier;
+	float tikhonov_strength;
+	const float* kernel; /* may be NULL */
+	int kernel_size;
+	int resampling_strategy; /* 0 = NEAREST_AND_AVERAGE, 1 = LINEAR */
+} orc_hier_params;
+
+/* Optional per-iteration dump of one level's warp field (after the update of every iteration). */
+typedef struct {
+	int level;           /* level to dump (0 = coarsest), -1 = none */
+	int max_iterations;  /* capacity of buffer in iterations */
+	float* buffer;       /* [max_iterations][level voxels][D] */
+	int count;           /* out: iterations dumped */
+} orc_iteration_dump;
+
+/* ---- primitives, 2D ---- */
+void orc_warp2d(const float* field, const float* warp, int H, int W, float* out);
+void orc_warp2d_replacement(const float* field, int C, const float* warp, int H, int W, float replacement, float* out);
+void orc_gradient2d(const float* field, int H, int W, float* out);
+void orc_laplacian2d(const float* vfield, int C, int H, int W, float* out);
+void orc_convolve2d(float* vfield, int C, int H, int W, const float* kernel, int K, int preserve_zeros);
+int orc_downsample2d(const float* field, int C, int H, int W, int linear, float* out);
+int orc_upsample2d(const float* field, int C, int H, int W, int linear, float* out);
+float orc_max_norm2d(const float* vfield, int C, long n);
+
+/* ---- primitives, 3D ---- */
+void orc_warp3d(const float* field, const float* warp, int X, int Y, int Z, float* out);
+void orc_warp3d_replacement(const float* field, int C, const float* warp, int X, int Y, int Z, float replacement,
+		float* out);
+void orc_gradient3d(const float* field, int X, int Y, int Z, float* out);
+void orc_laplacian3d(const float* vfield, int C, int X, int Y, int Z, float* out);
+void orc_convolve3d(float* vfield, int C, int X, int Y, int Z, const float* kernel, int K);
+int orc_downsample3d(const float* field, int C, int X, int Y, int Z, int linear, float* out);
+int orc_upsample3d(const float* field, int C, int X, int Y, int Z, int linear, float* out);
+
+/* ---- hierarchical optimizer ---- */
+/* returns number of levels (>0) or a negative error code; iteration_counts[level] receives the
+ * iterations executed per level, max_update_lengths[level] the last max ||gradient||. */
+int orc_hier_optimize2d(const orc_hier_params* p, const float* canonical, const float* live, int H, int W,
+		float* warp_out, int* iteration_counts, float* max_update_lengths, orc_iteration_dump* dump);
+int orc_hier_optimize3d(const orc_hier_params* p, const float* canonical, const float* live, int X, int Y, int Z,
+		float* warp_out, int* iteration_counts, float* max_update_lengths, orc_iteration_dump* dump);
+
+/* timing helper for bench.py's cpu_baseline: runs `iterations` fixed iterations of the finest-level
+ * hierarchical step on a 3D pair (no pyramid), returns seconds of wall time (omp_get_wtime). */
+double orc_hier_time_iterations3d(const orc_hier_params* p, const float* canonical, const float* live, int X, int Y,
+		int Z, int iterations);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
