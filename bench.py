@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- voxel-updates/s of the 3D warp-field optimisation at 256^3 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 256]
+
+A "step" is one full hierarchical optimize() of one synthetic 256^3 TSDF pair (4-level pyramid, data term +
+Tikhonov term + 7-tap Sobolev kernel, up to 100 iterations per level). voxel-updates = sum over levels of
+voxels(level) * iterations(level). With N > 1 (one process per GPU, launched by torch.distributed.run) every
+rank optimises its own pair (independent frame pairs, no data-path collective): weak scaling; the time is the
+max over ranks and `value` the total over ranks.
+
+Prints ONE JSON line (see the task contract): value (inputs resident in HBM), e2e (host buffers through the
+public API, H2D/D2H inside the timed region), roofline (fused-iteration kernels at the finest level, measured
+live with CUDA events), cpu_baseline (the CPU oracle on the host cores, bounded sample), clocks, gpu_launches.
+
+--impl reference times the CPU restatement of the reference (oracle/; the reference's own C++ cannot be built
+here: it needs Eigen + Boost.Python) on all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "voxel-updates/s of 3D warp-field optimization at 256^3"
+UNIT = "voxel-updates/s"
+ALGORITHMIC_BYTES_PER_VOXEL_UPDATE = 68  # hierarchical 3D with Tikhonov (+- kernel), see DESIGN.md
+
+
+def optimizer_kwargs():
+    from lsf_b200 import synthetic
+    # reference run script values (run_hierarchical_optimizer3d.py:63-98: rate 0.1, threshold 0.01, 100
+    # iterations, chunk 8) with the Tikhonov term and the Sobolev kernel switched on. tikhonov_strength 0.1:
+    # the reference's Laplacian-of-previous-gradient feedback amplifies the 3D checkerboard mode by
+    # 12 * strength * |K(pi)|^3 = 0.80 per iteration at 0.1 (stable) but 1.59 at the default 0.2 (diverges).
+    return dict(tikhonov_term_enabled=True, gradient_kernel_enabled=True, maximum_chunk_size=8, rate=0.1,
+                maximum_iteration_count=100, maximum_warp_update_threshold=0.01, data_term_amplifier=1.0,
+                tikhonov_strength=0.1, kernel=synthetic.sobolev_kernel_1d(7, 0.1), resampling_strategy=0)
+
+
+def workload_name(size):
+    return "hierarchical3d_%d_tikhonov_sobolev7_4level" % size
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.process = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.process = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.process = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.process.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.process is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.process.terminate()
+        try:
+            self.process.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.process.kill()
+        sm, sm_max, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                sm_max.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, value in zip(names, parts[5:9]):
+                if value.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(sm_max) if sm_max else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def voxel_updates(reports):
+    total = 0
+    for r in reports:
+        total += r.dims[0] * r.dims[1] * r.dims[2] * r.iteration_count
+    return total
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import lsf_b200
+    from lsf_b200 import synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the CUDA path has no fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=device)
+    lib = lsf_b200._lib.load()
+    size = args.size
+    kwargs = optimizer_kwargs()
+    optimizer = lsf_b200.HierarchicalOptimizer3d(**kwargs)
+
+    # every rank gets its own pair (C4-style variation of the C2 geometry), generated on the device
+    rng = np.random.default_rng(1234 + rank)
+    shift = (2.5 + rng.uniform(-0.5, 0.5), -1.5 + rng.uniform(-0.5, 0.5), 1.0 + rng.uniform(-0.5, 0.5)) \
+        if world > 1 else (2.5, -1.5, 1.0)
+    canonical, live = synthetic.sphere_plane_pair_3d(size, shift=shift, xp=torch, device=device)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        optimizer.optimize(canonical, live)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches_before = lib.lsf_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    updates = 0
+    start.record()
+    for _ in range(args.steps):
+        optimizer.optimize(canonical, live)
+        updates += voxel_updates(optimizer.get_per_level_convergence_reports())
+    stop.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = lib.lsf_launch_count() - launches_before
+    iteration_counts = optimizer.get_per_level_iteration_counts()
+
+    # ------------------------------------------------------------------ end to end through the public API (`e2e`)
+    pinned_c = torch.empty(canonical.shape, dtype=torch.float32, pin_memory=True)
+    pinned_l = torch.empty(live.shape, dtype=torch.float32, pin_memory=True)
+    pinned_out = torch.empty(tuple(canonical.shape) + (3,), dtype=torch.float32, pin_memory=True)
+    pinned_c.copy_(canonical)
+    pinned_l.copy_(live)
+    host_c, host_l, host_out = pinned_c.numpy(), pinned_l.numpy(), pinned_out.numpy()
+    optimizer.optimize(host_c, host_l, out=host_out)  # warm-up of the staging path
+    barrier()
+    e2e_updates = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        optimizer.optimize(host_c, host_l, out=host_out)  # H2D of both fields + D2H of the warp field inside
+        e2e_updates += voxel_updates(optimizer.get_per_level_convergence_reports())
+    torch.cuda.synchronize()
+    e2e_seconds = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        stats = torch.tensor([elapsed_ms, e2e_seconds], dtype=torch.float64, device=device)
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_seconds = float(stats[0]), float(stats[1])
+        sums = torch.tensor([updates, e2e_updates, launches], dtype=torch.float64, device=device)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        updates, e2e_updates, launches = int(sums[0]), int(sums[1]), int(sums[2])
+
+    result = None
+    if rank == 0:
+        # -------------------------------------------------------------- roofline of the finest-level iteration
+        import ctypes
+        N = size ** 3
+        iterations = 50
+        params = optimizer._params()
+        ms = ctypes.c_float(0.0)
+        n_launch = ctypes.c_int(0)
+        stage_ms = (ctypes.c_float * 4)()
+        ptr = lambda t: ctypes.cast(ctypes.c_void_p(t.data_ptr()), lsf_b200._lib.c_float_p)
+        stream = lsf_b200._lib.current_stream_handle()
+        for _ in range(2):  # first call warms up, second is kept
+            lsf_b200._lib.check(lib.lsf_hier_iterate_3d(ctypes.byref(params), ptr(canonical), ptr(live), size, size, size,
+                                                        iterations, ctypes.byref(ms), ctypes.byref(n_launch), None,
+                                                        stream))
+        iteration_ms = ms.value / iterations
+        lsf_b200._lib.check(lib.lsf_hier_iterate_3d(ctypes.byref(params), ptr(canonical), ptr(live), size, size, size,
+                                                    iterations, ctypes.byref(ms), ctypes.byref(n_launch), stage_ms,
+                                                    stream))
+        stages = [stage_ms[i] / iterations for i in range(4)]
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_source = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_source = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = ALGORITHMIC_BYTES_PER_VOXEL_UPDATE * N / (iteration_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None,
+            "kernel": "finest-level iteration = k_hier_gradient3d + k_convolve_axis3d x3 (%d launches/iteration)"
+                      % (n_launch.value // iterations),
+            "algorithmic_bytes_per_launch_group": ALGORITHMIC_BYTES_PER_VOXEL_UPDATE * N,
+            "ms_per_iteration": round(iteration_ms, 4),
+            "stage_ms": {"gradient": round(stages[0], 4), "conv_axis0": round(stages[1], 4),
+                         "conv_axis1": round(stages[2], 4), "conv_axis2_update_max": round(stages[3], 4)},
+            "peak_source": peak_source,
+        }
+        # -------------------------------------------------------------- CPU baseline (oracle port), bounded sample
+        cpu = cpu_baseline_sample(size, kwargs)
+        value = updates / (elapsed_ms * 1e-3)
+        result = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(size), "volume": [size] * 3, "pairs_per_gpu": 1,
+                       "levels": len(iteration_counts), "iterations_per_level": iteration_counts,
+                       "tikhonov_strength": kwargs["tikhonov_strength"], "kernel_taps": 7,
+                       "l2_policy": "working set ~1.1 GB per iteration >> 126 MB L2 (inputs larger than L2)",
+                       "parallelism": "independent pairs, 1 per GPU" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_updates / e2e_seconds, "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * 4 * N * world, "d2h_bytes_per_step": 3 * 4 * N * world,
+                    "ms_per_step": 1e3 * e2e_seconds / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if result is not None:
+        print(json.dumps(result))
+
+
+def cpu_baseline_sample(size, kwargs, iterations=3):
+    """Times the CPU oracle (kind "port": restatement of the reference's loops with OpenMP at the same sites) on
+    `iterations` finest-level iterations of the same 256^3 pair, all host threads."""
+    import oracle
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(size)
+    seconds = oracle.hier_time_iterations3d(canonical, live, iterations, **kwargs)
+    return {"value": iterations * size ** 3 / seconds, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+            "sample": "%d finest-level iterations (%d^3) of the same workload after 1 warm-up iteration; "
+                      "%.2f s" % (iterations, size, seconds)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from lsf_b200 import synthetic
+    size = args.size
+    kwargs = optimizer_kwargs()
+    canonical, live = synthetic.sphere_plane_pair_3d(size)
+    iterations_per_step = 2
+    for _ in range(min(args.warmup, 1)):
+        oracle.hier_time_iterations3d(canonical, live, 1, **kwargs)
+    total = 0.0
+    for _ in range(args.steps):
+        total += oracle.hier_time_iterations3d(canonical, live, iterations_per_step, **kwargs)
+    value = args.steps * iterations_per_step * size ** 3 / total
+    sample = ("each step = %d finest-level iterations (%d^3) of the workload on the CPU oracle (restatement of the "
+              "reference's C++/OpenMP loops; the reference itself needs Eigen+Boost.Python and cannot be built here)"
+              % (iterations_per_step, size))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(size), "volume": [size] * 3},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=5)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    parser.add_argument("--size", type=int, default=256)
+    args = parser.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+"""ctypes binding of liblsf_b200.so (the C-ABI declared in include/lsf_b200.h).
+
+There is NO CPU fallback: if the library is missing or no CUDA device is usable, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblsf_b200.so")
+
+LSF_HOST = 0
+LSF_DEVICE = 1
+LSF_MAX_LEVELS = 16
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+
+class HierParams(ctypes.Structure):
+    """lsf_hier_params"""
+    _fields_ = [
+        ("tikhonov_term_enabled", ctypes.c_int),
+        ("gradient_kernel_enabled", ctypes.c_int),
+        ("maximum_chunk_size", ctypes.c_int),
+        ("rate", ctypes.c_float),
+        ("maximum_iteration_count", ctypes.c_int),
+        ("maximum_warp_update_threshold", ctypes.c_float),
+        ("data_term_amplifier", ctypes.c_float),
+        ("tikhonov_strength", ctypes.c_float),
+        ("kernel", c_float_p),
+        ("kernel_size", ctypes.c_int),
+        ("resampling_strategy", ctypes.c_int),
+    ]
+
+
+class LevelReport(ctypes.Structure):
+    """lsf_level_report"""
+    _fields_ = [
+        ("iteration_count", ctypes.c_int),
+        ("iteration_limit_reached", ctypes.c_int),
+        ("max_update_length", ctypes.c_float),
+        ("dims", ctypes.c_int * 3),
+        ("warp_ratio_above_min_threshold", ctypes.c_float),
+        ("warp_length_min", ctypes.c_float),
+        ("warp_length_max", ctypes.c_float),
+        ("warp_length_mean", ctypes.c_float),
+        ("warp_length_std", ctypes.c_float),
+        ("warp_longest_location", ctypes.c_int * 3),
+        ("warp_is_largest_below_min_threshold", ctypes.c_int),
+        ("warp_is_largest_above_max_threshold", ctypes.c_int),
+        ("diff_min", ctypes.c_float),
+        ("diff_max", ctypes.c_float),
+        ("diff_mean", ctypes.c_float),
+        ("diff_std", ctypes.c_float),
+        ("diff_biggest_location", ctypes.c_int * 3),
+    ]
+
+
+class IterationCapture(ctypes.Structure):
+    """lsf_iteration_capture"""
+    _fields_ = [
+        ("level", ctypes.c_int),
+        ("max_iterations", ctypes.c_int),
+        ("buffer", c_float_p),
+        ("count", ctypes.c_int),
+    ]
+
+
+# every symbol include/lsf_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "lsf_last_error", "lsf_version", "lsf_launch_count",
+    "lsf_hier_optimize_3d", "lsf_hier_optimize_2d", "lsf_hier_optimize_3d_batch", "lsf_hier_iterate_3d",
+    "lsf_warp_3d", "lsf_warp_2d", "lsf_gradient_3d", "lsf_gradient_2d", "lsf_laplacian_3d", "lsf_laplacian_2d",
+    "lsf_convolve_3d", "lsf_convolve_2d", "lsf_downsample_3d", "lsf_upsample_3d", "lsf_downsample_2d",
+    "lsf_upsample_2d", "lsf_max_norm",
+]
+
+_lib = None
+
+
+class LsfError(RuntimeError):
+    """Raised for every failing library call (the reference raises RuntimeError through Boost.Python's
+    default translator for its AssertionFailureException, error_handling/throw_assert.hpp:67-74)."""
+
+
+def load():
+    """Loads liblsf_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LsfError("liblsf_b200.so is missing at %s: build it with `python __graft_entry__.py` "
+                           "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.lsf_last_error.restype = ctypes.c_char_p
+        lib.lsf_launch_count.restype = ctypes.c_longlong
+        for name in EXPORTED_SYMBOLS:
+            getattr(lib, name)  # AttributeError if the header and the library ever diverge
+        _lib = lib
+    return _lib
+
+
+def check(status):
+    if status < 0:
+        raise LsfError(load().lsf_last_error().decode("utf-8", "replace"))
+    return status
+
+
+def as_f32(array, name="array"):
+    """The reference's converters only accept float32 C-contiguous arrays
+    (python_export/eigen_numpy_tensor.cpp:120-156); be a little more lenient and convert."""
+    return np.ascontiguousarray(array, dtype=np.float32)
+
+
+def fptr(array):
+    return array.ctypes.data_as(c_float_p)
+
+
+def is_torch_cuda(obj):
+    return type(obj).__module__.startswith("torch") and hasattr(obj, "is_cuda") and obj.is_cuda
+
+
+def current_stream_handle():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,140 @@
+// common.cuh -- shared host/device helpers of liblsf_b200.so (sm_100a only).
+//
+// Numerics contract: every kernel reproduces the reference's float32 operation order without FMA
+// contraction (the reference CI build is plain SSE2), so the translation units are
+// compiled with --fmad=false and results are bit-identical to the CPU oracle.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+#include "../../include/lsf_b200.h"
+
+namespace lsf {
+
+// ---------------------------------------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+
+// Kernel-launch accounting (bench.py's `gpu_launches`): every launch site reports how many kernels it enqueued.
+void count_launches(int n);
+// wraps the grid argument of every <<<...>>> launch: counts the launch and passes the grid through
+inline dim3 counted(dim3 grid) {
+	count_launches(1);
+	return grid;
+}
+inline unsigned counted(unsigned grid) {
+	count_launches(1);
+	return grid;
+}
+
+#define LSF_CUDA(call)                                                                              \
+	do {                                                                                            \
+		cudaError_t lsf_cuda_err__ = (call);                                                        \
+		if (lsf_cuda_err__ != cudaSuccess) {                                                        \
+			lsf::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(lsf_cuda_err__), __FILE__, \
+					__LINE__, #call);                                                               \
+			return LSF_ERR_CUDA;                                                                    \
+		}                                                                                           \
+	} while (0)
+
+#define LSF_REQUIRE(cond, ...)                   \
+	do {                                         \
+		if (!(cond)) {                           \
+			lsf::set_error(__VA_ARGS__);         \
+			return LSF_ERR_INVALID_ARGUMENT;     \
+		}                                        \
+	} while (0)
+
+#define LSF_TRY(expr)                    \
+	do {                                 \
+		int lsf_status__ = (expr);       \
+		if (lsf_status__ < 0) return lsf_status__; \
+	} while (0)
+
+inline bool is_power_of_two(int v) {
+	return v > 0 && (v & (v - 1)) == 0;
+}
+
+inline unsigned div_up(long long a, long long b) {
+	return (unsigned) ((a + b - 1) / b);
+}
+
+// ---------------------------------------------------------------------------------------------- device memory
+// Stream-ordered scratch allocations (cudaMallocAsync pool, release threshold raised so repeated
+// optimize() calls reuse the same blocks). Freed in reverse order when the arena goes out of scope.
+class Arena {
+public:
+	explicit Arena(cudaStream_t stream);
+	~Arena();
+	template<typename T>
+	int alloc(T** out, size_t count) {
+		void* p = nullptr;
+		int status = alloc_bytes(&p, count * sizeof(T));
+		*out = static_cast<T*>(p);
+		return status;
+	}
+	int alloc_bytes(void** out, size_t bytes);
+	size_t bytes_allocated() const {
+		return total_;
+	}
+private:
+	cudaStream_t stream_;
+	std::vector<void*> blocks_;
+	size_t total_ = 0;
+};
+
+// Stages a host or device input so that kernels see a device pointer.
+int to_device(Arena& arena, const float* src, size_t count, int memory_kind, cudaStream_t stream, const float** out);
+// Copies a device result to the caller's buffer (host or device).
+int from_device(const float* src_dev, float* dst, size_t count, int memory_kind, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------- separable kernel taps
+struct Taps {
+	float k[LSF_MAX_KERNEL_SIZE];  // flipped: k[j] multiplies in[i - r + j]
+	int size;
+	int radius;
+};
+int make_taps(const float* kernel_host, int kernel_size, Taps* taps);
+
+// ---------------------------------------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+// Level termination test evaluated on the device so that the host never has to synchronise inside the
+// iteration loop: iteration `it` runs iff it == 0 or max||g|| of iteration it-1 is >= threshold
+// (reference optimizer.tpp:149,166-171). max_sq_bits[i] holds the bits of max ||g||^2 of iteration i.
+__device__ __forceinline__ bool level_converged(const unsigned* __restrict__ max_sq_bits, int iteration,
+		float threshold) {
+	if (iteration <= 0 || max_sq_bits == nullptr) return false;
+	const float max_norm = sqrtf(__uint_as_float(max_sq_bits[iteration - 1]));
+	return max_norm < threshold;
+}
+
+// Block-wide max of non-negative floats followed by one atomicMax on the float's bit pattern
+// (non-negative IEEE floats order like unsigned integers). NaNs are ignored, as in the reference's
+// `if (squared_length > max)` (statistics.tpp:65).
+__device__ __forceinline__ void block_atomic_max(float value, unsigned* target) {
+	__shared__ float warp_max[32];
+	if (!(value >= 0.0f)) value = 0.0f;  // NaN -> ignored
+#pragma unroll
+	for (int offset = 16; offset > 0; offset >>= 1) value = fmaxf(value, __shfl_xor_sync(0xffffffffu, value, offset));
+	const int linear = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+	const int lane = linear & 31, warp = linear >> 5;
+	const int warps = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
+	if (lane == 0) warp_max[warp] = value;
+	__syncthreads();
+	if (warp == 0) {
+		value = lane < warps ? warp_max[lane] : 0.0f;
+#pragma unroll
+		for (int offset = 16; offset > 0; offset >>= 1)
+			value = fmaxf(value, __shfl_xor_sync(0xffffffffu, value, offset));
+		if (lane == 0 && value > 0.0f) atomicMax(target, __float_as_uint(value));
+	}
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lsf

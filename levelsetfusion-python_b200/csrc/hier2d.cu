@@ -1,0 +1,274 @@
+// hier2d.cu -- 2D hierarchical optimizer driver: the reference's Optimizer<MatrixXf,MatrixXv2f>
+// (cpp/src/nonrigid_optimization/hierarchical/optimizer.tpp:83-212; Python twin
+// nonrigid_opt/hierarchical/hierarchical_optimizer2d.py:123-248). Same device-side termination scheme as
+// hier3d.cu.
+#include "kernels2d.cuh"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+namespace lsf {
+
+namespace {
+
+constexpr int POLL_CHUNK = 16;
+
+struct Plan2 {
+	bool tikhonov = false, use_kernel = false, linear = false;
+	int level_count = 0;
+	Taps taps;
+	float rate = 0, threshold = 0, amplifier = 0, strength = 0;
+	int max_iterations = 0;
+	Grid2 level_grid[LSF_MAX_LEVELS];
+};
+
+int make_plan(const lsf_hier_params* p, int H, int W, Plan2* plan) {
+	LSF_REQUIRE(p != nullptr, "params is NULL");
+	LSF_REQUIRE(H > 0 && W > 0, "field dimensions must be positive, got %d x %d", H, W);
+	LSF_REQUIRE(is_power_of_two(p->maximum_chunk_size),
+			"The argument 'maximum_chunk_size' must be an integer power of 2, i.e. 4, 8, 16, etc.");
+	const int power = (int) std::log2((double) p->maximum_chunk_size);
+	const int max_level_count = (int) std::min(std::log2((double) H), std::log2((double) W)) + 1;
+	LSF_REQUIRE(max_level_count > power, "Maximum chunk size too large for the field size.");
+	plan->level_count = power + 1;
+	LSF_REQUIRE(plan->level_count <= LSF_MAX_LEVELS, "too many pyramid levels (%d)", plan->level_count);
+	LSF_REQUIRE(p->resampling_strategy == LSF_RESAMPLING_LINEAR
+			|| p->resampling_strategy == LSF_RESAMPLING_NEAREST_AND_AVERAGE, "Unknown resampling strategy %d",
+			p->resampling_strategy);
+	plan->linear = p->resampling_strategy == LSF_RESAMPLING_LINEAR;
+	Grid2 g(H, W);
+	for (int level = plan->level_count - 1; level >= 0; level--) {
+		plan->level_grid[level] = g;
+		if (level > 0) {
+			if (plan->linear) {
+				// reference resampling.tpp:424-425
+				LSF_REQUIRE(g.H % 2 == 0 && g.W % 2 == 0 && g.H > 2 && g.W > 2,
+						"Each dimension of the argument 'field' must be divisible by 2 and greater than 2.");
+			} else {
+				// reference resampling.tpp:361-362
+				LSF_REQUIRE(is_power_of_two(g.H) && is_power_of_two(g.W),
+						"The argument 'field' must have a power of two for each dimension.");
+			}
+		}
+		g = g.half();
+	}
+	plan->tikhonov = p->tikhonov_term_enabled && p->tikhonov_strength > 0.0f;
+	plan->use_kernel = p->gradient_kernel_enabled && p->kernel_size > 0 && p->kernel != nullptr;
+	if (plan->use_kernel) LSF_TRY(make_taps(p->kernel, p->kernel_size, &plan->taps));
+	plan->rate = p->rate;
+	plan->threshold = p->maximum_warp_update_threshold;
+	plan->amplifier = p->data_term_amplifier;
+	plan->strength = p->tikhonov_strength;
+	plan->max_iterations = p->maximum_iteration_count;
+	return LSF_OK;
+}
+
+struct LevelState2 {
+	Grid2 g;
+	const float4* pack = nullptr;
+	const float* canonical = nullptr;
+	float* warp = nullptr;
+	float* g_post = nullptr;
+	float* scratch_a = nullptr;
+	unsigned* max_sq_bits = nullptr;
+};
+
+void enqueue_iteration(const Plan2& plan, LevelState2& s, int iteration, cudaStream_t stream) {
+	HierIterArgs2 a;
+	a.pack = s.pack;
+	a.canonical = s.canonical;
+	a.warp = s.warp;
+	a.warp_out = s.warp;
+	a.g_prev = s.g_post;
+	a.g = s.g;
+	a.amplifier = plan.amplifier;
+	a.strength = plan.strength;
+	a.rate = plan.rate;
+	a.threshold = plan.threshold;
+	a.max_sq_bits = s.max_sq_bits;
+	a.iteration = iteration;
+	a.check_convergence = 1;
+	const dim3 grid = grid2(s.g), block = block3();
+	if (!plan.use_kernel) {
+		if (plan.tikhonov) {
+			a.g_out = s.scratch_a;
+			k_hier_gradient2d<true, true> <<<counted(grid), block, 0, stream>>>(a);
+			std::swap(s.g_post, s.scratch_a);
+		} else {
+			a.g_out = nullptr;
+			k_hier_gradient2d<false, true> <<<counted(grid), block, 0, stream>>>(a);
+		}
+		return;
+	}
+	// g_pre -> g_post (stage 1), rows pass g_post -> scratch_a, columns pass scratch_a -> g_post (+ update)
+	a.g_out = s.scratch_a;
+	if (plan.tikhonov) k_hier_gradient2d<true, false> <<<counted(grid), block, 0, stream>>>(a);
+	else k_hier_gradient2d<false, false> <<<counted(grid), block, 0, stream>>>(a);
+	ConvArgs2 c;
+	c.g = s.g;
+	c.taps = plan.taps;
+	c.rate = plan.rate;
+	c.threshold = plan.threshold;
+	c.max_sq_bits = s.max_sq_bits;
+	c.iteration = iteration;
+	c.check_convergence = 1;
+	c.channels = 2;
+	c.preserve_zeros = 0;
+	c.warp = s.warp;
+	// stage 1 wrote scratch_a and no longer needs g_post (g_prev): reuse it as the rows-pass output
+	c.in = s.scratch_a;
+	c.out = s.g_post;
+	k_convolve_axis2d<0, false> <<<counted(grid), block, 0, stream>>>(c);
+	c.in = s.g_post;
+	c.out = s.scratch_a;
+	k_convolve_axis2d<1, true> <<<counted(grid), block, 0, stream>>>(c);
+	std::swap(s.g_post, s.scratch_a);
+}
+
+}  // namespace
+
+}  // namespace lsf
+
+using namespace lsf;
+
+extern "C" int lsf_hier_optimize_2d(const lsf_hier_params* params, const float* canonical, const float* live, int H,
+		int W, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
+		lsf_iteration_capture* capture, void* stream_handle) {
+	(void) collect_reports;
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
+	Plan2 plan;
+	LSF_TRY(make_plan(params, H, W, &plan));
+	LSF_REQUIRE(canonical && live && warp_out, "canonical, live and warp_out must not be NULL");
+	const int L = plan.level_count;
+	const Grid2 finest = plan.level_grid[L - 1];
+	const size_t N = (size_t) finest.N;
+	Arena arena(stream);
+	const float *canonical_dev, *live_dev;
+	LSF_TRY(to_device(arena, canonical, N, memory_kind, stream, &canonical_dev));
+	LSF_TRY(to_device(arena, live, N, memory_kind, stream, &live_dev));
+	float* out_dev = warp_out;
+	if (memory_kind == LSF_HOST) LSF_TRY(arena.alloc(&out_dev, N * 2));
+
+	// pyramids (reference pyramid.tpp:51-74): live + its full-resolution gradient restricted together
+	std::vector<float4*> packs(L, nullptr);
+	std::vector<const float*> canonicals(L, nullptr);
+	const float4 border = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+	for (int level = L - 1; level >= 0; level--) {
+		const Grid2& g = plan.level_grid[level];
+		LSF_TRY(arena.alloc(&packs[level], (size_t) g.padded_count()));
+		k_fill4<<<counted(div_up(g.padded_count(), 256)), 256, 0, stream>>>(packs[level], g.padded_count(), border);
+		if (level == L - 1) {
+			k_gradient_pack2d<<<counted(grid2(g)), block3(), 0, stream>>>(live_dev, packs[level], g);
+			canonicals[level] = canonical_dev;
+		} else {
+			const Grid2& src = plan.level_grid[level + 1];
+			float* canonical_level = nullptr;
+			LSF_TRY(arena.alloc(&canonical_level, (size_t) g.N));
+			if (plan.linear) {
+				k_downsample_linear2d<<<counted(grid2(g)), block3(), 0, stream>>>(PackAccess2 { packs[level + 1], packs[level] },
+						src, g);
+				k_downsample_linear2d<<<counted(grid2(g)), block3(), 0, stream>>>(
+						PlainAccess2 { canonicals[level + 1], canonical_level }, src, g);
+			} else {
+				k_downsample_average2d<<<counted(grid2(g)), block3(), 0, stream>>>(PackAccess2 { packs[level + 1], packs[level] },
+						src, g);
+				k_downsample_average2d<<<counted(grid2(g)), block3(), 0, stream>>>(
+						PlainAccess2 { canonicals[level + 1], canonical_level }, src, g);
+			}
+			canonicals[level] = canonical_level;
+		}
+	}
+	LSF_CUDA(cudaGetLastError());
+
+	float *warp_current, *warp_next, *g_post, *scratch_a;
+	unsigned* max_sq_bits;
+	LSF_TRY(arena.alloc(&warp_current, N * 2));
+	LSF_TRY(arena.alloc(&warp_next, N * 2));
+	LSF_TRY(arena.alloc(&g_post, N * 2));
+	LSF_TRY(arena.alloc(&scratch_a, N * 2));
+	const int slot_count = std::max(plan.max_iterations, 1);
+	LSF_TRY(arena.alloc(&max_sq_bits, (size_t) slot_count));
+	std::vector<unsigned> host_bits((size_t) slot_count);
+	LSF_CUDA(cudaMemsetAsync(warp_current, 0, (size_t) plan.level_grid[0].N * 2 * sizeof(float), stream));
+
+	float* capture_dev = nullptr;
+	if (capture) {
+		capture->count = 0;
+		if (capture->level >= 0 && capture->level < L && capture->max_iterations > 0 && capture->buffer) {
+			if (memory_kind == LSF_HOST)
+				LSF_TRY(arena.alloc(&capture_dev, (size_t) capture->max_iterations * plan.level_grid[capture->level].N * 2));
+			else capture_dev = capture->buffer;
+		}
+	}
+
+	for (int level = 0; level < L; level++) {
+		LevelState2 s;
+		s.g = plan.level_grid[level];
+		s.pack = packs[level];
+		s.canonical = canonicals[level];
+		s.warp = warp_current;
+		s.g_post = g_post;
+		s.scratch_a = scratch_a;
+		s.max_sq_bits = max_sq_bits;
+		LSF_CUDA(cudaMemsetAsync(s.g_post, 0, (size_t) s.g.N * 2 * sizeof(float), stream));
+		LSF_CUDA(cudaMemsetAsync(max_sq_bits, 0, (size_t) slot_count * sizeof(unsigned), stream));
+		const bool capturing = capture_dev != nullptr && capture->level == level;
+		int executed = 0, enqueued = 0;
+		bool converged = false;
+		float last_max = FLT_MAX;
+		while (!converged && enqueued < plan.max_iterations) {
+			const int chunk_end = std::min(plan.max_iterations, enqueued + POLL_CHUNK);
+			for (int it = enqueued; it < chunk_end; it++) {
+				enqueue_iteration(plan, s, it, stream);
+				if (capturing && it < capture->max_iterations)
+					k_planes_to_aos<<<counted(div_up(s.g.N, 256)), 256, 0, stream>>>(s.warp, capture_dev + (size_t) it * s.g.N * 2,
+							s.g.N, 2);
+			}
+			LSF_CUDA(cudaGetLastError());
+			LSF_CUDA(cudaMemcpyAsync(host_bits.data() + enqueued, max_sq_bits + enqueued,
+					(size_t) (chunk_end - enqueued) * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+			LSF_CUDA(cudaStreamSynchronize(stream));
+			for (int it = enqueued; it < chunk_end; it++) {
+				float sq;
+				std::memcpy(&sq, &host_bits[it], sizeof(float));
+				last_max = std::sqrt(sq);
+				executed = it + 1;
+				if (last_max < plan.threshold) {
+					converged = true;
+					break;
+				}
+			}
+			enqueued = chunk_end;
+		}
+		g_post = s.g_post;  // ping-pong state carries over (contents are reset per level)
+		scratch_a = s.scratch_a;
+		if (reports) {
+			lsf_level_report& r = reports[level];
+			std::memset(&r, 0, sizeof(r));
+			r.iteration_count = executed;
+			r.iteration_limit_reached = executed >= plan.max_iterations;
+			r.max_update_length = last_max;
+			r.dims[0] = s.g.H;
+			r.dims[1] = s.g.W;
+			r.dims[2] = 1;
+		}
+		if (capturing) capture->count = std::min(executed, capture->max_iterations);
+		if (level != L - 1) {
+			const Grid2& dg = plan.level_grid[level + 1];
+			k_upsample2d<<<counted(grid2(dg)), block3(), 0, stream>>>(warp_current, warp_next, 2, s.g, dg, plan.linear ? 1 : 0);
+			std::swap(warp_current, warp_next);
+		}
+	}
+	k_planes_to_aos<<<counted(div_up(finest.N, 256)), 256, 0, stream>>>(warp_current, out_dev, finest.N, 2);
+	LSF_CUDA(cudaGetLastError());
+	if (memory_kind == LSF_HOST) {
+		if (capture_dev)
+			LSF_CUDA(cudaMemcpyAsync(capture->buffer, capture_dev,
+					(size_t) capture->count * plan.level_grid[capture->level].N * 2 * sizeof(float),
+					cudaMemcpyDeviceToHost, stream));
+		LSF_TRY(from_device(out_dev, warp_out, N * 2, LSF_HOST, stream));
+	}
+	return L;
+}

@@ -1,0 +1,398 @@
+// hier3d.cu -- 3D hierarchical optimizer driver (host side of the C-ABI) on top of kernels3d.cuh.
+//
+// Restates the control flow of the reference's Optimizer<Tensor3f,Tensor3v3f>
+// (cpp/src/nonrigid_optimization/hierarchical/optimizer.tpp:83-212, pyramid.tpp:51-74) around fused
+// sm_100a kernels. The level loop never synchronises with the host inside an iteration: the
+// termination test (optimizer.tpp:166-171) is evaluated on the device at the head of every kernel from
+// the previous iteration's max ||g||^2 slot, and the host polls the slots once per chunk of iterations.
+#include "kernels3d.cuh"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+namespace lsf {
+
+namespace {
+
+constexpr int POLL_CHUNK = 16;  // iterations enqueued between two host polls of the convergence slots
+
+struct Plan3 {
+	bool tikhonov = false, use_kernel = false, linear = false;
+	int level_count = 0;
+	Taps taps;
+	float rate = 0, threshold = 0, amplifier = 0, strength = 0;
+	int max_iterations = 0;
+	Grid3 level_grid[LSF_MAX_LEVELS];  // [0] = coarsest
+};
+
+int make_plan(const lsf_hier_params* p, int X, int Y, int Z, Plan3* plan) {
+	LSF_REQUIRE(p != nullptr, "params is NULL");
+	LSF_REQUIRE(X > 0 && Y > 0 && Z > 0, "field dimensions must be positive, got %d x %d x %d", X, Y, Z);
+	// reference pyramid.tpp:53-60
+	LSF_REQUIRE(is_power_of_two(p->maximum_chunk_size),
+			"The argument 'maximum_chunk_size' must be an integer power of 2, i.e. 4, 8, 16, etc.");
+	const int power = (int) std::log2((double) p->maximum_chunk_size);
+	const int max_level_count = (int) std::min( { std::log2((double) X), std::log2((double) Y), std::log2(
+			(double) Z) }) + 1;
+	LSF_REQUIRE(max_level_count > power, "Maximum chunk size too large for the field size.");
+	plan->level_count = power + 1;
+	LSF_REQUIRE(plan->level_count <= LSF_MAX_LEVELS, "too many pyramid levels (%d)", plan->level_count);
+	plan->linear = p->resampling_strategy == LSF_RESAMPLING_LINEAR;
+	LSF_REQUIRE(p->resampling_strategy == LSF_RESAMPLING_LINEAR
+			|| p->resampling_strategy == LSF_RESAMPLING_NEAREST_AND_AVERAGE, "Unknown resampling strategy %d",
+			p->resampling_strategy);
+	const int divisor = 1 << (plan->level_count - 1);
+	// the reference halves with integer division and later doubles again (resampling.tpp:388-392,107-108):
+	// only sizes divisible by 2^(levels-1) survive the round trip
+	LSF_REQUIRE(X % divisor == 0 && Y % divisor == 0 && Z % divisor == 0,
+			"each dimension (%d x %d x %d) must be divisible by %d for a %d-level pyramid", X, Y, Z, divisor,
+			plan->level_count);
+	Grid3 g(X, Y, Z);
+	for (int level = plan->level_count - 1; level >= 0; level--) {
+		plan->level_grid[level] = g;
+		if (level > 0 && plan->linear) {
+			// reference resampling.tpp:547-549
+			LSF_REQUIRE(g.X % 2 == 0 && g.Y % 2 == 0 && g.Z % 2 == 0 && g.X > 2 && g.Y > 2 && g.Z > 2,
+					"Each dimension of the argument 'field' must be divisible by 2 and greater than 2.");
+		}
+		g = g.half();
+	}
+	// reference optimizer.tpp:65-66
+	plan->tikhonov = p->tikhonov_term_enabled && p->tikhonov_strength > 0.0f;
+	plan->use_kernel = p->gradient_kernel_enabled && p->kernel_size > 0 && p->kernel != nullptr;
+	if (plan->use_kernel) LSF_TRY(make_taps(p->kernel, p->kernel_size, &plan->taps));
+	plan->rate = p->rate;
+	plan->threshold = p->maximum_warp_update_threshold;
+	plan->amplifier = p->data_term_amplifier;
+	plan->strength = p->tikhonov_strength;
+	plan->max_iterations = p->maximum_iteration_count;
+	return LSF_OK;
+}
+
+struct LevelState {
+	Grid3 g;
+	const float4* pack = nullptr;
+	const float* canonical = nullptr;
+	float* warp = nullptr;       // planes
+	float* g_post = nullptr;     // planes: gradient after the iteration (g_prev of the next one)
+	float* scratch_a = nullptr;  // planes
+	float* scratch_b = nullptr;  // planes
+	unsigned* max_sq_bits = nullptr;
+};
+
+// Enqueues one iteration; returns the number of kernel launches.
+// `events` (optional, 5 entries): recorded before the first and after every kernel, for per-stage timing.
+int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool check_convergence, cudaStream_t stream,
+		cudaEvent_t* events = nullptr) {
+	auto mark = [&](int i) {
+		if (events) cudaEventRecord(events[i], stream);
+	};
+	mark(0);
+	HierIterArgs a;
+	a.pack = s.pack;
+	a.canonical = s.canonical;
+	a.warp = s.warp;
+	a.warp_out = s.warp;
+	a.g_prev = s.g_post;
+	a.g = s.g;
+	a.amplifier = plan.amplifier;
+	a.strength = plan.strength;
+	a.rate = plan.rate;
+	a.threshold = plan.threshold;
+	a.max_sq_bits = s.max_sq_bits;
+	a.iteration = iteration;
+	a.check_convergence = check_convergence ? 1 : 0;
+	const dim3 grid = grid3(s.g), block = block3();
+	if (!plan.use_kernel) {
+		if (plan.tikhonov) {
+			a.g_out = s.scratch_a;
+			k_hier_gradient3d<true, true> <<<counted(grid), block, 0, stream>>>(a);
+			std::swap(s.g_post, s.scratch_a);
+		} else {
+			a.g_out = nullptr;
+			k_hier_gradient3d<false, true> <<<counted(grid), block, 0, stream>>>(a);
+		}
+		mark(1);
+		return 1;
+	}
+	a.g_out = s.scratch_a;
+	if (plan.tikhonov) k_hier_gradient3d<true, false> <<<counted(grid), block, 0, stream>>>(a);
+	else k_hier_gradient3d<false, false> <<<counted(grid), block, 0, stream>>>(a);
+	mark(1);
+	ConvArgs c;
+	c.g = s.g;
+	c.taps = plan.taps;
+	c.rate = plan.rate;
+	c.threshold = plan.threshold;
+	c.max_sq_bits = s.max_sq_bits;
+	c.iteration = iteration;
+	c.check_convergence = a.check_convergence;
+	c.channels = 3;
+	c.warp = s.warp;
+	c.in = s.scratch_a;
+	c.out = s.scratch_b;
+	k_convolve_axis3d<0, false> <<<counted(grid), block, 0, stream>>>(c);
+	mark(2);
+	c.in = s.scratch_b;
+	c.out = s.scratch_a;
+	k_convolve_axis3d<1, false> <<<counted(grid), block, 0, stream>>>(c);
+	mark(3);
+	c.in = s.scratch_a;
+	c.out = s.g_post;
+	k_convolve_axis3d<2, true> <<<counted(grid), block, 0, stream>>>(c);
+	mark(4);
+	return 4;
+}
+
+template<typename Access>
+void launch_downsample(bool linear, Access access, const Grid3& src, const Grid3& dst, cudaStream_t stream) {
+	if (linear) k_downsample_linear3d<Access> <<<counted(grid3(dst)), block3(), 0, stream>>>(access, src, dst);
+	else k_downsample_average3d<Access> <<<counted(grid3(dst)), block3(), 0, stream>>>(access, src, dst);
+}
+
+int build_pack_pyramid(Arena& arena, const Plan3& plan, const float* live_dev, const float* canonical_dev,
+		std::vector<float4*>& packs, std::vector<const float*>& canonicals, cudaStream_t stream, int first_level = 0) {
+	const int L = plan.level_count;
+	packs.assign(L, nullptr);
+	canonicals.assign(L, nullptr);
+	const float4 border = make_float4(1.0f, 0.0f, 0.0f, 0.0f);  // TSDF -> 1 (field_warping.tpp:29-36), gradient -> 0
+	for (int level = L - 1; level >= first_level; level--) {
+		const Grid3& g = plan.level_grid[level];
+		LSF_TRY(arena.alloc(&packs[level], (size_t) g.padded_count()));
+		k_fill4<<<counted(div_up(g.padded_count(), 256)), 256, 0, stream>>>(packs[level], g.padded_count(), border);
+		if (level == L - 1) {
+			k_gradient_pack3d<<<counted(grid3(g)), block3(), 0, stream>>>(live_dev, packs[level], g);
+			canonicals[level] = canonical_dev;
+		} else {
+			const Grid3& src = plan.level_grid[level + 1];
+			launch_downsample(plan.linear, PackAccess { packs[level + 1], packs[level] }, src, g, stream);
+			float* canonical_level = nullptr;
+			LSF_TRY(arena.alloc(&canonical_level, (size_t) g.N));
+			launch_downsample(plan.linear, PlainAccess { canonicals[level + 1], canonical_level }, src, g, stream);
+			canonicals[level] = canonical_level;
+		}
+	}
+	LSF_CUDA(cudaGetLastError());
+	return LSF_OK;
+}
+
+int optimize_device(const Plan3& plan, const float* canonical_dev, const float* live_dev, float* warp_out_dev,
+		lsf_level_report* reports, lsf_iteration_capture* capture, float* capture_dev, cudaStream_t stream) {
+	Arena arena(stream);
+	const int L = plan.level_count;
+	const Grid3& finest = plan.level_grid[L - 1];
+	std::vector<float4*> packs;
+	std::vector<const float*> canonicals;
+	LSF_TRY(build_pack_pyramid(arena, plan, live_dev, canonical_dev, packs, canonicals, stream));
+
+	float *warp_a, *warp_b, *g_post, *scratch_a = nullptr, *scratch_b = nullptr;
+	unsigned* max_sq_bits;
+	LSF_TRY(arena.alloc(&warp_a, (size_t) finest.N * 3));
+	LSF_TRY(arena.alloc(&warp_b, (size_t) finest.N * 3 / 8 + 16));
+	LSF_TRY(arena.alloc(&g_post, (size_t) finest.N * 3));
+	if (plan.use_kernel || plan.tikhonov) LSF_TRY(arena.alloc(&scratch_a, (size_t) finest.N * 3));
+	if (plan.use_kernel) LSF_TRY(arena.alloc(&scratch_b, (size_t) finest.N * 3));
+	const int slot_count = std::max(plan.max_iterations, 1);
+	LSF_TRY(arena.alloc(&max_sq_bits, (size_t) slot_count));
+	std::vector<unsigned> host_bits((size_t) slot_count);
+
+	// the finest level lives in warp_a (3N floats), the level below it in warp_b (3N/8), and so on alternating
+	float* warp_current = ((L - 1) % 2 == 0) ? warp_a : warp_b;
+	float* warp_next = ((L - 1) % 2 == 0) ? warp_b : warp_a;
+	LSF_CUDA(cudaMemsetAsync(warp_current, 0, (size_t) plan.level_grid[0].N * 3 * sizeof(float), stream));
+	if (capture) capture->count = 0;
+
+	for (int level = 0; level < L; level++) {
+		LevelState s;
+		s.g = plan.level_grid[level];
+		s.pack = packs[level];
+		s.canonical = canonicals[level];
+		s.warp = warp_current;
+		s.g_post = g_post;
+		s.scratch_a = scratch_a;
+		s.scratch_b = scratch_b;
+		s.max_sq_bits = max_sq_bits;
+		// reference optimizer.tpp:142-143: gradient = 0 at the start of every level
+		LSF_CUDA(cudaMemsetAsync(g_post, 0, (size_t) s.g.N * 3 * sizeof(float), stream));
+		LSF_CUDA(cudaMemsetAsync(max_sq_bits, 0, (size_t) slot_count * sizeof(unsigned), stream));
+		const bool capturing = capture && capture->level == level && capture_dev != nullptr;
+
+		int executed = 0;      // iterations known to have run
+		int enqueued = 0;
+		bool converged = false;
+		float last_max = FLT_MAX;
+		while (!converged && enqueued < plan.max_iterations) {
+			const int chunk_end = std::min(plan.max_iterations, enqueued + POLL_CHUNK);
+			for (int it = enqueued; it < chunk_end; it++) {
+				enqueue_iteration(plan, s, it, true, stream);
+				if (capturing && it < capture->max_iterations) {
+					k_planes_to_aos<<<counted(div_up(s.g.N, 256)), 256, 0, stream>>>(s.warp,
+							capture_dev + (size_t) it * s.g.N * 3, s.g.N, 3);
+				}
+			}
+			LSF_CUDA(cudaGetLastError());
+			LSF_CUDA(cudaMemcpyAsync(host_bits.data() + enqueued, max_sq_bits + enqueued,
+					(size_t) (chunk_end - enqueued) * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+			LSF_CUDA(cudaStreamSynchronize(stream));
+			for (int it = enqueued; it < chunk_end; it++) {
+				float sq;
+				std::memcpy(&sq, &host_bits[it], sizeof(float));
+				last_max = std::sqrt(sq);
+				executed = it + 1;
+				if (last_max < plan.threshold) {  // reference optimizer.tpp:166-171
+					converged = true;
+					break;
+				}
+			}
+			enqueued = chunk_end;
+		}
+		if (reports) {
+			lsf_level_report& r = reports[level];
+			std::memset(&r, 0, sizeof(r));
+			r.iteration_count = executed;
+			r.iteration_limit_reached = executed >= plan.max_iterations;
+			r.max_update_length = last_max;
+			r.dims[0] = s.g.X;
+			r.dims[1] = s.g.Y;
+			r.dims[2] = s.g.Z;
+		}
+		if (capturing) capture->count = std::min(executed, capture->max_iterations);
+		if (level != L - 1) {
+			// reference optimizer.tpp:124-126: prolong the warp (values are NOT doubled)
+			const Grid3& dg = plan.level_grid[level + 1];
+			if (plan.linear) k_upsample_linear3d<<<counted(grid3(dg)), block3(), 0, stream>>>(warp_current, warp_next, 3, s.g, dg);
+			else k_upsample_nearest3d<<<counted(grid3(dg)), block3(), 0, stream>>>(warp_current, warp_next, 3, s.g, dg);
+			std::swap(warp_current, warp_next);
+		}
+	}
+	k_planes_to_aos<<<counted(div_up(finest.N, 256)), 256, 0, stream>>>(warp_current, warp_out_dev, finest.N, 3);
+	LSF_CUDA(cudaGetLastError());
+	return LSF_OK;
+}
+
+}  // namespace
+
+}  // namespace lsf
+
+using namespace lsf;
+
+extern "C" int lsf_hier_optimize_3d(const lsf_hier_params* params, const float* canonical, const float* live, int X,
+		int Y, int Z, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
+		lsf_iteration_capture* capture, void* stream_handle) {
+	(void) collect_reports;
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
+	Plan3 plan;
+	LSF_TRY(make_plan(params, X, Y, Z, &plan));
+	LSF_REQUIRE(canonical && live && warp_out, "canonical, live and warp_out must not be NULL");
+	const size_t N = (size_t) X * Y * Z;
+	Arena arena(stream);
+	const float *canonical_dev, *live_dev;
+	LSF_TRY(to_device(arena, canonical, N, memory_kind, stream, &canonical_dev));
+	LSF_TRY(to_device(arena, live, N, memory_kind, stream, &live_dev));
+	float* out_dev = warp_out;
+	if (memory_kind == LSF_HOST) LSF_TRY(arena.alloc(&out_dev, N * 3));
+	float* capture_dev = nullptr;
+	size_t capture_count = 0;
+	if (capture && capture->level >= 0 && capture->level < plan.level_count && capture->max_iterations > 0
+			&& capture->buffer) {
+		capture_count = (size_t) capture->max_iterations * plan.level_grid[capture->level].N * 3;
+		if (memory_kind == LSF_HOST) LSF_TRY(arena.alloc(&capture_dev, capture_count));
+		else capture_dev = capture->buffer;
+	}
+	LSF_TRY(optimize_device(plan, canonical_dev, live_dev, out_dev, reports, capture, capture_dev, stream));
+	if (memory_kind == LSF_HOST) {
+		if (capture_dev) {
+			const size_t used = (size_t) capture->count * plan.level_grid[capture->level].N * 3;
+			LSF_CUDA(cudaMemcpyAsync(capture->buffer, capture_dev, used * sizeof(float), cudaMemcpyDeviceToHost, stream));
+		}
+		LSF_TRY(from_device(out_dev, warp_out, N * 3, LSF_HOST, stream));
+	}
+	return plan.level_count;
+}
+
+extern "C" int lsf_hier_optimize_3d_batch(const lsf_hier_params* params, const float* canonical, const float* live,
+		int pair_count, int X, int Y, int Z, float* warp_out, int memory_kind, int* iteration_counts,
+		void* stream_handle) {
+	LSF_REQUIRE(pair_count >= 0, "pair_count must be non-negative");
+	const size_t N = (size_t) X * Y * Z;
+	int levels = 0;
+	std::vector<lsf_level_report> reports(LSF_MAX_LEVELS);
+	for (int pair = 0; pair < pair_count; pair++) {
+		levels = lsf_hier_optimize_3d(params, canonical + pair * N, live + pair * N, X, Y, Z, warp_out + pair * N * 3,
+				memory_kind, reports.data(), 0, nullptr, stream_handle);
+		if (levels < 0) return levels;
+		if (iteration_counts) {
+			for (int level = 0; level < LSF_MAX_LEVELS; level++)
+				iteration_counts[pair * LSF_MAX_LEVELS + level] = level < levels ? reports[level].iteration_count : 0;
+		}
+	}
+	if (pair_count == 0) {
+		Plan3 plan;
+		LSF_TRY(make_plan(params, X, Y, Z, &plan));
+		levels = plan.level_count;
+	}
+	return levels;
+}
+
+extern "C" int lsf_hier_iterate_3d(const lsf_hier_params* params, const float* canonical_dev, const float* live_dev,
+		int X, int Y, int Z, int iterations, float* elapsed_ms, int* kernel_launches, float* stage_ms,
+		void* stream_handle) {
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
+	Plan3 plan;
+	LSF_TRY(make_plan(params, X, Y, Z, &plan));
+	LSF_REQUIRE(iterations > 0, "iterations must be positive");
+	Arena arena(stream);
+	const int L = plan.level_count;
+	const Grid3& g = plan.level_grid[L - 1];
+	std::vector<float4*> packs;
+	std::vector<const float*> canonicals;
+	LSF_TRY(build_pack_pyramid(arena, plan, live_dev, canonical_dev, packs, canonicals, stream, L - 1));
+	LevelState s;
+	s.g = g;
+	s.pack = packs[L - 1];
+	s.canonical = canonical_dev;
+	LSF_TRY(arena.alloc(&s.warp, (size_t) g.N * 3));
+	LSF_TRY(arena.alloc(&s.g_post, (size_t) g.N * 3));
+	LSF_TRY(arena.alloc(&s.scratch_a, (size_t) g.N * 3));
+	LSF_TRY(arena.alloc(&s.scratch_b, (size_t) g.N * 3));
+	LSF_TRY(arena.alloc(&s.max_sq_bits, (size_t) iterations));
+	LSF_CUDA(cudaMemsetAsync(s.warp, 0, (size_t) g.N * 3 * sizeof(float), stream));
+	LSF_CUDA(cudaMemsetAsync(s.g_post, 0, (size_t) g.N * 3 * sizeof(float), stream));
+	LSF_CUDA(cudaMemsetAsync(s.max_sq_bits, 0, (size_t) iterations * sizeof(unsigned), stream));
+	cudaEvent_t start, stop;
+	LSF_CUDA(cudaEventCreate(&start));
+	LSF_CUDA(cudaEventCreate(&stop));
+	int launches = 0;
+	LSF_CUDA(cudaEventRecord(start, stream));
+	if (stage_ms) {
+		// per-stage mode: events around every kernel, accumulated per stage (the total then includes event overhead)
+		cudaEvent_t marks[5];
+		for (auto& m : marks) LSF_CUDA(cudaEventCreate(&m));
+		for (int i = 0; i < 4; i++) stage_ms[i] = 0.0f;
+		for (int it = 0; it < iterations; it++) {
+			const int n = enqueue_iteration(plan, s, it, false, stream, marks);
+			launches += n;
+			LSF_CUDA(cudaEventSynchronize(marks[n]));
+			for (int i = 0; i < n; i++) {
+				float part = 0.0f;
+				LSF_CUDA(cudaEventElapsedTime(&part, marks[i], marks[i + 1]));
+				stage_ms[i] += part;
+			}
+		}
+		for (auto& m : marks) cudaEventDestroy(m);
+	} else {
+		for (int it = 0; it < iterations; it++) launches += enqueue_iteration(plan, s, it, false, stream);
+	}
+	LSF_CUDA(cudaEventRecord(stop, stream));
+	LSF_CUDA(cudaEventSynchronize(stop));
+	LSF_CUDA(cudaGetLastError());
+	float ms = 0.0f;
+	LSF_CUDA(cudaEventElapsedTime(&ms, start, stop));
+	cudaEventDestroy(start);
+	cudaEventDestroy(stop);
+	if (elapsed_ms) *elapsed_ms = ms;
+	if (kernel_launches) *kernel_launches = launches;
+	return LSF_OK;
+}

@@ -1,0 +1,196 @@
+"""HierarchicalOptimizer2d / HierarchicalOptimizer3d -- host-side mirror of the reference's classes
+(cpp/src/python_export/hierarchical_optimizer.tpp:40-135; constructor defaults
+cpp/src/nonrigid_optimization/hierarchical/optimizer.hpp:51-65; Python twin
+nonrigid_opt/hierarchical/hierarchical_optimizer2d.py:62-121).
+
+``optimize(canonical_field, live_field)`` returns the warp field ([H,W,2] / [X,Y,Z,3] float32), exactly like the
+reference. numpy arguments are staged through the device by the library (LSF_HOST); torch CUDA tensors are used
+in place (LSF_DEVICE) on torch's current stream and a torch tensor is returned.
+"""
+import ctypes
+import enum
+
+import numpy as np
+
+from . import _lib
+
+
+class ConvergenceReport:
+    """Per-level outcome (reference telemetry::ConvergenceReport, cpp/src/telemetry/convergence_report.hpp:40-44)."""
+
+    def __init__(self, raw):
+        self.iteration_count = int(raw.iteration_count)
+        self.iteration_limit_reached = bool(raw.iteration_limit_reached)
+        self.max_update_length = float(raw.max_update_length)
+        self.dims = tuple(int(d) for d in raw.dims)
+
+    def __repr__(self):
+        return ("ConvergenceReport(iteration_count=%d, iteration_limit_reached=%s, max_update_length=%g)"
+                % (self.iteration_count, self.iteration_limit_reached, self.max_update_length))
+
+
+class _HierarchicalOptimizer:
+    _nd = 0
+
+    class ResamplingStrategy(enum.IntEnum):
+        NEAREST_AND_AVERAGE = 0
+        LINEAR = 1
+
+    class VerbosityParameters:
+        def __init__(self, print_max_warp_update=False, print_iteration_mean_tsdf_difference=False,
+                     print_iteration_std_tsdf_difference=False, print_iteration_data_energy=False,
+                     print_iteration_tikhonov_energy=False):
+            self.print_iteration_max_warp_update = print_max_warp_update
+            self.print_iteration_mean_tsdf_difference = print_iteration_mean_tsdf_difference
+            self.print_iteration_std_tsdf_difference = print_iteration_std_tsdf_difference
+            self.print_iteration_data_energy = print_iteration_data_energy
+            self.print_iteration_tikhonov_energy = print_iteration_tikhonov_energy
+            self.print_per_iteration_info = any((print_max_warp_update, print_iteration_mean_tsdf_difference,
+                                                 print_iteration_std_tsdf_difference, print_iteration_data_energy,
+                                                 print_iteration_tikhonov_energy))
+            self.print_per_level_info = self.print_per_iteration_info
+
+    class LoggingParameters:
+        def __init__(self, collect_per_level_convergence_reports=False, collect_per_level_iteration_data=False):
+            self.collect_per_level_convergence_reports = collect_per_level_convergence_reports
+            self.collect_per_level_iteration_data = collect_per_level_iteration_data
+
+    def __init__(self,
+                 tikhonov_term_enabled=True,
+                 gradient_kernel_enabled=True,
+                 maximum_chunk_size=8,
+                 rate=0.1,
+                 maximum_iteration_count=100,
+                 maximum_warp_update_threshold=0.001,
+                 data_term_amplifier=1.0,
+                 tikhonov_strength=0.2,
+                 kernel=None,
+                 resampling_strategy=None,
+                 verbosity_parameters=None,
+                 logging_parameters=None):
+        self.tikhonov_term_enabled = bool(tikhonov_term_enabled)
+        self.gradient_kernel_enabled = bool(gradient_kernel_enabled)
+        self.maximum_chunk_size = int(maximum_chunk_size)
+        self.rate = float(rate)
+        self.maximum_iteration_count = int(maximum_iteration_count)
+        self.maximum_warp_update_threshold = float(maximum_warp_update_threshold)
+        self.data_term_amplifier = float(data_term_amplifier)
+        self.tikhonov_strength = float(tikhonov_strength)
+        self.kernel = None if kernel is None else np.ascontiguousarray(np.asarray(kernel).ravel(), dtype=np.float32)
+        if resampling_strategy is None:
+            resampling_strategy = self.ResamplingStrategy.NEAREST_AND_AVERAGE
+        self.resampling_strategy = self.ResamplingStrategy(int(resampling_strategy))
+        self.verbosity_parameters = verbosity_parameters or self.VerbosityParameters()
+        self.logging_parameters = logging_parameters or self.LoggingParameters()
+        self._reports = []
+        self._iteration_data = []
+
+    # ------------------------------------------------------------------ C-ABI plumbing
+    def _params(self):
+        p = _lib.HierParams()
+        p.tikhonov_term_enabled = int(self.tikhonov_term_enabled)
+        p.gradient_kernel_enabled = int(self.gradient_kernel_enabled)
+        p.maximum_chunk_size = self.maximum_chunk_size
+        p.rate = self.rate
+        p.maximum_iteration_count = self.maximum_iteration_count
+        p.maximum_warp_update_threshold = self.maximum_warp_update_threshold
+        p.data_term_amplifier = self.data_term_amplifier
+        p.tikhonov_strength = self.tikhonov_strength
+        if self.kernel is not None and self.kernel.size > 0:
+            p.kernel = _lib.fptr(self.kernel)
+            p.kernel_size = int(self.kernel.size)
+        else:
+            p.kernel = None
+            p.kernel_size = 0
+        p.resampling_strategy = int(self.resampling_strategy)
+        return p
+
+    def optimize(self, canonical_field, live_field, capture_level=-1, capture_iterations=0, out=None):
+        """Find the warp that maps `live_field` onto `canonical_field` (reference optimizer.tpp:83-131).
+
+        capture_level / capture_iterations (extension used by the parity tests): additionally keeps the warp
+        field after each of the first `capture_iterations` iterations of pyramid level `capture_level`;
+        retrieve with get_captured_warps(). `out` (extension): preallocated float32 C-contiguous result buffer
+        (e.g. a pinned numpy view) to write the warp field into."""
+        nd = self._nd
+        on_device = _lib.is_torch_cuda(canonical_field) or _lib.is_torch_cuda(live_field)
+        if on_device:
+            import torch
+            if not (_lib.is_torch_cuda(canonical_field) and _lib.is_torch_cuda(live_field)):
+                raise ValueError("canonical_field and live_field must live on the same device")
+            canonical = canonical_field.contiguous().float()
+            live = live_field.contiguous().float()
+            shape = tuple(int(d) for d in canonical.shape)
+        else:
+            canonical = _lib.as_f32(canonical_field)
+            live = _lib.as_f32(live_field)
+            shape = canonical.shape
+        if len(shape) != nd or tuple(live.shape) != tuple(shape):
+            raise ValueError("expected two %dD fields of equal shape, got %s and %s"
+                             % (nd, tuple(canonical.shape), tuple(live.shape)))
+        lib = _lib.load()
+        params = self._params()
+        reports = (_lib.LevelReport * _lib.LSF_MAX_LEVELS)()
+        capture = _lib.IterationCapture()
+        capture.level = int(capture_level)
+        capture.max_iterations = int(capture_iterations)
+        capture_buffer = None
+        if capture_level >= 0 and capture_iterations > 0:
+            level_count = int(np.log2(self.maximum_chunk_size)) + 1
+            shrink = 2 ** (level_count - 1 - capture_level)
+            level_shape = tuple(d // shrink for d in shape)
+        if on_device:
+            import torch
+            warp = torch.empty(shape + (nd,), dtype=torch.float32, device=canonical.device)
+            kind, stream = _lib.LSF_DEVICE, _lib.current_stream_handle()
+            ptr = lambda t: ctypes.cast(ctypes.c_void_p(t.data_ptr()), _lib.c_float_p)
+            if capture_level >= 0 and capture_iterations > 0:
+                capture_buffer = torch.zeros((capture_iterations,) + level_shape + (nd,), dtype=torch.float32,
+                                             device=canonical.device)
+                capture.buffer = ptr(capture_buffer)
+        else:
+            if out is not None:
+                if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.c_contiguous
+                        and out.shape == tuple(shape) + (nd,)):
+                    raise ValueError("out must be a C-contiguous float32 array of shape %s" % (tuple(shape) + (nd,),))
+                warp = out
+            else:
+                warp = np.empty(tuple(shape) + (nd,), dtype=np.float32)
+            kind, stream = _lib.LSF_HOST, ctypes.c_void_p(0)
+            ptr = _lib.fptr
+            if capture_level >= 0 and capture_iterations > 0:
+                capture_buffer = np.zeros((capture_iterations,) + level_shape + (nd,), dtype=np.float32)
+                capture.buffer = ptr(capture_buffer)
+        fn = lib.lsf_hier_optimize_2d if nd == 2 else lib.lsf_hier_optimize_3d
+        collect = int(self.logging_parameters.collect_per_level_convergence_reports)
+        levels = _lib.check(fn(ctypes.byref(params), ptr(canonical), ptr(live), *[ctypes.c_int(d) for d in shape],
+                               ptr(warp), kind, reports, collect, ctypes.byref(capture), stream))
+        self._reports = [ConvergenceReport(reports[i]) for i in range(levels)]
+        self._captured = None if capture_buffer is None else capture_buffer[:capture.count]
+        if self.verbosity_parameters.print_per_level_info:
+            for level, report in enumerate(self._reports):
+                print("[LEVEL %d COMPLETED] iterations: %d max upd. l.: %g"
+                      % (level, report.iteration_count, report.max_update_length))
+        return warp
+
+    def get_per_level_convergence_reports(self):
+        return list(self._reports)
+
+    def get_per_level_iteration_counts(self):
+        return [r.iteration_count for r in self._reports]
+
+    def get_captured_warps(self):
+        return self._captured
+
+    def get_per_level_iteration_data(self):
+        return list(self._iteration_data)
+
+
+class HierarchicalOptimizer2d(_HierarchicalOptimizer):
+    """reference `level_set_fusion_optimization.HierarchicalOptimizer2d`"""
+    _nd = 2
+
+
+class HierarchicalOptimizer3d(_HierarchicalOptimizer):
+    """reference `level_set_fusion_optimization.HierarchicalOptimizer3d`"""
+    _nd = 3
