@@ -5,11 +5,13 @@
 // sm_100a kernels. The level loop never synchronises with the host inside an iteration: the
 // termination test (optimizer.tpp:166-171) is evaluated on the device at the head of every kernel from
 // the previous iteration's max ||g||^2 slot, and the host polls the slots once per chunk of iterations.
-#include "kernels3d.cuh"
+#include "kernels3d_fused.cuh"
 
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+#include <cstdint>
 #include <algorithm>
 
 namespace lsf {
@@ -24,6 +26,7 @@ struct Plan3 {
 	Taps taps;
 	float rate = 0, threshold = 0, amplifier = 0, strength = 0;
 	int max_iterations = 0;
+	bool allow_fast_kernels = true;    // false: first-generation kernels only (kept for A/B parity tests)
 	Grid3 level_grid[LSF_MAX_LEVELS];  // [0] = coarsest
 };
 
@@ -68,7 +71,13 @@ int make_plan(const lsf_hier_params* p, int X, int Y, int Z, Plan3* plan) {
 	plan->amplifier = p->data_term_amplifier;
 	plan->strength = p->tikhonov_strength;
 	plan->max_iterations = p->maximum_iteration_count;
+	const char* legacy = getenv("LSF_LEGACY_KERNELS");
+	plan->allow_fast_kernels = !(legacy && legacy[0] == '1');
 	return LSF_OK;
+}
+
+inline bool aligned16(const void* p) {
+	return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }
 
 struct LevelState {
@@ -104,23 +113,45 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 	a.max_sq_bits = s.max_sq_bits;
 	a.iteration = iteration;
 	a.check_convergence = check_convergence ? 1 : 0;
-	const dim3 grid = grid3(s.g), block = block3();
+	dim3 grid = grid3(s.g), block = block3();
+	// 4-voxel-per-thread stage 1 needs whole float4 groups along z, aligned planes and 32-bit voxel indices
+	const bool v4 = plan.allow_fast_kernels && s.g.Z % 4 == 0 && s.g.N * 3 < (1ll << 31) && s.g.padded_count() < (1ll << 31)
+			&& aligned16(s.canonical) && aligned16(s.warp) && aligned16(s.g_post) && aligned16(s.scratch_a);
+	if (v4) launch_shape_v4(s.g, &grid, &block);
 	if (!plan.use_kernel) {
 		if (plan.tikhonov) {
 			a.g_out = s.scratch_a;
-			k_hier_gradient3d<true, true> <<<counted(grid), block, 0, stream>>>(a);
+			if (v4) k_hier_gradient3d_v4<true, true> <<<counted(grid), block, 0, stream>>>(a);
+			else k_hier_gradient3d<true, true> <<<counted(grid), block, 0, stream>>>(a);
 			std::swap(s.g_post, s.scratch_a);
 		} else {
 			a.g_out = nullptr;
-			k_hier_gradient3d<false, true> <<<counted(grid), block, 0, stream>>>(a);
+			if (v4) k_hier_gradient3d_v4<false, true> <<<counted(grid), block, 0, stream>>>(a);
+			else k_hier_gradient3d<false, true> <<<counted(grid), block, 0, stream>>>(a);
 		}
 		mark(1);
 		return 1;
 	}
 	a.g_out = s.scratch_a;
-	if (plan.tikhonov) k_hier_gradient3d<true, false> <<<counted(grid), block, 0, stream>>>(a);
-	else k_hier_gradient3d<false, false> <<<counted(grid), block, 0, stream>>>(a);
+	if (plan.tikhonov) {
+		if (v4) k_hier_gradient3d_v4<true, false> <<<counted(grid), block, 0, stream>>>(a);
+		else k_hier_gradient3d<true, false> <<<counted(grid), block, 0, stream>>>(a);
+	} else {
+		if (v4) k_hier_gradient3d_v4<false, false> <<<counted(grid), block, 0, stream>>>(a);
+		else k_hier_gradient3d<false, false> <<<counted(grid), block, 0, stream>>>(a);
+	}
 	mark(1);
+	// stage 2: the three filter passes + update + max-norm in ONE kernel for the usual 3/5/7-tap kernels
+	if (plan.allow_fast_kernels && (plan.taps.radius >= 1 && plan.taps.radius <= 3)) {
+		float* filtered = plan.tikhonov ? s.g_post : nullptr;  // only the Tikhonov term reads g of the last iteration
+		const int check = a.check_convergence;
+		launch_fused_filter_any(plan.taps, plan.rate, plan.threshold, s.g, s.scratch_a, filtered, s.warp, s.max_sq_bits,
+				iteration, check, stream);
+		mark(2);
+		return 2;
+	}
+	grid = grid3(s.g);
+	block = block3();
 	ConvArgs c;
 	c.g = s.g;
 	c.taps = plan.taps;

@@ -3,6 +3,9 @@
 // (gather4 on the padded pack, laplace_term, k_convolve_axis*, restrict / prolong kernels) on API-layout
 // (interleaved) arrays, so the parity tests of the primitives exercise the optimizer's kernels.
 #include "kernels2d.cuh"
+#include "kernels3d_fused.cuh"
+
+#include <cstdlib>
 
 namespace lsf {
 namespace {
@@ -156,6 +159,13 @@ extern "C" int lsf_convolve_3d(float* vfield, int X, int Y, int Z, const float* 
 	LSF_TRY(st.arena.alloc(&a, (size_t) g.N * 3));
 	LSF_TRY(st.arena.alloc(&b, (size_t) g.N * 3));
 	k_aos_to_planes<<<counted(blocks_for(g.N)), 256, 0, st.stream>>>(in_dev, a, g.N, 3);
+	const char* legacy = getenv("LSF_LEGACY_KERNELS");
+	if (!(legacy && legacy[0] == '1')
+			&& launch_fused_filter_any(taps, 0.0f, 0.0f, g, a, b, nullptr, nullptr, 0, 0, st.stream)) {
+		// the optimizer's fused three-pass kernel, filter only
+		k_planes_to_aos<<<counted(blocks_for(g.N)), 256, 0, st.stream>>>(b, out_dev, g.N, 3);
+		return st.finish(out_dev, vfield, (size_t) g.N * 3);
+	}
 	ConvArgs c;
 	c.g = g;
 	c.taps = taps;

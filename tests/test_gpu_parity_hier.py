@@ -302,3 +302,26 @@ def test_full_size_properties_256(lsf):
     second = optimizer.optimize(canonical, live)
     assert bool((first == second).all())
     assert float(first.abs().max()) > 0.0
+
+
+@pytest.mark.parametrize("mode", ["tikhonov", "tikhonov_kernel", "kernel"])
+def test_fused_kernels_match_first_generation_kernels(lsf, mode, monkeypatch):
+    """A/B: the fused production kernels (4 voxels/thread stage 1, single-kernel separable filter) against the
+    straightforward one-voxel-per-thread kernels (LSF_LEGACY_KERNELS=1) -- bit-identical."""
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(64)
+    canonical, live = canonical[:, :48, :40].copy(), live[:, :48, :40].copy()  # tiles cut by the volume border
+    kwargs = dict(HIER_MODES[mode])
+    kwargs.update(maximum_chunk_size=4, maximum_iteration_count=12, kernel=synthetic.sobolev_kernel_1d())
+    fast = lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live)
+    monkeypatch.setenv("LSF_LEGACY_KERNELS", "1")
+    legacy = lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live)
+    assert np.array_equal(fast, legacy)
+    rng = np.random.default_rng(9)
+    vec = rng.standard_normal((70, 37, 45, 3)).astype(np.float32)
+    for taps in (3, 5, 7):
+        kernel = rng.random(taps).astype(np.float32)
+        slow = lsf.ops.convolve_with_kernel(vec, kernel)
+        monkeypatch.delenv("LSF_LEGACY_KERNELS")
+        assert np.array_equal(lsf.ops.convolve_with_kernel(vec, kernel), slow)
+        monkeypatch.setenv("LSF_LEGACY_KERNELS", "1")
