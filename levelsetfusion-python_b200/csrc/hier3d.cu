@@ -27,6 +27,9 @@ struct Plan3 {
 	float rate = 0, threshold = 0, amplifier = 0, strength = 0;
 	int max_iterations = 0;
 	bool allow_fast_kernels = true;    // false: first-generation kernels only (kept for A/B parity tests)
+	int lane_xv = 4;                   // planes per thread of the lane-contiguous stage 1 (LSF_LANE_XV overrides;
+	                                   // measured best on B200: 2 with the Tikhonov term, 4 without)
+	int stage1_variant = 2;            // LSF_STAGE1_VARIANT=1 selects the 4-voxel kernel (A/B)
 	Grid3 level_grid[LSF_MAX_LEVELS];  // [0] = coarsest
 };
 
@@ -73,6 +76,11 @@ int make_plan(const lsf_hier_params* p, int X, int Y, int Z, Plan3* plan) {
 	plan->max_iterations = p->maximum_iteration_count;
 	const char* legacy = getenv("LSF_LEGACY_KERNELS");
 	plan->allow_fast_kernels = !(legacy && legacy[0] == '1');
+	const char* stage1 = getenv("LSF_STAGE1_VARIANT");
+	if (stage1 && stage1[0] == '1') plan->stage1_variant = 1;
+	plan->lane_xv = plan->tikhonov ? 2 : 4;
+	const char* xv = getenv("LSF_LANE_XV");
+	if (xv && (atoi(xv) == 1 || atoi(xv) == 2 || atoi(xv) == 4 || atoi(xv) == 8)) plan->lane_xv = atoi(xv);
 	return LSF_OK;
 }
 
@@ -114,32 +122,42 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 	a.iteration = iteration;
 	a.check_convergence = check_convergence ? 1 : 0;
 	dim3 grid = grid3(s.g), block = block3();
-	// 4-voxel-per-thread stage 1 needs whole float4 groups along z, aligned planes and 32-bit voxel indices
-	const bool v4 = plan.allow_fast_kernels && s.g.Z % 4 == 0 && s.g.N * 3 < (1ll << 31) && s.g.padded_count() < (1ll << 31)
-			&& aligned16(s.canonical) && aligned16(s.warp) && aligned16(s.g_post) && aligned16(s.scratch_a);
-	if (v4) launch_shape_v4(s.g, &grid, &block);
+	// stage-1 variants: 0 = first generation (one voxel per thread, 64-bit indices), 1 = 4 z-voxels per thread
+	// (128-bit loads), 2 = lane-contiguous x-marching (default: best L1 behaviour, see profiles/)
+	const bool small_indices = s.g.N * 3 < (1ll << 31) && s.g.padded_count() < (1ll << 31);
+	int variant = 0;
+	if (plan.allow_fast_kernels && small_indices) {
+		variant = 2;
+		if (plan.stage1_variant == 1 && s.g.Z % 4 == 0 && aligned16(s.canonical) && aligned16(s.warp)
+				&& aligned16(s.g_post) && aligned16(s.scratch_a)) variant = 1;
+	}
+	if (variant == 1) launch_shape_v4(s.g, &grid, &block);
+	if (variant == 2) launch_shape_lane(s.g, plan.lane_xv, &grid, &block);
+#define LSF_LAUNCH_STAGE1(TIK, FUSE)                                                                      \
+	do {                                                                                                  \
+		if (variant == 2 && plan.lane_xv == 1) k_hier_gradient3d_lane<TIK, FUSE, 1> <<<counted(grid), block, 0, stream>>>(a); \
+		else if (variant == 2 && plan.lane_xv == 2) k_hier_gradient3d_lane<TIK, FUSE, 2> <<<counted(grid), block, 0, stream>>>(a); \
+		else if (variant == 2 && plan.lane_xv == 8) k_hier_gradient3d_lane<TIK, FUSE, 8> <<<counted(grid), block, 0, stream>>>(a); \
+		else if (variant == 2) k_hier_gradient3d_lane<TIK, FUSE, 4> <<<counted(grid), block, 0, stream>>>(a); \
+		else if (variant == 1) k_hier_gradient3d_v4<TIK, FUSE> <<<counted(grid), block, 0, stream>>>(a);       \
+		else k_hier_gradient3d<TIK, FUSE> <<<counted(grid), block, 0, stream>>>(a);                          \
+	} while (0)
 	if (!plan.use_kernel) {
 		if (plan.tikhonov) {
 			a.g_out = s.scratch_a;
-			if (v4) k_hier_gradient3d_v4<true, true> <<<counted(grid), block, 0, stream>>>(a);
-			else k_hier_gradient3d<true, true> <<<counted(grid), block, 0, stream>>>(a);
+			LSF_LAUNCH_STAGE1(true, true);
 			std::swap(s.g_post, s.scratch_a);
 		} else {
 			a.g_out = nullptr;
-			if (v4) k_hier_gradient3d_v4<false, true> <<<counted(grid), block, 0, stream>>>(a);
-			else k_hier_gradient3d<false, true> <<<counted(grid), block, 0, stream>>>(a);
+			LSF_LAUNCH_STAGE1(false, true);
 		}
 		mark(1);
 		return 1;
 	}
 	a.g_out = s.scratch_a;
-	if (plan.tikhonov) {
-		if (v4) k_hier_gradient3d_v4<true, false> <<<counted(grid), block, 0, stream>>>(a);
-		else k_hier_gradient3d<true, false> <<<counted(grid), block, 0, stream>>>(a);
-	} else {
-		if (v4) k_hier_gradient3d_v4<false, false> <<<counted(grid), block, 0, stream>>>(a);
-		else k_hier_gradient3d<false, false> <<<counted(grid), block, 0, stream>>>(a);
-	}
+	if (plan.tikhonov) LSF_LAUNCH_STAGE1(true, false);
+	else LSF_LAUNCH_STAGE1(false, false);
+#undef LSF_LAUNCH_STAGE1
 	mark(1);
 	// stage 2: the three filter passes + update + max-norm in ONE kernel for the usual 3/5/7-tap kernels
 	if (plan.allow_fast_kernels && (plan.taps.radius >= 1 && plan.taps.radius <= 3)) {

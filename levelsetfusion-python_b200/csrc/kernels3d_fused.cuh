@@ -170,6 +170,96 @@ inline void launch_shape_v4(const Grid3& g, dim3* grid, dim3* block) {
 	*grid = dim3(div_up(zgroups, bx), div_up(g.Y, by), div_up(g.X, bz));
 }
 
+// ---------------------------------------------------------------------------------------------- stage 1, lane-contiguous
+// Same arithmetic again (reference optimizer.tpp:186-200 [+ :207-211]), organised for the L1 pipe: the ncu capture of
+// the 4-voxel version (profiles/r1_ncu_fused_v1.md) showed 25 sectors per gather request because the lanes of a warp
+// addressed pack entries 64 B apart. Here the 32 lanes of a warp are 32 consecutive z voxels (every LDG.128 of the
+// gather touches 4 lines, every scalar load one), and a thread marches over XV planes along x so that the Tikhonov
+// term re-uses the x-1 / x / x+1 values of g_prev from registers.
+__device__ __forceinline__ float laplace_axis3(float prev, float cur, float next, int i, int n) {
+	if (n < 2) return 0.0f;
+	if (i == 0) return next - cur;
+	if (i == n - 1) return prev - cur;
+	return (next - 2.0f * cur) + prev;
+}
+
+template<bool TIKHONOV, bool FUSE_UPDATE, int XV>
+static __global__ void __launch_bounds__(256) k_hier_gradient3d_lane(HierIterArgs a) {
+	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
+	const int X = a.g.X, Y = a.g.Y, Z = a.g.Z;
+	const int YZ = Y * Z;
+	const int N = (int) a.g.N;
+	const int z = blockIdx.x * 32 + threadIdx.x;
+	const int y = blockIdx.y * 8 + threadIdx.y;
+	const int xb = blockIdx.z * XV;
+	float best = 0.0f;
+	if (z < Z && y < Y) {
+		int idx = (xb * Y + y) * Z + z;
+		float prev[3] = { 0.f, 0.f, 0.f }, cur[3] = { 0.f, 0.f, 0.f };
+		if (TIKHONOV) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				cur[c] = __ldg(a.g_prev + c * N + idx);
+				if (xb > 0) prev[c] = __ldg(a.g_prev + c * N + idx - YZ);
+			}
+		}
+#pragma unroll
+		for (int v = 0; v < XV; v++) {
+			const int x = xb + v;
+			if (x >= X) break;
+			const float wx = __ldg(a.warp + idx), wy = __ldg(a.warp + N + idx), wz = __ldg(a.warp + 2 * N + idx);
+			const float cn = __ldg(a.canonical + idx);
+			float lap[3] = { 0.f, 0.f, 0.f };
+			if (TIKHONOV) {
+#pragma unroll
+				for (int c = 0; c < 3; c++) {
+					const float* p = a.g_prev + c * N + idx;
+					const float next = (x + 1 < X) ? __ldg(p + YZ) : 0.0f;
+					const float yp = (y > 0) ? __ldg(p - Z) : 0.0f, yn = (y + 1 < Y) ? __ldg(p + Z) : 0.0f;
+					const float zp = (z > 0) ? __ldg(p - 1) : 0.0f, zn = (z + 1 < Z) ? __ldg(p + 1) : 0.0f;
+					float acc = laplace_axis3(prev[c], cur[c], next, x, X);
+					acc += laplace_axis3(yp, cur[c], yn, y, Y);
+					acc += laplace_axis3(zp, cur[c], zn, z, Z);
+					lap[c] = acc;
+					prev[c] = cur[c];
+					cur[c] = next;
+				}
+			}
+			const float4 s = gather4i(a.pack, X, Y, Z, x, y, z, wx, wy, wz);
+			const float diff = s.x - cn;
+			float gx = (s.y * diff) * a.amplifier;
+			float gy = (s.z * diff) * a.amplifier;
+			float gz = (s.w * diff) * a.amplifier;
+			if (TIKHONOV) {
+				gx = gx - lap[0] * a.strength;
+				gy = gy - lap[1] * a.strength;
+				gz = gz - lap[2] * a.strength;
+			}
+			if (a.g_out != nullptr) {
+				a.g_out[idx] = gx;
+				a.g_out[N + idx] = gy;
+				a.g_out[2 * N + idx] = gz;
+			}
+			if (FUSE_UPDATE) {
+				a.warp_out[idx] = wx - gx * a.rate;
+				a.warp_out[N + idx] = wy - gy * a.rate;
+				a.warp_out[2 * N + idx] = wz - gz * a.rate;
+				float sq = gx * gx;
+				sq += gy * gy;
+				sq += gz * gz;
+				if (sq > best) best = sq;
+			}
+			idx += YZ;
+		}
+	}
+	if (FUSE_UPDATE) block_atomic_max(best, a.max_sq_bits + a.iteration);
+}
+
+inline void launch_shape_lane(const Grid3& g, int xv, dim3* grid, dim3* block) {
+	*block = dim3(32, 8, 1);
+	*grid = dim3(div_up(g.Z, 32), div_up(g.Y, 8), div_up(g.X, xv));
+}
+
 // ---------------------------------------------------------------------------------------------- stage 2, fused
 template<int R>
 struct FusedConv {
