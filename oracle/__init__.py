@@ -46,8 +46,8 @@ class IterationDump(ctypes.Structure):
 
 def build(force=False):
     """Compile the oracle with the recipe in oracle/Makefile (g++ -O3 -fopenmp -ffp-contract=off)."""
-    src = os.path.join(_HERE, "lsf_oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    sources = [os.path.join(_HERE, name) for name in ("lsf_oracle.cpp", "lsf_oracle_slavcheva.cpp", "lsf_oracle.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(map(os.path.getmtime, sources)):
         subprocess.run(["make", "-C", _HERE, "-B", "liblsf_oracle.so"], check=True, capture_output=True)
     return _LIB_PATH
 
@@ -224,3 +224,166 @@ def hier_time_iterations3d(canonical, live, iterations, **kwargs):
     p = make_hier_params(**kwargs)
     return float(lib().orc_hier_time_iterations3d(ctypes.byref(p), _p(canonical), _p(live),
                                                   *map(ctypes.c_int, canonical.shape), int(iterations)))
+
+
+# ------------------------------------------------------------------ slavcheva (SobolevFusion / KillingFusion) optimizers
+SEMANTICS_CPP, SEMANTICS_PY_DIRECT, SEMANTICS_PY_VECTORIZED = 0, 1, 2
+DATA_TERM_BASIC, DATA_TERM_THRESHOLDED_FDM = 0, 1
+SMOOTHING_TIKHONOV, SMOOTHING_KILLING = 0, 1
+
+
+class SlavchevaParams(ctypes.Structure):
+    _fields_ = [
+        ("semantics", ctypes.c_int),
+        ("data_term_method", ctypes.c_int),
+        ("smoothing_term_method", ctypes.c_int),
+        ("level_set_term_enabled", ctypes.c_int),
+        ("sobolev_smoothing_enabled", ctypes.c_int),
+        ("gradient_descent_rate", ctypes.c_float),
+        ("data_term_weight", ctypes.c_float),
+        ("smoothing_term_weight", ctypes.c_float),
+        ("isomorphic_enforcement_factor", ctypes.c_float),
+        ("level_set_term_weight", ctypes.c_float),
+        ("maximum_warp_length_lower_threshold", ctypes.c_float),
+        ("maximum_warp_length_upper_threshold", ctypes.c_float),
+        ("max_iterations", ctypes.c_int),
+        ("min_iterations", ctypes.c_int),
+        ("kernel", c_float_p),
+        ("kernel_size", ctypes.c_int),
+    ]
+
+
+class WarpDeltaStatistics(ctypes.Structure):
+    _fields_ = [("ratio_above_min_threshold", ctypes.c_float), ("length_min", ctypes.c_float),
+                ("length_max", ctypes.c_float), ("length_mean", ctypes.c_float),
+                ("length_standard_deviation", ctypes.c_float), ("longest_warp_location", ctypes.c_int * 3),
+                ("is_largest_below_min_threshold", ctypes.c_int), ("is_largest_above_max_threshold", ctypes.c_int)]
+
+
+class TsdfDifferenceStatistics(ctypes.Structure):
+    _fields_ = [("difference_min", ctypes.c_float), ("difference_max", ctypes.c_float),
+                ("difference_mean", ctypes.c_float), ("difference_standard_deviation", ctypes.c_float),
+                ("biggest_difference_location", ctypes.c_int * 3)]
+
+
+def make_slavcheva_params(semantics=SEMANTICS_CPP, data_term_method=DATA_TERM_BASIC,
+                          smoothing_term_method=SMOOTHING_TIKHONOV, level_set_term_enabled=False,
+                          sobolev_smoothing_enabled=True, gradient_descent_rate=0.1, data_term_weight=1.0,
+                          smoothing_term_weight=0.2, isomorphic_enforcement_factor=0.1, level_set_term_weight=0.2,
+                          maximum_warp_length_lower_threshold=0.1, maximum_warp_length_upper_threshold=10000.0,
+                          max_iterations=100, min_iterations=1, sobolev_kernel=None):
+    p = SlavchevaParams()
+    p.semantics = int(semantics)
+    p.data_term_method = int(data_term_method)
+    p.smoothing_term_method = int(smoothing_term_method)
+    p.level_set_term_enabled = int(bool(level_set_term_enabled))
+    p.sobolev_smoothing_enabled = int(bool(sobolev_smoothing_enabled))
+    p.gradient_descent_rate = gradient_descent_rate
+    p.data_term_weight = data_term_weight
+    p.smoothing_term_weight = smoothing_term_weight
+    p.isomorphic_enforcement_factor = isomorphic_enforcement_factor
+    p.level_set_term_weight = level_set_term_weight
+    p.maximum_warp_length_lower_threshold = maximum_warp_length_lower_threshold
+    p.maximum_warp_length_upper_threshold = maximum_warp_length_upper_threshold
+    p.max_iterations = int(max_iterations)
+    p.min_iterations = int(min_iterations)
+    keep = None
+    if sobolev_kernel is not None and len(sobolev_kernel) > 0:
+        keep = _f32(sobolev_kernel)
+        p.kernel = _p(keep)
+        p.kernel_size = int(keep.size)
+    else:
+        p.kernel = None
+        p.kernel_size = 0
+    p._keep = keep
+    return p
+
+
+def _dims(shape):
+    return (ctypes.c_int * len(shape))(*[int(d) for d in shape])
+
+
+def slavcheva_optimize(live, canonical, dump_iterations=0, **kwargs):
+    """reference SobolevOptimizer2d.optimize(live, canonical) / SlavchevaOptimizer2d.optimize (+ 3D generalisation).
+    Returns dict(live, warp, iterations, max_warps, dump)."""
+    live, canonical = _f32(live), _f32(canonical)
+    assert live.shape == canonical.shape
+    nd = live.ndim
+    p = make_slavcheva_params(**kwargs)
+    live_out = np.empty_like(live)
+    warp_out = np.empty(live.shape + (nd,), dtype=np.float32)
+    iterations = ctypes.c_int(0)
+    capacity = max(int(p.max_iterations), int(p.min_iterations), 1)
+    max_warps = np.zeros(capacity, dtype=np.float32)
+    dump = IterationDump()
+    dump.level = 0
+    dump.max_iterations = int(dump_iterations)
+    dump_buffer = None
+    if dump_iterations > 0:
+        dump_buffer = np.zeros((dump_iterations,) + live.shape + (nd,), dtype=np.float32)
+        dump.buffer = _p(dump_buffer)
+    status = lib().orc_slavcheva_optimize(ctypes.byref(p), _p(live), _p(canonical), nd, _dims(live.shape), _p(live_out),
+                                          _p(warp_out), ctypes.byref(iterations), _p(max_warps), capacity,
+                                          ctypes.byref(dump))
+    if status != 0:
+        raise RuntimeError("oracle slavcheva optimizer precondition failed (status %d)" % status)
+    return dict(live=live_out, warp=warp_out, iterations=int(iterations.value),
+                max_warps=max_warps[:iterations.value].copy(),
+                dump=None if dump_buffer is None else dump_buffer[:dump.count])
+
+
+def slavcheva_data_term(live, canonical, band_union_only=False, **kwargs):
+    live, canonical = _f32(live), _f32(canonical)
+    p = make_slavcheva_params(**kwargs)
+    out = np.empty(live.shape + (live.ndim,), dtype=np.float32)
+    lib().orc_slavcheva_data_term(ctypes.byref(p), _p(live), _p(canonical), live.ndim, _dims(live.shape),
+                                  int(band_union_only), _p(out))
+    return out
+
+
+def slavcheva_smoothing_term(warp_field, live=None, canonical=None, band_union_only=False, **kwargs):
+    warp_field = _f32(warp_field)
+    nd = warp_field.ndim - 1
+    shape = warp_field.shape[:nd]
+    live = np.zeros(shape, np.float32) if live is None else _f32(live)
+    canonical = np.zeros(shape, np.float32) if canonical is None else _f32(canonical)
+    p = make_slavcheva_params(**kwargs)
+    out = np.empty_like(warp_field)
+    lib().orc_slavcheva_smoothing_term(ctypes.byref(p), _p(warp_field), _p(live), _p(canonical), nd, _dims(shape),
+                                       int(band_union_only), _p(out))
+    return out
+
+
+def slavcheva_level_set_term(live, **kwargs):
+    live = _f32(live)
+    p = make_slavcheva_params(**kwargs)
+    out = np.empty(live.shape + (live.ndim,), dtype=np.float32)
+    lib().orc_slavcheva_level_set_term(ctypes.byref(p), _p(live), live.ndim, _dims(live.shape), _p(out))
+    return out
+
+
+def warp_advanced(live, canonical, warp_field, band_union_only=False, known_values_only=False,
+                  substitute_original=False, truncation_float_threshold=1e-6, modify_warp=True):
+    """reference warp_2d_advanced (field_warping.cpp:64-154) / its 3D generalisation -> (new live, warp)"""
+    live, canonical = _f32(live), _f32(canonical)
+    warp_field = _f32(warp_field).copy()
+    new_live = np.empty_like(live)
+    lib().orc_warp_advanced(_p(live), _p(canonical), _p(warp_field), live.ndim, _dims(live.shape), int(band_union_only),
+                            int(known_values_only), int(substitute_original),
+                            ctypes.c_float(truncation_float_threshold), int(modify_warp), _p(new_live))
+    return new_live, warp_field
+
+
+def warp_delta_statistics(warp_field, canonical, live, min_threshold, max_threshold):
+    warp_field, canonical, live = _f32(warp_field), _f32(canonical), _f32(live)
+    out = WarpDeltaStatistics()
+    lib().orc_warp_delta_statistics(_p(warp_field), _p(canonical), _p(live), live.ndim, _dims(live.shape),
+                                    ctypes.c_float(min_threshold), ctypes.c_float(max_threshold), ctypes.byref(out))
+    return out
+
+
+def tsdf_difference_statistics(canonical, live):
+    canonical, live = _f32(canonical), _f32(live)
+    out = TsdfDifferenceStatistics()
+    lib().orc_tsdf_difference_statistics(_p(canonical), _p(live), live.ndim, _dims(live.shape), ctypes.byref(out))
+    return out

@@ -80,6 +80,65 @@ double orc_hier_time_iterations3d(const orc_hier_params* p, const float* canonic
 
 int orc_num_threads(void);
 
+/* ---- SobolevFusion / KillingFusion ("slavcheva") optimizers: lsf_oracle_slavcheva.cpp ---- */
+#define ORC_SEMANTICS_CPP 0            /* C++ SobolevOptimizer2d (+ dimensional generalisation) */
+#define ORC_SEMANTICS_PY_DIRECT 1      /* Python SlavchevaOptimizer2d, ComputeMethod.DIRECT */
+#define ORC_SEMANTICS_PY_VECTORIZED 2  /* Python SlavchevaOptimizer2d, ComputeMethod.VECTORIZED */
+#define ORC_DATA_TERM_BASIC 0
+#define ORC_DATA_TERM_THRESHOLDED_FDM 1
+#define ORC_SMOOTHING_TIKHONOV 0
+#define ORC_SMOOTHING_KILLING 1
+
+typedef struct {
+	int semantics;
+	int data_term_method;
+	int smoothing_term_method;
+	int level_set_term_enabled;
+	int sobolev_smoothing_enabled;
+	float gradient_descent_rate;
+	float data_term_weight;
+	float smoothing_term_weight;
+	float isomorphic_enforcement_factor;
+	float level_set_term_weight;
+	float maximum_warp_length_lower_threshold;
+	float maximum_warp_length_upper_threshold;
+	int max_iterations;
+	int min_iterations;
+	const float* kernel; /* may be NULL */
+	int kernel_size;
+} orc_slavcheva_params;
+
+typedef struct {
+	float ratio_above_min_threshold, length_min, length_max, length_mean, length_standard_deviation;
+	int longest_warp_location[3]; /* (x, y[, z]) = position along the axis of component 0, 1[, 2] */
+	int is_largest_below_min_threshold, is_largest_above_max_threshold;
+} orc_warp_delta_statistics_t;
+
+typedef struct {
+	float difference_min, difference_max, difference_mean, difference_standard_deviation;
+	int biggest_difference_location[3];
+} orc_tsdf_difference_statistics_t;
+
+/* optimize(live, canonical) -> warped live field (+ the last warp field). dims: nd extents in numpy order.
+ * max_warps[i] receives the maximum warp length reported by iteration i. dump (optional) receives the warp
+ * field after every iteration (level member ignored). Returns 0 or a negative error code. */
+int orc_slavcheva_optimize(const orc_slavcheva_params* p, const float* live, const float* canonical, int nd,
+		const int* dims, float* live_out, float* warp_out, int* iteration_count, float* max_warps, int max_warps_capacity,
+		orc_iteration_dump* dump);
+void orc_slavcheva_data_term(const orc_slavcheva_params* p, const float* live, const float* canonical, int nd,
+		const int* dims, int band_union_only, float* out);
+void orc_slavcheva_smoothing_term(const orc_slavcheva_params* p, const float* warp, const float* live,
+		const float* canonical, int nd, const int* dims, int band_union_only, float* out);
+void orc_slavcheva_level_set_term(const orc_slavcheva_params* p, const float* live, int nd, const int* dims, float* out);
+/* warp_2d_advanced and its 3D generalisation; warp is updated in place when modify_warp != 0 */
+void orc_warp_advanced(const float* live, const float* canonical, float* warp, int nd, const int* dims,
+		int band_union_only, int known_values_only, int substitute_original, float truncation_float_threshold,
+		int modify_warp, float* new_live);
+void orc_warp_delta_statistics(const float* warp, const float* canonical, const float* live, int nd, const int* dims,
+		float min_threshold, float max_threshold, orc_warp_delta_statistics_t* out);
+void orc_tsdf_difference_statistics(const float* canonical, const float* live, int nd, const int* dims,
+		orc_tsdf_difference_statistics_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,8 @@ Produces
                            * cpp/tests/*.cpp and cpp/tests/data/*.hpp (Eigen comma-initialisers and
                              Tensor::setValues blocks, parsed textually).
                            Key format:  "<file stem>/<test case or static name>/<variable>[#k]"
+  reference_slavcheva_runs.npz  per-voxel Killing / Tikhonov / level-set / data terms and whole runs of the reference's
+                           Python SlavchevaOptimizer2d (DIRECT), see collect_slavcheva_runs().
   reference_python_runs.npz  inputs + outputs obtained by RUNNING the reference's Python implementation
                            (math_utils, nonrigid_opt) on seeded inputs, with the C++ extension / matplotlib
                            imports stubbed out (the reference Python is the only runnable reference here,
@@ -234,13 +236,125 @@ def collect_python_runs():
     return out
 
 
+def collect_slavcheva_runs():
+    """Runs of the reference's Python SlavchevaOptimizer2d (ComputeMethod.DIRECT: the only implementation of the
+    Killing and level-set terms) and of its per-voxel term functions on seeded inputs. The visualizer is replaced by
+    a no-op and convergence-status logging (a C++-extension call) is off; the optimizer writes nothing else."""
+    install_stubs()
+    sys.path.insert(0, REF)
+    import contextlib
+    import io
+    import tempfile
+    out = {}
+    rng = np.random.default_rng(20190115)
+    import utils.sampling as sampling
+    sampling.set_focus_coordinates(-5, -5)  # no voxel matches: suppress the per-voxel debug prints
+    import nonrigid_opt.slavcheva.smoothing_term as st
+    import nonrigid_opt.slavcheva.data_term as dt
+    import nonrigid_opt.slavcheva.level_set_term as ls
+    import nonrigid_opt.slavcheva.slavcheva_optimizer2d as so
+    import nonrigid_opt.slavcheva.slavcheva_visualizer as viz
+
+    class NoVisualizer:
+        Settings = viz.SlavchevaVisualizer.Settings
+
+        def __init__(self, *args, **kwargs):
+            self.data_component_field = None
+            self.smoothing_component_field = None
+            self.level_set_component_field = None
+
+        def write_live_sdf_visualizations(self, *args, **kwargs):
+            pass
+
+        def write_all_iteration_visualizations(self, *args, **kwargs):
+            pass
+
+    so.viz.SlavchevaVisualizer = NoVisualizer
+
+    # ---- per-voxel terms on random fields
+    size = 9
+    warp = (rng.standard_normal((size, size, 2)) * 0.3).astype(np.float32)
+    live = np.clip(rng.standard_normal((size, size)) * 0.6, -1, 1).astype(np.float32)
+    out["terms/warp"] = warp
+    out["terms/live"] = live
+    killing = np.zeros_like(warp)
+    tikhonov = np.zeros_like(warp)
+    level_set = np.zeros_like(warp)
+    for y in range(size):
+        for x in range(size):
+            killing[y, x] = st.compute_local_smoothing_term_gradient_killing(warp, x, y, copy_if_zero=False,
+                                                                             isomorphic_enforcement_factor=0.1)[0]
+            tikhonov[y, x] = st.compute_local_smoothing_term_gradient_tikhonov(warp, x, y, copy_if_zero=False)[0]
+            level_set[y, x] = ls.level_set_term_at_location(live, x, y)[0]
+    out["terms/killing_lambda0.1"] = killing
+    out["terms/tikhonov_direct"] = tikhonov
+    out["terms/level_set"] = level_set
+    canonical = np.clip(live + (rng.standard_normal((size, size)) * 0.2).astype(np.float32), -1, 1).astype(np.float32)
+    out["terms/canonical"] = canonical
+    gy, gx = np.gradient(live)
+    basic = np.zeros_like(warp)
+    fdm = np.zeros_like(warp)
+    for y in range(size):
+        for x in range(size):
+            basic[y, x] = dt.compute_local_data_term_gradient_basic(live, canonical, x, y, gx, gy)[0]
+            fdm[y, x] = dt.compute_local_data_term_gradient_thresholded_fdm(live, canonical, x, y, gx, gy)[0]
+    out["terms/data_basic"] = basic
+    out["terms/data_thresholded_fdm"] = fdm
+
+    # ---- optimizer runs (32x32 synthetic pair, 7-tap Sobolev kernel of the reference)
+    import math_utils.convolution as mc
+    kernel7 = mc.sobolev_kernel_1d.astype(np.float32)
+    canonical, live = synthetic_pair_2d(32)
+    out["runs/canonical"] = canonical
+    out["runs/live"] = live
+    out["runs/kernel7"] = kernel7
+    cases = {
+        "tikhonov_sobolev": dict(smoothing_term_method=st.SmoothingTermMethod.TIKHONOV, level_set_term_enabled=False,
+                                 sobolev_smoothing_enabled=True),
+        "killing_levelset_sobolev": dict(smoothing_term_method=st.SmoothingTermMethod.KILLING,
+                                         level_set_term_enabled=True, sobolev_smoothing_enabled=True),
+        "killing_levelset_plain": dict(smoothing_term_method=st.SmoothingTermMethod.KILLING,
+                                       level_set_term_enabled=True, sobolev_smoothing_enabled=False),
+        "fdm_tikhonov_sobolev": dict(smoothing_term_method=st.SmoothingTermMethod.TIKHONOV,
+                                     data_term_method=dt.DataTermMethod.THRESHOLDED_FDM, level_set_term_enabled=False,
+                                     sobolev_smoothing_enabled=True),
+    }
+    with tempfile.TemporaryDirectory() as scratch:
+        for tag, kwargs in cases.items():
+            for iterations in (1, 5):
+                optimizer = so.SlavchevaOptimizer2d(out_path=scratch, field_size=32,
+                                                    compute_method=so.ComputeMethod.DIRECT,
+                                                    gradient_descent_rate=0.1, data_term_weight=1.0,
+                                                    smoothing_term_weight=0.2, isomorphic_enforcement_factor=0.1,
+                                                    level_set_term_weight=0.2,
+                                                    maximum_warp_length_lower_threshold=0.001,
+                                                    maximum_warp_length_upper_threshold=10000,
+                                                    max_iterations=iterations, min_iterations=1,
+                                                    sobolev_kernel=kernel7, enable_convergence_status_logging=False,
+                                                    **kwargs)
+                field = live.copy()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    optimizer.optimize(field, canonical.copy())
+                out["runs/%s/live_after_%d" % (tag, iterations)] = field.astype(np.float32)
+                out["runs/%s/max_warps_%d" % (tag, iterations)] = np.array(optimizer.log.max_warps, dtype=np.float32)
+    return out
+
+
 def main():
+    if "--slavcheva-only" in sys.argv:
+        runs = collect_slavcheva_runs()
+        np.savez_compressed(os.path.join(OUT, "reference_slavcheva_runs.npz"), **runs)
+        print("reference_slavcheva_runs.npz: %d arrays" % len(runs))
+        return
     literals = collect_literals()
     np.savez_compressed(os.path.join(OUT, "reference_literals.npz"), **literals)
     print("reference_literals.npz: %d arrays" % len(literals))
     runs = collect_python_runs()
     np.savez_compressed(os.path.join(OUT, "reference_python_runs.npz"), **runs)
     print("reference_python_runs.npz: %d arrays" % len(runs))
+    runs = collect_slavcheva_runs()
+    np.savez_compressed(os.path.join(OUT, "reference_slavcheva_runs.npz"), **runs)
+    print("reference_slavcheva_runs.npz: %d arrays" % len(runs))
 
 
 if __name__ == "__main__":
