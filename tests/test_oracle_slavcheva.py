@@ -183,14 +183,14 @@ def test_3d_filter_matches_the_pinned_3d_convolution():
     oracle's convolve3d (pinned by the reference's 3D convolution golden)"""
     rng = np.random.default_rng(11)
     live = np.clip(rng.standard_normal((10, 9, 8)) * 0.4, -0.9, 0.9).astype(np.float32)
-    canonical = np.clip(live + 0.05, -0.9, 0.9).astype(np.float32)
+    canonical = (live * 0.7 + 0.1).astype(np.float32)
     kernel = rng.random(5).astype(np.float32)
     plain = oracle.slavcheva_optimize(live, canonical, sobolev_smoothing_enabled=False, max_iterations=1,
                                       maximum_warp_length_lower_threshold=0.0)
     filtered = oracle.slavcheva_optimize(live, canonical, sobolev_smoothing_enabled=True, sobolev_kernel=kernel,
                                          max_iterations=1, maximum_warp_length_lower_threshold=0.0)
     # the warp before the resample step: no value snaps to +-1 here, so the returned warp is the filtered update
-    assert plain["warp"].all()
+    assert np.abs(plain["warp"]).max(axis=-1).all()  # no exactly-zero vector: the preserve-zeros rule stays idle
     assert np.array_equal(filtered["warp"], oracle.convolve_with_kernel(plain["warp"], kernel))
 
 
