@@ -142,6 +142,89 @@ int lsf_upsample_2d(const float* field, int channels, int H, int W, int linear, 
 int lsf_max_norm(const float* vfield, int channels, long long count, float* max_norm_out, int memory_kind,
 		void* stream);
 
+/* ---------------------------------------------------------------- SobolevFusion / KillingFusion ("slavcheva") optimizers
+ * reference: SobolevOptimizer2d::optimize(live_field, canonical_field) -> warped live field,
+ * cpp/src/nonrigid_optimization/slavcheva/sobolev_optimizer2d.cpp:71-138 (parameters: optimizer2d.hpp:59-78,
+ * sobolev_optimizer2d.hpp:39-70), and the Python class SlavchevaOptimizer2d,
+ * nonrigid_opt/slavcheva/slavcheva_optimizer2d.py:72-430.
+ * semantics selects whose arithmetic / loop structure is reproduced:
+ *   LSF_SEMANTICS_CPP            C++ SobolevOptimizer2d; with the Killing / level-set terms and in 3D it is the dimensional
+ *                                generalisation documented in DESIGN.md (the reference has no such optimizer)
+ *   LSF_SEMANTICS_PY_DIRECT      Python ComputeMethod.DIRECT (2D only)
+ *   LSF_SEMANTICS_PY_VECTORIZED  Python ComputeMethod.VECTORIZED (2D only; Tikhonov, no level-set term) */
+#define LSF_SEMANTICS_CPP 0
+#define LSF_SEMANTICS_PY_DIRECT 1
+#define LSF_SEMANTICS_PY_VECTORIZED 2
+#define LSF_DATA_TERM_BASIC 0            /* reference dt.DataTermMethod.BASIC, data_term.py:44-47 */
+#define LSF_DATA_TERM_THRESHOLDED_FDM 1
+#define LSF_SMOOTHING_TIKHONOV 0         /* reference st.SmoothingTermMethod, smoothing_term.py:27-29 */
+#define LSF_SMOOTHING_KILLING 1
+
+typedef struct {
+	int semantics;
+	int data_term_method;
+	int smoothing_term_method;
+	int level_set_term_enabled;
+	int sobolev_smoothing_enabled;
+	float gradient_descent_rate;
+	float data_term_weight;
+	float smoothing_term_weight;
+	float isomorphic_enforcement_factor;
+	float level_set_term_weight;
+	float maximum_warp_length_lower_threshold;
+	float maximum_warp_length_upper_threshold;
+	int maximum_iteration_count;
+	int minimum_iteration_count;
+	const float* sobolev_kernel; /* host pointer, odd size <= LSF_MAX_KERNEL_SIZE, may be NULL */
+	int sobolev_kernel_size;
+} lsf_slavcheva_params;
+
+/* reference telemetry::WarpDeltaStatistics, cpp/src/telemetry/warp_delta_statistics.hpp; locations are (x, y[, z]) =
+ * position along the axis of component 0, 1[, 2] */
+typedef struct {
+	float ratio_above_min_threshold, length_min, length_max, length_mean, length_standard_deviation;
+	int longest_warp_location[3];
+	int is_largest_below_min_threshold, is_largest_above_max_threshold;
+} lsf_warp_delta_statistics_t;
+
+/* reference telemetry::TsdfDifferenceStatistics, cpp/src/telemetry/tsdf_difference_statistics.hpp */
+typedef struct {
+	float difference_min, difference_max, difference_mean, difference_standard_deviation;
+	int biggest_difference_location[3];
+} lsf_tsdf_difference_statistics_t;
+
+/* reference telemetry::ConvergenceReport, cpp/src/telemetry/convergence_report.hpp:40-44 */
+typedef struct {
+	int iteration_count;
+	int iteration_limit_reached;
+	float last_max_warp_length;
+	int has_statistics; /* set when collect_statistics != 0 */
+	lsf_warp_delta_statistics_t warp_delta_statistics;
+	lsf_tsdf_difference_statistics_t tsdf_difference_statistics;
+} lsf_slavcheva_report;
+
+/* optimize(live, canonical): nd = 2 ([H][W], square) or 3 ([X][Y][Z]); dims in numpy order.
+ * live_out [dims]; warp_out [dims][nd] or NULL (the warp field of the last iteration); max_warps: host array of
+ * max_warps_capacity floats or NULL, receives the maximum warp length of every iteration; capture (level ignored)
+ * optionally receives the warp field after each of the first max_iterations iterations. */
+int lsf_slavcheva_optimize(const lsf_slavcheva_params* params, const float* live, const float* canonical, int nd,
+		const int* dims, float* live_out, float* warp_out, int memory_kind, lsf_slavcheva_report* report,
+		int collect_statistics, float* max_warps, int max_warps_capacity, lsf_iteration_capture* capture, void* stream);
+
+/* reference warp_2d_advanced / warp_2d_advanced_warp_unchanged, cpp/src/nonrigid_optimization/field_warping.cpp:64-154
+ * (exported as warp_field_advanced[_no_warp_change], python_export/slavcheva_optimizer.cpp:64-89) and its 3D form.
+ * warp [dims][nd] is updated in place when modify_warp != 0 (zeroed where the new value snaps to +-1). */
+int lsf_warp_advanced(const float* live, const float* canonical, float* warp, int nd, const int* dims,
+		int band_union_only, int known_values_only, int substitute_original, float truncation_float_threshold,
+		int modify_warp, float* live_out, int memory_kind, void* stream);
+
+/* reference build_warp_delta_statistics_{2d,3d} / build_tsdf_difference_statistics_{2d,3d},
+ * cpp/src/python_export/telemetry.tpp:50-145 */
+int lsf_warp_delta_statistics(const float* warp, const float* canonical, const float* live, int nd, const int* dims,
+		float min_threshold, float max_threshold, lsf_warp_delta_statistics_t* out, int memory_kind, void* stream);
+int lsf_tsdf_difference_statistics(const float* canonical, const float* live, int nd, const int* dims,
+		lsf_tsdf_difference_statistics_t* out, int memory_kind, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,11 +6,30 @@ The package directory is ``levelsetfusion-python_b200`` (not an importable name)
 
 Host-side mirror of the reference API for this path:
   * HierarchicalOptimizer2d / HierarchicalOptimizer3d      (hierarchical.py)
+  * SobolevOptimizer2d + SharedParameters / SobolevParameters, SlavchevaOptimizer2d / 3d, warp_field_advanced (slavcheva.py)
+  * telemetry types and builders (telemetry.py)
   * primitives warp / gradient / laplacian / convolution / resampling (ops.py)
 backed by liblsf_b200.so (csrc/, C-ABI in include/lsf_b200.h). No CPU fallback exists.
 """
 from . import _lib
-from .hierarchical import HierarchicalOptimizer2d, HierarchicalOptimizer3d, ConvergenceReport
+from .hierarchical import HierarchicalOptimizer2d, HierarchicalOptimizer3d
 from . import ops
+from . import telemetry
+from .telemetry import (Vector2i, Vector3i, Vector2f, WarpDeltaStatistics2d, WarpDeltaStatistics3d,
+                        TsdfDifferenceStatistics2d, TsdfDifferenceStatistics3d, ConvergenceReport2d, ConvergenceReport3d,
+                        build_warp_delta_statistics_2d, build_warp_delta_statistics_3d,
+                        build_tsdf_difference_statistics_2d, build_tsdf_difference_statistics_3d, mean_vector_length)
+from . import slavcheva
+from .slavcheva import (SobolevOptimizer2d, SharedParameters, SobolevParameters, SlavchevaOptimizer2d,
+                        SlavchevaOptimizer3d, ComputeMethod, AdaptiveLearningRateMethod, DataTermMethod,
+                        SmoothingTermMethod, warp_field_advanced, warp_field_advanced_no_warp_change,
+                        data_term_at_location)
 
-__all__ = ["HierarchicalOptimizer2d", "HierarchicalOptimizer3d", "ConvergenceReport", "ops", "_lib"]
+__all__ = ["HierarchicalOptimizer2d", "HierarchicalOptimizer3d", "SobolevOptimizer2d", "SharedParameters",
+           "SobolevParameters", "SlavchevaOptimizer2d", "SlavchevaOptimizer3d", "ComputeMethod",
+           "AdaptiveLearningRateMethod", "DataTermMethod", "SmoothingTermMethod", "warp_field_advanced",
+           "warp_field_advanced_no_warp_change", "data_term_at_location", "Vector2i", "Vector3i", "Vector2f",
+           "WarpDeltaStatistics2d", "WarpDeltaStatistics3d", "TsdfDifferenceStatistics2d", "TsdfDifferenceStatistics3d",
+           "ConvergenceReport2d", "ConvergenceReport3d", "build_warp_delta_statistics_2d",
+           "build_warp_delta_statistics_3d", "build_tsdf_difference_statistics_2d",
+           "build_tsdf_difference_statistics_3d", "mean_vector_length", "ops", "telemetry", "slavcheva", "_lib"]

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "liblsf_b200.so")
 LSF_HOST = 0
 LSF_DEVICE = 1
 LSF_MAX_LEVELS = 16
+LSF_SEMANTICS_CPP, LSF_SEMANTICS_PY_DIRECT, LSF_SEMANTICS_PY_VECTORIZED = 0, 1, 2
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_int_p = ctypes.POINTER(ctypes.c_int)
@@ -68,6 +69,65 @@ class IterationCapture(ctypes.Structure):
     ]
 
 
+class SlavchevaParams(ctypes.Structure):
+    """lsf_slavcheva_params"""
+    _fields_ = [
+        ("semantics", ctypes.c_int),
+        ("data_term_method", ctypes.c_int),
+        ("smoothing_term_method", ctypes.c_int),
+        ("level_set_term_enabled", ctypes.c_int),
+        ("sobolev_smoothing_enabled", ctypes.c_int),
+        ("gradient_descent_rate", ctypes.c_float),
+        ("data_term_weight", ctypes.c_float),
+        ("smoothing_term_weight", ctypes.c_float),
+        ("isomorphic_enforcement_factor", ctypes.c_float),
+        ("level_set_term_weight", ctypes.c_float),
+        ("maximum_warp_length_lower_threshold", ctypes.c_float),
+        ("maximum_warp_length_upper_threshold", ctypes.c_float),
+        ("maximum_iteration_count", ctypes.c_int),
+        ("minimum_iteration_count", ctypes.c_int),
+        ("sobolev_kernel", c_float_p),
+        ("sobolev_kernel_size", ctypes.c_int),
+    ]
+
+
+class WarpDeltaStatisticsRaw(ctypes.Structure):
+    """lsf_warp_delta_statistics_t"""
+    _fields_ = [
+        ("ratio_above_min_threshold", ctypes.c_float),
+        ("length_min", ctypes.c_float),
+        ("length_max", ctypes.c_float),
+        ("length_mean", ctypes.c_float),
+        ("length_standard_deviation", ctypes.c_float),
+        ("longest_warp_location", ctypes.c_int * 3),
+        ("is_largest_below_min_threshold", ctypes.c_int),
+        ("is_largest_above_max_threshold", ctypes.c_int),
+    ]
+
+
+class TsdfDifferenceStatisticsRaw(ctypes.Structure):
+    """lsf_tsdf_difference_statistics_t"""
+    _fields_ = [
+        ("difference_min", ctypes.c_float),
+        ("difference_max", ctypes.c_float),
+        ("difference_mean", ctypes.c_float),
+        ("difference_standard_deviation", ctypes.c_float),
+        ("biggest_difference_location", ctypes.c_int * 3),
+    ]
+
+
+class SlavchevaReport(ctypes.Structure):
+    """lsf_slavcheva_report"""
+    _fields_ = [
+        ("iteration_count", ctypes.c_int),
+        ("iteration_limit_reached", ctypes.c_int),
+        ("last_max_warp_length", ctypes.c_float),
+        ("has_statistics", ctypes.c_int),
+        ("warp_delta_statistics", WarpDeltaStatisticsRaw),
+        ("tsdf_difference_statistics", TsdfDifferenceStatisticsRaw),
+    ]
+
+
 # every symbol include/lsf_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "lsf_last_error", "lsf_version", "lsf_launch_count",
@@ -75,6 +135,7 @@ EXPORTED_SYMBOLS = [
     "lsf_warp_3d", "lsf_warp_2d", "lsf_gradient_3d", "lsf_gradient_2d", "lsf_laplacian_3d", "lsf_laplacian_2d",
     "lsf_convolve_3d", "lsf_convolve_2d", "lsf_downsample_3d", "lsf_upsample_3d", "lsf_downsample_2d",
     "lsf_upsample_2d", "lsf_max_norm",
+    "lsf_slavcheva_optimize", "lsf_warp_advanced", "lsf_warp_delta_statistics", "lsf_tsdf_difference_statistics",
 ]
 
 _lib = None

@@ -3,6 +3,7 @@
 // nonrigid_opt/hierarchical/hierarchical_optimizer2d.py:123-248). Same device-side termination scheme as
 // hier3d.cu.
 #include "kernels2d.cuh"
+#include "slavcheva.cuh"  // statistics_on_device
 
 #include <cfloat>
 #include <cmath>
@@ -127,6 +128,12 @@ void enqueue_iteration(const Plan2& plan, LevelState2& s, int iteration, cudaStr
 	std::swap(s.g_post, s.scratch_a);
 }
 
+static __global__ void k_unpack_live2d(const float4* __restrict__ pack, float* __restrict__ out, Grid2 g) {
+	LSF_PIXEL_2D(g);
+	if (!in_grid) return;
+	out[idx] = pack[g.padded_index(row, col)].x;
+}
+
 }  // namespace
 
 }  // namespace lsf
@@ -136,7 +143,6 @@ using namespace lsf;
 extern "C" int lsf_hier_optimize_2d(const lsf_hier_params* params, const float* canonical, const float* live, int H,
 		int W, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
 		lsf_iteration_capture* capture, void* stream_handle) {
-	(void) collect_reports;
 	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
 	Plan2 plan;
 	LSF_TRY(make_plan(params, H, W, &plan));
@@ -253,6 +259,29 @@ extern "C" int lsf_hier_optimize_2d(const lsf_hier_params* params, const float* 
 			r.dims[0] = s.g.H;
 			r.dims[1] = s.g.W;
 			r.dims[2] = 1;
+			if (collect_reports) {
+				// reference optimizer_with_telemetry.tpp:107-124
+				float* live_level;
+				LSF_TRY(arena.alloc(&live_level, (size_t) s.g.N));
+				k_unpack_live2d<<<counted(grid2(s.g)), block3(), 0, stream>>>(s.pack, live_level, s.g);
+				lsf_warp_delta_statistics_t w;
+				lsf_tsdf_difference_statistics_t d;
+				LSF_TRY(statistics_on_device(2, r.dims, s.warp, s.g.N, 1, s.canonical, live_level, plan.threshold, FLT_MAX, &w,
+						&d, arena, stream));
+				r.warp_ratio_above_min_threshold = w.ratio_above_min_threshold;
+				r.warp_length_min = w.length_min;
+				r.warp_length_max = w.length_max;
+				r.warp_length_mean = w.length_mean;
+				r.warp_length_std = w.length_standard_deviation;
+				for (int i = 0; i < 3; i++) r.warp_longest_location[i] = w.longest_warp_location[i];
+				r.warp_is_largest_below_min_threshold = w.is_largest_below_min_threshold;
+				r.warp_is_largest_above_max_threshold = w.is_largest_above_max_threshold;
+				r.diff_min = d.difference_min;
+				r.diff_max = d.difference_max;
+				r.diff_mean = d.difference_mean;
+				r.diff_std = d.difference_standard_deviation;
+				for (int i = 0; i < 3; i++) r.diff_biggest_location[i] = d.biggest_difference_location[i];
+			}
 		}
 		if (capturing) capture->count = std::min(executed, capture->max_iterations);
 		if (level != L - 1) {

@@ -6,6 +6,7 @@
 // termination test (optimizer.tpp:166-171) is evaluated on the device at the head of every kernel from
 // the previous iteration's max ||g||^2 slot, and the host polls the slots once per chunk of iterations.
 #include "kernels3d_fused.cuh"
+#include "slavcheva.cuh"  // statistics_on_device
 
 #include <cfloat>
 #include <cmath>
@@ -227,8 +228,33 @@ int build_pack_pyramid(Arena& arena, const Plan3& plan, const float* live_dev, c
 	return LSF_OK;
 }
 
+// live value of every voxel of a pack level (the .x lane of the padded float4 grid) as a plain scalar field
+static __global__ void k_unpack_live3d(const float4* __restrict__ pack, float* __restrict__ out, Grid3 g) {
+	LSF_VOXEL_3D(g);
+	if (!in_grid) return;
+	out[idx] = pack[g.padded_index(x, y, z)].x;
+}
+
+void fill_report_statistics(lsf_level_report& r, const lsf_warp_delta_statistics_t& w,
+		const lsf_tsdf_difference_statistics_t& d) {
+	r.warp_ratio_above_min_threshold = w.ratio_above_min_threshold;
+	r.warp_length_min = w.length_min;
+	r.warp_length_max = w.length_max;
+	r.warp_length_mean = w.length_mean;
+	r.warp_length_std = w.length_standard_deviation;
+	for (int i = 0; i < 3; i++) r.warp_longest_location[i] = w.longest_warp_location[i];
+	r.warp_is_largest_below_min_threshold = w.is_largest_below_min_threshold;
+	r.warp_is_largest_above_max_threshold = w.is_largest_above_max_threshold;
+	r.diff_min = d.difference_min;
+	r.diff_max = d.difference_max;
+	r.diff_mean = d.difference_mean;
+	r.diff_std = d.difference_standard_deviation;
+	for (int i = 0; i < 3; i++) r.diff_biggest_location[i] = d.biggest_difference_location[i];
+}
+
 int optimize_device(const Plan3& plan, const float* canonical_dev, const float* live_dev, float* warp_out_dev,
-		lsf_level_report* reports, lsf_iteration_capture* capture, float* capture_dev, cudaStream_t stream) {
+		lsf_level_report* reports, int collect_reports, lsf_iteration_capture* capture, float* capture_dev,
+		cudaStream_t stream) {
 	Arena arena(stream);
 	const int L = plan.level_count;
 	const Grid3& finest = plan.level_grid[L - 1];
@@ -306,6 +332,18 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 			r.dims[0] = s.g.X;
 			r.dims[1] = s.g.Y;
 			r.dims[2] = s.g.Z;
+			if (collect_reports) {
+				// reference optimizer_with_telemetry.tpp:107-124: statistics of the level's warp field over the band
+				// union of (canonical level, live level) and |live level - canonical level|
+				float* live_level;
+				LSF_TRY(arena.alloc(&live_level, (size_t) s.g.N));
+				k_unpack_live3d<<<counted(grid3(s.g)), block3(), 0, stream>>>(s.pack, live_level, s.g);
+				lsf_warp_delta_statistics_t w;
+				lsf_tsdf_difference_statistics_t d;
+				LSF_TRY(statistics_on_device(3, r.dims, s.warp, s.g.N, 1, s.canonical, live_level, plan.threshold, FLT_MAX, &w,
+						&d, arena, stream));
+				fill_report_statistics(r, w, d);
+			}
 		}
 		if (capturing) capture->count = std::min(executed, capture->max_iterations);
 		if (level != L - 1) {
@@ -330,7 +368,6 @@ using namespace lsf;
 extern "C" int lsf_hier_optimize_3d(const lsf_hier_params* params, const float* canonical, const float* live, int X,
 		int Y, int Z, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
 		lsf_iteration_capture* capture, void* stream_handle) {
-	(void) collect_reports;
 	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
 	Plan3 plan;
 	LSF_TRY(make_plan(params, X, Y, Z, &plan));
@@ -350,7 +387,7 @@ extern "C" int lsf_hier_optimize_3d(const lsf_hier_params* params, const float* 
 		if (memory_kind == LSF_HOST) LSF_TRY(arena.alloc(&capture_dev, capture_count));
 		else capture_dev = capture->buffer;
 	}
-	LSF_TRY(optimize_device(plan, canonical_dev, live_dev, out_dev, reports, capture, capture_dev, stream));
+	LSF_TRY(optimize_device(plan, canonical_dev, live_dev, out_dev, reports, collect_reports, capture, capture_dev, stream));
 	if (memory_kind == LSF_HOST) {
 		if (capture_dev) {
 			const size_t used = (size_t) capture->count * plan.level_grid[capture->level].N * 3;

@@ -1,0 +1,710 @@
+// slavcheva.cuh -- sm_100a kernels of the SobolevFusion / KillingFusion ("slavcheva") optimizers, 2D and 3D.
+//
+// One iteration (reference SobolevOptimizer2d::perform_optimization_iteration_and_return_max_warp,
+// cpp/src/nonrigid_optimization/slavcheva/sobolev_optimizer2d.cpp:121-138; Python twin
+// nonrigid_opt/slavcheva/slavcheva_optimizer2d.py:163-330) is
+//   k_slav_gradient      live gradient + data term + Tikhonov/Killing term + level-set term + band-union mask + weights
+//   k_slav_filter_axis   one pass of the separable Sobolev filter with the preserve-zeros rule (x D)
+//   k_slav_resample      re-warp of the live field by the new warp (masks, truncation snap, warp zeroing) + max ||warp||
+//   k_slav_decide        one thread: evaluates the termination test on the device (sticky), so the host polls once per
+//                        chunk of iterations
+// Device layout: scalar fields f[n0][n1][n2] (last axis contiguous), vector fields as D planes p[c][N].
+// Component c displaces along array axis comp_axis(c): 2D {1,0} (u -> columns, v -> rows), 3D {0,1,2}.
+//
+// Three semantics (see include/lsf_b200.h): CPP = the C++ SobolevOptimizer2d (and its 3D / Killing / level-set
+// generalisation), PY_DIRECT / PY_VECTORIZED = the two compute methods of the Python SlavchevaOptimizer2d. All
+// arithmetic is float32 in the reference's operation order, no FMA (compiled with --fmad=false); the Python DIRECT
+// re-warp interpolates in float64 like the reference's Python does.
+#pragma once
+
+#include "common.cuh"
+
+namespace lsf {
+
+struct SlavGeom {
+	int nd;
+	int n[3];
+	int stride[3];
+	int comp_axis[3];
+	long long N;
+};
+
+inline SlavGeom make_slav_geom(int nd, const int* dims) {
+	SlavGeom g;
+	g.nd = nd;
+	g.N = 1;
+	for (int a = 0; a < 3; a++) g.n[a] = a < nd ? dims[a] : 1;
+	for (int a = 2; a >= 0; a--) {
+		if (a < nd) {
+			g.stride[a] = (int) g.N;
+			g.N *= g.n[a];
+		} else g.stride[a] = 0;
+	}
+	if (nd == 2) {
+		g.comp_axis[0] = 1;
+		g.comp_axis[1] = 0;
+		g.comp_axis[2] = 0;
+	} else {
+		g.comp_axis[0] = 0;
+		g.comp_axis[1] = 1;
+		g.comp_axis[2] = 2;
+	}
+	return g;
+}
+
+struct SlavParams {
+	int semantics, data_term_method, smoothing_term_method, level_set;
+	float rate, data_weight, smoothing_weight, lambda, level_set_weight;
+	float lower, upper;
+	int min_iterations;
+};
+
+struct SlavGradientArgs {
+	SlavGeom g;
+	SlavParams p;
+	const float* live;
+	const float* canonical;
+	const float* warp;    // planes, previous iteration (after zeroing)
+	const float* stale;   // planes: gradient field of the previous iteration (PY_DIRECT), else nullptr
+	float* out;           // planes
+	const int* status;
+	int iteration;
+};
+
+struct SlavFilterArgs {
+	SlavGeom g;
+	const float* in;        // planes
+	float* out;             // planes
+	const float* original;  // planes: the field before the first pass (PY zero rule), else nullptr
+	float k[LSF_MAX_KERNEL_SIZE];
+	int size, radius;
+	int axis;
+	int zero_rule;          // 0 none, 1 C++ (pass-input vector exactly zero), 2 Python (|original component| < 1e-6)
+	const int* status;
+	int iteration;
+};
+
+struct SlavResampleArgs {
+	SlavGeom g;
+	SlavParams p;
+	const float* live;
+	const float* canonical;
+	const float* update;     // planes: filtered field (CPP: the new warp; PY: the gradient)
+	float* gradient_field;   // planes, zeroed where the value snaps (PY_DIRECT: aliases update), else nullptr
+	float* warp;             // planes out
+	float* new_live;
+	int band_union_only, known_values_only, substitute_original, modify_warp;
+	float threshold;
+	unsigned* max_sq_bits;   // slot of this iteration (nullptr: no reduction)
+	const int* status;
+	int iteration;
+};
+
+// Band-union warp statistics and TSDF difference statistics of device-resident fields (defined in slavcheva.cu; also
+// used by the hierarchical optimizers for their per-level convergence reports). `field` element (voxel i,
+// component c) = field[c * component_stride + i * voxel_stride]. Either output may be NULL.
+int statistics_on_device(int nd, const int* dims, const float* field, long long component_stride, int voxel_stride,
+		const float* canonical, const float* live, float min_threshold, float max_threshold,
+		lsf_warp_delta_statistics_t* warp_out, lsf_tsdf_difference_statistics_t* diff_out, Arena& arena,
+		cudaStream_t stream);
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ bool slav_truncated(float v) {
+	return fabsf(v) == 1.0f;  // reference boolean_operations.hpp:37-39
+}
+
+template<int D>
+__device__ __forceinline__ void slav_coords(const SlavGeom& g, int idx, int (&pos)[3]) {
+	pos[0] = pos[1] = pos[2] = 0;
+#pragma unroll
+	for (int a = 0; a < D; a++) {
+		pos[a] = idx / g.stride[a];
+		idx -= pos[a] * g.stride[a];
+	}
+}
+
+template<int D>
+__device__ __forceinline__ bool slav_inside(const SlavGeom& g, const int (&q)[3]) {
+	bool ok = true;
+#pragma unroll
+	for (int a = 0; a < D; a++) ok = ok && q[a] >= 0 && q[a] < g.n[a];
+	return ok;
+}
+
+template<int D>
+__device__ __forceinline__ int slav_index(const SlavGeom& g, const int (&q)[3]) {
+	int idx = 0;
+#pragma unroll
+	for (int a = 0; a < D; a++) idx += q[a] * g.stride[a];
+	return idx;
+}
+
+template<int D>
+__device__ __forceinline__ float slav_live_or_one(const SlavGeom& g, const float* __restrict__ live, const int (&q)[3]) {
+	return slav_inside<D>(g, q) ? __ldg(live + slav_index<D>(g, q)) : 1.0f;
+}
+
+// ---------------------------------------------------------------------------------------------- gradient terms
+// data term: reference data_term.cpp:63-84 (C++), data_term.py:169-227 (Python basic / thresholded FDM)
+template<int D>
+__device__ __forceinline__ void slav_data_term(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
+	const SlavGeom& g = a.g;
+	const float centre = __ldg(a.live + idx);
+	float grad[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+	for (int c = 0; c < D; c++) {
+		const int ax = g.comp_axis[c], i = pos[ax], n = g.n[ax], s = g.stride[ax];
+		if (n >= 2) {
+			if (i == 0) grad[c] = __ldg(a.live + idx + s) - centre;
+			else if (i == n - 1) grad[c] = centre - __ldg(a.live + idx - s);
+			else grad[c] = 0.5f * (__ldg(a.live + idx + s) - __ldg(a.live + idx - s));
+		}
+		if (a.p.data_term_method == LSF_DATA_TERM_THRESHOLDED_FDM && fabsf(grad[c]) > 0.5f) {
+			const float minus = i > 0 ? __ldg(a.live + idx - s) : 1.0f;
+			const float plus = i < n - 1 ? __ldg(a.live + idx + s) : 1.0f;
+			const float forward = plus - centre, backward = centre - minus;
+			float value = fabsf(forward) < fabsf(backward) ? forward : backward;
+			if (fabsf(value) > 0.5f) value = 0.0f;
+			grad[c] = value;
+		}
+	}
+	const float diff = centre - __ldg(a.canonical + idx);
+	if (a.p.semantics == LSF_SEMANTICS_CPP) {
+		const float scaled = 10.0f * diff;
+#pragma unroll
+		for (int c = 0; c < D; c++) out[c] = scaled * grad[c];
+	} else {
+#pragma unroll
+		for (int c = 0; c < D; c++) out[c] = (diff * grad[c]) * 10.0f;
+	}
+}
+
+template<int D>
+__device__ __forceinline__ float slav_warp_or_centre(const SlavGradientArgs& a, const int (&q)[3], int c, int centre_idx) {
+	const int at = slav_inside<D>(a.g, q) ? slav_index<D>(a.g, q) : centre_idx;
+	return __ldg(a.warp + c * a.g.N + at);
+}
+
+// C++ Tikhonov term: reference smoothing_term.cpp:43-108 (array axis 0 assigned, further axes added)
+template<int D>
+__device__ __forceinline__ void slav_tikhonov_cpp(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
+#pragma unroll
+	for (int c = 0; c < D; c++) {
+		const float* w = a.warp + c * a.g.N + idx;
+		const float centre = __ldg(w);
+		float total = 0.0f;
+#pragma unroll
+		for (int ax = 0; ax < D; ax++) {
+			const int i = pos[ax], n = a.g.n[ax], s = a.g.stride[ax];
+			float term;
+			if (n < 2) term = 0.0f;
+			else if (i == 0) term = -__ldg(w + s) + centre;
+			else if (i == n - 1) term = -__ldg(w - s) + centre;
+			else term = (-__ldg(w + s) + 2.0f * centre) - __ldg(w - s);
+			if (ax == 0) total = term;
+			else total += term;
+		}
+		out[c] = total;
+	}
+}
+
+// Python Tikhonov term: reference smoothing_term.py:103-139 (copy_if_zero=False)
+template<int D>
+__device__ __forceinline__ void slav_tikhonov_py(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
+#pragma unroll
+	for (int c = 0; c < D; c++) {
+		int q[3] = { pos[0], pos[1], pos[2] };
+		float acc = 0.0f;
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			const int ax = a.g.comp_axis[k];
+			q[ax] = pos[ax] + 1;
+			const float v = slav_warp_or_centre<D>(a, q, c, idx);
+			q[ax] = pos[ax];
+			acc = k == 0 ? v : acc + v;
+		}
+		acc = acc - (2.0f * D) * __ldg(a.warp + c * a.g.N + idx);
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			const int ax = a.g.comp_axis[k];
+			q[ax] = pos[ax] - 1;
+			acc = acc + slav_warp_or_centre<D>(a, q, c, idx);
+			q[ax] = pos[ax];
+		}
+		out[c] = -acc;
+	}
+}
+
+// Killing term: reference smoothing_term.py:50-100 (copy_if_zero=False), quirks kept; 3D form = the
+// same expression pattern
+template<int D>
+__device__ __forceinline__ void slav_killing(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
+	const float lambda = a.p.lambda;
+	const float c0 = (float) (-2.0 * (1.0 + (double) lambda));
+	const int ax0 = a.g.comp_axis[0];
+#pragma unroll
+	for (int ca = 0; ca < D; ca++) {
+		int q[3] = { pos[0], pos[1], pos[2] };
+		const float w = __ldg(a.warp + ca * a.g.N + idx);
+		q[ax0] = pos[ax0] + 1;
+		const float xp = slav_warp_or_centre<D>(a, q, ca, idx);
+		q[ax0] = pos[ax0] - 1;
+		const float xm = slav_warp_or_centre<D>(a, q, ca, idx);
+		q[ax0] = pos[ax0];
+		float acc = c0 * ((xp - 2.0f * w) + xm);
+#pragma unroll
+		for (int k = 1; k < D; k++) {
+			const int ax = a.g.comp_axis[k];
+			q[ax] = pos[ax] + 1;
+			const float yp = slav_warp_or_centre<D>(a, q, ca, idx);
+			q[ax] = pos[ax];
+			acc = acc + ((yp - 2.0f * w) + yp);
+		}
+#pragma unroll
+		for (int cb = 0; cb < D; cb++) {
+			if (cb == ca) continue;
+			const int first = a.g.comp_axis[ca < cb ? ca : cb], second = a.g.comp_axis[ca < cb ? cb : ca];
+			float v[4];
+			int k = 0;
+#pragma unroll
+			for (int s1 = 1; s1 >= -1; s1 -= 2)
+#pragma unroll
+				for (int s2 = 1; s2 >= -1; s2 -= 2) {
+					q[first] = pos[first] + s1;
+					q[second] = pos[second] + s2;
+					v[k++] = slav_warp_or_centre<D>(a, q, cb, idx);
+				}
+			q[first] = pos[first];
+			q[second] = pos[second];
+			const float mixed = (((v[0] - v[1]) - v[2]) + v[3]) / 4.0f;
+			acc = acc + lambda * mixed;
+		}
+		out[ca] = acc;
+	}
+}
+
+// level-set term: reference level_set_term.py:28-64 (out-of-bounds -> 1, quirks kept)
+template<int D>
+__device__ __forceinline__ void slav_level_set(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
+	const SlavGeom& g = a.g;
+	const float centre = __ldg(a.live + idx);
+	float grad[3] = { 0.f, 0.f, 0.f }, hessian[3][3];
+	int q[3] = { pos[0], pos[1], pos[2] };
+#pragma unroll
+	for (int c = 0; c < D; c++) {
+		const int ax = g.comp_axis[c];
+		q[ax] = pos[ax] + 1;
+		const float plus = slav_live_or_one<D>(g, a.live, q);
+		q[ax] = pos[ax] - 1;
+		const float minus = slav_live_or_one<D>(g, a.live, q);
+		q[ax] = pos[ax];
+		grad[c] = (0.5f * (plus - minus)) * 10.0f;
+		hessian[c][c] = ((plus - 2.0f * centre) + plus) * 10.0f;
+	}
+#pragma unroll
+	for (int c1 = 0; c1 < D; c1++)
+#pragma unroll
+		for (int c2 = c1 + 1; c2 < D; c2++) {
+			const int a1 = g.comp_axis[c1], a2 = g.comp_axis[c2];
+			float v[4];
+			int k = 0;
+#pragma unroll
+			for (int s2 = 1; s2 >= -1; s2 -= 2)
+#pragma unroll
+				for (int s1 = 1; s1 >= -1; s1 -= 2) {
+					q[a1] = pos[a1] + s1;
+					q[a2] = pos[a2] + s2;
+					v[k++] = slav_live_or_one<D>(g, a.live, q);
+				}
+			q[a1] = pos[a1];
+			q[a2] = pos[a2];
+			const float mixed = (0.25f * (((v[0] - v[1]) - v[2]) + v[3])) * 10.0f;
+			hessian[c1][c2] = mixed;
+			hessian[c2][c1] = mixed;
+		}
+	float sq = 0.0f;
+#pragma unroll
+	for (int c = 0; c < D; c++) sq += grad[c] * grad[c];
+	const float length = sqrtf(sq);
+	const float factor = (1.0f - length) / (length + 1e-5f);
+#pragma unroll
+	for (int ca = 0; ca < D; ca++) {
+		float acc = hessian[ca][0] * grad[0];
+#pragma unroll
+		for (int cb = 1; cb < D; cb++) acc = acc + hessian[ca][cb] * grad[cb];
+		out[ca] = factor * acc;
+	}
+}
+
+template<int D>
+static __global__ void __launch_bounds__(256) k_slav_gradient(SlavGradientArgs a) {
+	if (a.status[a.iteration]) return;
+	const long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (linear >= a.g.N) return;
+	const int idx = (int) linear;
+	int pos[3];
+	slav_coords<D>(a.g, idx, pos);
+	const float live_value = __ldg(a.live + idx);
+	const bool outside = slav_truncated(live_value) && slav_truncated(__ldg(a.canonical + idx));
+	const SlavParams& p = a.p;
+	float result[3] = { 0.f, 0.f, 0.f };
+	float data[3], smooth[3], ls[3];
+	if (p.semantics == LSF_SEMANTICS_CPP) {
+		if (outside) {
+#pragma unroll
+			for (int c = 0; c < D; c++) result[c] = (0.0f + 0.0f * p.smoothing_weight) * -p.rate;
+		} else {
+			slav_data_term<D>(a, idx, pos, data);
+			if (p.smoothing_term_method == LSF_SMOOTHING_KILLING) slav_killing<D>(a, idx, pos, smooth);
+			else slav_tikhonov_cpp<D>(a, idx, pos, smooth);
+			const bool ls_here = p.level_set && !slav_truncated(live_value);
+			if (ls_here) slav_level_set<D>(a, idx, pos, ls);
+#pragma unroll
+			for (int c = 0; c < D; c++) {
+				float total = data[c] * p.data_weight;
+				if (ls_here) total = total + ls[c] * p.level_set_weight;
+				total = total + smooth[c] * p.smoothing_weight;
+				result[c] = total * -p.rate;  // reference sobolev_optimizer2d.cpp:131-132
+			}
+		}
+	} else if (p.semantics == LSF_SEMANTICS_PY_DIRECT) {
+		if (outside) {
+			// reference slavcheva_optimizer2d.py:261-262: skipped voxels keep last iteration's gradient-field entry
+#pragma unroll
+			for (int c = 0; c < D; c++) result[c] = __ldg(a.stale + c * a.g.N + idx);
+		} else {
+			slav_data_term<D>(a, idx, pos, data);
+			float total[3];
+#pragma unroll
+			for (int c = 0; c < D; c++) total[c] = 0.0f + p.data_weight * data[c];
+			if (p.level_set && !slav_truncated(live_value)) {
+				slav_level_set<D>(a, idx, pos, ls);
+#pragma unroll
+				for (int c = 0; c < D; c++) total[c] = total[c] + p.level_set_weight * ls[c];
+			}
+			if (p.smoothing_term_method == LSF_SMOOTHING_KILLING) slav_killing<D>(a, idx, pos, smooth);
+			else slav_tikhonov_py<D>(a, idx, pos, smooth);
+#pragma unroll
+			for (int c = 0; c < D; c++) result[c] = total[c] + p.smoothing_weight * smooth[c];
+		}
+	} else {  // PY_VECTORIZED, reference slavcheva_optimizer2d.py:163-190
+		if (!outside) {
+			slav_data_term<D>(a, idx, pos, data);
+			slav_tikhonov_cpp<D>(a, idx, pos, smooth);
+#pragma unroll
+			for (int c = 0; c < D; c++) result[c] = p.data_weight * data[c] + p.smoothing_weight * smooth[c];
+		}
+	}
+#pragma unroll
+	for (int c = 0; c < D; c++) a.out[c * a.g.N + idx] = result[c];
+}
+
+// ---------------------------------------------------------------------------------------------- Sobolev filter pass
+// reference convolve_with_kernel_preserve_zeros, cpp/src/math/convolution.cpp:23-67,69-145 (C++ rule) and
+// math_utils/convolution.py:114-132 (Python rule)
+template<int D>
+static __global__ void __launch_bounds__(256) k_slav_filter_axis(SlavFilterArgs a) {
+	if (a.status[a.iteration]) return;
+	const long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (linear >= a.g.N) return;
+	const int idx = (int) linear;
+	int pos[3];
+	slav_coords<D>(a.g, idx, pos);
+	const int i = pos[a.axis], n = a.g.n[a.axis], s = a.g.stride[a.axis];
+	if (a.zero_rule == 1) {
+		bool all_zero = true;
+#pragma unroll
+		for (int c = 0; c < D; c++) all_zero = all_zero && __ldg(a.in + c * a.g.N + idx) == 0.0f;
+		if (all_zero) {
+#pragma unroll
+			for (int c = 0; c < D; c++) a.out[c * a.g.N + idx] = 0.0f;
+			return;
+		}
+	}
+#pragma unroll
+	for (int c = 0; c < D; c++) {
+		const float* line = a.in + c * a.g.N + idx;
+		float acc = 0.0f;
+		for (int j = 0; j < a.size; j++) {
+			const int src = i - a.radius + j;
+			const float value = (src >= 0 && src < n) ? __ldg(line + (j - a.radius) * s) : 0.0f;
+			acc += value * a.k[j];
+		}
+		if (a.zero_rule == 2 && fabsf(__ldg(a.original + c * a.g.N + idx)) < 1e-6f) acc = 0.0f;
+		a.out[c * a.g.N + idx] = acc;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- re-warp of the live field
+// reference warp_2d_advanced, cpp/src/nonrigid_optimization/field_warping.cpp:64-136 (float32), and its Python twin
+// nonrigid_opt/field_warping.py:112-151 + utils/sampling.py:160-215 (float64 interpolation), followed by the
+// maximum warp length (statistics.tpp:57-100; slavcheva_optimizer2d.py:309-318 measures BEFORE the re-warp).
+template<int D>
+static __global__ void __launch_bounds__(256) k_slav_resample(SlavResampleArgs a) {
+	if (a.status != nullptr && a.status[a.iteration]) return;
+	const SlavGeom& g = a.g;
+	const long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	float sq_report = 0.0f;
+	if (linear < g.N) {
+		const int idx = (int) linear;
+		const bool python = a.p.semantics != LSF_SEMANTICS_CPP;
+		const bool float64 = a.p.semantics == LSF_SEMANTICS_PY_DIRECT;
+		float w[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+		for (int c = 0; c < D; c++) {
+			const float u = __ldg(a.update + c * g.N + idx);
+			w[c] = python ? -u * a.p.rate : u;
+		}
+		float sq_before = 0.0f;
+#pragma unroll
+		for (int c = 0; c < D; c++) sq_before += w[c] * w[c];
+		const float live_value = __ldg(a.live + idx);
+		bool skip = false;
+		if (a.band_union_only && slav_truncated(live_value) && slav_truncated(__ldg(a.canonical + idx))) skip = true;
+		if (!skip && a.known_values_only && (float64 ? live_value == 1.0f : fabsf(live_value) == 1.0f)) skip = true;
+		float new_value = live_value;
+		if (!skip) {
+			int pos[3];
+			slav_coords<D>(g, idx, pos);
+			int base[3] = { 0, 0, 0 };
+			const float oob = a.substitute_original ? live_value : 1.0f;
+			double result;
+			if (float64) {
+				double ratio[3] = { 0, 0, 0 };
+#pragma unroll
+				for (int c = 0; c < D; c++) {
+					const int ax = g.comp_axis[c];
+					const double lookup = (double) pos[ax] + (double) w[c];
+					const double fl = floor(lookup);
+					base[ax] = (int) fl;
+					ratio[ax] = lookup - fl;
+				}
+				double value[1 << D];
+#pragma unroll
+				for (int corner = 0; corner < (1 << D); corner++) {
+					int q[3] = { 0, 0, 0 };
+#pragma unroll
+					for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
+					value[corner] = (double) (slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob);
+				}
+#pragma unroll
+				for (int c = D - 1; c >= 0; c--) {
+					const int ax = g.comp_axis[c];
+#pragma unroll
+					for (int corner = 0; corner < (1 << D); corner++) {
+						if ((corner >> ax) & 1) continue;
+						value[corner] = value[corner] * (1.0 - ratio[ax]) + value[corner | (1 << ax)] * ratio[ax];
+					}
+				}
+				result = value[0];
+				new_value = (float) result;
+			} else {
+				float ratio[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+				for (int c = 0; c < D; c++) {
+					const int ax = g.comp_axis[c];
+					const float lookup = (float) pos[ax] + w[c];
+					base[ax] = __float2int_rd(lookup);
+					ratio[ax] = lookup - (float) base[ax];
+				}
+				float value[1 << D];
+#pragma unroll
+				for (int corner = 0; corner < (1 << D); corner++) {
+					int q[3] = { 0, 0, 0 };
+#pragma unroll
+					for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
+					value[corner] = slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob;
+				}
+				// interpolation along the last component's axis first (reference field_warping.tpp:126-134,187-189)
+#pragma unroll
+				for (int c = D - 1; c >= 0; c--) {
+					const int ax = g.comp_axis[c];
+					const float r = ratio[ax], inverse = 1.0f - r;
+#pragma unroll
+					for (int corner = 0; corner < (1 << D); corner++) {
+						if ((corner >> ax) & 1) continue;
+						value[corner] = value[corner] * inverse + value[corner | (1 << ax)] * r;
+					}
+				}
+				new_value = value[0];
+				result = (double) new_value;
+			}
+			const bool snaps = float64 ? (1.0 - fabs(result) < 1e-6) : (1.0 - fabs((double) new_value) < (double) a.threshold);
+			if (a.modify_warp && snaps) {
+				if (float64) new_value = result > 0.0 ? 1.0f : (result < 0.0 ? -1.0f : 0.0f);
+				else new_value = copysignf(1.0f, new_value);
+#pragma unroll
+				for (int c = 0; c < D; c++) w[c] = 0.0f;
+				if (a.gradient_field != nullptr) {
+#pragma unroll
+					for (int c = 0; c < D; c++) a.gradient_field[c * g.N + idx] = 0.0f;
+				}
+			}
+		}
+		a.new_live[idx] = new_value;
+		if (a.warp != nullptr) {
+#pragma unroll
+			for (int c = 0; c < D; c++) a.warp[c * g.N + idx] = w[c];
+		}
+		if (python) sq_report = sq_before;
+		else {
+#pragma unroll
+			for (int c = 0; c < D; c++) sq_report += w[c] * w[c];
+		}
+	}
+	if (a.max_sq_bits != nullptr) block_atomic_max(sq_report, a.max_sq_bits);
+}
+
+// termination test on the device, sticky: status[it + 1] = status[it] || finished(it + 1, max of iteration it)
+// reference optimizer2d.cpp:76-82 (C++), slavcheva_optimizer2d.py:360-362 (Python)
+__device__ __forceinline__ bool slav_finished(const SlavParams& p, int completed, int max_iterations, float max_warp) {
+	if (p.semantics == LSF_SEMANTICS_CPP)
+		return completed >= p.min_iterations && (completed >= max_iterations || max_warp < p.lower || max_warp > p.upper);
+	return !(completed < p.min_iterations || (completed < max_iterations && p.lower < max_warp && max_warp < p.upper));
+}
+
+static __global__ void k_slav_decide(SlavParams p, const unsigned* max_sq_bits, int* status, int iteration,
+		int max_iterations) {
+	if (status[iteration]) {
+		status[iteration + 1] = 1;
+		return;
+	}
+	const float max_warp = sqrtf(__uint_as_float(max_sq_bits[iteration]));
+	status[iteration + 1] = slav_finished(p, iteration + 1, max_iterations, max_warp) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------- telemetry
+// reference cpp/src/telemetry/warp_delta_statistics.tpp:88-116, tsdf_difference_statistics.tpp:86-97,
+// cpp/src/math/filtered_statistics.tpp:34-144. Sums are accumulated in double (the reference does the same for the
+// warp lengths); maxima carry their location as the index in the reference's traversal order so that ties resolve
+// to the same voxel.
+struct StatsAccumulators {
+	double sum;                 // pass 0: total length / total difference; pass 1: total squared deviation
+	double count;               // band-union voxels (exact in double up to 2^53)
+	double above;               // lengths above the minimum threshold
+	unsigned long long max_key; // (float bits << 32) | (~order index): max with first-in-order tie break
+	unsigned min_bits;
+	unsigned pad;
+};
+
+template<int D>
+__device__ __forceinline__ unsigned eigen_order_index(const SlavGeom& g, const int (&pos)[3]) {
+	unsigned k = 0, scale = 1;
+#pragma unroll
+	for (int a = 0; a < D; a++) {
+		k += (unsigned) pos[a] * scale;
+		scale *= (unsigned) g.n[a];
+	}
+	return k;
+}
+
+// block-wide reductions of the statistics kernels (256 threads); results are valid in thread 0
+struct StatsBlock {
+	double sum, count, above;
+	unsigned long long key;
+	unsigned min_bits;
+};
+__device__ __forceinline__ StatsBlock stats_block_reduce(StatsBlock v) {
+	__shared__ StatsBlock partial[8];
+#pragma unroll
+	for (int offset = 16; offset > 0; offset >>= 1) {
+		v.sum += __shfl_xor_sync(0xffffffffu, v.sum, offset);
+		v.count += __shfl_xor_sync(0xffffffffu, v.count, offset);
+		v.above += __shfl_xor_sync(0xffffffffu, v.above, offset);
+		const unsigned long long other_key = __shfl_xor_sync(0xffffffffu, v.key, offset);
+		v.key = other_key > v.key ? other_key : v.key;
+		v.min_bits = min(v.min_bits, __shfl_xor_sync(0xffffffffu, v.min_bits, offset));
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane == 0) partial[warp] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int i = 1; i < (int) (blockDim.x >> 5); i++) {
+			v.sum += partial[i].sum;
+			v.count += partial[i].count;
+			v.above += partial[i].above;
+			v.key = partial[i].key > v.key ? partial[i].key : v.key;
+			v.min_bits = min(v.min_bits, partial[i].min_bits);
+		}
+	}
+	return v;
+}
+__device__ __forceinline__ void stats_commit(const StatsBlock& v, int pass, StatsAccumulators* acc) {
+	if (threadIdx.x != 0) return;
+	atomicAdd(&acc->sum, v.sum);
+	if (pass == 0) {
+		atomicAdd(&acc->count, v.count);
+		atomicAdd(&acc->above, v.above);
+		atomicMax(&acc->max_key, v.key);
+		atomicMin(&acc->min_bits, v.min_bits);
+	}
+}
+
+// vector field statistics over the band union; element (voxel i, component c) = field[c * component_stride + i * voxel_stride]
+// (interleaved: 1, D; planes: N, 1). pass 0: sums and extrema; pass 1: squared deviation from `mean`
+template<int D>
+static __global__ void __launch_bounds__(256) k_warp_statistics(SlavGeom g, const float* __restrict__ field,
+		long long component_stride, int voxel_stride, const float* __restrict__ live, const float* __restrict__ canonical,
+		float min_threshold, int pass, float mean, StatsAccumulators* acc) {
+	StatsBlock v = { 0.0, 0.0, 0.0, 0ull, 0x7f800000u };
+	const float threshold_sq = min_threshold * min_threshold;
+	for (long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x; linear < g.N;
+			linear += (long long) gridDim.x * blockDim.x) {
+		const int idx = (int) linear;
+		float sq = 0.0f;
+#pragma unroll
+		for (int c = 0; c < D; c++) {
+			const float component = field[c * component_stride + (long long) idx * voxel_stride];
+			sq += component * component;
+		}
+		if (pass == 0) {
+			int pos[3];
+			slav_coords<D>(g, idx, pos);
+			const unsigned long long candidate = ((unsigned long long) __float_as_uint(sq) << 32)
+					| (unsigned long long) (0xffffffffu - eigen_order_index<D>(g, pos));
+			if (candidate > v.key) v.key = candidate;
+			v.min_bits = min(v.min_bits, __float_as_uint(sq));
+		}
+		if (slav_truncated(live[idx]) && slav_truncated(canonical[idx])) continue;
+		const float length = sqrtf(sq);
+		if (pass == 0) {
+			v.sum += (double) length;
+			v.count += 1.0;
+			if (sq > threshold_sq) v.above += 1.0;
+		} else {
+			float deviation = length - mean;
+			deviation = deviation * deviation;
+			v.sum += (double) deviation;
+		}
+	}
+	stats_commit(stats_block_reduce(v), pass, acc);
+}
+
+template<int D>
+static __global__ void __launch_bounds__(256) k_difference_statistics(SlavGeom g, const float* __restrict__ live,
+		const float* __restrict__ canonical, int pass, float mean, StatsAccumulators* acc) {
+	StatsBlock v = { 0.0, 0.0, 0.0, 0ull, 0x7f800000u };
+	for (long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x; linear < g.N;
+			linear += (long long) gridDim.x * blockDim.x) {
+		const int idx = (int) linear;
+		const float d = fabsf(live[idx] - canonical[idx]);
+		if (pass == 0) {
+			int pos[3];
+			slav_coords<D>(g, idx, pos);
+			const unsigned long long candidate = ((unsigned long long) __float_as_uint(d) << 32)
+					| (unsigned long long) (0xffffffffu - eigen_order_index<D>(g, pos));
+			if (candidate > v.key) v.key = candidate;
+			v.min_bits = min(v.min_bits, __float_as_uint(d));
+			v.sum += (double) d;
+		} else {
+			const float deviation = d - mean;
+			v.sum += (double) (deviation * deviation);
+		}
+	}
+	stats_commit(stats_block_reduce(v), pass, acc);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lsf

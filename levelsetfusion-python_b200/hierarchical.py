@@ -13,20 +13,27 @@ import enum
 import numpy as np
 
 from . import _lib
+from . import telemetry
 
 
-class ConvergenceReport:
-    """Per-level outcome (reference telemetry::ConvergenceReport, cpp/src/telemetry/convergence_report.hpp:40-44)."""
-
-    def __init__(self, raw):
-        self.iteration_count = int(raw.iteration_count)
-        self.iteration_limit_reached = bool(raw.iteration_limit_reached)
-        self.max_update_length = float(raw.max_update_length)
-        self.dims = tuple(int(d) for d in raw.dims)
-
-    def __repr__(self):
-        return ("ConvergenceReport(iteration_count=%d, iteration_limit_reached=%s, max_update_length=%g)"
-                % (self.iteration_count, self.iteration_limit_reached, self.max_update_length))
+def _report_from_raw(nd, raw, with_statistics):
+    """lsf_level_report -> telemetry.ConvergenceReport{2d,3d} (reference telemetry::ConvergenceReport,
+    cpp/src/telemetry/convergence_report.hpp:40-44). max_update_length / dims are extensions."""
+    cls = telemetry.ConvergenceReport2d if nd == 2 else telemetry.ConvergenceReport3d
+    if with_statistics:
+        warp = cls._warp_class(raw.warp_ratio_above_min_threshold, raw.warp_length_min, raw.warp_length_max,
+                               raw.warp_length_mean, raw.warp_length_std,
+                               telemetry._coordinates(nd, raw.warp_longest_location),
+                               bool(raw.warp_is_largest_below_min_threshold),
+                               bool(raw.warp_is_largest_above_max_threshold))
+        diff = cls._diff_class(raw.diff_min, raw.diff_max, raw.diff_mean, raw.diff_std,
+                               telemetry._coordinates(nd, raw.diff_biggest_location))
+        report = cls(raw.iteration_count, bool(raw.iteration_limit_reached), warp, diff)
+    else:
+        report = cls(raw.iteration_count, bool(raw.iteration_limit_reached))
+    report.max_update_length = float(raw.max_update_length)
+    report.dims = tuple(int(d) for d in raw.dims)
+    return report
 
 
 class _HierarchicalOptimizer:
@@ -165,7 +172,7 @@ class _HierarchicalOptimizer:
         collect = int(self.logging_parameters.collect_per_level_convergence_reports)
         levels = _lib.check(fn(ctypes.byref(params), ptr(canonical), ptr(live), *[ctypes.c_int(d) for d in shape],
                                ptr(warp), kind, reports, collect, ctypes.byref(capture), stream))
-        self._reports = [ConvergenceReport(reports[i]) for i in range(levels)]
+        self._reports = [_report_from_raw(nd, reports[i], bool(collect)) for i in range(levels)]
         self._captured = None if capture_buffer is None else capture_buffer[:capture.count]
         if self.verbosity_parameters.print_per_level_info:
             for level, report in enumerate(self._reports):
