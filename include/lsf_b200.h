@@ -112,6 +112,47 @@ int lsf_hier_iterate_3d(const lsf_hier_params* params, const float* canonical_de
 		int X, int Y, int Z, int iterations, float* elapsed_ms, int* kernel_launches, float* stage_ms,
 		void* stream);
 
+/* ---------------------------------------------------------------- slab decomposition of one large volume (device pointers only)
+ * A rank owns planes [own_begin, own_end) of an allocation of `planes` planes along numpy axis 0 (owned planes plus
+ * halo planes towards interior cuts; no halo at the volume border). The reference has no counterpart: it is the
+ * partitioning of Optimizer<Tensor3f,Tensor3v3f>::optimize_iteration (optimizer.tpp:174-212) named by SURVEY.md 8(e);
+ * arithmetic per voxel is unchanged, so the sharded result is bit-identical to the whole-volume one. The host driver
+ * (levelsetfusion-python_b200/slab.py) exchanges the halo planes between the two phases of an iteration. */
+typedef struct {
+	int planes, Y, Z;          /* allocation geometry of canonical / warp / g fields */
+	int own_begin, own_end;    /* owned plane range inside the allocation */
+	int x_origin;              /* global plane index of allocation plane 0 */
+	int X_global;              /* planes of the whole level */
+	const void* pack;          /* float4 pack of global planes [pack_origin, pack_origin + pack_planes), padded by 2 */
+	int pack_planes, pack_origin;
+	int pack_interior_low, pack_interior_high; /* 1: that pack edge is a cut, not the volume border */
+	const float* canonical;    /* [planes][Y][Z] */
+	float* warp;               /* [3][planes][Y][Z], updated in place on the owned planes */
+	float* g_post;             /* [3][planes][Y][Z] filtered gradient (previous iteration in, this iteration out) */
+	float* g_pre;              /* [3][planes][Y][Z] gradient before the filter (phase 1 out, phase 2 in) */
+	unsigned* max_sq_bits;     /* one slot per iteration: bits of the rank-local max ||g||^2 */
+	int* violation;            /* set to 1 if a gather left the rank's pack region */
+} lsf_slab_level;
+
+/* phase 1: gather + data term + Tikhonov term on the owned planes -> g_pre (without a Sobolev kernel: the whole
+ * iteration, result in g_pre, caller swaps g_pre / g_post); phase 2: separable filter + warp update + max norm on the
+ * owned planes (reads the +-radius halo planes of g_pre). The level-termination test reads slot iteration-1, which
+ * the driver must have max-reduced over the ranks. */
+int lsf_hier_slab_iteration(const lsf_hier_params* params, const lsf_slab_level* level, int iteration, int phase,
+		void* stream);
+/* pack {live, gradient} of global planes [pack_origin, pack_origin + pack_planes) from the live planes
+ * [live_origin, live_origin + live_planes) (must contain the pack planes +-1 inside the volume) */
+int lsf_slab_pack_finest(const float* live_region, int live_planes, int live_origin, int X_global, int Y, int Z,
+		void* pack, int pack_planes, int pack_origin, void* stream);
+/* restrict x2 by averaging (reference downsampleX2_average, resampling.tpp:385-417) between two slab allocations whose
+ * plane 0 sits at global planes src_origin / dst_origin of their levels; kind 0 = scalar field, 1 = pack (planes
+ * counted without the padding). Writes dst planes [dst_begin, dst_end). */
+int lsf_slab_restrict(int kind, const void* src, int src_planes, int src_origin, int src_Y, int src_Z, void* dst,
+		int dst_planes, int dst_origin, int dst_begin, int dst_end, void* stream);
+/* prolong x2 nearest (reference upsampleX2_nearest, resampling.tpp:103-126) of a 3-component plane field */
+int lsf_slab_prolong_nearest(const float* src, int src_planes, int src_origin, int src_Y, int src_Z, float* dst,
+		int dst_planes, int dst_origin, int dst_begin, int dst_end, void* stream);
+
 /* ---------------------------------------------------------------- primitives (device or host pointers)
  * reference: warp / warp_with_replacement, cpp/src/nonrigid_optimization/field_warping.tpp:68-225 */
 int lsf_warp_3d(const float* field, int channels, const float* warp, int X, int Y, int Z, float oob_value,

@@ -69,6 +69,19 @@ class IterationCapture(ctypes.Structure):
     ]
 
 
+class SlabLevel(ctypes.Structure):
+    """lsf_slab_level"""
+    _fields_ = [
+        ("planes", ctypes.c_int), ("Y", ctypes.c_int), ("Z", ctypes.c_int),
+        ("own_begin", ctypes.c_int), ("own_end", ctypes.c_int),
+        ("x_origin", ctypes.c_int), ("X_global", ctypes.c_int),
+        ("pack", ctypes.c_void_p), ("pack_planes", ctypes.c_int), ("pack_origin", ctypes.c_int),
+        ("pack_interior_low", ctypes.c_int), ("pack_interior_high", ctypes.c_int),
+        ("canonical", ctypes.c_void_p), ("warp", ctypes.c_void_p), ("g_post", ctypes.c_void_p),
+        ("g_pre", ctypes.c_void_p), ("max_sq_bits", ctypes.c_void_p), ("violation", ctypes.c_void_p),
+    ]
+
+
 class SlavchevaParams(ctypes.Structure):
     """lsf_slavcheva_params"""
     _fields_ = [
@@ -135,6 +148,7 @@ EXPORTED_SYMBOLS = [
     "lsf_warp_3d", "lsf_warp_2d", "lsf_gradient_3d", "lsf_gradient_2d", "lsf_laplacian_3d", "lsf_laplacian_2d",
     "lsf_convolve_3d", "lsf_convolve_2d", "lsf_downsample_3d", "lsf_upsample_3d", "lsf_downsample_2d",
     "lsf_upsample_2d", "lsf_max_norm",
+    "lsf_hier_slab_iteration", "lsf_slab_pack_finest", "lsf_slab_restrict", "lsf_slab_prolong_nearest",
     "lsf_slavcheva_optimize", "lsf_warp_advanced", "lsf_warp_delta_statistics", "lsf_tsdf_difference_statistics",
 ]
 

@@ -98,12 +98,18 @@ struct LevelState {
 	float* scratch_a = nullptr;  // planes
 	float* scratch_b = nullptr;  // planes
 	unsigned* max_sq_bits = nullptr;
+	// slab decomposition (see HierIterArgs): defaults = whole volume
+	bool slab = false;
+	int x_begin = 0, x_end = 0, x_origin = 0, X_global = 0;
+	int pack_X = 0, pack_origin = 0, pack_interior_low = 0, pack_interior_high = 0;
+	int* violation = nullptr;
 };
 
 // Enqueues one iteration; returns the number of kernel launches.
 // `events` (optional, 5 entries): recorded before the first and after every kernel, for per-stage timing.
+// `phase`: 0 = whole iteration; 1 = stage 1 only, 2 = filter stage only (slab mode: the halo exchange sits between).
 int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool check_convergence, cudaStream_t stream,
-		cudaEvent_t* events = nullptr) {
+		cudaEvent_t* events = nullptr, int phase = 0) {
 	auto mark = [&](int i) {
 		if (events) cudaEventRecord(events[i], stream);
 	};
@@ -122,10 +128,24 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 	a.max_sq_bits = s.max_sq_bits;
 	a.iteration = iteration;
 	a.check_convergence = check_convergence ? 1 : 0;
+	whole_volume(a);
+	if (s.slab) {
+		a.x_begin = s.x_begin;
+		a.x_end = s.x_end;
+		a.x_origin = s.x_origin;
+		a.X_global = s.X_global;
+		a.pack_X = s.pack_X;
+		a.pack_origin = s.pack_origin;
+		a.pack_interior_low = s.pack_interior_low;
+		a.pack_interior_high = s.pack_interior_high;
+		a.violation = s.violation;
+	}
+	const int x_begin = a.x_begin, x_end = a.x_end;
 	dim3 grid = grid3(s.g), block = block3();
 	// stage-1 variants: 0 = first generation (one voxel per thread, 64-bit indices), 1 = 4 z-voxels per thread
 	// (128-bit loads), 2 = lane-contiguous x-marching (default: best L1 behaviour, see profiles/)
-	const bool small_indices = s.g.N * 3 < (1ll << 31) && s.g.padded_count() < (1ll << 31);
+	const long long pack_count = (long long) (a.pack_X + 4) * (s.g.Y + 4) * (s.g.Z + 4);
+	const bool small_indices = s.g.N * 3 < (1ll << 31) && pack_count < (1ll << 31);
 	int variant = 0;
 	if (plan.allow_fast_kernels && small_indices) {
 		variant = 2;
@@ -133,7 +153,7 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 				&& aligned16(s.g_post) && aligned16(s.scratch_a)) variant = 1;
 	}
 	if (variant == 1) launch_shape_v4(s.g, &grid, &block);
-	if (variant == 2) launch_shape_lane(s.g, plan.lane_xv, &grid, &block);
+	if (variant == 2) launch_shape_lane(s.g, x_end - x_begin, plan.lane_xv, &grid, &block);
 #define LSF_LAUNCH_STAGE1(TIK, FUSE)                                                                      \
 	do {                                                                                                  \
 		if (variant == 2 && plan.lane_xv == 1) k_hier_gradient3d_lane<TIK, FUSE, 1> <<<counted(grid), block, 0, stream>>>(a); \
@@ -144,6 +164,7 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 		else k_hier_gradient3d<TIK, FUSE> <<<counted(grid), block, 0, stream>>>(a);                          \
 	} while (0)
 	if (!plan.use_kernel) {
+		if (phase == 2) return 0;
 		if (plan.tikhonov) {
 			a.g_out = s.scratch_a;
 			LSF_LAUNCH_STAGE1(true, true);
@@ -156,18 +177,21 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 		return 1;
 	}
 	a.g_out = s.scratch_a;
-	if (plan.tikhonov) LSF_LAUNCH_STAGE1(true, false);
-	else LSF_LAUNCH_STAGE1(false, false);
+	if (phase != 2) {
+		if (plan.tikhonov) LSF_LAUNCH_STAGE1(true, false);
+		else LSF_LAUNCH_STAGE1(false, false);
+	}
 #undef LSF_LAUNCH_STAGE1
 	mark(1);
+	if (phase == 1) return 1;
 	// stage 2: the three filter passes + update + max-norm in ONE kernel for the usual 3/5/7-tap kernels
 	if (plan.allow_fast_kernels && (plan.taps.radius >= 1 && plan.taps.radius <= 3)) {
 		float* filtered = plan.tikhonov ? s.g_post : nullptr;  // only the Tikhonov term reads g of the last iteration
 		const int check = a.check_convergence;
 		launch_fused_filter_any(plan.taps, plan.rate, plan.threshold, s.g, s.scratch_a, filtered, s.warp, s.max_sq_bits,
-				iteration, check, stream);
+				iteration, check, stream, x_begin, x_end);
 		mark(2);
-		return 2;
+		return phase == 2 ? 1 : 2;
 	}
 	grid = grid3(s.g);
 	block = block3();
@@ -480,5 +504,174 @@ extern "C" int lsf_hier_iterate_3d(const lsf_hier_params* params, const float* c
 	cudaEventDestroy(stop);
 	if (elapsed_ms) *elapsed_ms = ms;
 	if (kernel_launches) *kernel_launches = launches;
+	return LSF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ slab decomposition
+namespace lsf {
+namespace {
+
+// gradient pack of a plane range from a region of the live field (same arithmetic as k_gradient_pack3d)
+static __global__ void k_gradient_pack3d_slab(const float* __restrict__ live, int live_planes, int live_origin,
+		int X_global, float4* __restrict__ pack, Grid3 pg, int pack_origin) {
+	LSF_VOXEL_3D(pg);
+	(void) idx;
+	if (!in_grid) return;
+	const int gx = x + pack_origin;
+	if (gx < 0 || gx >= X_global) return;  // stays at the out-of-bounds constants
+	const int lx = gx - live_origin;
+	const long long YZ = (long long) pg.Y * pg.Z;
+	const long long at = lx * YZ + (long long) y * pg.Z + z;
+	(void) live_planes;
+	float dx = 0.0f;
+	if (X_global >= 2) {
+		if (gx == 0) dx = live[at + YZ] - live[at];
+		else if (gx == X_global - 1) dx = live[at] - live[at - YZ];
+		else dx = 0.5f * (live[at + YZ] - live[at - YZ]);
+	}
+	const float dy = central_difference(live, at, pg.Z, y, pg.Y);
+	const float dz = central_difference(live, at, 1, z, pg.Z);
+	pack[pg.padded_index(x, y, z)] = make_float4(live[at], dx, dy, dz);
+}
+
+// reference downsampleX2_average (resampling.tpp:385-417) between slab allocations: dst plane x <- src planes
+// 2x + shift, 2x + shift + 1
+template<typename Access>
+static __global__ void k_downsample_average3d_slab(Access acc, Grid3 src, Grid3 dst, int dst_begin, int shift) {
+	const int z = blockIdx.x * BLOCK_Z + threadIdx.x;
+	const int y = blockIdx.y * BLOCK_Y + threadIdx.y;
+	const int x = dst_begin + blockIdx.z;
+	if (z >= dst.Z || y >= dst.Y) return;
+	const int sx = 2 * x + shift, sy = 2 * y, sz = 2 * z;
+	auto sum = acc.load(src, sx, sy, sz) + acc.load(src, sx + 1, sy, sz);
+	sum = sum + acc.load(src, sx, sy + 1, sz);
+	sum = sum + acc.load(src, sx + 1, sy + 1, sz);
+	sum = sum + acc.load(src, sx, sy, sz + 1);
+	sum = sum + acc.load(src, sx + 1, sy, sz + 1);
+	sum = sum + acc.load(src, sx, sy + 1, sz + 1);
+	sum = sum + acc.load(src, sx + 1, sy + 1, sz + 1);
+	acc.store(dst, x, y, z, sum / 8.0f);
+}
+
+static __global__ void k_upsample_nearest3d_slab(const float* __restrict__ src, float* __restrict__ dst, Grid3 sg,
+		Grid3 dg, int dst_begin, int dst_origin, int src_origin) {
+	const int z = blockIdx.x * BLOCK_Z + threadIdx.x;
+	const int y = blockIdx.y * BLOCK_Y + threadIdx.y;
+	const int x = dst_begin + blockIdx.z;
+	if (z >= dg.Z || y >= dg.Y) return;
+	const int sx = ((x + dst_origin) >> 1) - src_origin;
+	const long long sidx = ((long long) sx * sg.Y + (y >> 1)) * sg.Z + (z >> 1);
+	const long long idx = ((long long) x * dg.Y + y) * dg.Z + z;
+	for (int c = 0; c < 3; c++) dst[c * dg.N + idx] = src[c * sg.N + sidx];
+}
+
+}  // namespace
+}  // namespace lsf
+
+extern "C" int lsf_hier_slab_iteration(const lsf_hier_params* params, const lsf_slab_level* level, int iteration,
+		int phase, void* stream_handle) {
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
+	LSF_REQUIRE(params && level, "params and level must not be NULL");
+	LSF_REQUIRE(phase == 1 || phase == 2, "phase must be 1 or 2");
+	LSF_REQUIRE(level->planes > 0 && level->Y > 0 && level->Z > 0 && level->own_begin >= 0
+			&& level->own_begin < level->own_end && level->own_end <= level->planes, "invalid slab geometry");
+	Plan3 plan;
+	plan.tikhonov = params->tikhonov_term_enabled && params->tikhonov_strength > 0.0f;
+	plan.use_kernel = params->gradient_kernel_enabled && params->kernel_size > 0 && params->kernel != nullptr;
+	if (plan.use_kernel) {
+		LSF_TRY(make_taps(params->kernel, params->kernel_size, &plan.taps));
+		LSF_REQUIRE(plan.taps.radius >= 1 && plan.taps.radius <= 3, "slab mode supports 3, 5 and 7-tap kernels");
+		LSF_REQUIRE(level->own_begin == 0 || level->own_begin >= plan.taps.radius,
+				"the low halo (%d planes) is narrower than the kernel radius", level->own_begin);
+		LSF_REQUIRE(level->own_end == level->planes || level->planes - level->own_end >= plan.taps.radius,
+				"the high halo (%d planes) is narrower than the kernel radius", level->planes - level->own_end);
+	}
+	plan.rate = params->rate;
+	plan.threshold = params->maximum_warp_update_threshold;
+	plan.amplifier = params->data_term_amplifier;
+	plan.strength = params->tikhonov_strength;
+	plan.max_iterations = params->maximum_iteration_count;
+	plan.allow_fast_kernels = true;
+	plan.stage1_variant = 2;
+	plan.lane_xv = plan.tikhonov ? 2 : 4;
+	LevelState s;
+	s.g = Grid3(level->planes, level->Y, level->Z);
+	LSF_REQUIRE(s.g.N * 3 < (1ll << 31), "slab too large for 32-bit voxel indices (%lld voxels): use more ranks", s.g.N);
+	s.pack = static_cast<const float4*>(level->pack);
+	s.canonical = level->canonical;
+	s.warp = level->warp;
+	s.g_post = level->g_post;
+	s.scratch_a = level->g_pre;
+	s.scratch_b = nullptr;
+	s.max_sq_bits = level->max_sq_bits;
+	s.slab = true;
+	s.x_begin = level->own_begin;
+	s.x_end = level->own_end;
+	s.x_origin = level->x_origin;
+	s.X_global = level->X_global;
+	s.pack_X = level->pack_planes;
+	s.pack_origin = level->pack_origin;
+	s.pack_interior_low = level->pack_interior_low;
+	s.pack_interior_high = level->pack_interior_high;
+	s.violation = level->violation;
+	enqueue_iteration(plan, s, iteration, true, stream, nullptr, phase);
+	LSF_CUDA(cudaGetLastError());
+	return LSF_OK;
+}
+
+extern "C" int lsf_slab_pack_finest(const float* live_region, int live_planes, int live_origin, int X_global, int Y,
+		int Z, void* pack, int pack_planes, int pack_origin, void* stream_handle) {
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
+	LSF_REQUIRE(live_region && pack && live_planes > 0 && pack_planes > 0 && Y > 0 && Z > 0, "invalid arguments");
+	const int lo = std::max(pack_origin, 0), hi = std::min(pack_origin + pack_planes, X_global);
+	LSF_REQUIRE(std::max(lo - 1, 0) >= live_origin && std::min(hi + 1, X_global) <= live_origin + live_planes,
+			"the live region [%d, %d) does not cover the pack planes [%d, %d) +- 1", live_origin,
+			live_origin + live_planes, lo, hi);
+	const Grid3 pg(pack_planes, Y, Z);
+	const float4 border = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+	k_fill4<<<counted(div_up(pg.padded_count(), 256)), 256, 0, stream>>>(static_cast<float4*>(pack), pg.padded_count(), border);
+	k_gradient_pack3d_slab<<<counted(grid3(pg)), block3(), 0, stream>>>(live_region, live_planes, live_origin, X_global,
+			static_cast<float4*>(pack), pg, pack_origin);
+	LSF_CUDA(cudaGetLastError());
+	return LSF_OK;
+}
+
+extern "C" int lsf_slab_restrict(int kind, const void* src, int src_planes, int src_origin, int src_Y, int src_Z,
+		void* dst, int dst_planes, int dst_origin, int dst_begin, int dst_end, void* stream_handle) {
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
+	LSF_REQUIRE(src && dst && src_Y % 2 == 0 && src_Z % 2 == 0, "invalid arguments");
+	LSF_REQUIRE(0 <= dst_begin && dst_begin <= dst_end && dst_end <= dst_planes, "invalid destination plane range");
+	if (dst_begin == dst_end) return LSF_OK;
+	const int shift = 2 * dst_origin - src_origin;
+	LSF_REQUIRE(2 * dst_begin + shift >= 0 && 2 * (dst_end - 1) + shift + 1 < src_planes,
+			"the source planes do not cover the destination range");
+	const Grid3 sg(src_planes, src_Y, src_Z), dg(dst_planes, src_Y / 2, src_Z / 2);
+	const dim3 grid(div_up(dg.Z, BLOCK_Z), div_up(dg.Y, BLOCK_Y), dst_end - dst_begin);
+	if (kind == 1) {
+		const float4 border = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+		if (dst_begin == 0 && dst_end == dst_planes)
+			k_fill4<<<counted(div_up(dg.padded_count(), 256)), 256, 0, stream>>>(static_cast<float4*>(dst), dg.padded_count(), border);
+		k_downsample_average3d_slab<<<counted(grid), block3(), 0, stream>>>(
+				PackAccess { static_cast<const float4*>(src), static_cast<float4*>(dst) }, sg, dg, dst_begin, shift);
+	} else {
+		k_downsample_average3d_slab<<<counted(grid), block3(), 0, stream>>>(
+				PlainAccess { static_cast<const float*>(src), static_cast<float*>(dst) }, sg, dg, dst_begin, shift);
+	}
+	LSF_CUDA(cudaGetLastError());
+	return LSF_OK;
+}
+
+extern "C" int lsf_slab_prolong_nearest(const float* src, int src_planes, int src_origin, int src_Y, int src_Z,
+		float* dst, int dst_planes, int dst_origin, int dst_begin, int dst_end, void* stream_handle) {
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
+	LSF_REQUIRE(src && dst, "invalid arguments");
+	LSF_REQUIRE(0 <= dst_begin && dst_begin <= dst_end && dst_end <= dst_planes, "invalid destination plane range");
+	if (dst_begin == dst_end) return LSF_OK;
+	LSF_REQUIRE(((dst_begin + dst_origin) >> 1) - src_origin >= 0
+			&& ((dst_end - 1 + dst_origin) >> 1) - src_origin < src_planes, "the source planes do not cover the range");
+	const Grid3 sg(src_planes, src_Y, src_Z), dg(dst_planes, src_Y * 2, src_Z * 2);
+	const dim3 grid(div_up(dg.Z, BLOCK_Z), div_up(dg.Y, BLOCK_Y), dst_end - dst_begin);
+	k_upsample_nearest3d_slab<<<counted(grid), block3(), 0, stream>>>(src, dst, sg, dg, dst_begin, dst_origin, src_origin);
+	LSF_CUDA(cudaGetLastError());
 	return LSF_OK;
 }

@@ -221,7 +221,25 @@ struct HierIterArgs {
 	unsigned* max_sq_bits;
 	int iteration;
 	int check_convergence;
+	// slab decomposition along axis 0 (slab.py): the fields are an allocation of g.X planes (owned planes + halo
+	// planes); only planes [x_begin, x_end) are processed. Allocation plane 0 is global plane x_origin of a level of
+	// X_global planes; the pack covers global planes [pack_origin, pack_origin + pack_X). Whole volume: x_begin 0,
+	// x_end X, x_origin 0, X_global X, pack_origin 0, pack_X X, no interior pack edges.
+	int x_begin, x_end, x_origin, X_global;
+	int pack_X, pack_origin, pack_interior_low, pack_interior_high;
+	int* violation;          // set to 1 when a gather would leave the rank's pack region (nullptr: whole volume)
 };
+
+inline void whole_volume(HierIterArgs& a) {
+	a.x_begin = 0;
+	a.x_end = a.g.X;
+	a.x_origin = 0;
+	a.X_global = a.g.X;
+	a.pack_X = a.g.X;
+	a.pack_origin = 0;
+	a.pack_interior_low = a.pack_interior_high = 0;
+	a.violation = nullptr;
+}
 
 template<bool TIKHONOV, bool FUSE_UPDATE>
 static __global__ void __launch_bounds__(BLOCK_Z * BLOCK_Y) k_hier_gradient3d(HierIterArgs a) {

@@ -66,6 +66,42 @@ __device__ __forceinline__ float4 gather4i(const float4* __restrict__ pack, int 
 	return i0 * ix + i1 * rx;
 }
 
+// The same gather for a rank that holds only planes [pack_origin, pack_origin + pack_X) of the level's pack (slab
+// decomposition). The lookup is formed from the GLOBAL plane index so that the interpolation ratios are bit-identical
+// to the whole-volume run; a tap that would fall into another rank's part of the pack raises `violation`.
+__device__ __forceinline__ float4 gather4i_slab(const float4* __restrict__ pack, const HierIterArgs& a, int x_global,
+		int y, int z, float wx, float wy, float wz) {
+	const int Y = a.g.Y, Z = a.g.Z;
+	const float lookup_x = (float) x_global + wx;
+	const float lookup_y = (float) y + wy;
+	const float lookup_z = (float) z + wz;
+	int bx = __float2int_rd(lookup_x);
+	int by = __float2int_rd(lookup_y);
+	int bz = __float2int_rd(lookup_z);
+	const float rx = lookup_x - (float) bx, ry = lookup_y - (float) by, rz = lookup_z - (float) bz;
+	const float ix = 1.0f - rx, iy = 1.0f - ry, iz = 1.0f - rz;
+	bx = min(max(bx, -2), a.X_global) - a.pack_origin;
+	if ((a.pack_interior_low && bx < 0) || (a.pack_interior_high && bx + 1 > a.pack_X - 1)) {
+		if (a.violation != nullptr) *a.violation = 1;
+	}
+	bx = min(max(bx, -2), a.pack_X);
+	by = min(max(by, -2), Y);
+	bz = min(max(bz, -2), Z);
+	const int sy = Z + 4, sx = (Y + 4) * (Z + 4);
+	const float4* p = pack + ((bx + 2) * sx + (by + 2) * sy + (bz + 2));
+	const float4 v000 = __ldg(p), v001 = __ldg(p + 1);
+	const float4 v010 = __ldg(p + sy), v011 = __ldg(p + sy + 1);
+	const float4 v100 = __ldg(p + sx), v101 = __ldg(p + sx + 1);
+	const float4 v110 = __ldg(p + sx + sy), v111 = __ldg(p + sx + sy + 1);
+	const float4 i00 = v000 * iz + v001 * rz;
+	const float4 i01 = v010 * iz + v011 * rz;
+	const float4 i10 = v100 * iz + v101 * rz;
+	const float4 i11 = v110 * iz + v111 * rz;
+	const float4 i0 = i00 * iy + i01 * ry;
+	const float4 i1 = i10 * iy + i11 * ry;
+	return i0 * ix + i1 * rx;
+}
+
 // replicated-border Laplacian of one plane at 4 consecutive z voxels (reference gradients.tpp:28-35,114-171)
 __device__ __forceinline__ void laplacian4(const float* __restrict__ p, int idx, int x, int y, int z, int X, int Y,
 		int Z, float (&out)[4]) {
@@ -191,7 +227,7 @@ static __global__ void __launch_bounds__(256) k_hier_gradient3d_lane(HierIterArg
 	const int N = (int) a.g.N;
 	const int z = blockIdx.x * 32 + threadIdx.x;
 	const int y = blockIdx.y * 8 + threadIdx.y;
-	const int xb = blockIdx.z * XV;
+	const int xb = a.x_begin + blockIdx.z * XV;
 	float best = 0.0f;
 	if (z < Z && y < Y) {
 		int idx = (xb * Y + y) * Z + z;
@@ -206,7 +242,7 @@ static __global__ void __launch_bounds__(256) k_hier_gradient3d_lane(HierIterArg
 #pragma unroll
 		for (int v = 0; v < XV; v++) {
 			const int x = xb + v;
-			if (x >= X) break;
+			if (x >= a.x_end) break;
 			const float wx = __ldg(a.warp + idx), wy = __ldg(a.warp + N + idx), wz = __ldg(a.warp + 2 * N + idx);
 			const float cn = __ldg(a.canonical + idx);
 			float lap[3] = { 0.f, 0.f, 0.f };
@@ -225,7 +261,7 @@ static __global__ void __launch_bounds__(256) k_hier_gradient3d_lane(HierIterArg
 					cur[c] = next;
 				}
 			}
-			const float4 s = gather4i(a.pack, X, Y, Z, x, y, z, wx, wy, wz);
+			const float4 s = gather4i_slab(a.pack, a, x + a.x_origin, y, z, wx, wy, wz);
 			const float diff = s.x - cn;
 			float gx = (s.y * diff) * a.amplifier;
 			float gy = (s.z * diff) * a.amplifier;
@@ -255,9 +291,9 @@ static __global__ void __launch_bounds__(256) k_hier_gradient3d_lane(HierIterArg
 	if (FUSE_UPDATE) block_atomic_max(best, a.max_sq_bits + a.iteration);
 }
 
-inline void launch_shape_lane(const Grid3& g, int xv, dim3* grid, dim3* block) {
+inline void launch_shape_lane(const Grid3& g, int x_planes, int xv, dim3* grid, dim3* block) {
 	*block = dim3(32, 8, 1);
-	*grid = dim3(div_up(g.Z, 32), div_up(g.Y, 8), div_up(g.X, xv));
+	*grid = dim3(div_up(g.Z, 32), div_up(g.Y, 8), div_up(x_planes, xv));
 }
 
 // ---------------------------------------------------------------------------------------------- stage 2, fused
@@ -290,6 +326,7 @@ struct FusedConvArgs {
 	int iteration;
 	int check_convergence;
 	int x_chunk;       // planes per block along axis 0
+	int x_begin, x_end;  // planes filtered / updated (whole volume: 0, X); loads still see every plane of the allocation
 };
 
 // reference convolve_with_kernel (tensor), cpp/src/math/convolution.cpp:221-332, followed by
@@ -311,8 +348,8 @@ static __global__ void __launch_bounds__(FusedConv<R>::THREADS, 1) k_sobolev_fus
 	const int c = tid / C::GROUP;  // vector component of this thread (warp-uniform)
 	const int t = tid - c * C::GROUP;
 	const int z0 = blockIdx.x * C::TZ, y0 = blockIdx.y * C::TY;
-	const int x0 = blockIdx.z * a.x_chunk;
-	const int x1 = min(X, x0 + a.x_chunk);
+	const int x0 = a.x_begin + blockIdx.z * a.x_chunk;
+	const int x1 = min(a.x_end, x0 + a.x_chunk);
 	float k[K];
 #pragma unroll
 	for (int q = 0; q < K; q++) k[q] = a.k[q];
@@ -448,7 +485,7 @@ static __global__ void __launch_bounds__(FusedConv<R>::THREADS, 1) k_sobolev_fus
 // Chooses how many planes along axis 0 each block of the fused filter kernel marches over: enough blocks to fill
 // whole waves of the GPU, as few as possible because every chunk re-reads 2R priming planes.
 template<int R>
-int choose_x_chunk(const Grid3& g) {
+int choose_x_chunk(const Grid3& g, int x_planes) {
 	typedef FusedConv<R> C;
 	static int slots = 0;
 	if (slots == 0) {
@@ -459,11 +496,11 @@ int choose_x_chunk(const Grid3& g) {
 		slots = sms * std::max(per_sm, 1);
 	}
 	const long long tiles = (long long) div_up(g.Y, C::TY) * div_up(g.Z, C::TZ);
-	int best_chunk = g.X;
+	int best_chunk = x_planes;
 	double best_cost = 1e30;
-	for (int chunks = 1; chunks <= std::max(1, g.X / 8); chunks++) {
-		const int chunk = (g.X + chunks - 1) / chunks;
-		const long long blocks = tiles * ((g.X + chunk - 1) / chunk);
+	for (int chunks = 1; chunks <= std::max(1, x_planes / 8); chunks++) {
+		const int chunk = (x_planes + chunks - 1) / chunks;
+		const long long blocks = tiles * ((x_planes + chunk - 1) / chunk);
 		const double waves = (double) ((blocks + slots - 1) / slots);
 		const double cost = waves * (chunk + 2 * R * 0.35);
 		if (cost < best_cost - 1e-9) {
@@ -476,7 +513,7 @@ int choose_x_chunk(const Grid3& g) {
 
 template<int R>
 void launch_fused_filter(const Taps& taps, float rate, float threshold, const Grid3& g, const float* in, float* out,
-		float* warp, unsigned* max_sq_bits, int iteration, int check, cudaStream_t stream) {
+		float* warp, unsigned* max_sq_bits, int iteration, int check, cudaStream_t stream, int x_begin, int x_end) {
 	typedef FusedConv<R> C;
 	FusedConvArgs f;
 	f.in = in;
@@ -489,23 +526,26 @@ void launch_fused_filter(const Taps& taps, float rate, float threshold, const Gr
 	f.max_sq_bits = max_sq_bits;
 	f.iteration = iteration;
 	f.check_convergence = check;
-	f.x_chunk = choose_x_chunk<R>(g);
-	const dim3 grid(div_up(g.Z, C::TZ), div_up(g.Y, C::TY), div_up(g.X, f.x_chunk));
+	f.x_begin = x_begin;
+	f.x_end = x_end < 0 ? g.X : x_end;
+	f.x_chunk = choose_x_chunk<R>(g, f.x_end - f.x_begin);
+	const dim3 grid(div_up(g.Z, C::TZ), div_up(g.Y, C::TY), div_up(f.x_end - f.x_begin, f.x_chunk));
 	k_sobolev_fused3d<R> <<<counted(grid), C::THREADS, 0, stream>>>(f);
 }
 
 // dispatch on the filter radius (1, 2 or 3); returns false if the radius has no fused instantiation
 inline bool launch_fused_filter_any(const Taps& taps, float rate, float threshold, const Grid3& g, const float* in,
-		float* out, float* warp, unsigned* max_sq_bits, int iteration, int check, cudaStream_t stream) {
+		float* out, float* warp, unsigned* max_sq_bits, int iteration, int check, cudaStream_t stream, int x_begin = 0,
+		int x_end = -1) {
 	switch (taps.radius) {
 	case 1:
-		launch_fused_filter<1>(taps, rate, threshold, g, in, out, warp, max_sq_bits, iteration, check, stream);
+		launch_fused_filter<1>(taps, rate, threshold, g, in, out, warp, max_sq_bits, iteration, check, stream, x_begin, x_end);
 		return true;
 	case 2:
-		launch_fused_filter<2>(taps, rate, threshold, g, in, out, warp, max_sq_bits, iteration, check, stream);
+		launch_fused_filter<2>(taps, rate, threshold, g, in, out, warp, max_sq_bits, iteration, check, stream, x_begin, x_end);
 		return true;
 	case 3:
-		launch_fused_filter<3>(taps, rate, threshold, g, in, out, warp, max_sq_bits, iteration, check, stream);
+		launch_fused_filter<3>(taps, rate, threshold, g, in, out, warp, max_sq_bits, iteration, check, stream, x_begin, x_end);
 		return true;
 	default:
 		return false;

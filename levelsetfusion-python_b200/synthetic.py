@@ -5,18 +5,21 @@ import numpy as np
 NARROW_BAND_HALF_WIDTH = 10.0
 
 
-def sphere_plane_pair_3d(size=128, shift=(2.5, -1.5, 1.0), radius_scale=1.04, plane_shift=-2.5, xp=np, device=None):
+def sphere_plane_pair_3d(size=128, shift=(2.5, -1.5, 1.0), radius_scale=1.04, plane_shift=-2.5, xp=np, device=None,
+                         planes=None):
     """C2 geometry: canonical = sphere(centre size/2, r = 0.3 size) U half-space below the plane axis0 = 0.75 size;
     live = the same scene with the sphere moved by `shift` (scaled by size/128), grown by `radius_scale` and the
-    plane moved by `plane_shift`. Returns (canonical, live) float32 [size]^3. `xp` is numpy or torch."""
+    plane moved by `plane_shift`. Returns (canonical, live) float32 [size]^3. `xp` is numpy or torch.
+    `planes=(lo, hi)` generates only the axis-0 planes [lo, hi) (slab-sharded volumes: identical values)."""
     s = size / 128.0
+    lo, hi = (0, size) if planes is None else planes
     if xp is np:
         axis = np.arange(size, dtype=np.float32)
-        i, j, k = np.meshgrid(axis, axis, axis, indexing="ij")
+        i, j, k = np.meshgrid(axis[lo:hi], axis, axis, indexing="ij")
         sqrt, minimum, clip = np.sqrt, np.minimum, np.clip
     else:
         axis = xp.arange(size, dtype=xp.float32, device=device)
-        i, j, k = xp.meshgrid(axis, axis, axis, indexing="ij")
+        i, j, k = xp.meshgrid(axis[lo:hi], axis, axis, indexing="ij")
         sqrt, minimum, clip = xp.sqrt, xp.minimum, xp.clamp
 
     def scene(cx, cy, cz, r, plane):

@@ -1,0 +1,78 @@
+"""Slab decomposition of one volume on a single GPU: `world_size` virtual ranks run in lockstep and
+exchange halos by device copies (slab.LocalExchange); the assembled warp field must be BIT-IDENTICAL to the
+whole-volume optimizer's and the per-level iteration counts equal. The multi-process NCCL path uses the same kernels
+and the same exchange points (tools/slab_multigpu_check.py runs it on 2+ GPUs)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MODES = {
+    "tikhonov_kernel": dict(tikhonov_term_enabled=True, gradient_kernel_enabled=True, tikhonov_strength=0.1),
+    "kernel": dict(tikhonov_term_enabled=False, gradient_kernel_enabled=True),
+    "tikhonov": dict(tikhonov_term_enabled=True, gradient_kernel_enabled=False, tikhonov_strength=0.05),
+    "data_only": dict(tikhonov_term_enabled=False, gradient_kernel_enabled=False),
+}
+
+
+@pytest.fixture(scope="module")
+def lsf():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import lsf_b200
+    lsf_b200._lib.load()
+    return lsf_b200
+
+
+def make_optimizer(lsf, mode, iterations=12, threshold=0.01):
+    from lsf_b200 import synthetic
+    return lsf.HierarchicalOptimizer3d(maximum_chunk_size=4, maximum_iteration_count=iterations,
+                                       maximum_warp_update_threshold=threshold, kernel=synthetic.sobolev_kernel_1d(),
+                                       **MODES[mode])
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+@pytest.mark.parametrize("world_size", [2, 4])
+def test_slabs_match_whole_volume(lsf, mode, world_size):
+    from lsf_b200 import slab, synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(64)
+    canonical, live = canonical[:, :48, :56].copy(), live[:, :48, :56].copy()
+    optimizer = make_optimizer(lsf, mode)
+    whole = optimizer.optimize(canonical, live)
+    sharded = slab.SlabHierarchicalOptimizer3d(optimizer, pack_halo=16)
+    warp = sharded.optimize_emulated(canonical, live, world_size)
+    assert sharded.iteration_counts == optimizer.get_per_level_iteration_counts()
+    assert np.array_equal(warp, whole)
+    assert np.allclose(sharded.max_update_lengths,
+                       [r.max_update_length for r in optimizer.get_per_level_convergence_reports()], rtol=0, atol=0)
+
+
+def test_slabs_early_termination_and_single_rank(lsf):
+    from lsf_b200 import slab, synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(64)
+    optimizer = make_optimizer(lsf, "kernel", iterations=40, threshold=0.05)
+    whole = optimizer.optimize(canonical, live)
+    counts = optimizer.get_per_level_iteration_counts()
+    assert any(c < 40 for c in counts)
+    for world_size in (1, 2):
+        sharded = slab.SlabHierarchicalOptimizer3d(optimizer)
+        assert np.array_equal(sharded.optimize_emulated(canonical, live, world_size), whole)
+        assert sharded.iteration_counts == counts
+
+
+def test_gather_halo_violation_is_reported(lsf):
+    """a warp that reaches beyond the rank's static gather halo must raise, never silently read padding"""
+    from lsf_b200 import slab, synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(64, shift=(14.0, 0.0, 0.0), plane_shift=-14.0)
+    optimizer = make_optimizer(lsf, "data_only", iterations=60, threshold=0.0)
+    optimizer.rate = 0.5
+    sharded = slab.SlabHierarchicalOptimizer3d(optimizer, pack_halo=2)
+    with pytest.raises(RuntimeError, match="gather halo"):
+        sharded.optimize_emulated(canonical, live, 4)
+
+
+def test_slab_restrictions(lsf):
+    from lsf_b200 import slab
+    linear = lsf.HierarchicalOptimizer3d(resampling_strategy=lsf.HierarchicalOptimizer3d.ResamplingStrategy.LINEAR)
+    with pytest.raises(RuntimeError):
+        slab.SlabHierarchicalOptimizer3d(linear)
