@@ -75,10 +75,13 @@ class SlabPlan:
         self.rank, self.world_size = rank, world_size
         self.halo = max(int(radius), 1 if tikhonov else 0)
         self.levels = []
+        # gather halo: `pack_halo` planes at the finest level (at least 2 at the coarsest), exactly doubling from level
+        # to level so that every finer pack region covers the coarser one it is restricted to
+        coarsest_pack_halo = max(int(pack_halo) >> (self.level_count - 1), 2)
         for level in range(self.level_count):
             shrink = 2 ** (self.level_count - 1 - level)
             self.levels.append(SlabGeometry(X // shrink, Y // shrink, Z // shrink, rank, world_size, self.halo,
-                                            max(pack_halo // shrink, 2)))
+                                            coarsest_pack_halo << level))
         finest = self.levels[-1]
         self.live_lo = max(finest.pack_lo - 1, 0)
         self.live_hi = min(finest.pack_hi + 1, X)

@@ -61,14 +61,32 @@ def test_slabs_early_termination_and_single_rank(lsf):
 
 
 def test_gather_halo_violation_is_reported(lsf):
-    """a warp that reaches beyond the rank's static gather halo must raise, never silently read padding"""
-    from lsf_b200 import slab, synthetic
-    canonical, live = synthetic.sphere_plane_pair_3d(64, shift=(14.0, 0.0, 0.0), plane_shift=-14.0)
-    optimizer = make_optimizer(lsf, "data_only", iterations=60, threshold=0.0)
-    optimizer.rate = 0.5
+    """a warp that reaches beyond the rank's static gather halo must raise the flag, never silently read padding"""
+    import ctypes
+    import torch
+    from lsf_b200 import slab, synthetic, _lib
+    canonical, live = synthetic.sphere_plane_pair_3d(64)
+    optimizer = make_optimizer(lsf, "kernel")
     sharded = slab.SlabHierarchicalOptimizer3d(optimizer, pack_halo=2)
-    with pytest.raises(RuntimeError, match="gather halo"):
-        sharded.optimize_emulated(canonical, live, 4)
+    device = torch.device("cuda", torch.cuda.current_device())
+    flags = []
+    for displacement in (0.5, 9.0):
+        plan = sharded.plan(canonical.shape, 1, 4)  # an interior rank: both pack edges are cuts
+        own_lo, own_hi = plan.own_range()
+        live_lo, live_hi = plan.live_range()
+        state = slab._RankState(plan, torch.from_numpy(canonical[own_lo:own_hi]), torch.from_numpy(live[live_lo:live_hi]),
+                                device)
+        level = plan.level_count - 1
+        state.start_level(0, 4)
+        state.warp = torch.zeros((3, plan.levels[level].planes, 64, 64), dtype=torch.float32, device=device)
+        state.warp[0] = displacement
+        state.start_level(level, 4)
+        descriptor = state.descriptor(level)
+        params = optimizer._params()
+        _lib.check(_lib.load().lsf_hier_slab_iteration(ctypes.byref(params), ctypes.byref(descriptor), 0, 1,
+                                                       _lib.current_stream_handle()))
+        flags.append(int(state.violation.item()))
+    assert flags == [0, 1]  # finest-level gather halo is 8 planes here: 0.5 stays inside, 9.0 does not
 
 
 def test_slab_restrictions(lsf):
