@@ -34,6 +34,12 @@ import numpy as np
 METRIC = "voxel-updates/s of 3D warp-field optimization at 256^3"
 UNIT = "voxel-updates/s"
 ALGORITHMIC_BYTES_PER_VOXEL_UPDATE = 68  # hierarchical 3D with Tikhonov (+- kernel), see DESIGN.md
+# dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one finest-level 256^3 iteration, from the committed
+# `ncu --set full` capture (per launch group, like `achieved`)
+NCU_DRAM_BYTES_PER_ITERATION = 1724019968
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_fused_v1.md (930.8 MB + 793.2 MB)"
+STAGE_NAMES = {1: ("fused_iteration",), 2: ("gradient_stage", "fused_filter_update_max"),
+               4: ("gradient_stage", "filter_axis0", "filter_axis1", "filter_axis2_update_max")}
 
 
 def optimizer_kwargs():
@@ -218,13 +224,13 @@ def run_ours(args):
         achieved = ALGORITHMIC_BYTES_PER_VOXEL_UPDATE * N / (iteration_ms * 1e-3) / 1e9
         roofline = {
             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None,
-            "kernel": "finest-level iteration = k_hier_gradient3d + k_convolve_axis3d x3 (%d launches/iteration)"
-                      % (n_launch.value // iterations),
+            "frac": round(achieved / peak, 4), "traffic": NCU_DRAM_BYTES_PER_ITERATION if size == 256 else None,
+            "traffic_source": NCU_TRAFFIC_SOURCE if size == 256 else None,
+            "kernel": "finest-level iteration = k_hier_gradient3d_lane (gather + data + Tikhonov) + k_sobolev_fused3d "
+                      "(3 filter passes + warp update + max norm), %d launches/iteration" % (n_launch.value // iterations),
             "algorithmic_bytes_per_launch_group": ALGORITHMIC_BYTES_PER_VOXEL_UPDATE * N,
             "ms_per_iteration": round(iteration_ms, 4),
-            "stage_ms": {"gradient": round(stages[0], 4), "conv_axis0": round(stages[1], 4),
-                         "conv_axis1": round(stages[2], 4), "conv_axis2_update_max": round(stages[3], 4)},
+            "stage_ms": dict(zip(STAGE_NAMES[n_launch.value // iterations], (round(v, 4) for v in stages))),
             "peak_source": peak_source,
         }
         # -------------------------------------------------------------- CPU baseline (oracle port), bounded sample
@@ -259,6 +265,7 @@ def cpu_baseline_sample(size, kwargs, iterations=3):
     `iterations` finest-level iterations of the same 256^3 pair, all host threads."""
     import oracle
     from lsf_b200 import synthetic
+    oracle.use_all_cores()
     canonical, live = synthetic.sphere_plane_pair_3d(size)
     seconds = oracle.hier_time_iterations3d(canonical, live, iterations, **kwargs)
     return {"value": iterations * size ** 3 / seconds, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
@@ -272,6 +279,7 @@ def run_reference(args):
         return
     import oracle
     from lsf_b200 import synthetic
+    oracle.use_all_cores()
     size = args.size
     kwargs = optimizer_kwargs()
     canonical, live = synthetic.sphere_plane_pair_3d(size)

@@ -75,6 +75,13 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def use_all_cores():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU-baseline timings use every host core instead"""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(cores))
+    return num_threads()
+
+
 # ------------------------------------------------------------------ primitives
 def warp(field, warp_field):
     """reference `warp` (OOB -> 1.0): field_warping.tpp:68-140,145-194"""

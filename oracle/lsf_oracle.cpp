@@ -792,6 +792,10 @@ double orc_hier_time_iterations3d(const orc_hier_params* p, const float* canonic
 	return omp_get_wtime() - t0;
 }
 
+void orc_set_num_threads(int n) {
+	if (n > 0) omp_set_num_threads(n);
+}
+
 int orc_num_threads(void) {
 	return omp_get_max_threads();
 }

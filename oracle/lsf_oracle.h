@@ -79,6 +79,8 @@ double orc_hier_time_iterations3d(const orc_hier_params* p, const float* canonic
 		int Z, int iterations);
 
 int orc_num_threads(void);
+/* launchers such as torch.distributed.run export OMP_NUM_THREADS=1: lets the timing legs use every host core */
+void orc_set_num_threads(int n);
 
 /* ---- SobolevFusion / KillingFusion ("slavcheva") optimizers: lsf_oracle_slavcheva.cpp ---- */
 #define ORC_SEMANTICS_CPP 0            /* C++ SobolevOptimizer2d (+ dimensional generalisation) */
