@@ -6,6 +6,7 @@
 // termination test (optimizer.tpp:166-171) is evaluated on the device at the head of every kernel from
 // the previous iteration's max ||g||^2 slot, and the host polls the slots once per chunk of iterations.
 #include "kernels3d_fused.cuh"
+#include "kernels3d_split.cuh"
 #include "slavcheva.cuh"  // statistics_on_device
 
 #include <cfloat>
@@ -30,6 +31,8 @@ struct Plan3 {
 	bool allow_fast_kernels = true;    // false: first-generation kernels only (kept for A/B parity tests)
 	int lane_xv = 4;                   // planes per thread of the lane-contiguous stage 1 (LSF_LANE_XV overrides;
 	                                   // measured best on B200: 2 with the Tikhonov term, 4 without)
+	bool split_x = true;               // stage 1 + axis-0 pass | axis-1/2 passes + update (LSF_SPLIT_X=0: previous cut)
+	int x_chunk_stage1 = 64, x_chunk_filter = 16;  // planes per block of the two split kernels (LSF_XCHUNK_A / _B)
 	int stage1_variant = 2;            // LSF_STAGE1_VARIANT=1 selects the 4-voxel kernel (A/B)
 	Grid3 level_grid[LSF_MAX_LEVELS];  // [0] = coarsest
 };
@@ -80,6 +83,12 @@ int make_plan(const lsf_hier_params* p, int X, int Y, int Z, Plan3* plan) {
 	const char* stage1 = getenv("LSF_STAGE1_VARIANT");
 	if (stage1 && stage1[0] == '1') plan->stage1_variant = 1;
 	plan->lane_xv = plan->tikhonov ? 2 : 4;
+	const char* split = getenv("LSF_SPLIT_X");
+	if (split && split[0] == '0') plan->split_x = false;
+	const char* chunk_a = getenv("LSF_XCHUNK_A");
+	if (chunk_a && atoi(chunk_a) > 0) plan->x_chunk_stage1 = atoi(chunk_a);
+	const char* chunk_b = getenv("LSF_XCHUNK_B");
+	if (chunk_b && atoi(chunk_b) > 0) plan->x_chunk_filter = atoi(chunk_b);
 	const char* xv = getenv("LSF_LANE_XV");
 	if (xv && (atoi(xv) == 1 || atoi(xv) == 2 || atoi(xv) == 4 || atoi(xv) == 8)) plan->lane_xv = atoi(xv);
 	return LSF_OK;
@@ -175,6 +184,23 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 		}
 		mark(1);
 		return 1;
+	}
+	if (plan.split_x && variant == 2 && !s.slab && phase == 0 && plan.taps.radius >= 1 && plan.taps.radius <= 3) {
+		// second-generation cut: stage 1 + axis-0 pass, then axis-1/2 passes + update (kernels3d_split.cuh)
+		float* filtered = plan.tikhonov ? s.g_post : nullptr;
+		const int chunk_a = std::min(plan.x_chunk_stage1, s.g.X), chunk_b = std::min(plan.x_chunk_filter, s.g.X);
+		switch (plan.taps.radius) {
+		case 1:
+			launch_split_iteration<1>(plan.tikhonov, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_a, chunk_b, stream, events);
+			break;
+		case 2:
+			launch_split_iteration<2>(plan.tikhonov, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_a, chunk_b, stream, events);
+			break;
+		default:
+			launch_split_iteration<3>(plan.tikhonov, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_a, chunk_b, stream, events);
+			break;
+		}
+		return 2;
 	}
 	a.g_out = s.scratch_a;
 	if (phase != 2) {

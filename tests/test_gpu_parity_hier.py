@@ -314,6 +314,15 @@ def test_fused_kernels_match_first_generation_kernels(lsf, mode, monkeypatch):
     kwargs = dict(HIER_MODES[mode])
     kwargs.update(maximum_chunk_size=4, maximum_iteration_count=12, kernel=synthetic.sobolev_kernel_1d())
     fast = lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live)
+    # previous cut of the iteration (stage 1 | three-pass filter kernel) and odd chunk sizes of the split kernels
+    monkeypatch.setenv("LSF_SPLIT_X", "0")
+    assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
+    monkeypatch.delenv("LSF_SPLIT_X")
+    monkeypatch.setenv("LSF_XCHUNK_A", "7")
+    monkeypatch.setenv("LSF_XCHUNK_B", "5")
+    assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
+    monkeypatch.delenv("LSF_XCHUNK_A")
+    monkeypatch.delenv("LSF_XCHUNK_B")
     monkeypatch.setenv("LSF_LEGACY_KERNELS", "1")
     legacy = lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live)
     assert np.array_equal(fast, legacy)
