@@ -7,6 +7,7 @@
 // the previous iteration's max ||g||^2 slot, and the host polls the slots once per chunk of iterations.
 #include "kernels3d_fused.cuh"
 #include "kernels3d_split.cuh"
+#include "kernels3d_tma.cuh"
 #include "slavcheva.cuh"  // statistics_on_device
 
 #include <cfloat>
@@ -34,6 +35,8 @@ struct Plan3 {
 	bool split_x = true;               // stage 1 + axis-0 pass | axis-1/2 passes + update (LSF_SPLIT_X=0: previous cut)
 	int x_chunk_stage1 = 64, x_chunk_filter = 16;  // planes per block of the two split kernels (LSF_XCHUNK_A / _B)
 	int stage1_variant = 2;            // LSF_STAGE1_VARIANT=1 selects the 4-voxel kernel (A/B)
+	bool tma = true;                   // third generation: TMA-fed stage 1 + y-marching filter (LSF_TMA=0: second generation)
+	int x_chunk_tma = 64, y_chunk_tma = 64;  // planes / rows per block of the two TMA-generation kernels (LSF_XCHUNK_T / LSF_YCHUNK_T)
 	Grid3 level_grid[LSF_MAX_LEVELS];  // [0] = coarsest
 };
 
@@ -89,6 +92,12 @@ int make_plan(const lsf_hier_params* p, int X, int Y, int Z, Plan3* plan) {
 	if (chunk_a && atoi(chunk_a) > 0) plan->x_chunk_stage1 = atoi(chunk_a);
 	const char* chunk_b = getenv("LSF_XCHUNK_B");
 	if (chunk_b && atoi(chunk_b) > 0) plan->x_chunk_filter = atoi(chunk_b);
+	const char* tma = getenv("LSF_TMA");
+	if (tma && tma[0] == '0') plan->tma = false;
+	const char* chunk_t = getenv("LSF_XCHUNK_T");
+	if (chunk_t && atoi(chunk_t) > 0) plan->x_chunk_tma = atoi(chunk_t);
+	const char* chunk_y = getenv("LSF_YCHUNK_T");
+	if (chunk_y && atoi(chunk_y) > 0) plan->y_chunk_tma = atoi(chunk_y);
 	const char* xv = getenv("LSF_LANE_XV");
 	if (xv && (atoi(xv) == 1 || atoi(xv) == 2 || atoi(xv) == 4 || atoi(xv) == 8)) plan->lane_xv = atoi(xv);
 	return LSF_OK;
@@ -112,9 +121,10 @@ struct LevelState {
 	int x_begin = 0, x_end = 0, x_origin = 0, X_global = 0;
 	int pack_X = 0, pack_origin = 0, pack_interior_low = 0, pack_interior_high = 0;
 	int* violation = nullptr;
+	TmaMaps maps;                // tensor maps of this level's warp / canonical / gradient planes (encoded on first use)
 };
 
-// Enqueues one iteration; returns the number of kernel launches.
+// Enqueues one iteration; returns the number of kernel launches (negative: error status).
 // `events` (optional, 5 entries): recorded before the first and after every kernel, for per-stage timing.
 // `phase`: 0 = whole iteration; 1 = stage 1 only, 2 = filter stage only (slab mode: the halo exchange sits between).
 int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool check_convergence, cudaStream_t stream,
@@ -188,6 +198,22 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 	if (plan.split_x && variant == 2 && !s.slab && phase == 0 && plan.taps.radius >= 1 && plan.taps.radius <= 3) {
 		// second-generation cut: stage 1 + axis-0 pass, then axis-1/2 passes + update (kernels3d_split.cuh)
 		float* filtered = plan.tikhonov ? s.g_post : nullptr;
+		if (plan.tma && tma_supported(s.g, s.warp, s.canonical, s.g_post) && aligned16(s.scratch_a)) {
+			const int chunk_x = std::min(plan.x_chunk_tma, s.g.X), chunk_y = std::min(plan.y_chunk_tma, s.g.Y);
+			int status;
+			switch (plan.taps.radius) {
+			case 1:
+				status = launch_tma_iteration<1>(plan.tikhonov, s.maps, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_x, chunk_y, stream, events);
+				break;
+			case 2:
+				status = launch_tma_iteration<2>(plan.tikhonov, s.maps, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_x, chunk_y, stream, events);
+				break;
+			default:
+				status = launch_tma_iteration<3>(plan.tikhonov, s.maps, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_x, chunk_y, stream, events);
+				break;
+			}
+			return status < 0 ? status : 2;
+		}
 		const int chunk_a = std::min(plan.x_chunk_stage1, s.g.X), chunk_b = std::min(plan.x_chunk_filter, s.g.X);
 		switch (plan.taps.radius) {
 		case 1:
@@ -351,7 +377,7 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 		while (!converged && enqueued < plan.max_iterations) {
 			const int chunk_end = std::min(plan.max_iterations, enqueued + POLL_CHUNK);
 			for (int it = enqueued; it < chunk_end; it++) {
-				enqueue_iteration(plan, s, it, true, stream);
+				LSF_TRY(enqueue_iteration(plan, s, it, true, stream));
 				if (capturing && it < capture->max_iterations) {
 					k_planes_to_aos<<<counted(div_up(s.g.N, 256)), 256, 0, stream>>>(s.warp,
 							capture_dev + (size_t) it * s.g.N * 3, s.g.N, 3);
@@ -509,6 +535,7 @@ extern "C" int lsf_hier_iterate_3d(const lsf_hier_params* params, const float* c
 		for (int i = 0; i < 4; i++) stage_ms[i] = 0.0f;
 		for (int it = 0; it < iterations; it++) {
 			const int n = enqueue_iteration(plan, s, it, false, stream, marks);
+			LSF_TRY(n);
 			launches += n;
 			LSF_CUDA(cudaEventSynchronize(marks[n]));
 			for (int i = 0; i < n; i++) {
@@ -519,7 +546,11 @@ extern "C" int lsf_hier_iterate_3d(const lsf_hier_params* params, const float* c
 		}
 		for (auto& m : marks) cudaEventDestroy(m);
 	} else {
-		for (int it = 0; it < iterations; it++) launches += enqueue_iteration(plan, s, it, false, stream);
+		for (int it = 0; it < iterations; it++) {
+			const int n = enqueue_iteration(plan, s, it, false, stream);
+			LSF_TRY(n);
+			launches += n;
+		}
 	}
 	LSF_CUDA(cudaEventRecord(stop, stream));
 	LSF_CUDA(cudaEventSynchronize(stop));

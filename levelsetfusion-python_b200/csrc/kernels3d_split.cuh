@@ -28,6 +28,7 @@ namespace lsf {
 struct XPassArgs {
 	float k[7];   // flipped taps: k[q] multiplies in[i - R + q]
 	int x_chunk;  // output planes per block along axis 0
+	unsigned long long one2;  // {1.0f, 1.0f}: opaque multiplier of the packed adds (kernels3d_tma.cuh)
 };
 
 // one axis of the replicated-border Laplacian without branches (reference gradients.tpp:28-35,114-171):
@@ -269,6 +270,7 @@ void launch_split_iteration(bool tikhonov, HierIterArgs a, const Taps& taps, flo
 	XPassArgs t;
 	for (int q = 0; q < 7; q++) t.k[q] = q < C::K ? taps.k[q] : 0.0f;
 	t.x_chunk = x_chunk_stage1;
+	t.one2 = 0x3f8000003f800000ull;
 	a.g_out = h;
 	const dim3 block(32, 8, 1), grid(div_up(g.Z, 32), div_up(g.Y, 8), div_up(g.X, t.x_chunk));
 	if (tikhonov) k_hier_stage1_xpass<true, R> <<<counted(grid), block, 0, stream>>>(a, t);

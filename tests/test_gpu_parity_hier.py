@@ -334,3 +334,27 @@ def test_fused_kernels_match_first_generation_kernels(lsf, mode, monkeypatch):
         monkeypatch.delenv("LSF_LEGACY_KERNELS")
         assert np.array_equal(lsf.ops.convolve_with_kernel(vec, kernel), slow)
         monkeypatch.setenv("LSF_LEGACY_KERNELS", "1")
+
+
+@pytest.mark.parametrize("mode", ["tikhonov_kernel", "kernel"])
+@pytest.mark.parametrize("taps", [3, 5, 7])
+def test_tma_generation_matches_previous_generations(lsf, mode, taps, monkeypatch):
+    """A/B: the TMA-fed stage 1 + y-marching filter (default) against the second-generation split kernels
+    (LSF_TMA=0) and the first-generation kernels, on a volume whose tiles are cut by every face (Y and Z not
+    multiples of the 8 x 32 tile), with odd chunk sizes along the marching axes -- bit-identical."""
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(96)
+    canonical, live = canonical[8:80, 4:84, 10:78].copy(), live[8:80, 4:84, 10:78].copy()  # 72 x 80 x 68
+    kwargs = dict(HIER_MODES[mode])
+    kwargs.update(maximum_chunk_size=4, maximum_iteration_count=8, kernel=synthetic.sobolev_kernel_1d(taps))
+    fast = lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live)
+    assert np.abs(fast).max() > 0
+    monkeypatch.setenv("LSF_XCHUNK_T", "13")
+    monkeypatch.setenv("LSF_YCHUNK_T", "9")
+    assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
+    monkeypatch.delenv("LSF_XCHUNK_T")
+    monkeypatch.delenv("LSF_YCHUNK_T")
+    monkeypatch.setenv("LSF_TMA", "0")
+    assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
+    monkeypatch.setenv("LSF_LEGACY_KERNELS", "1")
+    assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
