@@ -36,9 +36,9 @@ UNIT = "voxel-updates/s"
 ALGORITHMIC_BYTES_PER_VOXEL_UPDATE = 68  # hierarchical 3D with Tikhonov (+- kernel), see DESIGN.md
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one finest-level 256^3 iteration, from the committed
 # `ncu --set full` capture (per launch group, like `achieved`)
-NCU_DRAM_BYTES_PER_ITERATION = 1724019968
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_fused_v1.md (930.8 MB + 793.2 MB)"
-STAGE_NAMES = {1: ("fused_iteration",), 2: ("gradient_stage", "fused_filter_update_max"),
+NCU_DRAM_BYTES_PER_ITERATION = 1725432000
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_tma_v3.md (963.5 MB + 761.9 MB)"
+STAGE_NAMES = {1: ("fused_iteration",), 2: ("stage1_gather_terms_axis0", "ymarch_axis12_update_max"),
                4: ("gradient_stage", "filter_axis0", "filter_axis1", "filter_axis2_update_max")}
 
 
@@ -226,8 +226,9 @@ def run_ours(args):
             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": NCU_DRAM_BYTES_PER_ITERATION if size == 256 else None,
             "traffic_source": NCU_TRAFFIC_SOURCE if size == 256 else None,
-            "kernel": "finest-level iteration = k_hier_gradient3d_lane (gather + data + Tikhonov) + k_sobolev_fused3d "
-                      "(3 filter passes + warp update + max norm), %d launches/iteration" % (n_launch.value // iterations),
+            "kernel": "finest-level iteration = k_hier_stage1_tma (TMA-fed gather + data + Tikhonov + axis-0 filter pass) + "
+                      "k_sobolev_ymarch (axis-1/2 filter passes + warp update + max norm), %d launches/iteration"
+                      % (n_launch.value // iterations),
             "algorithmic_bytes_per_launch_group": ALGORITHMIC_BYTES_PER_VOXEL_UPDATE * N,
             "ms_per_iteration": round(iteration_ms, 4),
             "stage_ms": dict(zip(STAGE_NAMES[n_launch.value // iterations], (round(v, 4) for v in stages))),
