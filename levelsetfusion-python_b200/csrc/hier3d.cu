@@ -7,7 +7,7 @@
 // the previous iteration's max ||g||^2 slot, and the host polls the slots once per chunk of iterations.
 #include "kernels3d_fused.cuh"
 #include "kernels3d_split.cuh"
-#include "kernels3d_tma.cuh"
+#include "kernels3d_pair.cuh"
 #include "slavcheva.cuh"  // statistics_on_device
 
 #include <cfloat>
@@ -36,7 +36,9 @@ struct Plan3 {
 	int x_chunk_stage1 = 64, x_chunk_filter = 16;  // planes per block of the two split kernels (LSF_XCHUNK_A / _B)
 	int stage1_variant = 2;            // LSF_STAGE1_VARIANT=1 selects the 4-voxel kernel (A/B)
 	bool tma = true;                   // third generation: TMA-fed stage 1 + y-marching filter (LSF_TMA=0: second generation)
-	int x_chunk_tma = 64, y_chunk_tma = 64;  // planes / rows per block of the two TMA-generation kernels (LSF_XCHUNK_T / LSF_YCHUNK_T)
+	int pair_tile_y = 0;               // fourth generation: two voxels per thread in stage 1, 64 x pair_tile_y tiles (LSF_PAIR_TY=0: third generation)
+	int x_chunk_tma = 0, y_chunk_tma = 64;  // planes / rows per block of the two TMA-generation kernels (LSF_XCHUNK_T /
+	                                        // LSF_YCHUNK_T); x: 0 = chosen per level by marching_chunk()
 	Grid3 level_grid[LSF_MAX_LEVELS];  // [0] = coarsest
 };
 
@@ -94,6 +96,8 @@ int make_plan(const lsf_hier_params* p, int X, int Y, int Z, Plan3* plan) {
 	if (chunk_b && atoi(chunk_b) > 0) plan->x_chunk_filter = atoi(chunk_b);
 	const char* tma = getenv("LSF_TMA");
 	if (tma && tma[0] == '0') plan->tma = false;
+	const char* pair_ty = getenv("LSF_PAIR_TY");
+	if (pair_ty) plan->pair_tile_y = atoi(pair_ty);
 	const char* chunk_t = getenv("LSF_XCHUNK_T");
 	if (chunk_t && atoi(chunk_t) > 0) plan->x_chunk_tma = atoi(chunk_t);
 	const char* chunk_y = getenv("LSF_YCHUNK_T");
@@ -101,6 +105,35 @@ int make_plan(const lsf_hier_params* p, int X, int Y, int Z, Plan3* plan) {
 	const char* xv = getenv("LSF_LANE_XV");
 	if (xv && (atoi(xv) == 1 || atoi(xv) == 2 || atoi(xv) == 4 || atoi(xv) == 8)) plan->lane_xv = atoi(xv);
 	return LSF_OK;
+}
+
+// Planes per block of a kernel that marches along an axis of `extent` planes with `tiles` tiles per plane, each block
+// starting with `lead` planes of re-computed halo. Blocks run in waves of `slots` (SMs x resident blocks per SM), so
+// the time is about waves x (chunk + lead) plane-steps: pick the split that minimises it. On B200 (444 slots) a 256^3
+// level gets 5 chunks of 52 planes -- measured 0.273 ms against 0.304 ms for 4 chunks of 64 (2.3 waves, the third one
+// a third full), in the order this model predicts for every split tried (profiles/r1_ncu_dec_v4.md).
+inline int marching_chunk(int extent, int tiles, int lead, int blocks_per_sm) {
+	static int sm_count = 0;
+	if (sm_count == 0) {
+		int device = 0;
+		cudaGetDevice(&device);
+		if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sm_count <= 0)
+			sm_count = 148;
+	}
+	const long long slots = (long long) sm_count * blocks_per_sm;
+	int best_chunk = extent;
+	long long best_cost = -1;
+	for (int parts = 1; parts <= extent; parts++) {
+		const int chunk = (extent + parts - 1) / parts;
+		if (chunk < 8 && parts > 1) break;
+		const long long blocks = (long long) tiles * ((extent + chunk - 1) / chunk);
+		const long long cost = ((blocks + slots - 1) / slots) * (chunk + lead);
+		if (best_cost < 0 || cost < best_cost) {
+			best_cost = cost;
+			best_chunk = chunk;
+		}
+	}
+	return best_chunk;
 }
 
 inline bool aligned16(const void* p) {
@@ -122,6 +155,7 @@ struct LevelState {
 	int pack_X = 0, pack_origin = 0, pack_interior_low = 0, pack_interior_high = 0;
 	int* violation = nullptr;
 	TmaMaps maps;                // tensor maps of this level's warp / canonical / gradient planes (encoded on first use)
+	TmaMaps maps_alt;            // the same with the gradient's other ping-pong buffer (iterations without a Sobolev kernel)
 };
 
 // Enqueues one iteration; returns the number of kernel launches (negative: error status).
@@ -184,6 +218,25 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 	} while (0)
 	if (!plan.use_kernel) {
 		if (phase == 2) return 0;
+		if (plan.tma && variant == 2 && !s.slab && tma_supported(s.g, s.warp, s.canonical, s.g_post)
+				&& (!plan.tikhonov || aligned16(s.scratch_a))) {
+			// TMA-fed stage 1 with the warp update and the max-norm fused (one launch per iteration)
+			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8));
+			const int chunk_x = plan.x_chunk_tma > 0 ? std::min(plan.x_chunk_tma, s.g.X) : marching_chunk(s.g.X, tiles, 0, 3);
+			int status;
+			if (plan.tikhonov) {
+				// the gradient ping-pongs between g_post and scratch_a: one set of tensor maps per direction
+				a.g_out = s.scratch_a;
+				TmaMaps& maps = (s.maps.key[2] == nullptr || s.maps.key[2] == a.g_prev) ? s.maps : s.maps_alt;
+				status = launch_stage1_fused_update<true>(maps, a, chunk_x, stream);
+				std::swap(s.g_post, s.scratch_a);
+			} else {
+				a.g_out = nullptr;
+				status = launch_stage1_fused_update<false>(s.maps, a, chunk_x, stream);
+			}
+			mark(1);
+			return status < 0 ? status : 1;
+		}
 		if (plan.tikhonov) {
 			a.g_out = s.scratch_a;
 			LSF_LAUNCH_STAGE1(true, true);
@@ -199,17 +252,20 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 		// second-generation cut: stage 1 + axis-0 pass, then axis-1/2 passes + update (kernels3d_split.cuh)
 		float* filtered = plan.tikhonov ? s.g_post : nullptr;
 		if (plan.tma && tma_supported(s.g, s.warp, s.canonical, s.g_post) && aligned16(s.scratch_a)) {
-			const int chunk_x = std::min(plan.x_chunk_tma, s.g.X), chunk_y = std::min(plan.y_chunk_tma, s.g.Y);
+			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8));
+			const int chunk_x = plan.x_chunk_tma > 0 ? std::min(plan.x_chunk_tma, s.g.X)
+					: marching_chunk(s.g.X, tiles, 2 * plan.taps.radius, 3);
+			const int chunk_y = std::min(plan.y_chunk_tma, s.g.Y);
 			int status;
 			switch (plan.taps.radius) {
 			case 1:
-				status = launch_tma_iteration<1>(plan.tikhonov, s.maps, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_x, chunk_y, stream, events);
+				status = launch_iteration_v4<1>(plan.tikhonov, s.maps, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_x, chunk_y, plan.pair_tile_y, stream, events);
 				break;
 			case 2:
-				status = launch_tma_iteration<2>(plan.tikhonov, s.maps, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_x, chunk_y, stream, events);
+				status = launch_iteration_v4<2>(plan.tikhonov, s.maps, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_x, chunk_y, plan.pair_tile_y, stream, events);
 				break;
 			default:
-				status = launch_tma_iteration<3>(plan.tikhonov, s.maps, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_x, chunk_y, stream, events);
+				status = launch_iteration_v4<3>(plan.tikhonov, s.maps, a, plan.taps, s.scratch_a, filtered, s.warp, chunk_x, chunk_y, plan.pair_tile_y, stream, events);
 				break;
 			}
 			return status < 0 ? status : 2;

@@ -87,6 +87,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 				: "=r"(done) : "r"(addr), "r"(parity) : "memory");
 	} while (!done);
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 // one box of a 4-D tensor map -> shared memory, completion on `bar`
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
 		uint64_t* bar) {
@@ -182,7 +185,7 @@ struct Stage1Tile {
 	static constexpr int STAGE_TX = GP_TX + WP_BYTES + CN_BYTES;
 };
 
-template<bool TIKHONOV, int R, int NS>
+template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false>
 static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_constant__ CUtensorMap map_g,
 		const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c, HierIterArgs a,
 		XPassArgs t) {
@@ -191,6 +194,7 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
 	extern __shared__ __align__(128) unsigned char stage_memory[];
 	__shared__ uint64_t full[NS];
+	__shared__ uint64_t empty[NS];  // DEC: one arrival per warp once it has read the slot
 
 	const int X = a.g.X, Y = a.g.Y, Z = a.g.Z;
 	const int tz = threadIdx.x, ty = threadIdx.y;
@@ -201,14 +205,20 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 	const int N = (int) a.g.N;
 	const int xs = blockIdx.z * t.x_chunk;
 	const int xe = min(X, xs + t.x_chunk);
-	const int x_first = max(xs - R, 0);  // planes below 0 contribute zeros to accumulators that are still zero
-	const int x_stop = xe + R;           // planes >= X contribute zeros
+	// FUSE (no Sobolev kernel configured): no filter pass, the warp update and the max-norm (reference
+	// optimizer.tpp:207-211) happen here and the kernel is the whole iteration
+	const int x_first = FUSE ? xs : max(xs - R, 0);  // planes below 0 contribute zeros to accumulators that are still zero
+	const int x_stop = FUSE ? xe : xe + R;           // planes >= X contribute zeros
 	const int p_last = min(x_stop, X - 1);  // last plane fetched (the Tikhonov term looks one plane ahead)
 	const bool leader = tz == 0 && ty == 0;
+	float best = 0.0f;
 
 	if (leader) {
 #pragma unroll
-		for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
+		for (int s = 0; s < NS; s++) {
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], T::TY);
+		}
 		mbar_fence_init();
 	}
 	__syncthreads();
@@ -299,6 +309,18 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 					}
 				}
 			}
+			if (DEC) {
+				// this warp (one row of the tile) has read everything it needs from `slot`; the leader refills the slot of
+				// the previous plane as soon as all warps have released it -- no block-wide barrier, the warps of a block
+				// drift up to NS - 1 planes apart and their gather latencies overlap
+				__syncwarp();
+				if (tz == 0) mbar_arrive(&empty[slot]);
+				if (leader && x > x_first) {
+					const int refill = slot == 0 ? NS - 1 : slot - 1;
+					mbar_wait(&empty[refill], slot == 0 ? phase ^ 1u : phase);
+					if (x - 1 + NS <= p_last) fetch(x - 1 + NS, refill);
+				}
+			}
 			const float4 s = gather4p(a.pack, X, Y, Z, x, y, z, wx, wy, wz, t.one2);
 			const float diff = s.x - cn;
 			g[0] = (s.y * diff) * a.amplifier;
@@ -309,29 +331,49 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 				g[1] = g[1] - lap[1] * a.strength;
 				g[2] = g[2] - lap[2] * a.strength;
 			}
+			if (FUSE && valid) {
+				const int at = out + R * YZ;  // this plane
+				if (a.g_out != nullptr) {
+					a.g_out[at] = g[0];
+					a.g_out[N + at] = g[1];
+					a.g_out[2 * N + at] = g[2];
+				}
+				a.warp_out[at] = wx - g[0] * a.rate;
+				a.warp_out[N + at] = wy - g[1] * a.rate;
+				a.warp_out[2 * N + at] = wz - g[2] * a.rate;
+				float sq = g[0] * g[0];
+				sq += g[1] * g[1];
+				sq += g[2] * g[2];
+				if (sq > best) best = sq;
+			}
 		}
-		// axis-0 filter pass: plane x is tap q of output plane x + R - q; acc[c][q] holds the partial sum (taps 0..q) of
-		// output x + R - q, so adding in place from the oldest output down reproduces sum_{q ascending} in[.]*k[q]
+		if (!FUSE) {
+			// axis-0 filter pass: plane x is tap q of output plane x + R - q; acc[c][q] holds the partial sum (taps 0..q)
+			// of output x + R - q, so adding in place from the oldest output down reproduces sum_{q ascending} in[.]*k[q]
 #pragma unroll
-		for (int c = 0; c < 3; c++) {
+			for (int c = 0; c < 3; c++) {
 #pragma unroll
-			for (int q = K - 1; q >= 1; q--) acc[c][q] = acc[c][q - 1] + g[c] * t.k[q];
-			acc[c][0] = g[c] * t.k[0];
+				for (int q = K - 1; q >= 1; q--) acc[c][q] = acc[c][q - 1] + g[c] * t.k[q];
+				acc[c][0] = g[c] * t.k[0];
+			}
+			if (x - R >= xs && valid) {
+				a.g_out[out] = acc[0][K - 1];
+				a.g_out[N + out] = acc[1][K - 1];
+				a.g_out[2 * N + out] = acc[2][K - 1];
+			}
 		}
-		if (x - R >= xs && valid) {
-			a.g_out[out] = acc[0][K - 1];
-			a.g_out[N + out] = acc[1][K - 1];
-			a.g_out[2 * N + out] = acc[2][K - 1];
+		if (!DEC) {
+			// every thread has read stage `slot`: refill it with the plane NS steps ahead
+			__syncthreads();
+			if (leader && x + NS <= p_last) fetch(x + NS, slot);
 		}
-		// every thread has read stage `slot`: refill it with the plane NS steps ahead
-		__syncthreads();
-		if (leader && x + NS <= p_last) fetch(x + NS, slot);
 		slot++;
 		if (slot == NS) {
 			slot = 0;
 			phase ^= 1u;
 		}
 	}
+	if (FUSE) block_atomic_max(best, a.max_sq_bits + a.iteration);
 }
 
 // ---------------------------------------------------------------------------------------------- axis-1 / axis-2 passes
@@ -457,6 +499,7 @@ static __global__ void __launch_bounds__(288) k_sobolev_ymarch(YMarchArgs a) {
 struct TmaMaps {
 	CUtensorMap g_prev, warp, canonical;
 	const void* key[3] = { nullptr, nullptr, nullptr };  // pointers the maps were encoded for
+	int tile_y = 0;                                       // 0: boxes of k_hier_stage1_tma; 1000 + TY: of k_hier_stage1_pair
 };
 
 inline bool tma_supported(const Grid3& g, const void* warp, const void* canonical, const void* g_prev) {
@@ -467,7 +510,8 @@ inline bool tma_supported(const Grid3& g, const void* warp, const void* canonica
 template<bool TIKHONOV>
 int ensure_maps(TmaMaps& maps, const Grid3& g, const float* warp, const float* canonical, const float* g_prev) {
 	typedef Stage1Tile<TIKHONOV> T;
-	if (maps.key[0] == warp && maps.key[1] == canonical && maps.key[2] == g_prev) return LSF_OK;
+	if (maps.key[0] == warp && maps.key[1] == canonical && maps.key[2] == g_prev && maps.tile_y == 0) return LSF_OK;
+	maps.tile_y = 0;
 	LSF_TRY(make_planes_map(&maps.warp, warp, 3, g.N, g, T::TZ, T::TY));
 	LSF_TRY(make_planes_map(&maps.canonical, canonical, 1, g.N, g, T::TZ, T::TY));
 	LSF_TRY(make_planes_map(&maps.g_prev, g_prev, 3, g.N, g, T::GZ, T::GY));
@@ -477,7 +521,7 @@ int ensure_maps(TmaMaps& maps, const Grid3& g, const float* warp, const float* c
 	return LSF_OK;
 }
 
-template<bool TIKHONOV, int R>
+template<bool TIKHONOV, int R, bool DEC = true>
 int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h, int x_chunk, cudaStream_t stream) {
 	typedef Stage1Tile<TIKHONOV> T;
 	constexpr int NS = 4;
@@ -491,11 +535,35 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 	const size_t shared = (size_t) NS * T::STAGE_BYTES;
 	static bool configured = false;
 	if (!configured) {
-		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				(int) shared));
 		configured = true;
 	}
-	k_hier_stage1_tma<TIKHONOV, R, NS> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp, maps.canonical, a, t);
+	k_hier_stage1_tma<TIKHONOV, R, NS, DEC> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp, maps.canonical, a, t);
+	return LSF_OK;
+}
+
+// Whole iteration when no Sobolev kernel is configured: stage 1 + warp update + max-norm in one TMA-fed kernel.
+// g_out (planes, may be nullptr without the Tikhonov term) must not alias a.g_prev; a.warp_out may alias a.warp.
+template<bool TIKHONOV>
+int launch_stage1_fused_update(TmaMaps& maps, HierIterArgs a, int x_chunk, cudaStream_t stream) {
+	typedef Stage1Tile<TIKHONOV> T;
+	constexpr int NS = 4;
+	LSF_TRY(ensure_maps<TIKHONOV>(maps, a.g, a.warp, a.canonical, a.g_prev));
+	XPassArgs t;
+	for (int q = 0; q < 7; q++) t.k[q] = 0.0f;
+	t.x_chunk = x_chunk;
+	t.one2 = F32X2_ONE;
+	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), div_up(a.g.X, x_chunk));
+	const size_t shared = (size_t) NS * T::STAGE_BYTES;
+	static bool configured = false;
+	if (!configured) {
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, 0, NS, true, true>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
+		configured = true;
+	}
+	k_hier_stage1_tma<TIKHONOV, 0, NS, true, true> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
+			maps.canonical, a, t);
 	return LSF_OK;
 }
 
@@ -528,7 +596,9 @@ void launch_ymarch(const Taps& taps, const HierIterArgs& a, const float* h, floa
 template<int R>
 int launch_tma_iteration(bool tikhonov, TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h, float* filtered,
 		float* warp, int x_chunk, int y_chunk, cudaStream_t stream, cudaEvent_t* events) {
-	if (tikhonov) LSF_TRY((launch_stage1_tma<true, R>(maps, a, taps, h, x_chunk, stream)));
+	const bool coupled = getenv("LSF_DECOUPLE") && getenv("LSF_DECOUPLE")[0] == '0';  // A/B: block barrier per plane
+	if (tikhonov && coupled) LSF_TRY((launch_stage1_tma<true, R, false>(maps, a, taps, h, x_chunk, stream)));
+	else if (tikhonov) LSF_TRY((launch_stage1_tma<true, R>(maps, a, taps, h, x_chunk, stream)));
 	else LSF_TRY((launch_stage1_tma<false, R>(maps, a, taps, h, x_chunk, stream)));
 	if (events) cudaEventRecord(events[1], stream);
 	launch_ymarch<R>(taps, a, h, filtered, warp, y_chunk, stream);

@@ -358,3 +358,29 @@ def test_tma_generation_matches_previous_generations(lsf, mode, taps, monkeypatc
     assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
     monkeypatch.setenv("LSF_LEGACY_KERNELS", "1")
     assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
+
+
+@pytest.mark.parametrize("mode", ["tikhonov_kernel", "kernel"])
+@pytest.mark.parametrize("taps", [3, 7])
+def test_pair_generation_matches_previous_generations(lsf, mode, taps, monkeypatch):
+    """A/B: the two-voxels-per-thread stage 1 (default where Z % 64 == 0) with 64 x 8 and 64 x 4 tiles and odd chunk
+    sizes against the third generation (LSF_PAIR_TY=0) and the first-generation kernels, on a volume with two z tiles
+    (both z faces and an interior tile edge) and ragged X -- bit-identical."""
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(128)
+    canonical, live = canonical[20:92, 24:104, :].copy(), live[20:92, 24:104, :].copy()  # 72 x 80 x 128
+    kwargs = dict(HIER_MODES[mode])
+    kwargs.update(maximum_chunk_size=2, maximum_iteration_count=8, kernel=synthetic.sobolev_kernel_1d(taps))
+    fast = lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live)
+    assert np.abs(fast).max() > 0
+    monkeypatch.setenv("LSF_PAIR_TY", "4")
+    monkeypatch.setenv("LSF_XCHUNK_T", "13")
+    assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
+    monkeypatch.setenv("LSF_PAIR_TY", "8")
+    monkeypatch.setenv("LSF_XCHUNK_T", "5")
+    assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
+    monkeypatch.delenv("LSF_XCHUNK_T")
+    monkeypatch.setenv("LSF_PAIR_TY", "0")
+    assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
+    monkeypatch.setenv("LSF_LEGACY_KERNELS", "1")
+    assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
