@@ -37,8 +37,8 @@ struct Plan3 {
 	int stage1_variant = 2;            // LSF_STAGE1_VARIANT=1 selects the 4-voxel kernel (A/B)
 	bool tma = true;                   // third generation: TMA-fed stage 1 + y-marching filter (LSF_TMA=0: second generation)
 	int pair_tile_y = 0;               // fourth generation: two voxels per thread in stage 1, 64 x pair_tile_y tiles (LSF_PAIR_TY=0: third generation)
-	int x_chunk_tma = 0, y_chunk_tma = 64;  // planes / rows per block of the two TMA-generation kernels (LSF_XCHUNK_T /
-	                                        // LSF_YCHUNK_T); x: 0 = chosen per level by marching_chunk()
+	int x_chunk_tma = 0, y_chunk_tma = 0;   // planes / rows per block of the two TMA-generation kernels (LSF_XCHUNK_T /
+	                                        // LSF_YCHUNK_T); 0 = chosen per level by marching_chunk()
 	Grid3 level_grid[LSF_MAX_LEVELS];  // [0] = coarsest
 };
 
@@ -255,7 +255,9 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8));
 			const int chunk_x = plan.x_chunk_tma > 0 ? std::min(plan.x_chunk_tma, s.g.X)
 					: marching_chunk(s.g.X, tiles, 2 * plan.taps.radius, 3);
-			const int chunk_y = std::min(plan.y_chunk_tma, s.g.Y);
+			const int filter_tiles = (int) (div_up(s.g.Z, 512) * s.g.X);
+			const int chunk_y = plan.y_chunk_tma > 0 ? std::min(plan.y_chunk_tma, s.g.Y)
+					: marching_chunk(s.g.Y, filter_tiles, 2 * plan.taps.radius, 6);
 			int status;
 			switch (plan.taps.radius) {
 			case 1:

@@ -359,20 +359,216 @@ int launch_stage1_pair(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h
 	return LSF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- axis-1 / axis-2 passes, paired
+// k_sobolev_ymarch with two z voxels per thread (same passes, same order of operations: convolution.cpp:268-331,
+// optimizer.tpp:207-211). The axis-1 chain, the warp update and the squared norm run on packed f32x2 registers. For
+// the axis-2 pass the row is kept twice in shared memory, once as is (A) and once shifted by one column (B[i] =
+// A[i + 1]): every tap's operand pair (v[z - R + q], v[z + 1 - R + q]) is then one aligned 64-bit LDS from A or B.
+struct YMarch2Args {
+	const float* in;   // planes after the axis-0 pass
+	float* out;        // planes: filtered gradient (nullptr when nothing reads it)
+	float* warp;       // planes, updated in place: warp -= out * rate
+	Grid3 g;
+	unsigned long long k2[7];  // flipped taps duplicated into both lanes
+	unsigned long long one2, neg2, rate2;
+	float threshold;
+	unsigned* max_sq_bits;
+	int iteration;
+	int check_convergence;
+	int y_chunk;       // output rows per block
+	int x_begin;       // first plane (blockIdx.y counts from here)
+	int tile_z;        // output columns per block (even); blockDim.x = tile_z / 2 (+ 32 halo threads when gridDim.x > 1)
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void sts_f32x2(uint32_t addr, f32x2 v) {
+	asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+	asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+template<int R>
+static __global__ void __launch_bounds__(288) k_sobolev_ymarch2(const __grid_constant__ YMarch2Args a) {
+	constexpr int K = 2 * R + 1;
+	constexpr int H = 4;  // halo columns kept either side of the tile (>= R, even)
+	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
+	extern __shared__ __align__(16) float row_memory2[];  // [2 buffers][3 components][A: W | B: W]
+	const int Y = a.g.Y, Z = a.g.Z;
+	const int NT = a.tile_z / 2;   // owner threads
+	const int W = a.tile_z + 2 * H;
+	const int tid = threadIdx.x;
+	const int z0 = blockIdx.x * a.tile_z;
+	const int x = a.x_begin + blockIdx.y;
+	const int ys = blockIdx.z * a.y_chunk;
+	const int ye = min(Y, ys + a.y_chunk);
+	// column pair of this thread in the row buffer: owners hold H .. H + tile_z - 1, the halo threads H columns either side
+	const bool owner = tid < NT;
+	const int j = tid - NT;
+	const int il = owner ? H + 2 * tid : (j < H / 2 ? 2 * j : a.tile_z + H + 2 * (j - H / 2));
+	const int z = z0 - H + il;
+	const bool active = (owner || j < H) && z >= 0 && z < Z;  // Z is even: a pair is inside or outside as a whole
+	const bool writes = owner && active;
+	for (int i = tid; i < 12 * W; i += blockDim.x) row_memory2[i] = 0.0f;  // columns outside the volume stay zero
+	__syncthreads();
+	const uint32_t rows = smem_addr(row_memory2);
+	const f32x2 one = a.one2, neg = a.neg2;
+
+	f32x2 acc[3][K];
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int q = 0; q < K; q++) acc[c][q] = 0ull;
+	const int r_first = max(ys - R, 0);
+	const int r_stop = ye + R;
+	const int r_load_end = min(r_stop, Y);
+	const int N = (int) a.g.N;
+	int at = (x * Y + r_first) * Z + z;  // row being consumed
+	f32x2 next[3] = { 0ull, 0ull, 0ull };
+	if (active) {
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			const float2 v = __ldg(reinterpret_cast<const float2*>(a.in + c * N + at));
+			next[c] = pack2(v.x, v.y);
+		}
+	}
+	float best = 0.0f;
+	int buffer = 0;
+#pragma unroll 1
+	for (int r = r_first; r < r_stop; r++, at += Z) {
+		const f32x2 v0 = next[0], v1 = next[1], v2 = next[2];
+		if (active && r + 1 < r_load_end) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const float2 v = __ldg(reinterpret_cast<const float2*>(a.in + c * N + at + Z));
+				next[c] = pack2(v.x, v.y);
+			}
+		} else {
+			next[0] = next[1] = next[2] = 0ull;
+		}
+		// axis-1 pass: row r is tap q of output row r + R - q (same chain as the axis-0 pass of stage 1)
+#pragma unroll
+		for (int q = K - 1; q >= 1; q--) {
+			acc[0][q] = add2(acc[0][q - 1], mul2(v0, a.k2[q]), one);
+			acc[1][q] = add2(acc[1][q - 1], mul2(v1, a.k2[q]), one);
+			acc[2][q] = add2(acc[2][q - 1], mul2(v2, a.k2[q]), one);
+		}
+		acc[0][0] = mul2(v0, a.k2[0]);
+		acc[1][0] = mul2(v1, a.k2[0]);
+		acc[2][0] = mul2(v2, a.k2[0]);
+		if (r - R < ys) continue;  // block-uniform: still priming
+		const uint32_t row = rows + buffer * (6 * W * 4);
+		f32x2 w[3] = { 0ull, 0ull, 0ull };
+		const int o = at - R * Z;  // voxel (x, r - R, z)
+		if (active) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const uint32_t pa = row + (c * 2 * W + il) * 4;  // A[il], A[il + 1]
+				float lo, hi;
+				unpack2(acc[c][K - 1], lo, hi);
+				sts_f32x2(pa, acc[c][K - 1]);
+				if (il > 0) sts_f32(pa + (W - 1) * 4, lo);  // B[il - 1] = A[il]
+				sts_f32(pa + W * 4, hi);        // B[il] = A[il + 1]
+			}
+		}
+		if (writes) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const float2 v = *reinterpret_cast<const float2*>(a.warp + c * N + o);
+				w[c] = pack2(v.x, v.y);
+			}
+		}
+		__syncthreads();
+		if (writes) {
+			// axis-2 pass: tap q multiplies the pair (A[il - R + q], A[il - R + q + 1])
+			f32x2 gq[3];
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const uint32_t pa = row + (c * 2 * W + il - R) * 4;
+				f32x2 sum = 0ull;
+#pragma unroll
+				for (int q = 0; q < K; q++) {
+					// il is even: the pair starts on an even column when (q - R) is even, else take it from the shifted copy
+					const f32x2 v = ((q - R) % 2 == 0) ? lds_f32x2(pa + q * 4) : lds_f32x2(pa + (W + q - 1) * 4);
+					sum = q == 0 ? mul2(v, a.k2[0]) : add2(sum, mul2(v, a.k2[q]), one);
+				}
+				gq[c] = sum;
+			}
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				float2 v;
+				if (a.out != nullptr) {
+					unpack2(gq[c], v.x, v.y);
+					*reinterpret_cast<float2*>(a.out + c * N + o) = v;
+				}
+				unpack2(sub2(w[c], mul2(gq[c], a.rate2), neg), v.x, v.y);
+				*reinterpret_cast<float2*>(a.warp + c * N + o) = v;
+			}
+			f32x2 sq = mul2(gq[0], gq[0]);
+			sq = add2(sq, mul2(gq[1], gq[1]), one);
+			sq = add2(sq, mul2(gq[2], gq[2]), one);
+			float sq_lo, sq_hi;
+			unpack2(sq, sq_lo, sq_hi);
+			if (sq_lo > best) best = sq_lo;
+			if (sq_hi > best) best = sq_hi;
+		}
+		buffer ^= 1;  // the row written two steps from now is read by nobody after the next barrier
+	}
+	if (a.max_sq_bits != nullptr) block_atomic_max(best, a.max_sq_bits + a.iteration);
+}
+
+inline bool ymarch2_supported(const Grid3& g, const float* h, const float* filtered, const float* warp) {
+	auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
+	return g.Z % 2 == 0 && g.N % 2 == 0 && aligned(h) && aligned(filtered) && aligned(warp);
+}
+
+template<int R>
+void launch_ymarch2(const Taps& taps, const HierIterArgs& a, const float* h, float* filtered, float* warp, int y_chunk,
+		cudaStream_t stream) {
+	const Grid3& g = a.g;
+	YMarch2Args f;
+	f.in = h;
+	f.out = filtered;
+	f.warp = warp;
+	f.g = g;
+	for (int q = 0; q < 7; q++) f.k2[q] = dup2(q < 2 * R + 1 ? taps.k[q] : 0.0f);
+	f.one2 = dup2(1.0f);
+	f.neg2 = dup2(-1.0f);
+	f.rate2 = dup2(a.rate);
+	f.threshold = a.threshold;
+	f.max_sq_bits = a.max_sq_bits;
+	f.iteration = a.iteration;
+	f.check_convergence = a.check_convergence;
+	f.y_chunk = y_chunk;
+	f.x_begin = 0;
+	f.tile_z = std::min(512, (int) div_up(g.Z, 64) * 64);
+	const int tiles = div_up(g.Z, f.tile_z);
+	const dim3 grid(tiles, g.X, div_up(g.Y, y_chunk));
+	const int threads = f.tile_z / 2 + (tiles > 1 ? 32 : 0);
+	const size_t shared = (size_t) 12 * (f.tile_z + 8) * sizeof(float);
+	k_sobolev_ymarch2<R> <<<counted(grid), threads, shared, stream>>>(f);
+}
+#endif  // __CUDACC__
+
 // One whole-volume iteration: paired stage 1 (tile_y = 4 or 8) when the level's shape allows it, else the third
 // generation; then the y-marching filter. Returns a negative status on failure.
 template<int R>
 int launch_iteration_v4(bool tikhonov, TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h, float* filtered,
 		float* warp, int x_chunk, int y_chunk, int tile_y, cudaStream_t stream, cudaEvent_t* events) {
-	if ((tile_y != 4 && tile_y != 8) || !pair_supported(a.g, tile_y))
-		return launch_tma_iteration<R>(tikhonov, maps, a, taps, h, filtered, warp, x_chunk, y_chunk, stream, events);
 	const int X = a.g.X;
-	if (tikhonov && tile_y == 8) LSF_TRY((launch_stage1_pair<true, R, 8, false>(maps, a, taps, h, x_chunk, 0, X, X, stream)));
+	if ((tile_y != 4 && tile_y != 8) || !pair_supported(a.g, tile_y)) {
+		const bool coupled = getenv("LSF_DECOUPLE") && getenv("LSF_DECOUPLE")[0] == '0';  // A/B: block barrier per plane
+		if (tikhonov && coupled) LSF_TRY((launch_stage1_tma<true, R, false>(maps, a, taps, h, x_chunk, stream)));
+		else if (tikhonov) LSF_TRY((launch_stage1_tma<true, R>(maps, a, taps, h, x_chunk, stream)));
+		else LSF_TRY((launch_stage1_tma<false, R>(maps, a, taps, h, x_chunk, stream)));
+	} else if (tikhonov && tile_y == 8) LSF_TRY((launch_stage1_pair<true, R, 8, false>(maps, a, taps, h, x_chunk, 0, X, X, stream)));
 	else if (tikhonov) LSF_TRY((launch_stage1_pair<true, R, 4, false>(maps, a, taps, h, x_chunk, 0, X, X, stream)));
 	else if (tile_y == 8) LSF_TRY((launch_stage1_pair<false, R, 8, false>(maps, a, taps, h, x_chunk, 0, X, X, stream)));
 	else LSF_TRY((launch_stage1_pair<false, R, 4, false>(maps, a, taps, h, x_chunk, 0, X, X, stream)));
 	if (events) cudaEventRecord(events[1], stream);
-	launch_ymarch<R>(taps, a, h, filtered, warp, y_chunk, stream);
+	const bool scalar_filter = getenv("LSF_YMARCH2") && getenv("LSF_YMARCH2")[0] == '0';  // A/B: one voxel per thread
+	if (!scalar_filter && ymarch2_supported(a.g, h, filtered, warp)) launch_ymarch2<R>(taps, a, h, filtered, warp, y_chunk, stream);
+	else launch_ymarch<R>(taps, a, h, filtered, warp, y_chunk, stream);
 	if (events) cudaEventRecord(events[2], stream);
 	return LSF_OK;
 }
