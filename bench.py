@@ -36,8 +36,8 @@ UNIT = "voxel-updates/s"
 ALGORITHMIC_BYTES_PER_VOXEL_UPDATE = 68  # hierarchical 3D with Tikhonov (+- kernel), see DESIGN.md
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one finest-level 256^3 iteration, from the committed
 # `ncu --set full` capture (per launch group, like `achieved`)
-NCU_DRAM_BYTES_PER_ITERATION = 1725432000
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_tma_v3.md (963.5 MB + 761.9 MB)"
+NCU_DRAM_BYTES_PER_ITERATION = 1735145000
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_v4.md (972.3 MB + 762.9 MB)"
 STAGE_NAMES = {1: ("fused_iteration",), 2: ("stage1_gather_terms_axis0", "ymarch_axis12_update_max"),
                4: ("gradient_stage", "filter_axis0", "filter_axis1", "filter_axis2_update_max")}
 
@@ -222,17 +222,35 @@ def run_ours(args):
         else:
             peak, peak_source = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = ALGORITHMIC_BYTES_PER_VOXEL_UPDATE * N / (iteration_ms * 1e-3) / 1e9
+        # the same measurement for the optimizer's other three term configurations (44 B per
+        # voxel-update without the Tikhonov term, 68 B with it); data-only is the reference run script's default
+        other = {}
+        for name, bytes_per_update, tikhonov, use_kernel in (("data_only", 44, False, False), ("tikhonov", 68, True, False),
+                                                             ("sobolev_kernel", 44, False, True)):
+            variant = dict(kwargs, tikhonov_term_enabled=tikhonov, gradient_kernel_enabled=use_kernel)
+            variant_params = lsf_b200.HierarchicalOptimizer3d(**variant)._params()
+            for _ in range(2):
+                lsf_b200._lib.check(lib.lsf_hier_iterate_3d(ctypes.byref(variant_params), ptr(canonical), ptr(live), size,
+                                                            size, size, iterations, ctypes.byref(ms),
+                                                            ctypes.byref(n_launch), None, stream))
+            variant_ms = ms.value / iterations
+            variant_achieved = bytes_per_update * N / (variant_ms * 1e-3) / 1e9
+            other[name] = {"ms_per_iteration": round(variant_ms, 4), "algorithmic_bytes_per_voxel_update": bytes_per_update,
+                           "achieved": round(variant_achieved, 1), "frac": round(variant_achieved / peak, 4),
+                           "launches_per_iteration": n_launch.value // iterations}
+        launches_per_iteration = len([v for v in stages if v > 0])
         roofline = {
             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": NCU_DRAM_BYTES_PER_ITERATION if size == 256 else None,
             "traffic_source": NCU_TRAFFIC_SOURCE if size == 256 else None,
             "kernel": "finest-level iteration = k_hier_stage1_tma (TMA-fed gather + data + Tikhonov + axis-0 filter pass) + "
-                      "k_sobolev_ymarch (axis-1/2 filter passes + warp update + max norm), %d launches/iteration"
-                      % (n_launch.value // iterations),
+                      "k_sobolev_ymarch2 (axis-1/2 filter passes + warp update + max norm), %d launches/iteration"
+                      % launches_per_iteration,
             "algorithmic_bytes_per_launch_group": ALGORITHMIC_BYTES_PER_VOXEL_UPDATE * N,
             "ms_per_iteration": round(iteration_ms, 4),
-            "stage_ms": dict(zip(STAGE_NAMES[n_launch.value // iterations], (round(v, 4) for v in stages))),
+            "stage_ms": dict(zip(STAGE_NAMES[launches_per_iteration], (round(v, 4) for v in stages))),
             "peak_source": peak_source,
+            "other_term_configurations": other,
         }
         # -------------------------------------------------------------- CPU baseline (oracle port), bounded sample
         cpu = cpu_baseline_sample(size, kwargs)

@@ -64,6 +64,23 @@ inline int make_planes_map(CUtensorMap* map, const float* base, int channels, lo
 	return LSF_OK;
 }
 
+// Tensor map over the padded pack of a level ([X + 4][Y + 4][Z + 4] float4 entries, seen as float32 rows of 4 (Z + 4)
+// elements); box = one plane of box_entries x box_rows entries. Only used for L2 prefetches.
+inline int make_pack_map(CUtensorMap* map, const float4* pack, int planes, const Grid3& g, int box_entries, int box_rows) {
+	EncodeTiledFn encode = encode_tiled_fn();
+	LSF_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+	const cuuint64_t dims[3] = { (cuuint64_t) (g.Z + 4) * 4, (cuuint64_t) g.Y + 4, (cuuint64_t) planes + 4 };
+	const cuuint64_t strides[2] = { (cuuint64_t) (g.Z + 4) * 16, (cuuint64_t) (g.Y + 4) * (g.Z + 4) * 16 };
+	const cuuint32_t box[3] = { (cuuint32_t) box_entries * 4, (cuuint32_t) box_rows, 1u };
+	const cuuint32_t element_strides[3] = { 1, 1, 1 };
+	const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float4*>(pack), dims, strides, box,
+			element_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+			CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	LSF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d for the pack (dims %d x %d x %d)", (int) r,
+			planes, g.Y, g.Z);
+	return LSF_OK;
+}
+
 #ifdef __CUDACC__
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -96,6 +113,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
 	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
 			::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
 			: "memory");
+}
+// hint: bring one box of a 3-D tensor map into L2 (no shared-memory destination, no completion)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+	asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+			::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
 	float v;
@@ -151,10 +173,11 @@ __device__ __forceinline__ float4 gather4p(const float4* __restrict__ pack, int 
 	bz = min(max(bz, -2), Z);
 	const int sy = Z + 4, sx = (Y + 4) * (Z + 4);
 	const ulonglong2* p = reinterpret_cast<const ulonglong2*>(pack) + ((bx + 2) * sx + (by + 2) * sy + (bz + 2));
-	const ulonglong2 v000 = __ldg(p), v001 = __ldg(p + 1);
-	const ulonglong2 v010 = __ldg(p + sy), v011 = __ldg(p + sy + 1);
+	// plane bx + 1 first: it is the one this x step touches for the first time (the likely L1 misses)
 	const ulonglong2 v100 = __ldg(p + sx), v101 = __ldg(p + sx + 1);
 	const ulonglong2 v110 = __ldg(p + sx + sy), v111 = __ldg(p + sx + sy + 1);
+	const ulonglong2 v000 = __ldg(p), v001 = __ldg(p + 1);
+	const ulonglong2 v010 = __ldg(p + sy), v011 = __ldg(p + sy + 1);
 	const f32x2 izz = pack2(iz, iz), rzz = pack2(rz, rz);
 	const ulonglong2 i00 = blend4(v000, v001, izz, rzz, one);
 	const ulonglong2 i01 = blend4(v010, v011, izz, rzz, one);
@@ -183,12 +206,15 @@ struct Stage1Tile {
 	static constexpr int CN_BYTES = TY * TZ * 4;
 	static constexpr int STAGE_BYTES = GP_BYTES + WP_BYTES + CN_BYTES;
 	static constexpr int STAGE_TX = GP_TX + WP_BYTES + CN_BYTES;
+	// L2 prefetch box of the pack: the tile's gather footprint (TZ + 1 entries x TY + 1 rows) with a margin either side
+	static constexpr int PACK_BOX_Z0 = 6, PACK_BOX_Y0 = 3;
+	static constexpr int PACK_BOX_Z = TZ + 1 + 2 * PACK_BOX_Z0 + 3, PACK_BOX_Y = TY + 1 + 2 * PACK_BOX_Y0;  // 48 x 15
 };
 
-template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false>
+template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false, int PD = 0>
 static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_constant__ CUtensorMap map_g,
-		const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c, HierIterArgs a,
-		XPassArgs t) {
+		const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
+		const __grid_constant__ CUtensorMap map_p, HierIterArgs a, XPassArgs t) {
 	typedef Stage1Tile<TIKHONOV> T;
 	constexpr int K = 2 * R + 1;
 	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
@@ -319,6 +345,22 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 					const int refill = slot == 0 ? NS - 1 : slot - 1;
 					mbar_wait(&empty[refill], slot == 0 ? phase ^ 1u : phase);
 					if (x - 1 + NS <= p_last) fetch(x - 1 + NS, refill);
+				}
+				if (PD > 0 && leader && x + PD < min(x_stop, X)) {
+					// L2 prefetch of the pack plane that the gather of plane x + PD touches for the first time, placed by the
+					// displacement of the tile's first voxel (a hint: the warp field is smooth, the box has a margin)
+					int s2 = slot + PD;
+					uint32_t phase2 = phase;
+					if (s2 >= NS) {
+						s2 -= NS;
+						phase2 ^= 1u;
+					}
+					mbar_wait(&full[s2], phase2);
+					const uint32_t st2 = stage_base + s2 * T::STAGE_BYTES + T::GP_BYTES;
+					const int bx = min(max(__float2int_rd((float) (x + PD) + lds_f32(st2)), -2), X) + 1;
+					const int by = min(max(__float2int_rd((float) y0 + lds_f32(st2 + W_COMP)), -2), Y);
+					const int bz = min(max(__float2int_rd((float) z0 + lds_f32(st2 + 2 * W_COMP)), -2), Z);
+					tma_prefetch_3d(&map_p, 4 * (bz + 2 - T::PACK_BOX_Z0), by + 2 - T::PACK_BOX_Y0, bx + 2);
 				}
 			}
 			const float4 s = gather4p(a.pack, X, Y, Z, x, y, z, wx, wy, wz, t.one2);
@@ -497,7 +539,8 @@ static __global__ void __launch_bounds__(288) k_sobolev_ymarch(YMarchArgs a) {
 
 // ---------------------------------------------------------------------------------------------- host-side launch helpers
 struct TmaMaps {
-	CUtensorMap g_prev, warp, canonical;
+	CUtensorMap g_prev, warp, canonical, pack;
+	const void* pack_key = nullptr;
 	const void* key[3] = { nullptr, nullptr, nullptr };  // pointers the maps were encoded for
 	int tile_y = 0;                                       // 0: boxes of k_hier_stage1_tma; 1000 + TY: of k_hier_stage1_pair
 };
@@ -521,11 +564,28 @@ int ensure_maps(TmaMaps& maps, const Grid3& g, const float* warp, const float* c
 	return LSF_OK;
 }
 
+template<typename T>
+int ensure_pack_map(TmaMaps& maps, const HierIterArgs& a) {
+	if (maps.pack_key == a.pack) return LSF_OK;
+	LSF_TRY(make_pack_map(&maps.pack, a.pack, a.g.X, a.g, T::PACK_BOX_Z, T::PACK_BOX_Y));
+	maps.pack_key = a.pack;
+	return LSF_OK;
+}
+
+// L2 prefetch of the pack by the tile leader (LSF_L2PF=0/1 overrides). Measured at 256^3: 4 % faster for the fused
+// whole-iteration kernels (no Sobolev kernel), 3 % slower for stage 1 with the axis-0 pass -- on by default for the former.
+inline bool l2_prefetch_enabled(bool fused_update) {
+	const char* e = getenv("LSF_L2PF");
+	if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+	return fused_update;
+}
+
 template<bool TIKHONOV, int R, bool DEC = true>
 int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h, int x_chunk, cudaStream_t stream) {
 	typedef Stage1Tile<TIKHONOV> T;
 	constexpr int NS = 4;
 	LSF_TRY(ensure_maps<TIKHONOV>(maps, a.g, a.warp, a.canonical, a.g_prev));
+	LSF_TRY(ensure_pack_map<T>(maps, a));
 	XPassArgs t;
 	for (int q = 0; q < 7; q++) t.k[q] = q < 2 * R + 1 ? taps.k[q] : 0.0f;
 	t.x_chunk = x_chunk;
@@ -535,11 +595,18 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 	const size_t shared = (size_t) NS * T::STAGE_BYTES;
 	static bool configured = false;
 	if (!configured) {
-		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int) shared));
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
 		configured = true;
 	}
-	k_hier_stage1_tma<TIKHONOV, R, NS, DEC> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp, maps.canonical, a, t);
+	if (DEC && l2_prefetch_enabled(false))
+		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
+				maps.canonical, maps.pack, a, t);
+	else
+		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
+				maps.canonical, maps.pack, a, t);
 	return LSF_OK;
 }
 
@@ -556,14 +623,21 @@ int launch_stage1_fused_update(TmaMaps& maps, HierIterArgs a, int x_chunk, cudaS
 	t.one2 = F32X2_ONE;
 	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), div_up(a.g.X, x_chunk));
 	const size_t shared = (size_t) NS * T::STAGE_BYTES;
+	LSF_TRY(ensure_pack_map<T>(maps, a));
 	static bool configured = false;
 	if (!configured) {
-		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, 0, NS, true, true>,
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 0>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 2>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
 		configured = true;
 	}
-	k_hier_stage1_tma<TIKHONOV, 0, NS, true, true> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
-			maps.canonical, a, t);
+	if (l2_prefetch_enabled(true))
+		k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 2> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
+				maps.canonical, maps.pack, a, t);
+	else
+		k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 0> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
+				maps.canonical, maps.pack, a, t);
 	return LSF_OK;
 }
 
