@@ -156,6 +156,10 @@ struct LevelState {
 	int* violation = nullptr;
 	TmaMaps maps;                // tensor maps of this level's warp / canonical / gradient planes (encoded on first use)
 	TmaMaps maps_alt;            // the same with the gradient's other ping-pong buffer (iterations without a Sobolev kernel)
+	                             // or the warp's other ping-pong buffer (deferred update)
+	float* warp_alt = nullptr;   // planes: second warp buffer. Non-null = deferred warp update (Tikhonov + Sobolev kernel):
+	                             // iteration i reads warp (i even) / warp_alt (i odd) and writes the other one; after E
+	                             // executed iterations finish_deferred() leaves the final warp in `warp`
 };
 
 // Enqueues one iteration; returns the number of kernel launches (negative: error status).
@@ -258,6 +262,24 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 			const int filter_tiles = (int) (div_up(s.g.Z, 512) * s.g.X);
 			const int chunk_y = plan.y_chunk_tma > 0 ? std::min(plan.y_chunk_tma, s.g.Y)
 					: marching_chunk(s.g.Y, filter_tiles, 2 * plan.taps.radius, 6);
+			if (s.warp_alt != nullptr) {
+				a.warp = iteration % 2 == 0 ? s.warp : s.warp_alt;
+				a.warp_out = iteration % 2 == 0 ? s.warp_alt : s.warp;
+				TmaMaps& maps = iteration % 2 == 0 ? s.maps : s.maps_alt;
+				int status;
+				switch (plan.taps.radius) {
+				case 1:
+					status = launch_iteration_deferred<1>(maps, a, plan.taps, s.scratch_a, filtered, chunk_x, chunk_y, stream, events);
+					break;
+				case 2:
+					status = launch_iteration_deferred<2>(maps, a, plan.taps, s.scratch_a, filtered, chunk_x, chunk_y, stream, events);
+					break;
+				default:
+					status = launch_iteration_deferred<3>(maps, a, plan.taps, s.scratch_a, filtered, chunk_x, chunk_y, stream, events);
+					break;
+				}
+				return status < 0 ? status : 2;
+			}
 			int status;
 			switch (plan.taps.radius) {
 			case 1:
@@ -386,6 +408,26 @@ void fill_report_statistics(lsf_level_report& r, const lsf_warp_delta_statistics
 	for (int i = 0; i < 3; i++) r.diff_biggest_location[i] = d.biggest_difference_location[i];
 }
 
+// Deferred warp update (k_hier_stage1_tma APPLY): usable when the level runs the TMA generation with both the Tikhonov
+// term and a Sobolev kernel, on the whole volume.
+bool deferred_update_applies(const Plan3& plan, const LevelState& s) {
+	const char* e = getenv("LSF_DEFER");  // A/B: LSF_DEFER=0 keeps the update in the filter kernel
+	if (e && e[0] == '0') return false;
+	const long long pack_count = (long long) (s.g.X + 4) * (s.g.Y + 4) * (s.g.Z + 4);
+	return plan.tikhonov && plan.use_kernel && plan.allow_fast_kernels && plan.split_x && plan.tma && !s.slab
+			&& plan.taps.radius >= 1 && plan.taps.radius <= 3 && plan.pair_tile_y == 0 && s.g.N * 3 < (1ll << 31)
+			&& pack_count < (1ll << 31) && tma_supported(s.g, s.warp, s.canonical, s.g_post) && aligned16(s.scratch_a)
+			&& deferred_update_supported(s.g, s.scratch_a, s.g_post);
+}
+
+// After `executed` iterations of a deferred level: apply the last iteration's pending update, result in s.warp.
+void finish_deferred(const Plan3& plan, LevelState& s, int executed, cudaStream_t stream) {
+	if (s.warp_alt == nullptr) return;
+	const float* current = executed % 2 == 0 ? s.warp : s.warp_alt;
+	const long long count = s.g.N * 3;
+	k_apply_update3d<<<counted(div_up(count, 256)), 256, 0, stream>>>(current, s.g_post, s.warp, plan.rate, count);
+}
+
 int optimize_device(const Plan3& plan, const float* canonical_dev, const float* live_dev, float* warp_out_dev,
 		lsf_level_report* reports, int collect_reports, lsf_iteration_capture* capture, float* capture_dev,
 		cudaStream_t stream) {
@@ -406,6 +448,8 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 	const int slot_count = std::max(plan.max_iterations, 1);
 	LSF_TRY(arena.alloc(&max_sq_bits, (size_t) slot_count));
 	std::vector<unsigned> host_bits((size_t) slot_count);
+	float* warp_pong = nullptr;  // second warp buffer of the deferred update
+	if (plan.tikhonov && plan.use_kernel) LSF_TRY(arena.alloc(&warp_pong, (size_t) finest.N * 3));
 
 	// the finest level lives in warp_a (3N floats), the level below it in warp_b (3N/8), and so on alternating
 	float* warp_current = ((L - 1) % 2 == 0) ? warp_a : warp_b;
@@ -427,6 +471,8 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 		LSF_CUDA(cudaMemsetAsync(g_post, 0, (size_t) s.g.N * 3 * sizeof(float), stream));
 		LSF_CUDA(cudaMemsetAsync(max_sq_bits, 0, (size_t) slot_count * sizeof(unsigned), stream));
 		const bool capturing = capture && capture->level == level && capture_dev != nullptr;
+		// per-iteration captures want the updated warp after every iteration: keep the update in the filter kernel there
+		if (!capturing && warp_pong != nullptr && deferred_update_applies(plan, s)) s.warp_alt = warp_pong;
 
 		int executed = 0;      // iterations known to have run
 		int enqueued = 0;
@@ -457,6 +503,7 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 			}
 			enqueued = chunk_end;
 		}
+		finish_deferred(plan, s, executed, stream);
 		if (reports) {
 			lsf_level_report& r = reports[level];
 			std::memset(&r, 0, sizeof(r));
@@ -581,6 +628,7 @@ extern "C" int lsf_hier_iterate_3d(const lsf_hier_params* params, const float* c
 	LSF_CUDA(cudaMemsetAsync(s.warp, 0, (size_t) g.N * 3 * sizeof(float), stream));
 	LSF_CUDA(cudaMemsetAsync(s.g_post, 0, (size_t) g.N * 3 * sizeof(float), stream));
 	LSF_CUDA(cudaMemsetAsync(s.max_sq_bits, 0, (size_t) iterations * sizeof(unsigned), stream));
+	if (deferred_update_applies(plan, s)) LSF_TRY(arena.alloc(&s.warp_alt, (size_t) g.N * 3));
 	cudaEvent_t start, stop;
 	LSF_CUDA(cudaEventCreate(&start));
 	LSF_CUDA(cudaEventCreate(&stop));
@@ -610,6 +658,8 @@ extern "C" int lsf_hier_iterate_3d(const lsf_hier_params* params, const float* c
 			launches += n;
 		}
 	}
+	finish_deferred(plan, s, iterations, stream);
+	if (s.warp_alt != nullptr) launches++;
 	LSF_CUDA(cudaEventRecord(stop, stream));
 	LSF_CUDA(cudaEventSynchronize(stop));
 	LSF_CUDA(cudaGetLastError());

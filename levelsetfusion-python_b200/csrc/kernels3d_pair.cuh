@@ -367,7 +367,7 @@ int launch_stage1_pair(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h
 struct YMarch2Args {
 	const float* in;   // planes after the axis-0 pass
 	float* out;        // planes: filtered gradient (nullptr when nothing reads it)
-	float* warp;       // planes, updated in place: warp -= out * rate
+	float* warp;       // planes, updated in place: warp -= out * rate (nullptr: deferred to the next stage 1)
 	Grid3 g;
 	unsigned long long k2[7];  // flipped taps duplicated into both lanes
 	unsigned long long one2, neg2, rate2;
@@ -471,7 +471,7 @@ static __global__ void __launch_bounds__(288) k_sobolev_ymarch2(const __grid_con
 				sts_f32(pa + W * 4, hi);        // B[il] = A[il + 1]
 			}
 		}
-		if (writes) {
+		if (writes && a.warp != nullptr) {
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
 				const float2 v = *reinterpret_cast<const float2*>(a.warp + c * N + o);
@@ -501,8 +501,10 @@ static __global__ void __launch_bounds__(288) k_sobolev_ymarch2(const __grid_con
 					unpack2(gq[c], v.x, v.y);
 					*reinterpret_cast<float2*>(a.out + c * N + o) = v;
 				}
-				unpack2(sub2(w[c], mul2(gq[c], a.rate2), neg), v.x, v.y);
-				*reinterpret_cast<float2*>(a.warp + c * N + o) = v;
+				if (a.warp != nullptr) {
+					unpack2(sub2(w[c], mul2(gq[c], a.rate2), neg), v.x, v.y);
+					*reinterpret_cast<float2*>(a.warp + c * N + o) = v;
+				}
 			}
 			f32x2 sq = mul2(gq[0], gq[0]);
 			sq = add2(sq, mul2(gq[1], gq[1]), one);
@@ -552,6 +554,29 @@ void launch_ymarch2(const Taps& taps, const HierIterArgs& a, const float* h, flo
 
 // One whole-volume iteration: paired stage 1 (tile_y = 4 or 8) when the level's shape allows it, else the third
 // generation; then the y-marching filter. Returns a negative status on failure.
+// Pending update of a deferred iteration (see k_hier_stage1_tma APPLY): warp_out = warp - g * rate
+static __global__ void k_apply_update3d(const float* __restrict__ warp, const float* __restrict__ g, float* __restrict__ warp_out,
+		float rate, long long count) {
+	const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) warp_out[i] = warp[i] - g[i] * rate;
+}
+
+inline bool deferred_update_supported(const Grid3& g, const float* h, const float* filtered) {
+	return ymarch2_supported(g, h, filtered, filtered);
+}
+
+// One iteration with the warp update deferred into the next stage 1: a.warp (read, before the previous update),
+// a.warp_out (written, after it) and a.g_prev = filtered (previous gradient in, this iteration's gradient out).
+template<int R>
+int launch_iteration_deferred(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h, float* filtered, int x_chunk,
+		int y_chunk, cudaStream_t stream, cudaEvent_t* events) {
+	LSF_TRY((launch_stage1_tma<true, R, true, true>(maps, a, taps, h, x_chunk, stream)));
+	if (events) cudaEventRecord(events[1], stream);
+	launch_ymarch2<R>(taps, a, h, filtered, nullptr, y_chunk, stream);
+	if (events) cudaEventRecord(events[2], stream);
+	return LSF_OK;
+}
+
 template<int R>
 int launch_iteration_v4(bool tikhonov, TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h, float* filtered,
 		float* warp, int x_chunk, int y_chunk, int tile_y, cudaStream_t stream, cudaEvent_t* events) {

@@ -211,7 +211,11 @@ struct Stage1Tile {
 	static constexpr int PACK_BOX_Z = TZ + 1 + 2 * PACK_BOX_Z0 + 3, PACK_BOX_Y = TY + 1 + 2 * PACK_BOX_Y0;  // 48 x 15
 };
 
-template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false, int PD = 0>
+// APPLY (deferred warp update, needs TIKHONOV): the previous iteration's filter kernel wrote only its gradient; this
+// kernel reads the warp BEFORE that update from a.warp, applies `warp - g_prev * rate` (reference optimizer.tpp:207,
+// the same two roundings, one kernel later) for the gather and writes the updated warp of its own planes to
+// a.warp_out (a different buffer: neighbouring x-chunks still read the old planes). One warp read less per iteration.
+template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false, int PD = 0, bool APPLY = false>
 static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_constant__ CUtensorMap map_g,
 		const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
 		const __grid_constant__ CUtensorMap map_p, HierIterArgs a, XPassArgs t) {
@@ -296,8 +300,19 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 			const uint32_t st = stage_base + slot * T::STAGE_BYTES;
 			const int next_slot = slot + 1 == NS ? 0 : slot + 1;
 			mbar_wait(&full[slot], phase);
-			const float wx = lds_f32(st + off_w), wy = lds_f32(st + off_w + W_COMP), wz = lds_f32(st + off_w + 2 * W_COMP);
+			float wx = lds_f32(st + off_w), wy = lds_f32(st + off_w + W_COMP), wz = lds_f32(st + off_w + 2 * W_COMP);
 			const float cn = lds_f32(st + off_c);
+			if (APPLY) {
+				wx = wx - cur[0] * a.rate;  // cur[] is the previous gradient at this voxel
+				wy = wy - cur[1] * a.rate;
+				wz = wz - cur[2] * a.rate;
+				if (valid && x >= xs && x < xe) {
+					const int at = out + R * YZ;
+					a.warp_out[at] = wx;
+					a.warp_out[N + at] = wy;
+					a.warp_out[2 * N + at] = wz;
+				}
+			}
 			float lap[3] = { 0.f, 0.f, 0.f };
 			if (TIKHONOV) {
 				const bool has_next = x + 1 < X;
@@ -580,7 +595,7 @@ inline bool l2_prefetch_enabled(bool fused_update) {
 	return fused_update;
 }
 
-template<bool TIKHONOV, int R, bool DEC = true>
+template<bool TIKHONOV, int R, bool DEC = true, bool APPLY = false>
 int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h, int x_chunk, cudaStream_t stream) {
 	typedef Stage1Tile<TIKHONOV> T;
 	constexpr int NS = 4;
@@ -595,17 +610,17 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 	const size_t shared = (size_t) NS * T::STAGE_BYTES;
 	static bool configured = false;
 	if (!configured) {
-		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0>,
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
-		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2>,
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
 		configured = true;
 	}
 	if (DEC && l2_prefetch_enabled(false))
-		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
+		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
 				maps.canonical, maps.pack, a, t);
 	else
-		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
+		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
 				maps.canonical, maps.pack, a, t);
 	return LSF_OK;
 }
