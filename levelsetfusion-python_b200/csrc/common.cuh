@@ -100,6 +100,35 @@ struct Taps {
 };
 int make_taps(const float* kernel_host, int kernel_size, Taps* taps);
 
+// Planes per block of a kernel that marches along an axis of `extent` planes with `tiles` tiles per plane, each block
+// starting with `lead` planes of re-computed halo. Blocks run in waves of `slots` (SMs x resident blocks per SM), so
+// the time is about waves x (chunk + lead) plane-steps: pick the split that minimises it. On B200 (444 slots) a 256^3
+// level gets 5 chunks of 52 planes -- measured 0.273 ms against 0.304 ms for 4 chunks of 64 (2.3 waves, the third one
+// a third full), in the order this model predicts for every split tried (profiles/r1_ncu_dec_v4.md).
+inline int marching_chunk(int extent, int tiles, int lead, int blocks_per_sm) {
+	static int sm_count = 0;
+	if (sm_count == 0) {
+		int device = 0;
+		cudaGetDevice(&device);
+		if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sm_count <= 0)
+			sm_count = 148;
+	}
+	const long long slots = (long long) sm_count * blocks_per_sm;
+	int best_chunk = extent;
+	long long best_cost = -1;
+	for (int parts = 1; parts <= extent; parts++) {
+		const int chunk = (extent + parts - 1) / parts;
+		if (chunk < 8 && parts > 1) break;
+		const long long blocks = (long long) tiles * ((extent + chunk - 1) / chunk);
+		const long long cost = ((blocks + slots - 1) / slots) * (chunk + lead);
+		if (best_cost < 0 || cost < best_cost) {
+			best_cost = cost;
+			best_chunk = chunk;
+		}
+	}
+	return best_chunk;
+}
+
 // ---------------------------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 

@@ -6,6 +6,7 @@
 // (nonrigid_opt/slavcheva/slavcheva_optimizer2d.py:332-408). The termination test runs on the device (k_slav_decide);
 // the host polls the status flags once per chunk of iterations.
 #include "slavcheva.cuh"
+#include "slavcheva_fast.cuh"
 #include "kernels3d.cuh"  // k_aos_to_planes / k_planes_to_aos
 
 #include <cmath>
@@ -152,6 +153,8 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	bool finished = host_finished(p, 0, max_iterations, initial_max) || bound == 0;
 	int enqueued = 0;
 	const unsigned blocks = blocks_for(g.N);
+	const char* legacy_filter = getenv("LSF_SLAV_FAST");  // A/B: LSF_SLAV_FAST=0 keeps the first-generation kernels
+	const bool fast_filter = !(legacy_filter && legacy_filter[0] == '0');
 	while (!finished) {
 		const int chunk_end = std::min(bound, enqueued + POLL_CHUNK);
 		for (int it = enqueued; it < chunk_end; it++) {
@@ -180,12 +183,20 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 				// pass order: array axis 0 first (2D: rows then columns, convolution.cpp:69-145; 3D: axes 0, 1, 2)
 				const float* in = field_a;
 				float* outs[3] = { field_b, field_f, field_b };
-				for (int axis = 0; axis < D; axis++) {
-					fa.in = in;
-					fa.out = outs[axis];
-					fa.axis = axis;
-					k_slav_filter_axis<D> <<<counted(blocks), 256, 0, stream>>>(fa);
-					in = outs[axis];
+				if (D == 3 && cpp && fast_filter && slav_fast_filter_supported(g, taps, field_a, field_b)) {
+					// second generation: axis-0 marching kernel, then axes 1 and 2 in one kernel (slavcheva_fast.cuh);
+					// the result lands where the three-pass version leaves it
+					if (taps.radius == 1) launch_slav_fast_filter<1>(g, taps, field_a, field_f, field_b, status, it, stream);
+					else if (taps.radius == 2) launch_slav_fast_filter<2>(g, taps, field_a, field_f, field_b, status, it, stream);
+					else launch_slav_fast_filter<3>(g, taps, field_a, field_f, field_b, status, it, stream);
+				} else {
+					for (int axis = 0; axis < D; axis++) {
+						fa.in = in;
+						fa.out = outs[axis];
+						fa.axis = axis;
+						k_slav_filter_axis<D> <<<counted(blocks), 256, 0, stream>>>(fa);
+						in = outs[axis];
+					}
 				}
 				final_field = outs[D - 1];
 			}

@@ -140,29 +140,38 @@ __device__ __forceinline__ int slav_index(const SlavGeom& g, const int (&q)[3]) 
 	return idx;
 }
 
+// IN = true: the caller knows that the voxel is an interior one (every stencil tap is inside the field), so the bounds
+// tests drop out; 3D fields have component c along array axis c, so the axis look-ups fold away as well.
 template<int D>
+__device__ __forceinline__ int slav_axis(const SlavGeom& g, int component) {
+	return D == 3 ? component : g.comp_axis[component];
+}
+
+template<int D, bool IN = false>
 __device__ __forceinline__ float slav_live_or_one(const SlavGeom& g, const float* __restrict__ live, const int (&q)[3]) {
-	return slav_inside<D>(g, q) ? __ldg(live + slav_index<D>(g, q)) : 1.0f;
+	return (IN || slav_inside<D>(g, q)) ? __ldg(live + slav_index<D>(g, q)) : 1.0f;
 }
 
 // ---------------------------------------------------------------------------------------------- gradient terms
 // data term: reference data_term.cpp:63-84 (C++), data_term.py:169-227 (Python basic / thresholded FDM)
-template<int D>
+template<int D, bool IN = false>
 __device__ __forceinline__ void slav_data_term(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
 	const SlavGeom& g = a.g;
 	const float centre = __ldg(a.live + idx);
 	float grad[3] = { 0.f, 0.f, 0.f };
 #pragma unroll
 	for (int c = 0; c < D; c++) {
-		const int ax = g.comp_axis[c], i = pos[ax], n = g.n[ax], s = g.stride[ax];
-		if (n >= 2) {
+		const int ax = slav_axis<D>(g, c), i = pos[ax], n = g.n[ax], s = g.stride[ax];
+		if (IN) {
+			grad[c] = 0.5f * (__ldg(a.live + idx + s) - __ldg(a.live + idx - s));
+		} else if (n >= 2) {
 			if (i == 0) grad[c] = __ldg(a.live + idx + s) - centre;
 			else if (i == n - 1) grad[c] = centre - __ldg(a.live + idx - s);
 			else grad[c] = 0.5f * (__ldg(a.live + idx + s) - __ldg(a.live + idx - s));
 		}
 		if (a.p.data_term_method == LSF_DATA_TERM_THRESHOLDED_FDM && fabsf(grad[c]) > 0.5f) {
-			const float minus = i > 0 ? __ldg(a.live + idx - s) : 1.0f;
-			const float plus = i < n - 1 ? __ldg(a.live + idx + s) : 1.0f;
+			const float minus = (IN || i > 0) ? __ldg(a.live + idx - s) : 1.0f;
+			const float plus = (IN || i < n - 1) ? __ldg(a.live + idx + s) : 1.0f;
 			const float forward = plus - centre, backward = centre - minus;
 			float value = fabsf(forward) < fabsf(backward) ? forward : backward;
 			if (fabsf(value) > 0.5f) value = 0.0f;
@@ -180,14 +189,14 @@ __device__ __forceinline__ void slav_data_term(const SlavGradientArgs& a, int id
 	}
 }
 
-template<int D>
+template<int D, bool IN = false>
 __device__ __forceinline__ float slav_warp_or_centre(const SlavGradientArgs& a, const int (&q)[3], int c, int centre_idx) {
-	const int at = slav_inside<D>(a.g, q) ? slav_index<D>(a.g, q) : centre_idx;
+	const int at = (IN || slav_inside<D>(a.g, q)) ? slav_index<D>(a.g, q) : centre_idx;
 	return __ldg(a.warp + c * a.g.N + at);
 }
 
 // C++ Tikhonov term: reference smoothing_term.cpp:43-108 (array axis 0 assigned, further axes added)
-template<int D>
+template<int D, bool IN = false>
 __device__ __forceinline__ void slav_tikhonov_cpp(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
 #pragma unroll
 	for (int c = 0; c < D; c++) {
@@ -198,9 +207,9 @@ __device__ __forceinline__ void slav_tikhonov_cpp(const SlavGradientArgs& a, int
 		for (int ax = 0; ax < D; ax++) {
 			const int i = pos[ax], n = a.g.n[ax], s = a.g.stride[ax];
 			float term;
-			if (n < 2) term = 0.0f;
-			else if (i == 0) term = -__ldg(w + s) + centre;
-			else if (i == n - 1) term = -__ldg(w - s) + centre;
+			if (!IN && n < 2) term = 0.0f;
+			else if (!IN && i == 0) term = -__ldg(w + s) + centre;
+			else if (!IN && i == n - 1) term = -__ldg(w - s) + centre;
 			else term = (-__ldg(w + s) + 2.0f * centre) - __ldg(w - s);
 			if (ax == 0) total = term;
 			else total += term;
@@ -238,33 +247,33 @@ __device__ __forceinline__ void slav_tikhonov_py(const SlavGradientArgs& a, int 
 
 // Killing term: reference smoothing_term.py:50-100 (copy_if_zero=False), quirks kept; 3D form = the
 // same expression pattern
-template<int D>
+template<int D, bool IN = false>
 __device__ __forceinline__ void slav_killing(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
 	const float lambda = a.p.lambda;
 	const float c0 = (float) (-2.0 * (1.0 + (double) lambda));
-	const int ax0 = a.g.comp_axis[0];
+	const int ax0 = slav_axis<D>(a.g, 0);
 #pragma unroll
 	for (int ca = 0; ca < D; ca++) {
 		int q[3] = { pos[0], pos[1], pos[2] };
 		const float w = __ldg(a.warp + ca * a.g.N + idx);
 		q[ax0] = pos[ax0] + 1;
-		const float xp = slav_warp_or_centre<D>(a, q, ca, idx);
+		const float xp = slav_warp_or_centre<D, IN>(a, q, ca, idx);
 		q[ax0] = pos[ax0] - 1;
-		const float xm = slav_warp_or_centre<D>(a, q, ca, idx);
+		const float xm = slav_warp_or_centre<D, IN>(a, q, ca, idx);
 		q[ax0] = pos[ax0];
 		float acc = c0 * ((xp - 2.0f * w) + xm);
 #pragma unroll
 		for (int k = 1; k < D; k++) {
-			const int ax = a.g.comp_axis[k];
+			const int ax = slav_axis<D>(a.g, k);
 			q[ax] = pos[ax] + 1;
-			const float yp = slav_warp_or_centre<D>(a, q, ca, idx);
+			const float yp = slav_warp_or_centre<D, IN>(a, q, ca, idx);
 			q[ax] = pos[ax];
 			acc = acc + ((yp - 2.0f * w) + yp);
 		}
 #pragma unroll
 		for (int cb = 0; cb < D; cb++) {
 			if (cb == ca) continue;
-			const int first = a.g.comp_axis[ca < cb ? ca : cb], second = a.g.comp_axis[ca < cb ? cb : ca];
+			const int first = slav_axis<D>(a.g, ca < cb ? ca : cb), second = slav_axis<D>(a.g, ca < cb ? cb : ca);
 			float v[4];
 			int k = 0;
 #pragma unroll
@@ -273,7 +282,7 @@ __device__ __forceinline__ void slav_killing(const SlavGradientArgs& a, int idx,
 				for (int s2 = 1; s2 >= -1; s2 -= 2) {
 					q[first] = pos[first] + s1;
 					q[second] = pos[second] + s2;
-					v[k++] = slav_warp_or_centre<D>(a, q, cb, idx);
+					v[k++] = slav_warp_or_centre<D, IN>(a, q, cb, idx);
 				}
 			q[first] = pos[first];
 			q[second] = pos[second];
@@ -285,7 +294,7 @@ __device__ __forceinline__ void slav_killing(const SlavGradientArgs& a, int idx,
 }
 
 // level-set term: reference level_set_term.py:28-64 (out-of-bounds -> 1, quirks kept)
-template<int D>
+template<int D, bool IN = false>
 __device__ __forceinline__ void slav_level_set(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
 	const SlavGeom& g = a.g;
 	const float centre = __ldg(a.live + idx);
@@ -293,11 +302,11 @@ __device__ __forceinline__ void slav_level_set(const SlavGradientArgs& a, int id
 	int q[3] = { pos[0], pos[1], pos[2] };
 #pragma unroll
 	for (int c = 0; c < D; c++) {
-		const int ax = g.comp_axis[c];
+		const int ax = slav_axis<D>(g, c);
 		q[ax] = pos[ax] + 1;
-		const float plus = slav_live_or_one<D>(g, a.live, q);
+		const float plus = slav_live_or_one<D, IN>(g, a.live, q);
 		q[ax] = pos[ax] - 1;
-		const float minus = slav_live_or_one<D>(g, a.live, q);
+		const float minus = slav_live_or_one<D, IN>(g, a.live, q);
 		q[ax] = pos[ax];
 		grad[c] = (0.5f * (plus - minus)) * 10.0f;
 		hessian[c][c] = ((plus - 2.0f * centre) + plus) * 10.0f;
@@ -306,7 +315,7 @@ __device__ __forceinline__ void slav_level_set(const SlavGradientArgs& a, int id
 	for (int c1 = 0; c1 < D; c1++)
 #pragma unroll
 		for (int c2 = c1 + 1; c2 < D; c2++) {
-			const int a1 = g.comp_axis[c1], a2 = g.comp_axis[c2];
+			const int a1 = slav_axis<D>(g, c1), a2 = slav_axis<D>(g, c2);
 			float v[4];
 			int k = 0;
 #pragma unroll
@@ -315,7 +324,7 @@ __device__ __forceinline__ void slav_level_set(const SlavGradientArgs& a, int id
 				for (int s1 = 1; s1 >= -1; s1 -= 2) {
 					q[a1] = pos[a1] + s1;
 					q[a2] = pos[a2] + s2;
-					v[k++] = slav_live_or_one<D>(g, a.live, q);
+					v[k++] = slav_live_or_one<D, IN>(g, a.live, q);
 				}
 			q[a1] = pos[a1];
 			q[a2] = pos[a2];
@@ -355,11 +364,21 @@ static __global__ void __launch_bounds__(256) k_slav_gradient(SlavGradientArgs a
 #pragma unroll
 			for (int c = 0; c < D; c++) result[c] = (0.0f + 0.0f * p.smoothing_weight) * -p.rate;
 		} else {
-			slav_data_term<D>(a, idx, pos, data);
-			if (p.smoothing_term_method == LSF_SMOOTHING_KILLING) slav_killing<D>(a, idx, pos, smooth);
-			else slav_tikhonov_cpp<D>(a, idx, pos, smooth);
+			bool interior = D == 3;  // 3D: interior voxels take the paths without bounds tests (same arithmetic)
+#pragma unroll
+			for (int ax = 0; ax < D; ax++) interior = interior && pos[ax] >= 1 && pos[ax] < a.g.n[ax] - 1;
 			const bool ls_here = p.level_set && !slav_truncated(live_value);
-			if (ls_here) slav_level_set<D>(a, idx, pos, ls);
+			if (interior) {
+				slav_data_term<D, true>(a, idx, pos, data);
+				if (p.smoothing_term_method == LSF_SMOOTHING_KILLING) slav_killing<D, true>(a, idx, pos, smooth);
+				else slav_tikhonov_cpp<D, true>(a, idx, pos, smooth);
+				if (ls_here) slav_level_set<D, true>(a, idx, pos, ls);
+			} else {
+				slav_data_term<D>(a, idx, pos, data);
+				if (p.smoothing_term_method == LSF_SMOOTHING_KILLING) slav_killing<D>(a, idx, pos, smooth);
+				else slav_tikhonov_cpp<D>(a, idx, pos, smooth);
+				if (ls_here) slav_level_set<D>(a, idx, pos, ls);
+			}
 #pragma unroll
 			for (int c = 0; c < D; c++) {
 				float total = data[c] * p.data_weight;

@@ -1,0 +1,255 @@
+// slavcheva_fast.cuh -- second generation of the 3D SobolevFusion / KillingFusion Sobolev filter (sm_100a).
+//
+// First generation (slavcheva.cuh: k_slav_filter_axis x 3) moves 3 x 24 B per voxel and re-reads every tap through the
+// cache: 3 x 194 us per 256^3 iteration, 1.8 TB/s (profiles/r1_killing_v1.md). Here the three passes of
+// convolve_with_kernel_preserve_zeros (reference cpp/src/math/convolution.cpp:23-67,69-145, C++ zero rule: a voxel whose
+// pass-input vector is exactly zero yields the zero vector) run in two marching kernels on voxel pairs with packed
+// f32x2 chains, the organisation of kernels3d_pair.cuh:
+//   k_slav_xmarch<R>   axis-0 pass: a thread owns a z pair of one row and marches along axis 0 (pure streaming, the
+//                      partial sums of the K outputs in flight live in registers);
+//   k_slav_ymarch2<R>  axis-1 and axis-2 passes: marching along axis 1, axis-2 taps from a double-buffered shared row
+//                      kept twice (as is / shifted by one column) so that every operand pair is one aligned LDS.64.
+// Arithmetic per output: sum over taps q ascending of in[i - R + q] * k[q], zeros outside the field -- the order of
+// k_slav_filter_axis; results are bit-identical (tests/test_gpu_parity_slavcheva.py).
+#pragma once
+
+#include "kernels3d_pair.cuh"
+#include "slavcheva.cuh"
+
+namespace lsf {
+
+struct SlavMarchArgs {
+	const float* in;   // planes
+	float* out;        // planes
+	int X, Y, Z;
+	unsigned long long k2[7];  // taps duplicated into both lanes: k2[q] multiplies in[i - R + q]
+	unsigned long long one2;
+	const int* status;
+	int iteration;
+	int chunk;         // outputs per block along the marching axis
+	int tile_z;        // k_slav_ymarch2: output columns per block (even)
+};
+
+#ifdef __CUDACC__
+
+// zero flags of a voxel pair: bit 0 = low voxel's vector is exactly zero, bit 1 = high voxel's
+__device__ __forceinline__ unsigned pair_zero_flags(f32x2 v0, f32x2 v1, f32x2 v2) {
+	float a0, a1, b0, b1, c0, c1;
+	unpack2(v0, a0, a1);
+	unpack2(v1, b0, b1);
+	unpack2(v2, c0, c1);
+	return ((a0 == 0.0f && b0 == 0.0f && c0 == 0.0f) ? 1u : 0u) | ((a1 == 0.0f && b1 == 0.0f && c1 == 0.0f) ? 2u : 0u);
+}
+__device__ __forceinline__ f32x2 pair_clear(f32x2 v, unsigned flags) {
+	float lo, hi;
+	unpack2(v, lo, hi);
+	return pack2((flags & 1u) ? 0.0f : lo, (flags & 2u) ? 0.0f : hi);
+}
+
+template<int R>
+static __global__ void __launch_bounds__(256) k_slav_xmarch(const __grid_constant__ SlavMarchArgs a) {
+	constexpr int K = 2 * R + 1;
+	if (a.status[a.iteration]) return;
+	const int pairs_per_plane = a.Y * a.Z / 2;
+	const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pair >= pairs_per_plane) return;
+	const int YZ = a.Y * a.Z;
+	const long long N = (long long) a.X * YZ;
+	const int xs = blockIdx.y * a.chunk;
+	const int xe = min(a.X, xs + a.chunk);
+	const int x_first = max(xs - R, 0), x_stop = xe + R;
+	const f32x2 one = a.one2;
+	f32x2 acc[3][K];
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int q = 0; q < K; q++) acc[c][q] = 0ull;
+	unsigned flags = 0;  // 2 bits per plane, newest in the low bits
+	long long at = (long long) x_first * YZ + 2 * pair;
+	f32x2 next[3] = { 0ull, 0ull, 0ull };
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		const float2 v = __ldg(reinterpret_cast<const float2*>(a.in + c * N + at));
+		next[c] = pack2(v.x, v.y);
+	}
+#pragma unroll 1
+	for (int x = x_first; x < x_stop; x++, at += YZ) {
+		const f32x2 v0 = next[0], v1 = next[1], v2 = next[2];
+		if (x + 1 < a.X && x + 1 < x_stop) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const float2 v = __ldg(reinterpret_cast<const float2*>(a.in + c * N + at + YZ));
+				next[c] = pack2(v.x, v.y);
+			}
+		} else {
+			next[0] = next[1] = next[2] = 0ull;
+		}
+		flags = (flags << 2) | pair_zero_flags(v0, v1, v2);  // planes >= X: zero vectors (never written)
+		// plane x is tap q of output plane x + R - q
+#pragma unroll
+		for (int q = K - 1; q >= 1; q--) {
+			acc[0][q] = add2(acc[0][q - 1], mul2(v0, a.k2[q]), one);
+			acc[1][q] = add2(acc[1][q - 1], mul2(v1, a.k2[q]), one);
+			acc[2][q] = add2(acc[2][q - 1], mul2(v2, a.k2[q]), one);
+		}
+		acc[0][0] = mul2(v0, a.k2[0]);
+		acc[1][0] = mul2(v1, a.k2[0]);
+		acc[2][0] = mul2(v2, a.k2[0]);
+		if (x - R >= xs) {
+			const unsigned zero = (flags >> (2 * R)) & 3u;  // flags of plane x - R
+			const long long o = at - (long long) R * YZ;
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				float2 v;
+				unpack2(pair_clear(acc[c][K - 1], zero), v.x, v.y);
+				*reinterpret_cast<float2*>(a.out + c * N + o) = v;
+			}
+		}
+	}
+}
+
+template<int R>
+static __global__ void __launch_bounds__(288) k_slav_ymarch2(const __grid_constant__ SlavMarchArgs a) {
+	constexpr int K = 2 * R + 1;
+	constexpr int H = 4;  // halo columns kept either side of the tile (>= R, even)
+	if (a.status[a.iteration]) return;
+	extern __shared__ __align__(16) float slav_rows[];  // [2 buffers][3 components][A: W | B: W]
+	const int Y = a.Y, Z = a.Z;
+	const int NT = a.tile_z / 2;
+	const int W = a.tile_z + 2 * H;
+	const int tid = threadIdx.x;
+	const int z0 = blockIdx.x * a.tile_z;
+	const int x = blockIdx.y;
+	const int ys = blockIdx.z * a.chunk;
+	const int ye = min(Y, ys + a.chunk);
+	const bool owner = tid < NT;
+	const int j = tid - NT;
+	const int il = owner ? H + 2 * tid : (j < H / 2 ? 2 * j : a.tile_z + H + 2 * (j - H / 2));
+	const int z = z0 - H + il;
+	const bool active = (owner || j < H) && z >= 0 && z < Z;
+	const bool writes = owner && active;
+	for (int i = tid; i < 12 * W; i += blockDim.x) slav_rows[i] = 0.0f;  // columns outside the field stay zero
+	__syncthreads();
+	const uint32_t rows = smem_addr(slav_rows);
+	const f32x2 one = a.one2;
+	f32x2 acc[3][K];
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int q = 0; q < K; q++) acc[c][q] = 0ull;
+	unsigned flags = 0;
+	const int r_first = max(ys - R, 0), r_stop = ye + R, r_load_end = min(r_stop, Y);
+	const long long N = (long long) a.X * Y * Z;
+	long long at = ((long long) x * Y + r_first) * Z + z;
+	f32x2 next[3] = { 0ull, 0ull, 0ull };
+	if (active) {
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			const float2 v = __ldg(reinterpret_cast<const float2*>(a.in + c * N + at));
+			next[c] = pack2(v.x, v.y);
+		}
+	}
+	int buffer = 0;
+#pragma unroll 1
+	for (int r = r_first; r < r_stop; r++, at += Z) {
+		const f32x2 v0 = next[0], v1 = next[1], v2 = next[2];
+		if (active && r + 1 < r_load_end) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const float2 v = __ldg(reinterpret_cast<const float2*>(a.in + c * N + at + Z));
+				next[c] = pack2(v.x, v.y);
+			}
+		} else {
+			next[0] = next[1] = next[2] = 0ull;
+		}
+		flags = (flags << 2) | pair_zero_flags(v0, v1, v2);
+#pragma unroll
+		for (int q = K - 1; q >= 1; q--) {
+			acc[0][q] = add2(acc[0][q - 1], mul2(v0, a.k2[q]), one);
+			acc[1][q] = add2(acc[1][q - 1], mul2(v1, a.k2[q]), one);
+			acc[2][q] = add2(acc[2][q - 1], mul2(v2, a.k2[q]), one);
+		}
+		acc[0][0] = mul2(v0, a.k2[0]);
+		acc[1][0] = mul2(v1, a.k2[0]);
+		acc[2][0] = mul2(v2, a.k2[0]);
+		if (r - R < ys) continue;  // block-uniform: still priming
+		const uint32_t row = rows + buffer * (6 * W * 4);
+		const long long o = at - (long long) R * Z;  // voxel (x, r - R, z)
+		// axis-1 result of this pair, with the axis-1 zero rule; it is the input (and the zero test) of the axis-2 pass
+		const unsigned zero1 = (flags >> (2 * R)) & 3u;
+		f32x2 mid[3];
+#pragma unroll
+		for (int c = 0; c < 3; c++) mid[c] = pair_clear(acc[c][K - 1], zero1);
+		if (active) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const uint32_t pa = row + (c * 2 * W + il) * 4;
+				float lo, hi;
+				unpack2(mid[c], lo, hi);
+				sts_f32x2(pa, mid[c]);
+				if (il > 0) sts_f32(pa + (W - 1) * 4, lo);  // B[il - 1] = A[il]
+				sts_f32(pa + W * 4, hi);                      // B[il] = A[il + 1]
+			}
+		}
+		__syncthreads();
+		if (writes) {
+			const unsigned zero2 = pair_zero_flags(mid[0], mid[1], mid[2]);
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const uint32_t pa = row + (c * 2 * W + il - R) * 4;
+				f32x2 sum = 0ull;
+#pragma unroll
+				for (int q = 0; q < K; q++) {
+					const f32x2 v = ((q - R) % 2 == 0) ? lds_f32x2(pa + q * 4) : lds_f32x2(pa + (W + q - 1) * 4);
+					sum = q == 0 ? mul2(v, a.k2[0]) : add2(sum, mul2(v, a.k2[q]), one);
+				}
+				float2 v;
+				unpack2(pair_clear(sum, zero2), v.x, v.y);
+				*reinterpret_cast<float2*>(a.out + c * N + o) = v;
+			}
+		}
+		buffer ^= 1;
+	}
+}
+
+inline bool slav_fast_filter_supported(const SlavGeom& g, const Taps& taps, const float* a, const float* b) {
+	auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
+	return g.nd == 3 && taps.radius >= 1 && taps.radius <= 3 && g.n[2] % 2 == 0 && g.N * 3 < (1ll << 31) && aligned(a)
+			&& aligned(b);
+}
+
+// in -> scratch (axis 0) -> out (axes 1, 2); returns the number of launches
+template<int R>
+int launch_slav_fast_filter(const SlavGeom& g, const Taps& taps, const float* in, float* scratch, float* out,
+		const int* status, int iteration, cudaStream_t stream) {
+	SlavMarchArgs f;
+	f.X = g.n[0];
+	f.Y = g.n[1];
+	f.Z = g.n[2];
+	for (int q = 0; q < 7; q++) f.k2[q] = dup2(q < 2 * R + 1 ? taps.k[q] : 0.0f);
+	f.one2 = dup2(1.0f);
+	f.status = status;
+	f.iteration = iteration;
+	// axis 0: one thread per z pair of a plane, chunks along x sized to fill the GPU a few times over
+	f.in = in;
+	f.out = scratch;
+	const int pairs = f.Y * f.Z / 2;
+	const int plane_blocks = (int) div_up(pairs, 256);
+	f.chunk = marching_chunk(f.X, plane_blocks, 2 * R, 3);
+	f.tile_z = 0;
+	k_slav_xmarch<R> <<<counted(dim3(plane_blocks, (unsigned) div_up(f.X, f.chunk))), 256, 0, stream>>>(f);
+	// axes 1 and 2
+	f.in = scratch;
+	f.out = out;
+	f.tile_z = std::min(512, (int) div_up(f.Z, 64) * 64);
+	const int tiles = (int) div_up(f.Z, f.tile_z);
+	f.chunk = marching_chunk(f.Y, tiles * f.X, 2 * R, 6);
+	const int threads = f.tile_z / 2 + (tiles > 1 ? 32 : 0);
+	const size_t shared = (size_t) 12 * (f.tile_z + 8) * sizeof(float);
+	k_slav_ymarch2<R> <<<counted(dim3(tiles, f.X, (unsigned) div_up(f.Y, f.chunk))), threads, shared, stream>>>(f);
+	return 2;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lsf

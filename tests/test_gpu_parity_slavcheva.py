@@ -354,3 +354,31 @@ def test_full_size_properties_256(lsf):
     assert float((first - canonical).abs().mean()) < float((live - canonical).abs().mean())
     second = optimizer.optimize(live, canonical)
     assert bool((first == second).all())
+
+
+@pytest.mark.parametrize("taps", [3, 5, 7])
+def test_fast_filter_matches_three_pass_filter(lsf, taps, monkeypatch):
+    """A/B: the marching Sobolev filter kernels of the 3D optimizer (slavcheva_fast.cuh) against the first-generation
+    three-pass kernel (LSF_SLAV_FAST=0) -- bit-identical live field, warp field and iteration count, on a ragged
+    volume and on a long thin one whose rows span three z tiles (halo columns between tiles)."""
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(64)
+    cases = [(canonical[10:50, 14:50, :].copy(), live[10:50, 14:50, :].copy())]
+    rng = np.random.default_rng(5)
+    long_c = np.clip(np.cumsum(rng.standard_normal((6, 10, 1040)).astype(np.float32) * 0.05, axis=2), -1, 1)
+    long_l = np.clip(long_c + rng.standard_normal(long_c.shape).astype(np.float32) * 0.02, -1, 1).astype(np.float32)
+    cases.append((long_c.astype(np.float32), long_l))
+    for canonical_case, live_case in cases:
+        results = []
+        for fast in ("1", "0"):
+            monkeypatch.setenv("LSF_SLAV_FAST", fast)
+            optimizer = lsf.SlavchevaOptimizer3d(smoothing_term_method=lsf.SmoothingTermMethod.KILLING,
+                                                 level_set_term_enabled=True, max_iterations=6,
+                                                 maximum_warp_length_lower_threshold=0.0,
+                                                 sobolev_kernel=synthetic.sobolev_kernel_1d(taps))
+            out = optimizer.optimize(live_case.copy(), canonical_case)
+            results.append((np.array(out), np.array(optimizer.get_last_warp_field()), optimizer.get_iteration_count()))
+        assert results[0][2] == results[1][2]
+        assert np.abs(results[0][1]).max() > 0
+        assert np.array_equal(results[0][0], results[1][0])
+        assert np.array_equal(results[0][1], results[1][1])
