@@ -35,6 +35,7 @@ struct Plan3 {
 	bool split_x = true;               // stage 1 + axis-0 pass | axis-1/2 passes + update (LSF_SPLIT_X=0: previous cut)
 	int x_chunk_stage1 = 64, x_chunk_filter = 16;  // planes per block of the two split kernels (LSF_XCHUNK_A / _B)
 	int stage1_variant = 2;            // LSF_STAGE1_VARIANT=1 selects the 4-voxel kernel (A/B)
+	bool slab_fast = true;             // slab mode: TMA-fed stage 1 and marching filter kernels (LSF_SLAB_FAST=0: first generation)
 	bool tma = true;                   // third generation: TMA-fed stage 1 + y-marching filter (LSF_TMA=0: second generation)
 	int pair_tile_y = 0;               // fourth generation: two voxels per thread in stage 1, 64 x pair_tile_y tiles (LSF_PAIR_TY=0: third generation)
 	int x_chunk_tma = 0, y_chunk_tma = 0;   // planes / rows per block of the two TMA-generation kernels (LSF_XCHUNK_T /
@@ -128,6 +129,7 @@ struct LevelState {
 	TmaMaps maps;                // tensor maps of this level's warp / canonical / gradient planes (encoded on first use)
 	TmaMaps maps_alt;            // the same with the gradient's other ping-pong buffer (iterations without a Sobolev kernel)
 	                             // or the warp's other ping-pong buffer (deferred update)
+	float* scratch_h = nullptr;  // planes: slab mode, the gradient after the axis-0 pass (fast filter phase)
 	float* warp_alt = nullptr;   // planes: second warp buffer. Non-null = deferred warp update (Tikhonov + Sobolev kernel):
 	                             // iteration i reads warp (i even) / warp_alt (i odd) and writes the other one; after E
 	                             // executed iterations finish_deferred() leaves the final warp in `warp`
@@ -193,21 +195,24 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 	} while (0)
 	if (!plan.use_kernel) {
 		if (phase == 2) return 0;
-		if (plan.tma && variant == 2 && !s.slab && tma_supported(s.g, s.warp, s.canonical, s.g_post)
+		if (plan.tma && variant == 2 && (!s.slab || plan.slab_fast) && tma_supported(s.g, s.warp, s.canonical, s.g_post)
 				&& (!plan.tikhonov || aligned16(s.scratch_a))) {
 			// TMA-fed stage 1 with the warp update and the max-norm fused (one launch per iteration)
 			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8));
-			const int chunk_x = plan.x_chunk_tma > 0 ? std::min(plan.x_chunk_tma, s.g.X) : marching_chunk(s.g.X, tiles, 0, 3);
+			const int planes = x_end - x_begin;
+			const int chunk_x = plan.x_chunk_tma > 0 ? std::min(plan.x_chunk_tma, planes) : marching_chunk(planes, tiles, 0, 3);
 			int status;
 			if (plan.tikhonov) {
 				// the gradient ping-pongs between g_post and scratch_a: one set of tensor maps per direction
 				a.g_out = s.scratch_a;
 				TmaMaps& maps = (s.maps.key[2] == nullptr || s.maps.key[2] == a.g_prev) ? s.maps : s.maps_alt;
-				status = launch_stage1_fused_update<true>(maps, a, chunk_x, stream);
+				status = s.slab ? launch_stage1_fused_update<true, true>(maps, a, chunk_x, stream)
+						: launch_stage1_fused_update<true>(maps, a, chunk_x, stream);
 				std::swap(s.g_post, s.scratch_a);
 			} else {
 				a.g_out = nullptr;
-				status = launch_stage1_fused_update<false>(s.maps, a, chunk_x, stream);
+				status = s.slab ? launch_stage1_fused_update<false, true>(s.maps, a, chunk_x, stream)
+						: launch_stage1_fused_update<false>(s.maps, a, chunk_x, stream);
 			}
 			mark(1);
 			return status < 0 ? status : 1;
@@ -278,6 +283,29 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 			break;
 		}
 		return 2;
+	}
+	if (s.slab && plan.slab_fast && plan.tma && variant == 2 && (phase == 1 || s.scratch_h != nullptr) && plan.taps.radius >= 1
+			&& plan.taps.radius <= 3 && tma_supported(s.g, s.warp, s.canonical, s.g_post) && aligned16(s.scratch_a)
+			&& ymarch2_supported(s.g, s.scratch_h, s.g_post, s.warp)) {
+		// slab mode, fourth-generation kernels: phase 1 = TMA-fed stage 1 writing the unfiltered gradient of the own
+		// planes, [halo exchange by the caller,] phase 2 = axis-0 marching kernel + paired y-marching kernel
+		int launched = 0;
+		if (phase != 2) {
+			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8));
+			a.g_out = s.scratch_a;
+			a.warp_out = nullptr;
+			const int chunk_x = marching_chunk(x_end - x_begin, tiles, 0, 3);
+			const int status = plan.tikhonov ? launch_stage1_fused_update<true, true>(s.maps, a, chunk_x, stream)
+					: launch_stage1_fused_update<false, true>(s.maps, a, chunk_x, stream);
+			if (status < 0) return status;
+			launched++;
+		}
+		if (phase == 1) return launched;
+		float* filtered = s.g_post;
+		if (plan.taps.radius == 1) launch_slab_filter<1>(plan.taps, a, s.scratch_a, s.scratch_h, filtered, s.warp, stream);
+		else if (plan.taps.radius == 2) launch_slab_filter<2>(plan.taps, a, s.scratch_a, s.scratch_h, filtered, s.warp, stream);
+		else launch_slab_filter<3>(plan.taps, a, s.scratch_a, s.scratch_h, filtered, s.warp, stream);
+		return launched + 2;
 	}
 	a.g_out = s.scratch_a;
 	if (phase != 2) {
@@ -750,7 +778,12 @@ extern "C" int lsf_hier_slab_iteration(const lsf_hier_params* params, const lsf_
 	s.pack_interior_low = level->pack_interior_low;
 	s.pack_interior_high = level->pack_interior_high;
 	s.violation = level->violation;
-	enqueue_iteration(plan, s, iteration, true, stream, nullptr, phase);
+	const char* slab_fast = getenv("LSF_SLAB_FAST");
+	plan.slab_fast = !(slab_fast && slab_fast[0] == '0');
+	Arena arena(stream);
+	if (plan.slab_fast && plan.use_kernel && phase == 2) LSF_TRY(arena.alloc(&s.scratch_h, (size_t) s.g.N * 3));
+	const int launched = enqueue_iteration(plan, s, iteration, true, stream, nullptr, phase);
+	LSF_TRY(launched);
 	LSF_CUDA(cudaGetLastError());
 	return LSF_OK;
 }

@@ -47,50 +47,6 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b, f32x2 neg) {
 	return r;
 }
 
-// trilinear gather with packed blends (arithmetic and citations: gather4i / gather4i_slab); the voxel's coordinates
-// arrive as floats (hoisted conversions)
-template<bool SLAB>
-__device__ __forceinline__ float4 gather4q(const HierIterArgs& a, int sx, int sy, float fx, float fy, float fz, float wx,
-		float wy, float wz, f32x2 one) {
-	const float lookup_x = fx + wx;
-	const float lookup_y = fy + wy;
-	const float lookup_z = fz + wz;
-	int bx = __float2int_rd(lookup_x);
-	int by = __float2int_rd(lookup_y);
-	int bz = __float2int_rd(lookup_z);
-	const float rx = lookup_x - (float) bx, ry = lookup_y - (float) by, rz = lookup_z - (float) bz;
-	const float ix = 1.0f - rx, iy = 1.0f - ry, iz = 1.0f - rz;
-	if (SLAB) {
-		bx = min(max(bx, -2), a.X_global) - a.pack_origin;
-		if ((a.pack_interior_low && bx < 0) || (a.pack_interior_high && bx + 1 > a.pack_X - 1)) {
-			if (a.violation != nullptr) *a.violation = 1;
-		}
-		bx = min(max(bx, -2), a.pack_X);
-	} else {
-		bx = min(max(bx, -2), a.g.X);
-	}
-	by = min(max(by, -2), a.g.Y);
-	bz = min(max(bz, -2), a.g.Z);
-	const ulonglong2* p = reinterpret_cast<const ulonglong2*>(a.pack) + ((bx + 2) * sx + (by + 2) * sy + (bz + 2));
-	const ulonglong2 v000 = __ldg(p), v001 = __ldg(p + 1);
-	const ulonglong2 v010 = __ldg(p + sy), v011 = __ldg(p + sy + 1);
-	const ulonglong2 v100 = __ldg(p + sx), v101 = __ldg(p + sx + 1);
-	const ulonglong2 v110 = __ldg(p + sx + sy), v111 = __ldg(p + sx + sy + 1);
-	const f32x2 izz = pack2(iz, iz), rzz = pack2(rz, rz);
-	const ulonglong2 i00 = blend4(v000, v001, izz, rzz, one);
-	const ulonglong2 i01 = blend4(v010, v011, izz, rzz, one);
-	const ulonglong2 i10 = blend4(v100, v101, izz, rzz, one);
-	const ulonglong2 i11 = blend4(v110, v111, izz, rzz, one);
-	const f32x2 iyy = pack2(iy, iy), ryy = pack2(ry, ry);
-	const ulonglong2 i0 = blend4(i00, i01, iyy, ryy, one);
-	const ulonglong2 i1 = blend4(i10, i11, iyy, ryy, one);
-	const ulonglong2 o = blend4(i0, i1, pack2(ix, ix), pack2(rx, rx), one);
-	float4 s;
-	unpack2(o.x, s.x, s.y);
-	unpack2(o.y, s.z, s.w);
-	return s;
-}
-
 template<bool TIKHONOV, int TY>
 struct PairTile {
 	static constexpr int TZ = 64;                     // voxels per block along z (32 lanes x 2)
@@ -526,7 +482,7 @@ inline bool ymarch2_supported(const Grid3& g, const float* h, const float* filte
 
 template<int R>
 void launch_ymarch2(const Taps& taps, const HierIterArgs& a, const float* h, float* filtered, float* warp, int y_chunk,
-		cudaStream_t stream) {
+		cudaStream_t stream, int x_begin = 0, int planes = -1) {
 	const Grid3& g = a.g;
 	YMarch2Args f;
 	f.in = h;
@@ -542,13 +498,118 @@ void launch_ymarch2(const Taps& taps, const HierIterArgs& a, const float* h, flo
 	f.iteration = a.iteration;
 	f.check_convergence = a.check_convergence;
 	f.y_chunk = y_chunk;
-	f.x_begin = 0;
+	f.x_begin = x_begin;
 	f.tile_z = std::min(512, (int) div_up(g.Z, 64) * 64);
 	const int tiles = div_up(g.Z, f.tile_z);
-	const dim3 grid(tiles, g.X, div_up(g.Y, y_chunk));
+	const dim3 grid(tiles, planes < 0 ? g.X : planes, div_up(g.Y, y_chunk));
 	const int threads = f.tile_z / 2 + (tiles > 1 ? 32 : 0);
 	const size_t shared = (size_t) 12 * (f.tile_z + 8) * sizeof(float);
 	k_sobolev_ymarch2<R> <<<counted(grid), threads, shared, stream>>>(f);
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------- axis-0 pass alone
+// Slab mode (slab.py) exchanges the halo planes of the unfiltered gradient between stage 1 and the filter, so the
+// axis-0 pass cannot ride on stage 1 there: this kernel does it on its own (reference convolution.cpp:240-267), a thread
+// marching along axis 0 with one z pair. Planes outside the allocation count as zeros (the allocation's halo planes
+// beyond the volume are zero as well).
+struct XMarchArgs {
+	const float* in;
+	float* out;
+	int X, Y, Z;           // allocation
+	int x_begin, x_end;    // output planes
+	unsigned long long k2[7];
+	unsigned long long one2;
+	unsigned* max_sq_bits;
+	float threshold;
+	int iteration, check_convergence;
+	int chunk;
+};
+
+#ifdef __CUDACC__
+template<int R>
+static __global__ void __launch_bounds__(256) k_hier_xmarch(const __grid_constant__ XMarchArgs a) {
+	constexpr int K = 2 * R + 1;
+	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
+	const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pair >= a.Y * a.Z / 2) return;
+	const int YZ = a.Y * a.Z;
+	const int N = a.X * YZ;
+	const int xs = a.x_begin + blockIdx.y * a.chunk;
+	const int xe = min(a.x_end, xs + a.chunk);
+	const int x_first = max(xs - R, 0), x_stop = xe + R;
+	const f32x2 one = a.one2;
+	f32x2 acc[3][K];
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int q = 0; q < K; q++) acc[c][q] = 0ull;
+	int at = x_first * YZ + 2 * pair;
+	f32x2 next[3];
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		const float2 v = __ldg(reinterpret_cast<const float2*>(a.in + c * N + at));
+		next[c] = pack2(v.x, v.y);
+	}
+#pragma unroll 1
+	for (int x = x_first; x < x_stop; x++, at += YZ) {
+		const f32x2 v0 = next[0], v1 = next[1], v2 = next[2];
+		if (x + 1 < a.X && x + 1 < x_stop) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const float2 v = __ldg(reinterpret_cast<const float2*>(a.in + c * N + at + YZ));
+				next[c] = pack2(v.x, v.y);
+			}
+		} else {
+			next[0] = next[1] = next[2] = 0ull;
+		}
+#pragma unroll
+		for (int q = K - 1; q >= 1; q--) {
+			acc[0][q] = add2(acc[0][q - 1], mul2(v0, a.k2[q]), one);
+			acc[1][q] = add2(acc[1][q - 1], mul2(v1, a.k2[q]), one);
+			acc[2][q] = add2(acc[2][q - 1], mul2(v2, a.k2[q]), one);
+		}
+		acc[0][0] = mul2(v0, a.k2[0]);
+		acc[1][0] = mul2(v1, a.k2[0]);
+		acc[2][0] = mul2(v2, a.k2[0]);
+		if (x - R >= xs) {
+			const int o = at - R * YZ;
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				float2 v;
+				unpack2(acc[c][K - 1], v.x, v.y);
+				*reinterpret_cast<float2*>(a.out + c * N + o) = v;
+			}
+		}
+	}
+}
+
+// Filter phase of a slab iteration: axis-0 pass of planes [x_begin, x_end) into `h`, then the paired y-marching kernel
+// (axes 1 and 2, warp update, max-norm).
+template<int R>
+void launch_slab_filter(const Taps& taps, const HierIterArgs& a, const float* in, float* h, float* filtered, float* warp,
+		cudaStream_t stream) {
+	XMarchArgs f;
+	f.in = in;
+	f.out = h;
+	f.X = a.g.X;
+	f.Y = a.g.Y;
+	f.Z = a.g.Z;
+	f.x_begin = a.x_begin;
+	f.x_end = a.x_end;
+	for (int q = 0; q < 7; q++) f.k2[q] = dup2(q < 2 * R + 1 ? taps.k[q] : 0.0f);
+	f.one2 = dup2(1.0f);
+	f.max_sq_bits = a.max_sq_bits;
+	f.threshold = a.threshold;
+	f.iteration = a.iteration;
+	f.check_convergence = a.check_convergence;
+	const int planes = a.x_end - a.x_begin;
+	const int plane_blocks = (int) div_up((long long) f.Y * f.Z / 2, 256);
+	f.chunk = marching_chunk(planes, plane_blocks, 2 * R, 3);
+	k_hier_xmarch<R> <<<counted(dim3(plane_blocks, (unsigned) div_up(planes, f.chunk))), 256, 0, stream>>>(f);
+	const int tiles = (int) div_up(a.g.Z, 512);
+	const int y_chunk = marching_chunk(a.g.Y, tiles * planes, 2 * R, 6);
+	launch_ymarch2<R>(taps, a, h, filtered, warp, y_chunk, stream, a.x_begin, planes);
 }
 #endif  // __CUDACC__
 

@@ -193,6 +193,50 @@ __device__ __forceinline__ float4 gather4p(const float4* __restrict__ pack, int 
 	return s;
 }
 
+// trilinear gather with packed blends (arithmetic and citations: gather4i / gather4i_slab); the voxel's coordinates
+// arrive as floats (hoisted conversions)
+template<bool SLAB>
+__device__ __forceinline__ float4 gather4q(const HierIterArgs& a, int sx, int sy, float fx, float fy, float fz, float wx,
+		float wy, float wz, f32x2 one) {
+	const float lookup_x = fx + wx;
+	const float lookup_y = fy + wy;
+	const float lookup_z = fz + wz;
+	int bx = __float2int_rd(lookup_x);
+	int by = __float2int_rd(lookup_y);
+	int bz = __float2int_rd(lookup_z);
+	const float rx = lookup_x - (float) bx, ry = lookup_y - (float) by, rz = lookup_z - (float) bz;
+	const float ix = 1.0f - rx, iy = 1.0f - ry, iz = 1.0f - rz;
+	if (SLAB) {
+		bx = min(max(bx, -2), a.X_global) - a.pack_origin;
+		if ((a.pack_interior_low && bx < 0) || (a.pack_interior_high && bx + 1 > a.pack_X - 1)) {
+			if (a.violation != nullptr) *a.violation = 1;
+		}
+		bx = min(max(bx, -2), a.pack_X);
+	} else {
+		bx = min(max(bx, -2), a.g.X);
+	}
+	by = min(max(by, -2), a.g.Y);
+	bz = min(max(bz, -2), a.g.Z);
+	const ulonglong2* p = reinterpret_cast<const ulonglong2*>(a.pack) + ((bx + 2) * sx + (by + 2) * sy + (bz + 2));
+	const ulonglong2 v000 = __ldg(p), v001 = __ldg(p + 1);
+	const ulonglong2 v010 = __ldg(p + sy), v011 = __ldg(p + sy + 1);
+	const ulonglong2 v100 = __ldg(p + sx), v101 = __ldg(p + sx + 1);
+	const ulonglong2 v110 = __ldg(p + sx + sy), v111 = __ldg(p + sx + sy + 1);
+	const f32x2 izz = pack2(iz, iz), rzz = pack2(rz, rz);
+	const ulonglong2 i00 = blend4(v000, v001, izz, rzz, one);
+	const ulonglong2 i01 = blend4(v010, v011, izz, rzz, one);
+	const ulonglong2 i10 = blend4(v100, v101, izz, rzz, one);
+	const ulonglong2 i11 = blend4(v110, v111, izz, rzz, one);
+	const f32x2 iyy = pack2(iy, iy), ryy = pack2(ry, ry);
+	const ulonglong2 i0 = blend4(i00, i01, iyy, ryy, one);
+	const ulonglong2 i1 = blend4(i10, i11, iyy, ryy, one);
+	const ulonglong2 o = blend4(i0, i1, pack2(ix, ix), pack2(rx, rx), one);
+	float4 s;
+	unpack2(o.x, s.x, s.y);
+	unpack2(o.y, s.z, s.w);
+	return s;
+}
+
 // ---------------------------------------------------------------------------------------------- stage 1 + axis-0 pass
 template<bool TIKHONOV>
 struct Stage1Tile {
@@ -215,7 +259,7 @@ struct Stage1Tile {
 // kernel reads the warp BEFORE that update from a.warp, applies `warp - g_prev * rate` (reference optimizer.tpp:207,
 // the same two roundings, one kernel later) for the gather and writes the updated warp of its own planes to
 // a.warp_out (a different buffer: neighbouring x-chunks still read the old planes). One warp read less per iteration.
-template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false, int PD = 0, bool APPLY = false>
+template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false, int PD = 0, bool APPLY = false, bool SLAB = false>
 static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_constant__ CUtensorMap map_g,
 		const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
 		const __grid_constant__ CUtensorMap map_p, HierIterArgs a, XPassArgs t) {
@@ -233,8 +277,11 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 	const bool valid = z < Z && y < Y;
 	const int YZ = Y * Z;
 	const int N = (int) a.g.N;
-	const int xs = blockIdx.z * t.x_chunk;
-	const int xe = min(X, xs + t.x_chunk);
+	// SLAB (slab decomposition, slab.py): the fields are an allocation of X planes of which [x_begin, x_end) are processed;
+	// allocation plane p is plane p + x_origin of a level of X_global planes (border rules, gather look-ups)
+	const int xs = (SLAB ? a.x_begin : 0) + blockIdx.z * t.x_chunk;
+	const int xe = min(SLAB ? a.x_end : X, xs + t.x_chunk);
+	const int origin = SLAB ? a.x_origin : 0, Xg = SLAB ? a.X_global : X;
 	// FUSE (no Sobolev kernel configured): no filter pass, the warp update and the max-norm (reference
 	// optimizer.tpp:207-211) happen here and the kernel is the whole iteration
 	const int x_first = FUSE ? xs : max(xs - R, 0);  // planes below 0 contribute zeros to accumulators that are still zero
@@ -315,11 +362,11 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 			}
 			float lap[3] = { 0.f, 0.f, 0.f };
 			if (TIKHONOV) {
-				const bool has_next = x + 1 < X;
+				const bool has_next = x + origin + 1 < Xg;
 				if (has_next) mbar_wait(&full[next_slot], next_slot == 0 ? phase ^ 1u : phase);
 				const uint32_t nst = stage_base + next_slot * T::STAGE_BYTES;
-				if (yz_border || x == 0 || !has_next) {
-					const int kind_x = border_kind(x, X);
+				if (yz_border || x + origin == 0 || !has_next) {
+					const int kind_x = border_kind(x + origin, Xg);
 #pragma unroll
 					for (int c = 0; c < 3; c++) {
 						const uint32_t p = st + off_g + c * G_COMP;
@@ -378,7 +425,8 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 					tma_prefetch_3d(&map_p, 4 * (bz + 2 - T::PACK_BOX_Z0), by + 2 - T::PACK_BOX_Y0, bx + 2);
 				}
 			}
-			const float4 s = gather4p(a.pack, X, Y, Z, x, y, z, wx, wy, wz, t.one2);
+			const float4 s = SLAB ? gather4q<true>(a, (Y + 4) * (Z + 4), Z + 4, (float) (x + origin), (float) y, (float) z, wx, wy,
+					wz, t.one2) : gather4p(a.pack, X, Y, Z, x, y, z, wx, wy, wz, t.one2);
 			const float diff = s.x - cn;
 			g[0] = (s.y * diff) * a.amplifier;
 			g[1] = (s.z * diff) * a.amplifier;
@@ -395,13 +443,15 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 					a.g_out[N + at] = g[1];
 					a.g_out[2 * N + at] = g[2];
 				}
-				a.warp_out[at] = wx - g[0] * a.rate;
-				a.warp_out[N + at] = wy - g[1] * a.rate;
-				a.warp_out[2 * N + at] = wz - g[2] * a.rate;
-				float sq = g[0] * g[0];
-				sq += g[1] * g[1];
-				sq += g[2] * g[2];
-				if (sq > best) best = sq;
+				if (a.warp_out != nullptr) {  // nullptr: gradient only (slab mode, the filter phase updates the warp)
+					a.warp_out[at] = wx - g[0] * a.rate;
+					a.warp_out[N + at] = wy - g[1] * a.rate;
+					a.warp_out[2 * N + at] = wz - g[2] * a.rate;
+					float sq = g[0] * g[0];
+					sq += g[1] * g[1];
+					sq += g[2] * g[2];
+					if (sq > best) best = sq;
+				}
 			}
 		}
 		if (!FUSE) {
@@ -430,7 +480,7 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 			phase ^= 1u;
 		}
 	}
-	if (FUSE) block_atomic_max(best, a.max_sq_bits + a.iteration);
+	if (FUSE && a.warp_out != nullptr) block_atomic_max(best, a.max_sq_bits + a.iteration);
 }
 
 // ---------------------------------------------------------------------------------------------- axis-1 / axis-2 passes
@@ -582,7 +632,7 @@ int ensure_maps(TmaMaps& maps, const Grid3& g, const float* warp, const float* c
 template<typename T>
 int ensure_pack_map(TmaMaps& maps, const HierIterArgs& a) {
 	if (maps.pack_key == a.pack) return LSF_OK;
-	LSF_TRY(make_pack_map(&maps.pack, a.pack, a.g.X, a.g, T::PACK_BOX_Z, T::PACK_BOX_Y));
+	LSF_TRY(make_pack_map(&maps.pack, a.pack, a.pack_X, a.g, T::PACK_BOX_Z, T::PACK_BOX_Y));
 	maps.pack_key = a.pack;
 	return LSF_OK;
 }
@@ -627,7 +677,7 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 
 // Whole iteration when no Sobolev kernel is configured: stage 1 + warp update + max-norm in one TMA-fed kernel.
 // g_out (planes, may be nullptr without the Tikhonov term) must not alias a.g_prev; a.warp_out may alias a.warp.
-template<bool TIKHONOV>
+template<bool TIKHONOV, bool SLAB = false>
 int launch_stage1_fused_update(TmaMaps& maps, HierIterArgs a, int x_chunk, cudaStream_t stream) {
 	typedef Stage1Tile<TIKHONOV> T;
 	constexpr int NS = 4;
@@ -636,22 +686,22 @@ int launch_stage1_fused_update(TmaMaps& maps, HierIterArgs a, int x_chunk, cudaS
 	for (int q = 0; q < 7; q++) t.k[q] = 0.0f;
 	t.x_chunk = x_chunk;
 	t.one2 = F32X2_ONE;
-	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), div_up(a.g.X, x_chunk));
+	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), div_up(a.x_end - a.x_begin, x_chunk));
 	const size_t shared = (size_t) NS * T::STAGE_BYTES;
 	LSF_TRY(ensure_pack_map<T>(maps, a));
 	static bool configured = false;
 	if (!configured) {
-		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 0>,
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 0, false, SLAB>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
-		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 2>,
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 2, false, SLAB>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
 		configured = true;
 	}
-	if (l2_prefetch_enabled(true))
-		k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 2> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
+	if (!SLAB && l2_prefetch_enabled(true))
+		k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 2, false, SLAB> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
 				maps.canonical, maps.pack, a, t);
 	else
-		k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 0> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
+		k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 0, false, SLAB> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
 				maps.canonical, maps.pack, a, t);
 	return LSF_OK;
 }
