@@ -217,7 +217,12 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			ra.max_sq_bits = max_sq_bits + it;
 			ra.status = status;
 			ra.iteration = it;
-			k_slav_resample<D> <<<counted(blocks), 256, 0, stream>>>(ra);
+			auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+			if (D == 3 && fast_filter && g.n[2] % 4 == 0 && aligned16(ra.update) && aligned16(ra.live) && aligned16(ra.canonical)
+					&& aligned16(ra.warp) && aligned16(ra.new_live))
+				k_slav_resample_v4<D> <<<counted(blocks_for(g.N / 4)), 256, 0, stream>>>(ra);  // four voxels per thread
+			else
+				k_slav_resample<D> <<<counted(blocks), 256, 0, stream>>>(ra);
 			k_slav_decide<<<counted(1u), 1, 0, stream>>>(p, max_sq_bits, status, it, max_iterations);
 			// the filtered field becomes the persistent gradient field read as `stale` next iteration; the live buffers
 			// swap. Both swaps also happen for iterations the device skips (status set): skipped kernels write nothing,

@@ -459,6 +459,112 @@ static __global__ void __launch_bounds__(256) k_slav_filter_axis(SlavFilterArgs 
 // reference warp_2d_advanced, cpp/src/nonrigid_optimization/field_warping.cpp:64-136 (float32), and its Python twin
 // nonrigid_opt/field_warping.py:112-151 + utils/sampling.py:160-215 (float64 interpolation), followed by the
 // maximum warp length (statistics.tpp:57-100; slavcheva_optimizer2d.py:309-318 measures BEFORE the re-warp).
+// one voxel of the re-warp: `update` = its filtered update vector, live_value / canonical_value = the fields at the voxel;
+// returns the new live value, the voxel's new warp vector and its contribution to the maximum warp length
+template<int D>
+__device__ __forceinline__ void slav_resample_voxel(const SlavResampleArgs& a, int idx, const float (&update)[3],
+		float live_value, float canonical_value, float& new_value, float (&w)[3], float& sq_report) {
+	const SlavGeom& g = a.g;
+	const bool python = a.p.semantics != LSF_SEMANTICS_CPP;
+	const bool float64 = a.p.semantics == LSF_SEMANTICS_PY_DIRECT;
+#pragma unroll
+	for (int c = 0; c < 3; c++) w[c] = 0.0f;
+#pragma unroll
+	for (int c = 0; c < D; c++) w[c] = python ? -update[c] * a.p.rate : update[c];
+	float sq_before = 0.0f;
+#pragma unroll
+	for (int c = 0; c < D; c++) sq_before += w[c] * w[c];
+	bool skip = false;
+	if (a.band_union_only && slav_truncated(live_value) && slav_truncated(canonical_value)) skip = true;
+	if (!skip && a.known_values_only && (float64 ? live_value == 1.0f : fabsf(live_value) == 1.0f)) skip = true;
+	new_value = live_value;
+	if (!skip) {
+		int pos[3];
+		slav_coords<D>(g, idx, pos);
+		int base[3] = { 0, 0, 0 };
+		const float oob = a.substitute_original ? live_value : 1.0f;
+		double result;
+		if (float64) {
+			double ratio[3] = { 0, 0, 0 };
+#pragma unroll
+			for (int c = 0; c < D; c++) {
+				const int ax = slav_axis<D>(g, c);
+				const double lookup = (double) pos[ax] + (double) w[c];
+				const double fl = floor(lookup);
+				base[ax] = (int) fl;
+				ratio[ax] = lookup - fl;
+			}
+			double value[1 << D];
+#pragma unroll
+			for (int corner = 0; corner < (1 << D); corner++) {
+				int q[3] = { 0, 0, 0 };
+#pragma unroll
+				for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
+				value[corner] = (double) (slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob);
+			}
+#pragma unroll
+			for (int c = D - 1; c >= 0; c--) {
+				const int ax = slav_axis<D>(g, c);
+#pragma unroll
+				for (int corner = 0; corner < (1 << D); corner++) {
+					if ((corner >> ax) & 1) continue;
+					value[corner] = value[corner] * (1.0 - ratio[ax]) + value[corner | (1 << ax)] * ratio[ax];
+				}
+			}
+			result = value[0];
+			new_value = (float) result;
+		} else {
+			float ratio[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+			for (int c = 0; c < D; c++) {
+				const int ax = slav_axis<D>(g, c);
+				const float lookup = (float) pos[ax] + w[c];
+				base[ax] = __float2int_rd(lookup);
+				ratio[ax] = lookup - (float) base[ax];
+			}
+			float value[1 << D];
+#pragma unroll
+			for (int corner = 0; corner < (1 << D); corner++) {
+				int q[3] = { 0, 0, 0 };
+#pragma unroll
+				for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
+				value[corner] = slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob;
+			}
+			// interpolation along the last component's axis first (reference field_warping.tpp:126-134,187-189)
+#pragma unroll
+			for (int c = D - 1; c >= 0; c--) {
+				const int ax = slav_axis<D>(g, c);
+				const float r = ratio[ax], inverse = 1.0f - r;
+#pragma unroll
+				for (int corner = 0; corner < (1 << D); corner++) {
+					if ((corner >> ax) & 1) continue;
+					value[corner] = value[corner] * inverse + value[corner | (1 << ax)] * r;
+				}
+			}
+			new_value = value[0];
+			result = (double) new_value;
+		}
+		const bool snaps = float64 ? (1.0 - fabs(result) < 1e-6) : (1.0 - fabs((double) new_value) < (double) a.threshold);
+		if (a.modify_warp && snaps) {
+			if (float64) new_value = result > 0.0 ? 1.0f : (result < 0.0 ? -1.0f : 0.0f);
+			else new_value = copysignf(1.0f, new_value);
+#pragma unroll
+			for (int c = 0; c < D; c++) w[c] = 0.0f;
+			if (a.gradient_field != nullptr) {
+#pragma unroll
+				for (int c = 0; c < D; c++) a.gradient_field[c * g.N + idx] = 0.0f;
+			}
+		}
+	}
+	if (python) sq_report = fmaxf(sq_report, sq_before);
+	else {
+		float sq = 0.0f;
+#pragma unroll
+		for (int c = 0; c < D; c++) sq += w[c] * w[c];
+		sq_report = fmaxf(sq_report, sq);
+	}
+}
+
 template<int D>
 static __global__ void __launch_bounds__(256) k_slav_resample(SlavResampleArgs a) {
 	if (a.status != nullptr && a.status[a.iteration]) return;
@@ -467,110 +573,53 @@ static __global__ void __launch_bounds__(256) k_slav_resample(SlavResampleArgs a
 	float sq_report = 0.0f;
 	if (linear < g.N) {
 		const int idx = (int) linear;
-		const bool python = a.p.semantics != LSF_SEMANTICS_CPP;
-		const bool float64 = a.p.semantics == LSF_SEMANTICS_PY_DIRECT;
-		float w[3] = { 0.f, 0.f, 0.f };
+		float update[3] = { 0.f, 0.f, 0.f }, w[3], new_value;
 #pragma unroll
-		for (int c = 0; c < D; c++) {
-			const float u = __ldg(a.update + c * g.N + idx);
-			w[c] = python ? -u * a.p.rate : u;
-		}
-		float sq_before = 0.0f;
-#pragma unroll
-		for (int c = 0; c < D; c++) sq_before += w[c] * w[c];
+		for (int c = 0; c < D; c++) update[c] = __ldg(a.update + c * g.N + idx);
 		const float live_value = __ldg(a.live + idx);
-		bool skip = false;
-		if (a.band_union_only && slav_truncated(live_value) && slav_truncated(__ldg(a.canonical + idx))) skip = true;
-		if (!skip && a.known_values_only && (float64 ? live_value == 1.0f : fabsf(live_value) == 1.0f)) skip = true;
-		float new_value = live_value;
-		if (!skip) {
-			int pos[3];
-			slav_coords<D>(g, idx, pos);
-			int base[3] = { 0, 0, 0 };
-			const float oob = a.substitute_original ? live_value : 1.0f;
-			double result;
-			if (float64) {
-				double ratio[3] = { 0, 0, 0 };
-#pragma unroll
-				for (int c = 0; c < D; c++) {
-					const int ax = g.comp_axis[c];
-					const double lookup = (double) pos[ax] + (double) w[c];
-					const double fl = floor(lookup);
-					base[ax] = (int) fl;
-					ratio[ax] = lookup - fl;
-				}
-				double value[1 << D];
-#pragma unroll
-				for (int corner = 0; corner < (1 << D); corner++) {
-					int q[3] = { 0, 0, 0 };
-#pragma unroll
-					for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
-					value[corner] = (double) (slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob);
-				}
-#pragma unroll
-				for (int c = D - 1; c >= 0; c--) {
-					const int ax = g.comp_axis[c];
-#pragma unroll
-					for (int corner = 0; corner < (1 << D); corner++) {
-						if ((corner >> ax) & 1) continue;
-						value[corner] = value[corner] * (1.0 - ratio[ax]) + value[corner | (1 << ax)] * ratio[ax];
-					}
-				}
-				result = value[0];
-				new_value = (float) result;
-			} else {
-				float ratio[3] = { 0.f, 0.f, 0.f };
-#pragma unroll
-				for (int c = 0; c < D; c++) {
-					const int ax = g.comp_axis[c];
-					const float lookup = (float) pos[ax] + w[c];
-					base[ax] = __float2int_rd(lookup);
-					ratio[ax] = lookup - (float) base[ax];
-				}
-				float value[1 << D];
-#pragma unroll
-				for (int corner = 0; corner < (1 << D); corner++) {
-					int q[3] = { 0, 0, 0 };
-#pragma unroll
-					for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
-					value[corner] = slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob;
-				}
-				// interpolation along the last component's axis first (reference field_warping.tpp:126-134,187-189)
-#pragma unroll
-				for (int c = D - 1; c >= 0; c--) {
-					const int ax = g.comp_axis[c];
-					const float r = ratio[ax], inverse = 1.0f - r;
-#pragma unroll
-					for (int corner = 0; corner < (1 << D); corner++) {
-						if ((corner >> ax) & 1) continue;
-						value[corner] = value[corner] * inverse + value[corner | (1 << ax)] * r;
-					}
-				}
-				new_value = value[0];
-				result = (double) new_value;
-			}
-			const bool snaps = float64 ? (1.0 - fabs(result) < 1e-6) : (1.0 - fabs((double) new_value) < (double) a.threshold);
-			if (a.modify_warp && snaps) {
-				if (float64) new_value = result > 0.0 ? 1.0f : (result < 0.0 ? -1.0f : 0.0f);
-				else new_value = copysignf(1.0f, new_value);
-#pragma unroll
-				for (int c = 0; c < D; c++) w[c] = 0.0f;
-				if (a.gradient_field != nullptr) {
-#pragma unroll
-					for (int c = 0; c < D; c++) a.gradient_field[c * g.N + idx] = 0.0f;
-				}
-			}
-		}
+		const float canonical_value = a.band_union_only ? __ldg(a.canonical + idx) : 0.0f;
+		slav_resample_voxel<D>(a, idx, update, live_value, canonical_value, new_value, w, sq_report);
 		a.new_live[idx] = new_value;
 		if (a.warp != nullptr) {
 #pragma unroll
 			for (int c = 0; c < D; c++) a.warp[c * g.N + idx] = w[c];
 		}
-		if (python) sq_report = sq_before;
-		else {
+	}
+	if (a.max_sq_bits != nullptr) block_atomic_max(sq_report, a.max_sq_bits);
+}
+
+// The same re-warp with four consecutive voxels of the last axis per thread (128-bit loads and stores; four voxels'
+// loads in flight per thread). Requires n[D-1] % 4 == 0, 16-byte aligned fields and a warp output.
+template<int D>
+static __global__ void __launch_bounds__(256) k_slav_resample_v4(SlavResampleArgs a) {
+	if (a.status != nullptr && a.status[a.iteration]) return;
+	const SlavGeom& g = a.g;
+	const long long group = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	float sq_report = 0.0f;
+	if (group * 4 < g.N) {
+		const int base = (int) (group * 4);
+		float4 u4[3];
 #pragma unroll
-			for (int c = 0; c < D; c++) sq_report += w[c] * w[c];
+		for (int c = 0; c < D; c++) u4[c] = __ldg(reinterpret_cast<const float4*>(a.update + c * g.N + base));
+		const float4 live4 = __ldg(reinterpret_cast<const float4*>(a.live + base));
+		const float4 canonical4 = a.band_union_only ? __ldg(reinterpret_cast<const float4*>(a.canonical + base))
+				: make_float4(0.f, 0.f, 0.f, 0.f);
+		const float live_v[4] = { live4.x, live4.y, live4.z, live4.w };
+		const float canonical_v[4] = { canonical4.x, canonical4.y, canonical4.z, canonical4.w };
+		float out_live[4], out_w[3][4];
+#pragma unroll
+		for (int v = 0; v < 4; v++) {
+			float update[3] = { 0.f, 0.f, 0.f }, w[3];
+#pragma unroll
+			for (int c = 0; c < D; c++) update[c] = v == 0 ? u4[c].x : (v == 1 ? u4[c].y : (v == 2 ? u4[c].z : u4[c].w));
+			slav_resample_voxel<D>(a, base + v, update, live_v[v], canonical_v[v], out_live[v], w, sq_report);
+#pragma unroll
+			for (int c = 0; c < D; c++) out_w[c][v] = w[c];
 		}
+		*reinterpret_cast<float4*>(a.new_live + base) = make_float4(out_live[0], out_live[1], out_live[2], out_live[3]);
+#pragma unroll
+		for (int c = 0; c < D; c++)
+			*reinterpret_cast<float4*>(a.warp + c * g.N + base) = make_float4(out_w[c][0], out_w[c][1], out_w[c][2], out_w[c][3]);
 	}
 	if (a.max_sq_bits != nullptr) block_atomic_max(sq_report, a.max_sq_bits);
 }

@@ -354,6 +354,15 @@ def test_tma_generation_matches_previous_generations(lsf, mode, taps, monkeypatc
     assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
     monkeypatch.delenv("LSF_XCHUNK_T")
     monkeypatch.delenv("LSF_YCHUNK_T")
+    # fourth-generation switches one at a time: warp update inside the filter kernel instead of deferred into the next
+    # stage 1, one-voxel-per-thread y-marching filter, block barrier per plane in stage 1, L2 prefetch of the pack
+    for switches in ({"LSF_DEFER": "0"}, {"LSF_DEFER": "0", "LSF_YMARCH2": "0"}, {"LSF_DEFER": "0", "LSF_DECOUPLE": "0"},
+                     {"LSF_L2PF": "1"}):
+        for name, value in switches.items():
+            monkeypatch.setenv(name, value)
+        assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast), switches
+        for name in switches:
+            monkeypatch.delenv(name)
     monkeypatch.setenv("LSF_TMA", "0")
     assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
     monkeypatch.setenv("LSF_LEGACY_KERNELS", "1")
