@@ -168,7 +168,12 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			ga.out = field_a;
 			ga.status = status;
 			ga.iteration = it;
-			k_slav_gradient<D> <<<counted(blocks), 256, 0, stream>>>(ga);
+			auto aligned_field = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+			if (D == 3 && cpp && fast_filter && g.n[2] % 4 == 0 && aligned_field(ga.live) && aligned_field(ga.canonical)
+					&& aligned_field(ga.out))
+				k_slav_gradient_cpp3_v4<<<counted(blocks_for(g.N / 4)), 256, 0, stream>>>(ga);  // four voxels per thread
+			else
+				k_slav_gradient<D> <<<counted(blocks), 256, 0, stream>>>(ga);
 			float* final_field = field_a;
 			if (use_kernel) {
 				SlavFilterArgs fa;
