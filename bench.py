@@ -252,6 +252,8 @@ def run_ours(args):
             "peak_source": peak_source,
             "other_term_configurations": other,
         }
+        # -------------------------------------------------------------- BASELINE.json configs[2]: 3D KillingFusion at 256^3
+        other_workloads = {"killingfusion3d_%d" % size: killingfusion_iteration(lsf_b200, canonical, live, size, peak)}
         # -------------------------------------------------------------- CPU baseline (oracle port), bounded sample
         cpu = cpu_baseline_sample(size, kwargs)
         value = updates / (elapsed_ms * 1e-3)
@@ -269,6 +271,7 @@ def run_ours(args):
                     "ms_per_step": 1e3 * e2e_seconds / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "other_workloads": other_workloads,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
@@ -277,6 +280,38 @@ def run_ours(args):
         dist.destroy_process_group()
     if result is not None:
         print(json.dumps(result))
+
+
+def killingfusion_iteration(lsf_b200, canonical, live, size, peak, iterations=10):
+    """ms per iteration of the 3D slavcheva optimizer with the Killing and level-set terms and the 7-tap Sobolev filter
+    (CUDA events around optimize() calls of n and 3n iterations; set-up and read-back cancel in the difference),
+    voxel-updates/s and the fraction of the HBM roofline at SURVEY.md 8(d)'s 36 B per voxel-update."""
+    import torch
+    from lsf_b200 import synthetic
+    from lsf_b200.slavcheva import SmoothingTermMethod
+
+    def run(n):
+        optimizer = lsf_b200.SlavchevaOptimizer3d(max_iterations=n, min_iterations=n, maximum_warp_length_lower_threshold=0.0,
+                                                  sobolev_kernel=synthetic.sobolev_kernel_1d(),
+                                                  smoothing_term_method=SmoothingTermMethod.KILLING,
+                                                  level_set_term_enabled=True)
+        best = None
+        for _ in range(3):
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            start.record()
+            optimizer.optimize(live.clone(), canonical)
+            stop.record()
+            torch.cuda.synchronize()
+            best = start.elapsed_time(stop) if best is None else min(best, start.elapsed_time(stop))
+        return best
+
+    per_iteration = (run(3 * iterations) - run(iterations)) / (2 * iterations)
+    updates = size ** 3 / (per_iteration * 1e-3)
+    achieved = 36 * updates / 1e9
+    return {"ms_per_iteration": round(per_iteration, 4), "value": updates, "unit": UNIT,
+            "terms": "data + Killing + level set, 7-tap Sobolev filter, masked re-warp",
+            "algorithmic_bytes_per_voxel_update": 36, "achieved": round(achieved, 1), "frac": round(achieved / peak, 4)}
 
 
 def cpu_baseline_sample(size, kwargs, iterations=3):

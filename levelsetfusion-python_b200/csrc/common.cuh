@@ -114,11 +114,13 @@ inline int marching_chunk(int extent, int tiles, int lead, int blocks_per_sm) {
 			sm_count = 148;
 	}
 	const long long slots = (long long) sm_count * blocks_per_sm;
+	// without a halo there is nothing to amortise: short marches balance best (measured flat between 10 and 26 planes)
+	if (lead == 0) return extent < 16 ? extent : 16;
 	int best_chunk = extent;
 	long long best_cost = -1;
 	for (int parts = 1; parts <= extent; parts++) {
 		const int chunk = (extent + parts - 1) / parts;
-		if (chunk < 8 && parts > 1) break;
+		if (chunk < 4 && parts > 1) break;
 		const long long blocks = (long long) tiles * ((extent + chunk - 1) / chunk);
 		const long long cost = ((blocks + slots - 1) / slots) * (chunk + lead);
 		if (best_cost < 0 || cost < best_cost) {
