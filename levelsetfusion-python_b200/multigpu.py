@@ -29,8 +29,72 @@ def pair_indices_of_rank(pair_count, rank, world_size):
     return list(range(rank, int(pair_count), world_size))
 
 
-def optimize_pairs(optimize, pair_count, load_pair, rank=None, world_size=None, gather=True, group=None):
+def _run_local_pairs(optimize, indices, load_pair, streams):
+    """This rank's pairs, `streams` of them at a time: each worker thread owns one CUDA stream (the library takes the
+    stream of the calling thread and keeps no shared mutable state), so the launch-bound coarse pyramid levels of one
+    pair overlap the bandwidth-bound fine level of another. `optimize` may be a callable or a factory result per worker:
+    if it has a `clone_for_worker()` method it is cloned per thread (optimizer objects keep per-call reports)."""
+    if streams <= 1 or len(indices) <= 1:
+        return {index: optimize(*load_pair(index)) for index in indices}
+    import threading
+    import torch
+    local, errors, lock = {}, [], threading.Lock()
+    queue = list(indices)
+    device = torch.cuda.current_device()
+
+    def worker():
+        torch.cuda.set_device(device)
+        stream = torch.cuda.Stream()
+        run = optimize.clone_for_worker() if hasattr(optimize, "clone_for_worker") else optimize
+        try:
+            with torch.cuda.stream(stream):
+                while True:
+                    with lock:
+                        if not queue:
+                            break
+                        index = queue.pop(0)
+                    result = run(*load_pair(index))
+                    with lock:
+                        local[index] = result
+            stream.synchronize()
+        except BaseException as error:  # re-raised in the caller's thread
+            with lock:
+                errors.append(error)
+
+    threads = [threading.Thread(target=worker) for _ in range(min(streams, len(indices)))]
+    torch.cuda.current_stream().synchronize()  # inputs produced on the caller's stream are complete
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return local
+
+
+class PerWorkerOptimizer:
+    """Wraps an optimizer factory for optimize_pairs(..., streams=k): every worker thread gets its own optimizer object.
+    `call` maps (optimizer, canonical, live) to the per-pair result (default: the warp field)."""
+
+    def __init__(self, factory, call=None):
+        self.factory = factory
+        self.call = call or (lambda optimizer, canonical, live: optimizer.optimize(canonical, live))
+        self._optimizer = None
+
+    def clone_for_worker(self):
+        return PerWorkerOptimizer(self.factory, self.call)
+
+    def __call__(self, canonical, live):
+        if self._optimizer is None:
+            self._optimizer = self.factory()
+        return self.call(self._optimizer, canonical, live)
+
+
+def optimize_pairs(optimize, pair_count, load_pair, rank=None, world_size=None, gather=True, group=None, streams=1):
     """Runs `optimize(canonical, live)` on this rank's share of `pair_count` independent frame pairs.
+
+    streams    -- pairs in flight per GPU (worker threads with one CUDA stream each, see _run_local_pairs); with more
+                  than one, pass a PerWorkerOptimizer (or any callable that is safe to call from several threads)
 
     optimize   -- callable(canonical, live) -> result (e.g. HierarchicalOptimizer3d(...).optimize, or a lambda that also
                   returns the optimizer's per-level reports)
@@ -42,10 +106,7 @@ def optimize_pairs(optimize, pair_count, load_pair, rank=None, world_size=None, 
     detected_rank, detected_world, _ = world()
     rank = detected_rank if rank is None else rank
     world_size = detected_world if world_size is None else world_size
-    local = {}
-    for index in pair_indices_of_rank(pair_count, rank, world_size):
-        canonical, live = load_pair(index)
-        local[index] = optimize(canonical, live)
+    local = _run_local_pairs(optimize, pair_indices_of_rank(pair_count, rank, world_size), load_pair, int(streams))
     if not gather:
         return local
     if world_size == 1:
