@@ -33,8 +33,13 @@ def make_optimizer(lsf, mode, iterations=12, threshold=0.01):
 
 @pytest.mark.parametrize("mode", sorted(MODES))
 @pytest.mark.parametrize("world_size", [2, 4])
-def test_slabs_match_whole_volume(lsf, mode, world_size):
+@pytest.mark.parametrize("slab_kernels", ["fast", "first_generation"])
+def test_slabs_match_whole_volume(lsf, mode, world_size, slab_kernels, monkeypatch):
+    """slab_kernels: the TMA-fed stage 1 + marching filter kernels of slab mode (default) and the first-generation
+    slab kernels (LSF_SLAB_FAST=0) -- both bit-identical to the whole-volume optimizer"""
     from lsf_b200 import slab, synthetic
+    if slab_kernels == "first_generation":
+        monkeypatch.setenv("LSF_SLAB_FAST", "0")
     canonical, live = synthetic.sphere_plane_pair_3d(64)
     canonical, live = canonical[:, :48, :56].copy(), live[:, :48, :56].copy()
     optimizer = make_optimizer(lsf, mode)
