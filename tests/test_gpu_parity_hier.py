@@ -393,3 +393,24 @@ def test_pair_generation_matches_previous_generations(lsf, mode, taps, monkeypat
     assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
     monkeypatch.setenv("LSF_LEGACY_KERNELS", "1")
     assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast)
+
+
+@pytest.mark.parametrize("threshold", [0.03, 0.05, 0.08])
+def test_deferred_update_with_early_termination(lsf, threshold):
+    """Tikhonov + Sobolev kernel runs defer the warp update into the next stage 1 (ping-pong warp buffers); the level
+    ends after an odd or an even number of iterations depending on the threshold, and iterations enqueued beyond the
+    converged one are skipped on the device. Warp, iteration counts and final update lengths equal the oracle's."""
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(64)
+    kwargs = dict(HIER_MODES["tikhonov_kernel"])
+    kwargs.update(maximum_chunk_size=4, maximum_iteration_count=45, maximum_warp_update_threshold=threshold,
+                  kernel=synthetic.sobolev_kernel_1d())
+    expected = oracle.hier_optimize(canonical, live, **kwargs)
+    optimizer = lsf.HierarchicalOptimizer3d(**kwargs)
+    warp = optimizer.optimize(canonical, live)
+    counts = optimizer.get_per_level_iteration_counts()
+    assert counts == expected["iterations"]
+    assert any(c < 45 for c in counts), counts
+    assert np.array_equal(warp, expected["warp"])
+    reports = optimizer.get_per_level_convergence_reports()
+    assert np.allclose([r.max_update_length for r in reports], expected["max_updates"], rtol=0, atol=0)
