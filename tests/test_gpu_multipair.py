@@ -1,5 +1,7 @@
 """GPU test of the multipair driver (BASELINE.json configs[3]): several pairs in flight per GPU (one CUDA
 stream per worker thread) give exactly the results of the serial loop."""
+import os
+
 import numpy as np
 import pytest
 
@@ -46,3 +48,34 @@ def test_streams_match_serial_loop(lsf):
     with pytest.raises(RuntimeError, match="boom"):
         multigpu.optimize_pairs(multigpu.PerWorkerOptimizer(lambda: lsf.HierarchicalOptimizer3d(**kwargs), failing),
                                 len(pairs), lambda i: pairs[i], rank=0, world_size=1, streams=2)
+
+
+def test_run_multipair_matches_serial_reports(lsf, tmp_path):
+    """the experiment driver (pair cache -> optimize over streams -> report table) against a plain serial loop"""
+    pytest.importorskip("pandas")
+    from lsf_b200 import multipair, synthetic
+    rng = np.random.default_rng(11)
+    data_path, out_path = str(tmp_path / "data"), str(tmp_path / "out")
+    for frame in (3, 12, 7):
+        shift = tuple(np.array([2.5, -1.5, 1.0]) + rng.uniform(-2, 2, 3))
+        canonical, live = synthetic.sphere_plane_pair_3d(32, shift=shift)
+        multipair.save_pair(data_path, frame, 214, canonical, live)
+    kwargs = dict(tikhonov_term_enabled=False, gradient_kernel_enabled=True, kernel=synthetic.sobolev_kernel_1d(),
+                  maximum_chunk_size=4, maximum_iteration_count=12, maximum_warp_update_threshold=0.02,
+                  logging_parameters=lsf.HierarchicalOptimizer3d.LoggingParameters(
+                      collect_per_level_convergence_reports=True))
+    factory = lambda: lsf.HierarchicalOptimizer3d(**kwargs)
+    table = multipair.run_multipair(data_path, out_path, factory, streams=2, save_warps=True)
+    entries = multipair.list_pair_cache(data_path)
+    assert list(table["canonical_frame"]) == [frame for frame, _, _ in entries] == [12, 3, 7]
+    optimizer = factory()
+    report_sets = []
+    for frame, row, path in entries:
+        canonical, live = multipair.load_pair(path)
+        warp = optimizer.optimize(canonical, live)
+        report_sets.append(optimizer.get_per_level_convergence_reports())
+        assert np.array_equal(np.load(os.path.join(out_path, "warp_%d_%d.npy" % (frame, row))), warp)
+    expected = multipair.post_process_convergence_report_sets(report_sets, [(f, r) for f, r, _ in entries])
+    assert table.equals(expected)
+    assert os.path.exists(os.path.join(out_path, "convergence_reports.pk"))
+    assert os.path.exists(os.path.join(out_path, "analysis.txt"))

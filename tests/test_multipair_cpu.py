@@ -1,0 +1,66 @@
+"""Host-side logic of the multi-pair experiment driver: the pair cache's file names and order, the
+convergence-report table's columns (reference run_hierarchical_optimizer3d_multipair.py:85-131) and the analysis file.
+No GPU needed: the reports are built by hand."""
+import os
+
+import numpy as np
+import pytest
+
+from lsf_b200 import multipair, telemetry
+
+# the reference's column list, written out (run_hierarchical_optimizer3d_multipair.py:88-106)
+REFERENCE_LEVEL_COLUMNS = ["iter_count", "iter_lim_reached", "warp_delta_amt_ratio", "warp_delta_min", "warp_delta_max",
+                           "warp_delta_mean", "warp_delta_std", "warp_delta_max_x", "warp_delta_max_y",
+                           "warps_below_min_thresh", "warps_above_max_thresh", "diff_delta_min", "diff_delta_max",
+                           "diff_delta_mean", "diff_delta_std", "diff_max_x", "diff_max_y"]
+
+
+def make_report(iterations, limit_reached, seed):
+    rng = np.random.default_rng(seed)
+    wds = telemetry.WarpDeltaStatistics3d(float(rng.random()), float(rng.random()), float(rng.random()), float(rng.random()),
+                                          float(rng.random()), telemetry.Vector3i(1 + seed, 2, 3), False, seed % 2 == 0)
+    tds = telemetry.TsdfDifferenceStatistics3d(float(rng.random()), float(rng.random()), float(rng.random()),
+                                               float(rng.random()), telemetry.Vector3i(4, 5 + seed, 6))
+    return telemetry.ConvergenceReport3d(iterations, limit_reached, wds, tds)
+
+
+def test_pair_cache_names_order_and_range(tmp_path):
+    data = tmp_path / "data"
+    canonical = np.arange(8, dtype=np.float32).reshape(2, 2, 2)
+    for frame, row in ((2, 214), (10, 214), (2, 30)):
+        path = multipair.save_pair(str(data), frame, row, canonical * frame, canonical + row)
+        assert os.path.basename(path) == "data_%d_%d.npz" % (frame, row)
+    os.makedirs(data / "images")
+    entries = multipair.list_pair_cache(str(data))
+    # the reference sorts the FILE NAMES (lexicographic): data_10_214 < data_2_214 < data_2_30
+    assert [(f, r) for f, r, _ in entries] == [(10, 214), (2, 214), (2, 30)]
+    assert [(f, r) for f, r, _ in multipair.list_pair_cache(str(data), 1, 2)] == [(2, 214)]
+    loaded_canonical, loaded_live = multipair.load_pair(entries[0][2])
+    assert loaded_canonical.dtype == np.float32 and loaded_canonical.flags["C_CONTIGUOUS"]
+    assert np.array_equal(loaded_canonical, canonical * 10) and np.array_equal(loaded_live, canonical + 214)
+    assert multipair.infer_frame_number_and_pixel_row_from_filename("data_17_233.npz") == (17, 233)
+
+
+def test_report_table_columns_and_analysis(tmp_path):
+    pytest.importorskip("pandas")
+    report_sets = [[make_report(100, True, 0), make_report(7, False, 1)], [make_report(3, False, 2), make_report(100, True, 3)],
+                   [make_report(5, False, 4), make_report(9, False, 5)]]
+    pairs = [(10, 214), (11, 214), (12, 300)]
+    frame = multipair.post_process_convergence_report_sets(report_sets, pairs)
+    expected_columns = ["canonical_frame", "pixel_row"] + ["l%d_%s" % (level, c) for level in range(2)
+                                                            for c in REFERENCE_LEVEL_COLUMNS]
+    assert list(frame.columns) == expected_columns
+    assert multipair.infer_level_count(frame) == 2
+    assert list(frame["canonical_frame"]) == [10, 11, 12] and list(frame["pixel_row"]) == [214, 214, 300]
+    assert list(frame["l0_iter_count"]) == [100, 3, 5] and list(frame["l1_iter_lim_reached"]) == [False, True, False]
+    assert frame["l0_warp_delta_max_x"][1] == report_sets[1][0].warp_delta_statistics.longest_warp_location.x
+    assert frame["l1_diff_max_y"][2] == report_sets[2][1].tsdf_difference_statistics.biggest_difference_location.y
+    assert multipair.get_converged_ratio_for_level(frame, 0) == pytest.approx(2 / 3)
+    assert multipair.get_mean_iteration_count_for_level(frame, 1) == pytest.approx((7 + 100 + 9) / 3)
+    written = multipair.write_reports(frame, str(tmp_path))
+    assert os.path.basename(written[0]) == "convergence_reports.pk" and all(os.path.exists(p) for p in written)
+    import pandas as pd
+    assert pd.read_pickle(written[0]).equals(frame)
+    log = multipair.analyze_convergence_data(frame, str(tmp_path))
+    text = open(log).read()
+    assert "Per-level convergence ratios" in text and "level 1" in text
