@@ -155,6 +155,11 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	const unsigned blocks = blocks_for(g.N);
 	const char* legacy_filter = getenv("LSF_SLAV_FAST");  // A/B: LSF_SLAV_FAST=0 keeps the first-generation kernels
 	const bool fast_filter = !(legacy_filter && legacy_filter[0] == '0');
+	// LSF_SLAV_FUSE_REWARP=1 runs the re-warp in the filter kernel's epilogue. Parity-tested, but measured slower at 256^3
+	// (0.64 against 0.56 ms per KillingFusion iteration: the divergent gather inside the marching loop costs more than the
+	// 24 B per voxel it saves), so it is off by default.
+	const char* fused_env = getenv("LSF_SLAV_FUSE_REWARP");
+	const bool fuse_rewarp = fused_env && fused_env[0] == '1';
 	while (!finished) {
 		const int chunk_end = std::min(bound, enqueued + POLL_CHUNK);
 		for (int it = enqueued; it < chunk_end; it++) {
@@ -175,6 +180,22 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			else
 				k_slav_gradient<D> <<<counted(blocks), 256, 0, stream>>>(ga);
 			float* final_field = field_a;
+			SlavResampleArgs ra;
+			ra.g = g;
+			ra.p = p;
+			ra.live = live_a;
+			ra.canonical = canonical;
+			ra.warp = warp;
+			ra.new_live = live_b;
+			ra.band_union_only = cpp ? 1 : 0;  // sobolev_optimizer2d.cpp:134 vs slavcheva_optimizer2d.py:227-228,324-328
+			ra.known_values_only = 0;
+			ra.substitute_original = 0;
+			ra.modify_warp = 1;
+			ra.threshold = 1e-6f;
+			ra.max_sq_bits = max_sq_bits + it;
+			ra.status = status;
+			ra.iteration = it;
+			bool rewarped = false;  // the re-warp ran in the filter kernel's epilogue
 			if (use_kernel) {
 				SlavFilterArgs fa;
 				fa.g = g;
@@ -189,11 +210,15 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 				const float* in = field_a;
 				float* outs[3] = { field_b, field_f, field_b };
 				if (D == 3 && cpp && fast_filter && slav_fast_filter_supported(g, taps, field_a, field_b)) {
-					// second generation: axis-0 marching kernel, then axes 1 and 2 in one kernel (slavcheva_fast.cuh);
-					// the result lands where the three-pass version leaves it
-					if (taps.radius == 1) launch_slav_fast_filter<1>(g, taps, field_a, field_f, field_b, status, it, stream);
-					else if (taps.radius == 2) launch_slav_fast_filter<2>(g, taps, field_a, field_f, field_b, status, it, stream);
-					else launch_slav_fast_filter<3>(g, taps, field_a, field_f, field_b, status, it, stream);
+					// second generation: axis-0 marching kernel, then axes 1 and 2 in one kernel (slavcheva_fast.cuh) whose
+					// epilogue also re-warps the live field (the filtered field itself is then never stored)
+					ra.update = nullptr;
+					ra.gradient_field = nullptr;
+					const SlavResampleArgs* fused = fuse_rewarp ? &ra : nullptr;
+					if (taps.radius == 1) launch_slav_fast_filter<1>(g, taps, field_a, field_f, field_b, status, it, stream, fused);
+					else if (taps.radius == 2) launch_slav_fast_filter<2>(g, taps, field_a, field_f, field_b, status, it, stream, fused);
+					else launch_slav_fast_filter<3>(g, taps, field_a, field_f, field_b, status, it, stream, fused);
+					rewarped = fuse_rewarp;
 				} else {
 					for (int axis = 0; axis < D; axis++) {
 						fa.in = in;
@@ -205,26 +230,13 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 				}
 				final_field = outs[D - 1];
 			}
-			SlavResampleArgs ra;
-			ra.g = g;
-			ra.p = p;
-			ra.live = live_a;
-			ra.canonical = canonical;
 			ra.update = final_field;
 			ra.gradient_field = direct ? final_field : nullptr;
-			ra.warp = warp;
-			ra.new_live = live_b;
-			ra.band_union_only = cpp ? 1 : 0;  // sobolev_optimizer2d.cpp:134 vs slavcheva_optimizer2d.py:227-228,324-328
-			ra.known_values_only = 0;
-			ra.substitute_original = 0;
-			ra.modify_warp = 1;
-			ra.threshold = 1e-6f;
-			ra.max_sq_bits = max_sq_bits + it;
-			ra.status = status;
-			ra.iteration = it;
 			auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-			if (D == 3 && fast_filter && g.n[2] % 4 == 0 && aligned16(ra.update) && aligned16(ra.live) && aligned16(ra.canonical)
-					&& aligned16(ra.warp) && aligned16(ra.new_live))
+			if (rewarped) {
+				// done
+			} else if (D == 3 && fast_filter && g.n[2] % 4 == 0 && aligned16(ra.update) && aligned16(ra.live)
+					&& aligned16(ra.canonical) && aligned16(ra.warp) && aligned16(ra.new_live))
 				k_slav_resample_v4<D> <<<counted(blocks_for(g.N / 4)), 256, 0, stream>>>(ra);  // four voxels per thread
 			else
 				k_slav_resample<D> <<<counted(blocks), 256, 0, stream>>>(ra);

@@ -16,6 +16,8 @@
 #include "kernels3d_pair.cuh"
 #include "slavcheva.cuh"
 
+#include <cstring>
+
 namespace lsf {
 
 struct SlavMarchArgs {
@@ -108,8 +110,12 @@ static __global__ void __launch_bounds__(256) k_slav_xmarch(const __grid_constan
 	}
 }
 
-template<int R>
-static __global__ void __launch_bounds__(288) k_slav_ymarch2(const __grid_constant__ SlavMarchArgs a) {
+// REWARP: the masked re-warp of the live field (k_slav_resample: reference warp_2d_advanced, field_warping.cpp:64-136,
+// + maximum warp length) runs in the epilogue on the voxel pair's freshly filtered update vectors, so the filtered
+// field is neither written nor read back (a.out may be nullptr).
+template<int R, bool REWARP>
+static __global__ void __launch_bounds__(288) k_slav_ymarch2(const __grid_constant__ SlavMarchArgs a,
+		const __grid_constant__ SlavResampleArgs ra) {
 	constexpr int K = 2 * R + 1;
 	constexpr int H = 4;  // halo columns kept either side of the tile (>= R, even)
 	if (a.status[a.iteration]) return;
@@ -150,6 +156,7 @@ static __global__ void __launch_bounds__(288) k_slav_ymarch2(const __grid_consta
 		}
 	}
 	int buffer = 0;
+	float sq_report = 0.0f;
 #pragma unroll 1
 	for (int r = r_first; r < r_stop; r++, at += Z) {
 		const f32x2 v0 = next[0], v1 = next[1], v2 = next[2];
@@ -194,6 +201,7 @@ static __global__ void __launch_bounds__(288) k_slav_ymarch2(const __grid_consta
 		__syncthreads();
 		if (writes) {
 			const unsigned zero2 = pair_zero_flags(mid[0], mid[1], mid[2]);
+			float update_lo[3], update_hi[3];
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
 				const uint32_t pa = row + (c * 2 * W + il - R) * 4;
@@ -203,13 +211,24 @@ static __global__ void __launch_bounds__(288) k_slav_ymarch2(const __grid_consta
 					const f32x2 v = ((q - R) % 2 == 0) ? lds_f32x2(pa + q * 4) : lds_f32x2(pa + (W + q - 1) * 4);
 					sum = q == 0 ? mul2(v, a.k2[0]) : add2(sum, mul2(v, a.k2[q]), one);
 				}
-				float2 v;
-				unpack2(pair_clear(sum, zero2), v.x, v.y);
-				*reinterpret_cast<float2*>(a.out + c * N + o) = v;
+				unpack2(pair_clear(sum, zero2), update_lo[c], update_hi[c]);
+				if (a.out != nullptr) *reinterpret_cast<float2*>(a.out + c * N + o) = make_float2(update_lo[c], update_hi[c]);
+			}
+			if (REWARP) {
+				const float2 live2 = __ldg(reinterpret_cast<const float2*>(ra.live + o));
+				const float2 canonical2 = ra.band_union_only ? __ldg(reinterpret_cast<const float2*>(ra.canonical + o))
+						: make_float2(0.f, 0.f);
+				float new_lo, new_hi, w_lo[3], w_hi[3];
+				slav_resample_voxel<3>(ra, (int) o, update_lo, live2.x, canonical2.x, new_lo, w_lo, sq_report);
+				slav_resample_voxel<3>(ra, (int) o + 1, update_hi, live2.y, canonical2.y, new_hi, w_hi, sq_report);
+				*reinterpret_cast<float2*>(ra.new_live + o) = make_float2(new_lo, new_hi);
+#pragma unroll
+				for (int c = 0; c < 3; c++) *reinterpret_cast<float2*>(ra.warp + c * N + o) = make_float2(w_lo[c], w_hi[c]);
 			}
 		}
 		buffer ^= 1;
 	}
+	if (REWARP && ra.max_sq_bits != nullptr) block_atomic_max(sq_report, ra.max_sq_bits);
 }
 
 inline bool slav_fast_filter_supported(const SlavGeom& g, const Taps& taps, const float* a, const float* b) {
@@ -219,9 +238,10 @@ inline bool slav_fast_filter_supported(const SlavGeom& g, const Taps& taps, cons
 }
 
 // in -> scratch (axis 0) -> out (axes 1, 2); returns the number of launches
+// `rewarp` (optional): run the masked re-warp in the second kernel's epilogue instead of writing the filtered field
 template<int R>
 int launch_slav_fast_filter(const SlavGeom& g, const Taps& taps, const float* in, float* scratch, float* out,
-		const int* status, int iteration, cudaStream_t stream) {
+		const int* status, int iteration, cudaStream_t stream, const SlavResampleArgs* rewarp = nullptr) {
 	SlavMarchArgs f;
 	f.X = g.n[0];
 	f.Y = g.n[1];
@@ -246,7 +266,15 @@ int launch_slav_fast_filter(const SlavGeom& g, const Taps& taps, const float* in
 	f.chunk = marching_chunk(f.Y, tiles * f.X, 2 * R, 6);
 	const int threads = f.tile_z / 2 + (tiles > 1 ? 32 : 0);
 	const size_t shared = (size_t) 12 * (f.tile_z + 8) * sizeof(float);
-	k_slav_ymarch2<R> <<<counted(dim3(tiles, f.X, (unsigned) div_up(f.Y, f.chunk))), threads, shared, stream>>>(f);
+	const dim3 grid(tiles, f.X, (unsigned) div_up(f.Y, f.chunk));
+	if (rewarp != nullptr) {
+		f.out = nullptr;
+		k_slav_ymarch2<R, true> <<<counted(grid), threads, shared, stream>>>(f, *rewarp);
+	} else {
+		SlavResampleArgs none;
+		std::memset(&none, 0, sizeof(none));
+		k_slav_ymarch2<R, false> <<<counted(grid), threads, shared, stream>>>(f, none);
+	}
 	return 2;
 }
 

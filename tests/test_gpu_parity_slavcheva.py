@@ -370,15 +370,19 @@ def test_fast_filter_matches_three_pass_filter(lsf, taps, monkeypatch):
     cases.append((long_c.astype(np.float32), long_l))
     for canonical_case, live_case in cases:
         results = []
-        for fast in ("1", "0"):
+        # marching filter + four-voxel re-warp kernel (default) | marching filter with the re-warp in its epilogue |
+        # first-generation kernels
+        for fast, fused in (("1", "0"), ("1", "1"), ("0", "0")):
             monkeypatch.setenv("LSF_SLAV_FAST", fast)
+            monkeypatch.setenv("LSF_SLAV_FUSE_REWARP", fused)
             optimizer = lsf.SlavchevaOptimizer3d(smoothing_term_method=lsf.SmoothingTermMethod.KILLING,
                                                  level_set_term_enabled=True, max_iterations=6,
                                                  maximum_warp_length_lower_threshold=0.0,
                                                  sobolev_kernel=synthetic.sobolev_kernel_1d(taps))
             out = optimizer.optimize(live_case.copy(), canonical_case)
             results.append((np.array(out), np.array(optimizer.get_last_warp_field()), optimizer.get_iteration_count()))
-        assert results[0][2] == results[1][2]
         assert np.abs(results[0][1]).max() > 0
-        assert np.array_equal(results[0][0], results[1][0])
-        assert np.array_equal(results[0][1], results[1][1])
+        for other in results[1:]:
+            assert results[0][2] == other[2]
+            assert np.array_equal(results[0][0], other[0])
+            assert np.array_equal(results[0][1], other[1])
