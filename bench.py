@@ -36,8 +36,8 @@ UNIT = "voxel-updates/s"
 ALGORITHMIC_BYTES_PER_VOXEL_UPDATE = 68  # hierarchical 3D with Tikhonov (+- kernel), see DESIGN.md
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one finest-level 256^3 iteration, from the committed
 # `ncu --set full` capture (per launch group, like `achieved`)
-NCU_DRAM_BYTES_PER_ITERATION = 1735145000
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_v4.md (972.3 MB + 762.9 MB)"
+NCU_DRAM_BYTES_PER_ITERATION = 1530480000
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_v4.md, final build (1162.5 MB + 368.0 MB)"
 STAGE_NAMES = {1: ("fused_iteration",), 2: ("stage1_gather_terms_axis0", "ymarch_axis12_update_max"),
                4: ("gradient_stage", "filter_axis0", "filter_axis1", "filter_axis2_update_max")}
 
@@ -243,8 +243,9 @@ def run_ours(args):
             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": NCU_DRAM_BYTES_PER_ITERATION if size == 256 else None,
             "traffic_source": NCU_TRAFFIC_SOURCE if size == 256 else None,
-            "kernel": "finest-level iteration = k_hier_stage1_tma (TMA-fed gather + data + Tikhonov + axis-0 filter pass) + "
-                      "k_sobolev_ymarch2 (axis-1/2 filter passes + warp update + max norm), %d launches/iteration"
+            "kernel": "finest-level iteration = k_hier_stage1_tma<APPLY> (TMA-fed: previous warp update + gather + data + "
+                      "Tikhonov + axis-0 filter pass) + k_sobolev_ymarch2 (axis-1/2 filter passes + max norm), "
+                      "%d launches/iteration"
                       % launches_per_iteration,
             "algorithmic_bytes_per_launch_group": ALGORITHMIC_BYTES_PER_VOXEL_UPDATE * N,
             "ms_per_iteration": round(iteration_ms, 4),
