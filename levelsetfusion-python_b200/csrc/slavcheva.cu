@@ -158,6 +158,8 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	// LSF_SLAV_FUSE_REWARP=1 runs the re-warp in the filter kernel's epilogue. Parity-tested, but measured slower at 256^3
 	// (0.64 against 0.56 ms per KillingFusion iteration: the divergent gather inside the marching loop costs more than the
 	// 24 B per voxel it saves), so it is off by default.
+	const char* band_env = getenv("LSF_SLAV_BAND");  // A/B: LSF_SLAV_BAND=0 keeps the uncompacted four-voxel kernels
+	const bool band_compaction = !(band_env && band_env[0] == '0');
 	const char* fused_env = getenv("LSF_SLAV_FUSE_REWARP");
 	const bool fuse_rewarp = fused_env && fused_env[0] == '1';
 	while (!finished) {
@@ -176,7 +178,10 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			auto aligned_field = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
 			if (D == 3 && cpp && fast_filter && g.n[2] % 4 == 0 && aligned_field(ga.live) && aligned_field(ga.canonical)
 					&& aligned_field(ga.out))
-				k_slav_gradient_cpp3_v4<<<counted(blocks_for(g.N / 4)), 256, 0, stream>>>(ga);  // four voxels per thread
+			{
+				if (band_compaction) k_slav_gradient_cpp3_band<<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ga);
+				else k_slav_gradient_cpp3_v4<<<counted(blocks_for(g.N / 4)), 256, 0, stream>>>(ga);  // four voxels per thread
+			}
 			else
 				k_slav_gradient<D> <<<counted(blocks), 256, 0, stream>>>(ga);
 			float* final_field = field_a;

@@ -475,6 +475,77 @@ static __global__ void __launch_bounds__(256) k_slav_gradient_cpp3_v4(SlavGradie
 		*reinterpret_cast<float4*>(a.out + c * a.g.N + base) = make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
 }
 
+// The same branch once more, with the narrow band compacted per block. Only the voxels inside the band union (17 % of
+// a 256^3 sphere/plane pair) evaluate the stencils, and in k_slav_gradient_cpp3_v4 they sit in a few lanes of many
+// warps: the warps run the long term code at a fraction of their width. Here a block of 256 threads owns 1024
+// consecutive voxels; every thread classifies its four voxels, stores the constant result of the ones outside the band
+// and appends the others to a list in shared memory; after a barrier the block works through the list with all its
+// threads, one band voxel per thread and pass. Same per-voxel functions, same arithmetic, same results.
+static __global__ void __launch_bounds__(256) k_slav_gradient_cpp3_band(SlavGradientArgs a) {
+	if (a.status[a.iteration]) return;
+	__shared__ unsigned short band_list[1024];
+	__shared__ int band_count;
+	const SlavParams& p = a.p;
+	const long long block_base = (long long) blockIdx.x * 1024;
+	if (threadIdx.x == 0) band_count = 0;
+	__syncthreads();
+	const long long first = block_base + threadIdx.x * 4;
+	if (first < a.g.N) {
+		const int base = (int) first;
+		const float4 live4 = __ldg(reinterpret_cast<const float4*>(a.live + base));
+		const float4 canonical4 = __ldg(reinterpret_cast<const float4*>(a.canonical + base));
+		const float live_v[4] = { live4.x, live4.y, live4.z, live4.w };
+		const float canonical_v[4] = { canonical4.x, canonical4.y, canonical4.z, canonical4.w };
+		const float outside_value = (0.0f + 0.0f * p.smoothing_weight) * -p.rate;
+		unsigned in_band = 0;
+#pragma unroll
+		for (int v = 0; v < 4; v++)
+			if (!(slav_truncated(live_v[v]) && slav_truncated(canonical_v[v]))) in_band |= 1u << v;
+		if (in_band != 0) {
+			const int at = atomicAdd(&band_count, __popc(in_band));
+			int k = 0;
+#pragma unroll
+			for (int v = 0; v < 4; v++)
+				if (in_band & (1u << v)) band_list[at + k++] = (unsigned short) (threadIdx.x * 4 + v);
+		}
+		// the band voxels' slots are overwritten after the barrier
+		const float4 constant = make_float4(outside_value, outside_value, outside_value, outside_value);
+#pragma unroll
+		for (int c = 0; c < 3; c++) *reinterpret_cast<float4*>(a.out + c * a.g.N + base) = constant;
+	}
+	__syncthreads();
+	const int count = band_count;
+	const bool killing = p.smoothing_term_method == LSF_SMOOTHING_KILLING;
+	for (int j = threadIdx.x; j < count; j += 256) {
+		const int idx = (int) block_base + band_list[j];
+		int q[3];
+		slav_coords<3>(a.g, idx, q);
+		const float live_value = __ldg(a.live + idx);
+		float data[3], smooth[3], ls[3];
+		const bool ls_here = p.level_set && !slav_truncated(live_value);
+		const bool interior = q[0] >= 1 && q[0] < a.g.n[0] - 1 && q[1] >= 1 && q[1] < a.g.n[1] - 1 && q[2] >= 1
+				&& q[2] < a.g.n[2] - 1;
+		if (interior) {
+			slav_data_term<3, true>(a, idx, q, data);
+			if (killing) slav_killing<3, true>(a, idx, q, smooth);
+			else slav_tikhonov_cpp<3, true>(a, idx, q, smooth);
+			if (ls_here) slav_level_set<3, true>(a, idx, q, ls);
+		} else {
+			slav_data_term<3>(a, idx, q, data);
+			if (killing) slav_killing<3>(a, idx, q, smooth);
+			else slav_tikhonov_cpp<3>(a, idx, q, smooth);
+			if (ls_here) slav_level_set<3>(a, idx, q, ls);
+		}
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			float total = data[c] * p.data_weight;
+			if (ls_here) total = total + ls[c] * p.level_set_weight;
+			total = total + smooth[c] * p.smoothing_weight;
+			a.out[c * a.g.N + idx] = total * -p.rate;  // reference sobolev_optimizer2d.cpp:131-132
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------------------------- Sobolev filter pass
 // reference convolve_with_kernel_preserve_zeros, cpp/src/math/convolution.cpp:23-67,69-145 (C++ rule) and
 // math_utils/convolution.py:114-132 (Python rule)

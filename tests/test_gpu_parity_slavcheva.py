@@ -370,11 +370,13 @@ def test_fast_filter_matches_three_pass_filter(lsf, taps, monkeypatch):
     cases.append((long_c.astype(np.float32), long_l))
     for canonical_case, live_case in cases:
         results = []
-        # marching filter + four-voxel re-warp kernel (default) | marching filter with the re-warp in its epilogue |
-        # first-generation kernels
-        for fast, fused in (("1", "0"), ("1", "1"), ("0", "0")):
-            monkeypatch.setenv("LSF_SLAV_FAST", fast)
-            monkeypatch.setenv("LSF_SLAV_FUSE_REWARP", fused)
+        # default (band-compacted gradient, marching filter, four-voxel re-warp) | without the band compaction |
+        # re-warp in the filter kernel's epilogue | first-generation kernels
+        for switches in ({}, {"LSF_SLAV_BAND": "0"}, {"LSF_SLAV_FUSE_REWARP": "1"}, {"LSF_SLAV_FAST": "0"}):
+            for name in ("LSF_SLAV_BAND", "LSF_SLAV_FUSE_REWARP", "LSF_SLAV_FAST"):
+                monkeypatch.delenv(name, raising=False)
+            for name, value in switches.items():
+                monkeypatch.setenv(name, value)
             optimizer = lsf.SlavchevaOptimizer3d(smoothing_term_method=lsf.SmoothingTermMethod.KILLING,
                                                  level_set_term_enabled=True, max_iterations=6,
                                                  maximum_warp_length_lower_threshold=0.0,
