@@ -242,7 +242,11 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 				// done
 			} else if (D == 3 && fast_filter && g.n[2] % 4 == 0 && aligned16(ra.update) && aligned16(ra.live)
 					&& aligned16(ra.canonical) && aligned16(ra.warp) && aligned16(ra.new_live))
-				k_slav_resample_v4<D> <<<counted(blocks_for(g.N / 4)), 256, 0, stream>>>(ra);  // four voxels per thread
+			{
+				if (band_compaction && cpp && ra.band_union_only && !ra.known_values_only)
+					k_slav_resample_band<D> <<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ra);
+				else k_slav_resample_v4<D> <<<counted(blocks_for(g.N / 4)), 256, 0, stream>>>(ra);  // four voxels per thread
+			}
 			else
 				k_slav_resample<D> <<<counted(blocks), 256, 0, stream>>>(ra);
 			k_slav_decide<<<counted(1u), 1, 0, stream>>>(p, max_sq_bits, status, it, max_iterations);

@@ -751,6 +751,72 @@ static __global__ void __launch_bounds__(256) k_slav_resample_v4(SlavResampleArg
 	if (a.max_sq_bits != nullptr) block_atomic_max(sq_report, a.max_sq_bits);
 }
 
+// k_slav_resample_v4 with the band compacted per block (see k_slav_gradient_cpp3_band): voxels skipped by the band-union
+// rule (reference field_warping.cpp:88-91) keep their live value and take the update vector as their warp directly;
+// the others are listed in shared memory and re-warped by the whole block after a barrier. Requires band_union_only,
+// n[D-1] % 4 == 0, 16-byte aligned fields and a warp output.
+template<int D>
+static __global__ void __launch_bounds__(256) k_slav_resample_band(SlavResampleArgs a) {
+	if (a.status != nullptr && a.status[a.iteration]) return;
+	__shared__ unsigned short band_list[1024];
+	__shared__ int band_count;
+	const SlavGeom& g = a.g;
+	const long long block_base = (long long) blockIdx.x * 1024;
+	if (threadIdx.x == 0) band_count = 0;
+	__syncthreads();
+	float sq_report = 0.0f;
+	const long long first = block_base + threadIdx.x * 4;
+	if (first < g.N) {
+		const int base = (int) first;
+		float4 u4[3];
+#pragma unroll
+		for (int c = 0; c < D; c++) u4[c] = __ldg(reinterpret_cast<const float4*>(a.update + c * g.N + base));
+		const float4 live4 = __ldg(reinterpret_cast<const float4*>(a.live + base));
+		const float4 canonical4 = __ldg(reinterpret_cast<const float4*>(a.canonical + base));
+		const float live_v[4] = { live4.x, live4.y, live4.z, live4.w };
+		const float canonical_v[4] = { canonical4.x, canonical4.y, canonical4.z, canonical4.w };
+		unsigned in_band = 0;
+#pragma unroll
+		for (int v = 0; v < 4; v++) {
+			if (!(slav_truncated(live_v[v]) && slav_truncated(canonical_v[v]))) in_band |= 1u << v;
+			else {
+				float sq = 0.0f;
+#pragma unroll
+				for (int c = 0; c < D; c++) {
+					const float w = v == 0 ? u4[c].x : (v == 1 ? u4[c].y : (v == 2 ? u4[c].z : u4[c].w));
+					sq += w * w;
+				}
+				sq_report = fmaxf(sq_report, sq);
+			}
+		}
+		if (in_band != 0) {
+			const int at = atomicAdd(&band_count, __popc(in_band));
+			int k = 0;
+#pragma unroll
+			for (int v = 0; v < 4; v++)
+				if (in_band & (1u << v)) band_list[at + k++] = (unsigned short) (threadIdx.x * 4 + v);
+		}
+		// skipped voxels: new live = live, warp = update (the band voxels' slots are overwritten after the barrier)
+		*reinterpret_cast<float4*>(a.new_live + base) = live4;
+#pragma unroll
+		for (int c = 0; c < D; c++) *reinterpret_cast<float4*>(a.warp + c * g.N + base) = u4[c];
+	}
+	__syncthreads();
+	const int count = band_count;
+	for (int j = threadIdx.x; j < count; j += 256) {
+		const int idx = (int) block_base + band_list[j];
+		float update[3] = { 0.f, 0.f, 0.f }, w[3], new_value;
+#pragma unroll
+		for (int c = 0; c < D; c++) update[c] = __ldg(a.update + c * g.N + idx);
+		slav_resample_voxel<D>(a, idx, update, __ldg(a.live + idx), __ldg(a.canonical + idx), new_value, w, sq_report);
+		a.new_live[idx] = new_value;
+#pragma unroll
+		for (int c = 0; c < D; c++) a.warp[c * g.N + idx] = w[c];
+	}
+	if (a.max_sq_bits != nullptr) block_atomic_max(sq_report, a.max_sq_bits);
+}
+
+
 // termination test on the device, sticky: status[it + 1] = status[it] || finished(it + 1, max of iteration it)
 // reference optimizer2d.cpp:76-82 (C++), slavcheva_optimizer2d.py:360-362 (Python)
 __device__ __forceinline__ bool slav_finished(const SlavParams& p, int completed, int max_iterations, float max_warp) {
