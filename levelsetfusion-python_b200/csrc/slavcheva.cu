@@ -153,6 +153,7 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	bool finished = host_finished(p, 0, max_iterations, initial_max) || bound == 0;
 	int enqueued = 0;
 	const unsigned blocks = blocks_for(g.N);
+	int *band_list = nullptr, *band_counts = nullptr, *leave_list = nullptr, *leave_counts = nullptr;
 	const char* legacy_filter = getenv("LSF_SLAV_FAST");  // A/B: LSF_SLAV_FAST=0 keeps the first-generation kernels
 	const bool fast_filter = !(legacy_filter && legacy_filter[0] == '0');
 	// LSF_SLAV_FUSE_REWARP=1 runs the re-warp in the filter kernel's epilogue. Parity-tested, but measured slower at 256^3
@@ -162,6 +163,23 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	const bool band_compaction = !(band_env && band_env[0] == '0');
 	const char* fused_env = getenv("LSF_SLAV_FUSE_REWARP");
 	const bool fuse_rewarp = fused_env && fused_env[0] == '1';
+	// narrow-band sparse iteration (slavcheva_fast.cuh): LSF_SLAV_SPARSE=0 keeps the dense kernels
+	const char* sparse_env = getenv("LSF_SLAV_SPARSE");
+	auto aligned_16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+	const bool sparse = D == 3 && cpp && fast_filter && band_compaction && use_kernel && !(sparse_env && sparse_env[0] == '0')
+			&& g.n[2] % 4 == 0 && g.N * 3 < (1ll << 31) && aligned_16(live_a) && aligned_16(canonical) && !finished;
+	if (sparse) {
+		LSF_TRY(arena.alloc(&band_list, N));
+		LSF_TRY(arena.alloc(&leave_list, N));
+		LSF_TRY(arena.alloc(&band_counts, (size_t) bound + 1));
+		LSF_TRY(arena.alloc(&leave_counts, (size_t) bound + 1));
+		LSF_CUDA(cudaMemsetAsync(band_counts, 0, ((size_t) bound + 1) * sizeof(int), stream));
+		LSF_CUDA(cudaMemsetAsync(leave_counts, 0, ((size_t) bound + 1) * sizeof(int), stream));
+		// invariants outside the band: update fields zero, both live buffers equal (the warp is zero already)
+		LSF_CUDA(cudaMemsetAsync(field_a, 0, N * D * sizeof(float), stream));
+		LSF_CUDA(cudaMemsetAsync(field_b, 0, N * D * sizeof(float), stream));
+		LSF_CUDA(cudaMemcpyAsync(live_b, live_a, N * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+	}
 	while (!finished) {
 		const int chunk_end = std::min(bound, enqueued + POLL_CHUNK);
 		for (int it = enqueued; it < chunk_end; it++) {
@@ -176,7 +194,17 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			ga.status = status;
 			ga.iteration = it;
 			auto aligned_field = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-			if (D == 3 && cpp && fast_filter && g.n[2] % 4 == 0 && aligned_field(ga.live) && aligned_field(ga.canonical)
+			SlavBandArgs band;
+			band.g = g;
+			band.list = band_list;
+			band.count = band_counts ? band_counts + it : nullptr;
+			band.leave_list = leave_list;
+			band.leave_count = leave_counts ? leave_counts + it : nullptr;
+			band.status = status;
+			band.iteration = it;
+			const unsigned band_blocks = 148 * 8;
+			if (sparse) k_slav_band_gradient<<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ga, band);
+			else if (D == 3 && cpp && fast_filter && g.n[2] % 4 == 0 && aligned_field(ga.live) && aligned_field(ga.canonical)
 					&& aligned_field(ga.out))
 			{
 				if (band_compaction) k_slav_gradient_cpp3_band<<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ga);
@@ -214,7 +242,18 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 				// pass order: array axis 0 first (2D: rows then columns, convolution.cpp:69-145; 3D: axes 0, 1, 2)
 				const float* in = field_a;
 				float* outs[3] = { field_b, field_f, field_b };
-				if (D == 3 && cpp && fast_filter && slav_fast_filter_supported(g, taps, field_a, field_b)) {
+				if (sparse) {
+					// a -> f (axis 0) -> b (axis 1) -> a (axis 2), at the band voxels only
+					float* band_outs[3] = { field_f, field_b, field_a };
+					for (int axis = 0; axis < D; axis++) {
+						fa.in = in;
+						fa.out = band_outs[axis];
+						fa.axis = axis;
+						k_slav_band_filter_axis<<<counted(band_blocks), 256, 0, stream>>>(fa, band);
+						in = band_outs[axis];
+					}
+					outs[D - 1] = field_a;
+				} else if (D == 3 && cpp && fast_filter && slav_fast_filter_supported(g, taps, field_a, field_b)) {
 					// second generation: axis-0 marching kernel, then axes 1 and 2 in one kernel (slavcheva_fast.cuh) whose
 					// epilogue also re-warps the live field (the filtered field itself is then never stored)
 					ra.update = nullptr;
@@ -240,6 +279,9 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
 			if (rewarped) {
 				// done
+			} else if (sparse) {
+				k_slav_band_resample<<<counted(band_blocks), 256, 0, stream>>>(ra, band);
+				k_slav_band_leave<<<counted(64u), 256, 0, stream>>>(band, live_b, live_a, field_a, field_b, field_f);
 			} else if (D == 3 && fast_filter && g.n[2] % 4 == 0 && aligned16(ra.update) && aligned16(ra.live)
 					&& aligned16(ra.canonical) && aligned16(ra.warp) && aligned16(ra.new_live))
 			{

@@ -280,4 +280,167 @@ int launch_slav_fast_filter(const SlavGeom& g, const Taps& taps, const float* in
 
 #endif  // __CUDACC__
 
+// ---------------------------------------------------------------------------------------------- narrow-band sparse iteration
+// The C++-semantics 3D iteration touches, in effect, only the narrow band: a voxel whose live and canonical values are
+// both truncated gets a zero update (data_term.cpp:72-83, smoothing_term.cpp:43-108 skip it), the zero rule of
+// convolve_with_kernel_preserve_zeros keeps its filtered update at zero (convolution.cpp:23-67), and the re-warp leaves
+// its live value alone (field_warping.cpp:88-91) -- and since such a voxel never changes again, the band only shrinks.
+// The sparse iteration keeps these invariants in the buffers instead of re-establishing them every iteration:
+//   * outside the band the three update fields and the warp are zero and the two live buffers hold the same value
+//     (set up once per optimize(); a voxel that leaves the band is patched by k_slav_band_leave);
+//   * k_slav_band_gradient scans the two scalar fields, evaluates the terms at the band voxels only (per-block list in
+//     shared memory, as k_slav_gradient_cpp3_band) and appends them to a global list;
+//   * the three filter passes, the re-warp and the maximum warp length run over that list.
+// Per-voxel arithmetic is that of the dense kernels (same device functions); taps that fall outside the band read the
+// zeros the dense path would have computed there.
+struct SlavBandArgs {
+	SlavGeom g;
+	int* list;          // band voxels of this iteration (order arbitrary)
+	int* count;         // their number (slot of this iteration, zero before the gradient kernel)
+	int* leave_list;    // voxels that left the band in this iteration's re-warp
+	int* leave_count;
+	const int* status;
+	int iteration;
+};
+
+#ifdef __CUDACC__
+
+static __global__ void __launch_bounds__(256) k_slav_band_gradient(SlavGradientArgs a, SlavBandArgs b) {
+	if (a.status[a.iteration]) return;
+	__shared__ unsigned short band_local[1024];
+	__shared__ int band_count, band_base;
+	const SlavParams& p = a.p;
+	const long long block_base = (long long) blockIdx.x * 1024;
+	if (threadIdx.x == 0) band_count = 0;
+	__syncthreads();
+	const long long first = block_base + threadIdx.x * 4;
+	if (first < a.g.N) {
+		const int base = (int) first;
+		const float4 live4 = __ldg(reinterpret_cast<const float4*>(a.live + base));
+		const float4 canonical4 = __ldg(reinterpret_cast<const float4*>(a.canonical + base));
+		const float live_v[4] = { live4.x, live4.y, live4.z, live4.w };
+		const float canonical_v[4] = { canonical4.x, canonical4.y, canonical4.z, canonical4.w };
+		unsigned in_band = 0;
+#pragma unroll
+		for (int v = 0; v < 4; v++)
+			if (!(slav_truncated(live_v[v]) && slav_truncated(canonical_v[v]))) in_band |= 1u << v;
+		if (in_band != 0) {
+			const int at = atomicAdd(&band_count, __popc(in_band));
+			int k = 0;
+#pragma unroll
+			for (int v = 0; v < 4; v++)
+				if (in_band & (1u << v)) band_local[at + k++] = (unsigned short) (threadIdx.x * 4 + v);
+		}
+	}
+	__syncthreads();
+	const int count = band_count;
+	if (count == 0) return;
+	if (threadIdx.x == 0) band_base = atomicAdd(b.count, count);
+	__syncthreads();
+	const bool killing = p.smoothing_term_method == LSF_SMOOTHING_KILLING;
+	for (int j = threadIdx.x; j < count; j += 256) {
+		const int idx = (int) block_base + band_local[j];
+		b.list[band_base + j] = idx;
+		int q[3];
+		slav_coords<3>(a.g, idx, q);
+		const float live_value = __ldg(a.live + idx);
+		float data[3], smooth[3], ls[3];
+		const bool ls_here = p.level_set && !slav_truncated(live_value);
+		const bool interior = q[0] >= 1 && q[0] < a.g.n[0] - 1 && q[1] >= 1 && q[1] < a.g.n[1] - 1 && q[2] >= 1
+				&& q[2] < a.g.n[2] - 1;
+		if (interior) {
+			slav_data_term<3, true>(a, idx, q, data);
+			if (killing) slav_killing<3, true>(a, idx, q, smooth);
+			else slav_tikhonov_cpp<3, true>(a, idx, q, smooth);
+			if (ls_here) slav_level_set<3, true>(a, idx, q, ls);
+		} else {
+			slav_data_term<3>(a, idx, q, data);
+			if (killing) slav_killing<3>(a, idx, q, smooth);
+			else slav_tikhonov_cpp<3>(a, idx, q, smooth);
+			if (ls_here) slav_level_set<3>(a, idx, q, ls);
+		}
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			float total = data[c] * p.data_weight;
+			if (ls_here) total = total + ls[c] * p.level_set_weight;
+			total = total + smooth[c] * p.smoothing_weight;
+			a.out[c * a.g.N + idx] = total * -p.rate;  // reference sobolev_optimizer2d.cpp:131-132
+		}
+	}
+}
+
+// one pass of convolve_with_kernel_preserve_zeros (C++ zero rule) at the band voxels; `in` is zero outside the band
+static __global__ void __launch_bounds__(256) k_slav_band_filter_axis(SlavFilterArgs a, SlavBandArgs b) {
+	if (a.status[a.iteration]) return;
+	const int count = *b.count;
+	const int n = a.g.n[a.axis], s = a.g.stride[a.axis];
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+		const int idx = b.list[j];
+		int pos[3];
+		slav_coords<3>(a.g, idx, pos);
+		const int i = pos[a.axis];
+		float centre[3];
+		bool all_zero = true;
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			centre[c] = __ldg(a.in + c * a.g.N + idx);
+			all_zero = all_zero && centre[c] == 0.0f;
+		}
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			float acc = 0.0f;
+			if (!all_zero) {
+				const float* line = a.in + c * a.g.N + idx;
+				for (int t = 0; t < a.size; t++) {
+					const int src = i - a.radius + t;
+					const float value = (src >= 0 && src < n) ? __ldg(line + (t - a.radius) * s) : 0.0f;
+					acc += value * a.k[t];
+				}
+			}
+			a.out[c * a.g.N + idx] = acc;
+		}
+	}
+}
+
+// re-warp of the band voxels (k_slav_resample's per-voxel function) + maximum warp length; voxels whose new value is
+// truncated while the canonical one is too have left the band for good and are queued for k_slav_band_leave
+static __global__ void __launch_bounds__(256) k_slav_band_resample(SlavResampleArgs a, SlavBandArgs b) {
+	if (a.status != nullptr && a.status[a.iteration]) return;
+	const int count = *b.count;
+	const SlavGeom& g = a.g;
+	float sq_report = 0.0f;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+		const int idx = b.list[j];
+		float update[3], w[3], new_value;
+#pragma unroll
+		for (int c = 0; c < 3; c++) update[c] = __ldg(a.update + c * g.N + idx);
+		const float canonical_value = __ldg(a.canonical + idx);
+		slav_resample_voxel<3>(a, idx, update, __ldg(a.live + idx), canonical_value, new_value, w, sq_report);
+		a.new_live[idx] = new_value;
+#pragma unroll
+		for (int c = 0; c < 3; c++) a.warp[c * g.N + idx] = w[c];
+		if (slav_truncated(new_value) && slav_truncated(canonical_value)) b.leave_list[atomicAdd(b.leave_count, 1)] = idx;
+	}
+	if (a.max_sq_bits != nullptr) block_atomic_max(sq_report, a.max_sq_bits);
+}
+
+// restores the invariants at the voxels that left the band: both live buffers equal, update fields zero
+static __global__ void __launch_bounds__(256) k_slav_band_leave(SlavBandArgs b, const float* new_live, float* old_live,
+		float* field_a, float* field_b, float* field_f) {
+	if (b.status[b.iteration]) return;
+	const int count = *b.leave_count;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+		const int idx = b.leave_list[j];
+		old_live[idx] = new_live[idx];
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			field_a[c * b.g.N + idx] = 0.0f;
+			field_b[c * b.g.N + idx] = 0.0f;
+			field_f[c * b.g.N + idx] = 0.0f;
+		}
+	}
+}
+
+#endif  // __CUDACC__
+
 }  // namespace lsf

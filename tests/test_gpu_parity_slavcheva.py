@@ -370,10 +370,11 @@ def test_fast_filter_matches_three_pass_filter(lsf, taps, monkeypatch):
     cases.append((long_c.astype(np.float32), long_l))
     for canonical_case, live_case in cases:
         results = []
-        # default (band-compacted gradient, marching filter, four-voxel re-warp) | without the band compaction |
-        # re-warp in the filter kernel's epilogue | first-generation kernels
-        for switches in ({}, {"LSF_SLAV_BAND": "0"}, {"LSF_SLAV_FUSE_REWARP": "1"}, {"LSF_SLAV_FAST": "0"}):
-            for name in ("LSF_SLAV_BAND", "LSF_SLAV_FUSE_REWARP", "LSF_SLAV_FAST"):
+        # default (narrow-band sparse iteration) | dense with band-compacted gradient / re-warp and marching filter |
+        # without the band compaction | re-warp in the filter kernel's epilogue | first-generation kernels
+        for switches in ({}, {"LSF_SLAV_SPARSE": "0"}, {"LSF_SLAV_BAND": "0"}, {"LSF_SLAV_SPARSE": "0", "LSF_SLAV_FUSE_REWARP": "1"},
+                         {"LSF_SLAV_FAST": "0"}):
+            for name in ("LSF_SLAV_SPARSE", "LSF_SLAV_BAND", "LSF_SLAV_FUSE_REWARP", "LSF_SLAV_FAST"):
                 monkeypatch.delenv(name, raising=False)
             for name, value in switches.items():
                 monkeypatch.setenv(name, value)
