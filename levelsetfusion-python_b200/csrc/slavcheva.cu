@@ -167,7 +167,8 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	const char* sparse_env = getenv("LSF_SLAV_SPARSE");
 	auto aligned_16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
 	const bool sparse = D == 3 && cpp && fast_filter && band_compaction && use_kernel && !(sparse_env && sparse_env[0] == '0')
-			&& g.n[2] % 4 == 0 && g.N * 3 < (1ll << 31) && aligned_16(live_a) && aligned_16(canonical) && !finished;
+			&& taps.radius >= 1 && taps.radius <= 3 && g.n[2] % 4 == 0 && g.N * 3 < (1ll << 31) && aligned_16(live_a)
+			&& aligned_16(canonical) && !finished;
 	if (sparse) {
 		LSF_TRY(arena.alloc(&band_list, N));
 		LSF_TRY(arena.alloc(&leave_list, N));
@@ -249,7 +250,9 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 						fa.in = in;
 						fa.out = band_outs[axis];
 						fa.axis = axis;
-						k_slav_band_filter_axis<<<counted(band_blocks), 256, 0, stream>>>(fa, band);
+						if (taps.radius == 1) k_slav_band_filter_axis<1> <<<counted(band_blocks), 256, 0, stream>>>(fa, band);
+						else if (taps.radius == 2) k_slav_band_filter_axis<2> <<<counted(band_blocks), 256, 0, stream>>>(fa, band);
+						else k_slav_band_filter_axis<3> <<<counted(band_blocks), 256, 0, stream>>>(fa, band);
 						in = band_outs[axis];
 					}
 					outs[D - 1] = field_a;

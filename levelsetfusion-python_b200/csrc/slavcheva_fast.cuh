@@ -308,29 +308,42 @@ struct SlavBandArgs {
 static __global__ void __launch_bounds__(256) k_slav_band_gradient(SlavGradientArgs a, SlavBandArgs b) {
 	if (a.status[a.iteration]) return;
 	__shared__ unsigned short band_local[1024];
+	__shared__ int warp_totals[8];
 	__shared__ int band_count, band_base;
 	const SlavParams& p = a.p;
 	const long long block_base = (long long) blockIdx.x * 1024;
-	if (threadIdx.x == 0) band_count = 0;
-	__syncthreads();
 	const long long first = block_base + threadIdx.x * 4;
+	unsigned in_band = 0;
 	if (first < a.g.N) {
 		const int base = (int) first;
 		const float4 live4 = __ldg(reinterpret_cast<const float4*>(a.live + base));
 		const float4 canonical4 = __ldg(reinterpret_cast<const float4*>(a.canonical + base));
 		const float live_v[4] = { live4.x, live4.y, live4.z, live4.w };
 		const float canonical_v[4] = { canonical4.x, canonical4.y, canonical4.z, canonical4.w };
-		unsigned in_band = 0;
 #pragma unroll
 		for (int v = 0; v < 4; v++)
 			if (!(slav_truncated(live_v[v]) && slav_truncated(canonical_v[v]))) in_band |= 1u << v;
-		if (in_band != 0) {
-			const int at = atomicAdd(&band_count, __popc(in_band));
-			int k = 0;
+	}
+	// ordered compaction (exclusive scan over the block): the list keeps the voxels in memory order, so that
+	// neighbouring threads of the list kernels touch neighbouring addresses
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int mine = __popc(in_band);
+	int inclusive = mine;
 #pragma unroll
-			for (int v = 0; v < 4; v++)
-				if (in_band & (1u << v)) band_local[at + k++] = (unsigned short) (threadIdx.x * 4 + v);
-		}
+	for (int offset = 1; offset < 32; offset <<= 1) {
+		const int other = __shfl_up_sync(0xffffffffu, inclusive, offset);
+		if (lane >= offset) inclusive += other;
+	}
+	if (lane == 31) warp_totals[warp] = inclusive;
+	__syncthreads();
+	int before = inclusive - mine;
+	for (int w = 0; w < warp; w++) before += warp_totals[w];
+	if (threadIdx.x == 255) band_count = before + mine;
+	{
+		int k = 0;
+#pragma unroll
+		for (int v = 0; v < 4; v++)
+			if (in_band & (1u << v)) band_local[before + k++] = (unsigned short) (threadIdx.x * 4 + v);
 	}
 	__syncthreads();
 	const int count = band_count;
@@ -370,6 +383,7 @@ static __global__ void __launch_bounds__(256) k_slav_band_gradient(SlavGradientA
 }
 
 // one pass of convolve_with_kernel_preserve_zeros (C++ zero rule) at the band voxels; `in` is zero outside the band
+template<int R>
 static __global__ void __launch_bounds__(256) k_slav_band_filter_axis(SlavFilterArgs a, SlavBandArgs b) {
 	if (a.status[a.iteration]) return;
 	const int count = *b.count;
@@ -391,9 +405,10 @@ static __global__ void __launch_bounds__(256) k_slav_band_filter_axis(SlavFilter
 			float acc = 0.0f;
 			if (!all_zero) {
 				const float* line = a.in + c * a.g.N + idx;
-				for (int t = 0; t < a.size; t++) {
-					const int src = i - a.radius + t;
-					const float value = (src >= 0 && src < n) ? __ldg(line + (t - a.radius) * s) : 0.0f;
+#pragma unroll
+				for (int t = 0; t < 2 * R + 1; t++) {
+					const int src = i - R + t;
+					const float value = (src >= 0 && src < n) ? __ldg(line + (t - R) * s) : 0.0f;
 					acc += value * a.k[t];
 				}
 			}
