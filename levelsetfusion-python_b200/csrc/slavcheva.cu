@@ -153,7 +153,7 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	bool finished = host_finished(p, 0, max_iterations, initial_max) || bound == 0;
 	int enqueued = 0;
 	const unsigned blocks = blocks_for(g.N);
-	int *band_list = nullptr, *band_counts = nullptr, *leave_list = nullptr, *leave_counts = nullptr;
+	int *band_list = nullptr, *band_positions = nullptr, *band_counts = nullptr, *leave_list = nullptr, *leave_counts = nullptr;
 	const char* legacy_filter = getenv("LSF_SLAV_FAST");  // A/B: LSF_SLAV_FAST=0 keeps the first-generation kernels
 	const bool fast_filter = !(legacy_filter && legacy_filter[0] == '0');
 	// LSF_SLAV_FUSE_REWARP=1 runs the re-warp in the filter kernel's epilogue. Parity-tested, but measured slower at 256^3
@@ -167,10 +167,12 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	const char* sparse_env = getenv("LSF_SLAV_SPARSE");
 	auto aligned_16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
 	const bool sparse = D == 3 && cpp && fast_filter && band_compaction && use_kernel && !(sparse_env && sparse_env[0] == '0')
-			&& taps.radius >= 1 && taps.radius <= 3 && g.n[2] % 4 == 0 && g.N * 3 < (1ll << 31) && aligned_16(live_a)
+			&& taps.radius >= 1 && taps.radius <= 3 && g.n[0] <= 1024 && g.n[1] <= 1024 && g.n[2] <= 1024 && g.n[2] % 4 == 0
+			&& g.N * 3 < (1ll << 31) && aligned_16(live_a)
 			&& aligned_16(canonical) && !finished;
 	if (sparse) {
 		LSF_TRY(arena.alloc(&band_list, N));
+		LSF_TRY(arena.alloc(&band_positions, N));
 		LSF_TRY(arena.alloc(&leave_list, N));
 		LSF_TRY(arena.alloc(&band_counts, (size_t) bound + 1));
 		LSF_TRY(arena.alloc(&leave_counts, (size_t) bound + 1));
@@ -198,6 +200,7 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			SlavBandArgs band;
 			band.g = g;
 			band.list = band_list;
+			band.positions = band_positions;
 			band.count = band_counts ? band_counts + it : nullptr;
 			band.leave_list = leave_list;
 			band.leave_count = leave_counts ? leave_counts + it : nullptr;

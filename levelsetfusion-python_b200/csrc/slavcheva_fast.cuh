@@ -295,7 +295,8 @@ int launch_slav_fast_filter(const SlavGeom& g, const Taps& taps, const float* in
 // zeros the dense path would have computed there.
 struct SlavBandArgs {
 	SlavGeom g;
-	int* list;          // band voxels of this iteration (order arbitrary)
+	int* list;          // band voxels of this iteration (blocks in arbitrary order, memory order inside a block)
+	int* positions;     // their coordinates, 10 bits per axis (x | y << 10 | z << 20); every dimension is <= 1024
 	int* count;         // their number (slot of this iteration, zero before the gradient kernel)
 	int* leave_list;    // voxels that left the band in this iteration's re-warp
 	int* leave_count;
@@ -356,6 +357,7 @@ static __global__ void __launch_bounds__(256) k_slav_band_gradient(SlavGradientA
 		b.list[band_base + j] = idx;
 		int q[3];
 		slav_coords<3>(a.g, idx, q);
+		b.positions[band_base + j] = q[0] | (q[1] << 10) | (q[2] << 20);
 		const float live_value = __ldg(a.live + idx);
 		float data[3], smooth[3], ls[3];
 		const bool ls_here = p.level_set && !slav_truncated(live_value);
@@ -390,30 +392,35 @@ static __global__ void __launch_bounds__(256) k_slav_band_filter_axis(SlavFilter
 	const int n = a.g.n[a.axis], s = a.g.stride[a.axis];
 	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
 		const int idx = b.list[j];
-		int pos[3];
-		slav_coords<3>(a.g, idx, pos);
-		const int i = pos[a.axis];
-		float centre[3];
+		const int i = (b.positions[j] >> (10 * a.axis)) & 1023;
+		const int N = (int) a.g.N;
 		bool all_zero = true;
 #pragma unroll
-		for (int c = 0; c < 3; c++) {
-			centre[c] = __ldg(a.in + c * a.g.N + idx);
-			all_zero = all_zero && centre[c] == 0.0f;
-		}
+		for (int c = 0; c < 3; c++) all_zero = all_zero && __ldg(a.in + c * N + idx) == 0.0f;
+		float acc[3] = { 0.0f, 0.0f, 0.0f };
+		if (!all_zero) {
+			if (i >= R && i < n - R) {  // every tap inside the field
 #pragma unroll
-		for (int c = 0; c < 3; c++) {
-			float acc = 0.0f;
-			if (!all_zero) {
-				const float* line = a.in + c * a.g.N + idx;
+				for (int c = 0; c < 3; c++) {
+					const float* line = a.in + c * N + idx;
 #pragma unroll
-				for (int t = 0; t < 2 * R + 1; t++) {
-					const int src = i - R + t;
-					const float value = (src >= 0 && src < n) ? __ldg(line + (t - R) * s) : 0.0f;
-					acc += value * a.k[t];
+					for (int t = 0; t < 2 * R + 1; t++) acc[c] += __ldg(line + (t - R) * s) * a.k[t];
+				}
+			} else {
+#pragma unroll
+				for (int c = 0; c < 3; c++) {
+					const float* line = a.in + c * N + idx;
+#pragma unroll
+					for (int t = 0; t < 2 * R + 1; t++) {
+						const int src = i - R + t;
+						const float value = (src >= 0 && src < n) ? __ldg(line + (t - R) * s) : 0.0f;
+						acc[c] += value * a.k[t];
+					}
 				}
 			}
-			a.out[c * a.g.N + idx] = acc;
 		}
+#pragma unroll
+		for (int c = 0; c < 3; c++) a.out[c * N + idx] = acc[c];
 	}
 }
 
