@@ -389,3 +389,33 @@ def test_fast_filter_matches_three_pass_filter(lsf, taps, monkeypatch):
             assert results[0][2] == other[2]
             assert np.array_equal(results[0][0], other[0])
             assert np.array_equal(results[0][1], other[1])
+
+
+def test_sparse_iteration_long_run_with_band_shrinkage(lsf, monkeypatch):
+    """The narrow-band sparse iteration keeps invariants outside the band (zero update fields, equal live buffers) and
+    patches them where a voxel leaves the band (k_slav_band_leave). A long run in which the band demonstrably shrinks
+    must stay bit-identical to the dense kernels and to the CPU oracle."""
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(64)
+    canonical, live = canonical[8:56, 8:56, 8:56].copy(), live[8:56, 8:56, 8:56].copy()
+    results = []
+    for sparse in ("1", "0"):
+        monkeypatch.setenv("LSF_SLAV_SPARSE", sparse)
+        optimizer = lsf.SlavchevaOptimizer3d(smoothing_term_method=lsf.SmoothingTermMethod.KILLING,
+                                             level_set_term_enabled=True, max_iterations=60, min_iterations=60,
+                                             maximum_warp_length_lower_threshold=0.0, gradient_descent_rate=0.2,
+                                             sobolev_kernel=synthetic.sobolev_kernel_1d())
+        out = np.array(optimizer.optimize(live.copy(), canonical))
+        results.append((out, np.array(optimizer.get_last_warp_field()), np.array(optimizer.get_max_warps())))
+    assert np.array_equal(results[0][0], results[1][0])
+    assert np.array_equal(results[0][1], results[1][1])
+    assert np.array_equal(results[0][2], results[1][2])
+    outside_before = int(((np.abs(live) == 1.0) & (np.abs(canonical) == 1.0)).sum())
+    outside_after = int(((np.abs(results[0][0]) == 1.0) & (np.abs(canonical) == 1.0)).sum())
+    assert outside_after > outside_before, (outside_before, outside_after)
+    expected = oracle.slavcheva_optimize(live, canonical, semantics=0, smoothing_term_method=1, level_set_term_enabled=True,
+                                         max_iterations=60, min_iterations=60, maximum_warp_length_lower_threshold=0.0,
+                                         gradient_descent_rate=0.2, sobolev_kernel=synthetic.sobolev_kernel_1d())
+    assert expected["iterations"] == 60
+    assert np.array_equal(results[0][0], expected["live"])
+    assert np.array_equal(results[0][1], expected["warp"])
