@@ -104,7 +104,7 @@ int make_taps(const float* kernel_host, int kernel_size, Taps* taps);
 // starting with `lead` planes of re-computed halo. Blocks run in waves of `slots` (SMs x resident blocks per SM), so
 // the time is about waves x (chunk + lead) plane-steps: pick the split that minimises it. On B200 (444 slots) a 256^3
 // level gets 5 chunks of 52 planes -- measured 0.273 ms against 0.304 ms for 4 chunks of 64 (2.3 waves, the third one
-// a third full), in the order this model predicts for every split tried (profiles/r1_ncu_dec_v4.md).
+// a third full), in the order this model predicts for every split tried (profiles/r1_sweep_chunks_v3.log, profiles/r1_ncu_v4.md).
 inline int marching_chunk(int extent, int tiles, int lead, int blocks_per_sm) {
 	static int sm_count = 0;
 	if (sm_count == 0) {

@@ -1,6 +1,6 @@
 // kernels3d_split.cuh -- second-generation split of the 3D hierarchical iteration (sm_100a).
 //
-// ncu (profiles/r1_ncu_lane_v2.md) showed the lane-contiguous stage 1 to be ISSUE bound (70 % issue-active, 435
+// ncu of that kernel (capture not kept; figures quoted in profiles/r1_ncu_tma_v3.md) showed the lane-contiguous stage 1 to be ISSUE bound (70 % issue-active, 435
 // executed instructions per voxel, a third of them integer / branch overhead) and the single-kernel three-pass filter
 // to be latency bound (one 768-thread block per SM because its axis-0 sliding window costs 48 registers per thread,
 // barrier + long-scoreboard stalls). The iteration is therefore cut at a different place:

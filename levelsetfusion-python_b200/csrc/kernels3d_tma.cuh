@@ -1,7 +1,7 @@
 // kernels3d_tma.cuh -- third generation of the 3D hierarchical iteration (sm_100a): TMA-fed stage 1 and a
 // y-marching filter kernel.
 //
-// ncu of the second generation (profiles/r1_ncu_split_v2.md) showed both kernels to be limited by instruction issue,
+// ncu of the second generation (capture not kept; figures quoted in profiles/r1_ncu_tma_v3.md) showed both kernels to be limited by instruction issue,
 // not by HBM: 452 + 255 executed thread-instructions per voxel, a quarter of them 64-bit address arithmetic for
 // global loads (IADD3/IADD3.X/LEA/LEA.HI.X per distinct address), the rest inflated by branch-free border selects and
 // by one block-wide barrier per filter pass. This generation removes that overhead instead of re-tiling it:

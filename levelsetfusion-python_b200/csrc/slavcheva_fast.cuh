@@ -1,7 +1,7 @@
 // slavcheva_fast.cuh -- second generation of the 3D SobolevFusion / KillingFusion Sobolev filter (sm_100a).
 //
 // First generation (slavcheva.cuh: k_slav_filter_axis x 3) moves 3 x 24 B per voxel and re-reads every tap through the
-// cache: 3 x 194 us per 256^3 iteration, 1.8 TB/s (profiles/r1_killing_v1.md). Here the three passes of
+// cache: 3 x 194 us per 256^3 iteration, 1.8 TB/s (profiles/r1_killing_v4.md). Here the three passes of
 // convolve_with_kernel_preserve_zeros (reference cpp/src/math/convolution.cpp:23-67,69-145, C++ zero rule: a voxel whose
 // pass-input vector is exactly zero yields the zero vector) run in two marching kernels on voxel pairs with packed
 // f32x2 chains, the organisation of kernels3d_pair.cuh:
