@@ -153,6 +153,7 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	bool finished = host_finished(p, 0, max_iterations, initial_max) || bound == 0;
 	int enqueued = 0;
 	const unsigned blocks = blocks_for(g.N);
+	unsigned char* band_dead = nullptr;
 	int *band_list = nullptr, *band_positions = nullptr, *band_counts = nullptr, *leave_list = nullptr, *leave_counts = nullptr;
 	const char* legacy_filter = getenv("LSF_SLAV_FAST");  // A/B: LSF_SLAV_FAST=0 keeps the first-generation kernels
 	const bool fast_filter = !(legacy_filter && legacy_filter[0] == '0');
@@ -174,6 +175,8 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 		LSF_TRY(arena.alloc(&band_list, N));
 		LSF_TRY(arena.alloc(&band_positions, N));
 		LSF_TRY(arena.alloc(&leave_list, N));
+		LSF_TRY(arena.alloc(&band_dead, (N + 1023) / 1024));
+		LSF_CUDA(cudaMemsetAsync(band_dead, 0, (N + 1023) / 1024, stream));
 		LSF_TRY(arena.alloc(&band_counts, (size_t) bound + 1));
 		LSF_TRY(arena.alloc(&leave_counts, (size_t) bound + 1));
 		LSF_CUDA(cudaMemsetAsync(band_counts, 0, ((size_t) bound + 1) * sizeof(int), stream));
@@ -201,6 +204,7 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			band.g = g;
 			band.list = band_list;
 			band.positions = band_positions;
+			band.dead = band_dead;
 			band.count = band_counts ? band_counts + it : nullptr;
 			band.leave_list = leave_list;
 			band.leave_count = leave_counts ? leave_counts + it : nullptr;

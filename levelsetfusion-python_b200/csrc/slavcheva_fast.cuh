@@ -298,6 +298,7 @@ struct SlavBandArgs {
 	int* list;          // band voxels of this iteration (blocks in arbitrary order, memory order inside a block)
 	int* positions;     // their coordinates, 10 bits per axis (x | y << 10 | z << 20); every dimension is <= 1024
 	int* count;         // their number (slot of this iteration, zero before the gradient kernel)
+	unsigned char* dead;  // per block of 1024 voxels: no band voxel left (the band only shrinks: never looked at again)
 	int* leave_list;    // voxels that left the band in this iteration's re-warp
 	int* leave_count;
 	const int* status;
@@ -307,7 +308,7 @@ struct SlavBandArgs {
 #ifdef __CUDACC__
 
 static __global__ void __launch_bounds__(256) k_slav_band_gradient(SlavGradientArgs a, SlavBandArgs b) {
-	if (a.status[a.iteration]) return;
+	if (a.status[a.iteration] || b.dead[blockIdx.x]) return;
 	__shared__ unsigned short band_local[1024];
 	__shared__ int warp_totals[8];
 	__shared__ int band_count, band_base;
@@ -348,7 +349,10 @@ static __global__ void __launch_bounds__(256) k_slav_band_gradient(SlavGradientA
 	}
 	__syncthreads();
 	const int count = band_count;
-	if (count == 0) return;
+	if (count == 0) {
+		if (threadIdx.x == 0) b.dead[blockIdx.x] = 1;
+		return;
+	}
 	if (threadIdx.x == 0) band_base = atomicAdd(b.count, count);
 	__syncthreads();
 	const bool killing = p.smoothing_term_method == LSF_SMOOTHING_KILLING;
