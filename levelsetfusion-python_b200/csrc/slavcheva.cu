@@ -211,7 +211,10 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			band.status = status;
 			band.iteration = it;
 			const unsigned band_blocks = 148 * 8;
-			if (sparse) k_slav_band_gradient<<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ga, band);
+			if (sparse) {
+				k_slav_band_scan<<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ga, band);
+				k_slav_band_terms<<<counted(band_blocks), 256, 0, stream>>>(ga, band);
+			}
 			else if (D == 3 && cpp && fast_filter && g.n[2] % 4 == 0 && aligned_field(ga.live) && aligned_field(ga.canonical)
 					&& aligned_field(ga.out))
 			{

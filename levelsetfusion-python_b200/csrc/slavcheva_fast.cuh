@@ -288,8 +288,9 @@ int launch_slav_fast_filter(const SlavGeom& g, const Taps& taps, const float* in
 // The sparse iteration keeps these invariants in the buffers instead of re-establishing them every iteration:
 //   * outside the band the three update fields and the warp are zero and the two live buffers hold the same value
 //     (set up once per optimize(); a voxel that leaves the band is patched by k_slav_band_leave);
-//   * k_slav_band_gradient scans the two scalar fields, evaluates the terms at the band voxels only (per-block list in
-//     shared memory, as k_slav_gradient_cpp3_band) and appends them to a global list;
+//   * k_slav_band_scan classifies the voxels of the two scalar fields (blocks of 1024 voxels that hold no band voxel are
+//     flagged and never looked at again) and writes the band list in memory order; k_slav_band_terms evaluates the
+//     gradient terms at the listed voxels in full warps;
 //   * the three filter passes, the re-warp and the maximum warp length run over that list.
 // Per-voxel arithmetic is that of the dense kernels (same device functions); taps that fall outside the band read the
 // zeros the dense path would have computed there.
@@ -307,12 +308,11 @@ struct SlavBandArgs {
 
 #ifdef __CUDACC__
 
-static __global__ void __launch_bounds__(256) k_slav_band_gradient(SlavGradientArgs a, SlavBandArgs b) {
+static __global__ void __launch_bounds__(256) k_slav_band_scan(SlavGradientArgs a, SlavBandArgs b) {
 	if (a.status[a.iteration] || b.dead[blockIdx.x]) return;
 	__shared__ unsigned short band_local[1024];
 	__shared__ int warp_totals[8];
 	__shared__ int band_count, band_base;
-	const SlavParams& p = a.p;
 	const long long block_base = (long long) blockIdx.x * 1024;
 	const long long first = block_base + threadIdx.x * 4;
 	unsigned in_band = 0;
@@ -355,13 +355,25 @@ static __global__ void __launch_bounds__(256) k_slav_band_gradient(SlavGradientA
 	}
 	if (threadIdx.x == 0) band_base = atomicAdd(b.count, count);
 	__syncthreads();
-	const bool killing = p.smoothing_term_method == LSF_SMOOTHING_KILLING;
 	for (int j = threadIdx.x; j < count; j += 256) {
 		const int idx = (int) block_base + band_local[j];
-		b.list[band_base + j] = idx;
 		int q[3];
 		slav_coords<3>(a.g, idx, q);
+		b.list[band_base + j] = idx;
 		b.positions[band_base + j] = q[0] | (q[1] << 10) | (q[2] << 20);
+	}
+}
+
+// the gradient terms at the listed band voxels (full warps: the list is dense)
+static __global__ void __launch_bounds__(256) k_slav_band_terms(SlavGradientArgs a, SlavBandArgs b) {
+	if (a.status[a.iteration]) return;
+	const SlavParams& p = a.p;
+	const int count = *b.count;
+	const bool killing = p.smoothing_term_method == LSF_SMOOTHING_KILLING;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+		const int idx = b.list[j];
+		const int packed = b.positions[j];
+		const int q[3] = { packed & 1023, (packed >> 10) & 1023, (packed >> 20) & 1023 };
 		const float live_value = __ldg(a.live + idx);
 		float data[3], smooth[3], ls[3];
 		const bool ls_here = p.level_set && !slav_truncated(live_value);
