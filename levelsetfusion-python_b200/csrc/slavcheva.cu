@@ -165,6 +165,8 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	const char* fused_env = getenv("LSF_SLAV_FUSE_REWARP");
 	const bool fuse_rewarp = fused_env && fused_env[0] == '1';
 	// narrow-band sparse iteration (slavcheva_fast.cuh): LSF_SLAV_SPARSE=0 keeps the dense kernels
+	const char* rescan_env = getenv("LSF_SLAV_RESCAN");  // iterations between two scans of the band (default below)
+	const int rescan_period = rescan_env && atoi(rescan_env) >= 1 ? atoi(rescan_env) : 32;
 	const char* sparse_env = getenv("LSF_SLAV_SPARSE");
 	auto aligned_16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
 	const bool sparse = D == 3 && cpp && fast_filter && band_compaction && use_kernel && !(sparse_env && sparse_env[0] == '0')
@@ -205,14 +207,16 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			band.list = band_list;
 			band.positions = band_positions;
 			band.dead = band_dead;
-			band.count = band_counts ? band_counts + it : nullptr;
+			// the band list is rebuilt every `rescan_period` iterations and re-used in between (the band only shrinks)
+			const bool rescan = it % rescan_period == 0;
+			band.count = band_counts ? band_counts + (it / rescan_period) * rescan_period : nullptr;
 			band.leave_list = leave_list;
 			band.leave_count = leave_counts ? leave_counts + it : nullptr;
 			band.status = status;
 			band.iteration = it;
 			const unsigned band_blocks = 148 * 8;
 			if (sparse) {
-				k_slav_band_scan<<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ga, band);
+				if (rescan) k_slav_band_scan<<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ga, band);
 				k_slav_band_terms<<<counted(band_blocks), 256, 0, stream>>>(ga, band);
 			}
 			else if (D == 3 && cpp && fast_filter && g.n[2] % 4 == 0 && aligned_field(ga.live) && aligned_field(ga.canonical)

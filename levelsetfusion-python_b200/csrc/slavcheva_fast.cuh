@@ -290,10 +290,12 @@ int launch_slav_fast_filter(const SlavGeom& g, const Taps& taps, const float* in
 //     (set up once per optimize(); a voxel that leaves the band is patched by k_slav_band_leave);
 //   * k_slav_band_scan classifies the voxels of the two scalar fields (blocks of 1024 voxels that hold no band voxel are
 //     flagged and never looked at again) and writes the band list in memory order; k_slav_band_terms evaluates the
-//     gradient terms at the listed voxels in full warps;
+//     gradient terms at the listed voxels in full warps; the list can be re-used for several iterations (LSF_SLAV_RESCAN; voxels
+//     that have left the band meanwhile are recognised and handled like the dense path handles them);
 //   * the three filter passes, the re-warp and the maximum warp length run over that list.
 // Per-voxel arithmetic is that of the dense kernels (same device functions); taps that fall outside the band read the
 // zeros the dense path would have computed there.
+
 struct SlavBandArgs {
 	SlavGeom g;
 	int* list;          // band voxels of this iteration (blocks in arbitrary order, memory order inside a block)
@@ -375,6 +377,12 @@ static __global__ void __launch_bounds__(256) k_slav_band_terms(SlavGradientArgs
 		const int packed = b.positions[j];
 		const int q[3] = { packed & 1023, (packed >> 10) & 1023, (packed >> 20) & 1023 };
 		const float live_value = __ldg(a.live + idx);
+		if (slav_truncated(live_value) && slav_truncated(__ldg(a.canonical + idx))) {
+			// the list is re-used for several iterations: this voxel has left the band since the last scan
+#pragma unroll
+			for (int c = 0; c < 3; c++) a.out[c * a.g.N + idx] = (0.0f + 0.0f * p.smoothing_weight) * -p.rate;
+			continue;
+		}
 		float data[3], smooth[3], ls[3];
 		const bool ls_here = p.level_set && !slav_truncated(live_value);
 		const bool interior = q[0] >= 1 && q[0] < a.g.n[0] - 1 && q[1] >= 1 && q[1] < a.g.n[1] - 1 && q[2] >= 1

@@ -399,17 +399,24 @@ def test_sparse_iteration_long_run_with_band_shrinkage(lsf, monkeypatch):
     canonical, live = synthetic.sphere_plane_pair_3d(64)
     canonical, live = canonical[8:56, 8:56, 8:56].copy(), live[8:56, 8:56, 8:56].copy()
     results = []
-    for sparse in ("1", "0"):
+    # sparse with the default scan period (the band list is re-used for 32 iterations: voxels that leave the band in
+    # between stay listed and are recognised) | list rebuilt every iteration | every 16 iterations | dense
+    for sparse, rescan in (("1", None), ("1", "1"), ("1", "16"), ("0", None)):
         monkeypatch.setenv("LSF_SLAV_SPARSE", sparse)
+        if rescan is None:
+            monkeypatch.delenv("LSF_SLAV_RESCAN", raising=False)
+        else:
+            monkeypatch.setenv("LSF_SLAV_RESCAN", rescan)
         optimizer = lsf.SlavchevaOptimizer3d(smoothing_term_method=lsf.SmoothingTermMethod.KILLING,
                                              level_set_term_enabled=True, max_iterations=60, min_iterations=60,
                                              maximum_warp_length_lower_threshold=0.0, gradient_descent_rate=0.2,
                                              sobolev_kernel=synthetic.sobolev_kernel_1d())
         out = np.array(optimizer.optimize(live.copy(), canonical))
         results.append((out, np.array(optimizer.get_last_warp_field()), np.array(optimizer.get_max_warps())))
-    assert np.array_equal(results[0][0], results[1][0])
-    assert np.array_equal(results[0][1], results[1][1])
-    assert np.array_equal(results[0][2], results[1][2])
+    for other in results[1:]:
+        assert np.array_equal(results[0][0], other[0])
+        assert np.array_equal(results[0][1], other[1])
+        assert np.array_equal(results[0][2], other[2])
     outside_before = int(((np.abs(live) == 1.0) & (np.abs(canonical) == 1.0)).sum())
     outside_after = int(((np.abs(results[0][0]) == 1.0) & (np.abs(canonical) == 1.0)).sum())
     assert outside_after > outside_before, (outside_before, outside_after)
