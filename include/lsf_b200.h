@@ -88,6 +88,16 @@ int lsf_version(void);
 /* number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches) */
 long long lsf_launch_count(void);
 
+/* Debug / test introspection: kernel family used by the last 3D hierarchical iteration enqueued by this process
+ * (the parity tests assert that they ran the kernels bench.py measures). */
+#define LSF_PATH_OTHER 1            /* earlier kernel generations (A/B switches, unsupported shapes) */
+#define LSF_PATH_TMA_STAGE1 2       /* k_hier_stage1_tma */
+#define LSF_PATH_DEFERRED_UPDATE 4  /* ... with the warp update deferred into the next stage 1 (APPLY) */
+#define LSF_PATH_FUSED_UPDATE 8     /* ... as the whole iteration (no Sobolev kernel configured) */
+#define LSF_PATH_YMARCH2 16         /* k_sobolev_ymarch2 */
+#define LSF_PATH_YMARCH3 32         /* k_sobolev_ymarch3 */
+int lsf_debug_last_path(void);
+
 /* ---------------------------------------------------------------- hierarchical optimizer
  * reference: Optimizer<S,V>::optimize(canonical_field, live_field) -> warp field,
  * cpp/src/nonrigid_optimization/hierarchical/optimizer.tpp:83-131 (level loop :134-171, iteration :174-212).

@@ -149,6 +149,7 @@ EXPORTED_SYMBOLS = [
     "lsf_convolve_3d", "lsf_convolve_2d", "lsf_downsample_3d", "lsf_upsample_3d", "lsf_downsample_2d",
     "lsf_upsample_2d", "lsf_max_norm",
     "lsf_hier_slab_iteration", "lsf_slab_pack_finest", "lsf_slab_restrict", "lsf_slab_prolong_nearest",
+    "lsf_debug_last_path",
     "lsf_slavcheva_optimize", "lsf_warp_advanced", "lsf_warp_delta_statistics", "lsf_tsdf_difference_statistics",
 ]
 

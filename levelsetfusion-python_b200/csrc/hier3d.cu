@@ -8,6 +8,7 @@
 #include "kernels3d_fused.cuh"
 #include "kernels3d_split.cuh"
 #include "kernels3d_pair.cuh"
+#include "kernels3d_ymarch3.cuh"
 #include "slavcheva.cuh"  // statistics_on_device
 
 #include <cfloat>
@@ -16,12 +17,52 @@
 #include <cstdlib>
 #include <cstdint>
 #include <algorithm>
+#include <atomic>
 
 namespace lsf {
 
 namespace {
 
+// which kernel family the last enqueued 3D iteration used (lsf_debug_last_path; the parity tests assert that they
+// exercised the kernels bench.py measures)
+std::atomic<int> g_last_path { 0 };
+
 constexpr int POLL_CHUNK = 16;  // iterations enqueued between two host polls of the convergence slots
+
+// Per-thread polling resources of optimize(): a pinned staging buffer for the convergence slots (a pageable destination
+// would make cudaMemcpyAsync block the host) and two events, one per chunk in flight.
+struct PollState {
+	unsigned* host_bits = nullptr;
+	size_t capacity = 0;
+	cudaEvent_t events[2] = { nullptr, nullptr };
+	int device = -1;
+	int reserve(size_t count) {
+		int current = 0;
+		LSF_CUDA(cudaGetDevice(&current));
+		if (events[0] != nullptr && current != device) {  // the calling thread moved to another GPU
+			cudaEventDestroy(events[0]);
+			cudaEventDestroy(events[1]);
+			events[0] = events[1] = nullptr;
+		}
+		device = current;
+		if (events[0] == nullptr) {
+			LSF_CUDA(cudaEventCreateWithFlags(&events[0], cudaEventDisableTiming));
+			LSF_CUDA(cudaEventCreateWithFlags(&events[1], cudaEventDisableTiming));
+		}
+		if (count > capacity) {
+			if (host_bits) cudaFreeHost(host_bits);
+			host_bits = nullptr;
+			capacity = 0;
+			LSF_CUDA(cudaMallocHost(&host_bits, count * sizeof(unsigned)));
+			capacity = count;
+		}
+		return LSF_OK;
+	}
+};
+PollState& poll_state() {
+	static thread_local PollState state;
+	return state;
+}
 
 struct Plan3 {
 	bool tikhonov = false, use_kernel = false, linear = false;
@@ -144,6 +185,7 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 		if (events) cudaEventRecord(events[i], stream);
 	};
 	mark(0);
+	g_last_path = LSF_PATH_OTHER;
 	HierIterArgs a;
 	a.pack = s.pack;
 	a.canonical = s.canonical;
@@ -198,6 +240,7 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 		if (plan.tma && variant == 2 && (!s.slab || plan.slab_fast) && tma_supported(s.g, s.warp, s.canonical, s.g_post)
 				&& (!plan.tikhonov || aligned16(s.scratch_a))) {
 			// TMA-fed stage 1 with the warp update and the max-norm fused (one launch per iteration)
+			g_last_path = LSF_PATH_TMA_STAGE1 | LSF_PATH_FUSED_UPDATE;
 			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8));
 			const int planes = x_end - x_begin;
 			const int chunk_x = plan.x_chunk_tma > 0 ? std::min(plan.x_chunk_tma, planes) : marching_chunk(planes, tiles, 0, 3);
@@ -239,6 +282,8 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 			const int chunk_y = plan.y_chunk_tma > 0 ? std::min(plan.y_chunk_tma, s.g.Y)
 					: marching_chunk(s.g.Y, filter_tiles, 2 * plan.taps.radius, 6);
 			if (s.warp_alt != nullptr) {
+				g_last_path = LSF_PATH_TMA_STAGE1 | LSF_PATH_DEFERRED_UPDATE
+						| (ymarch3_supported(s.g, s.scratch_a, s.g_post, s.g_post) ? LSF_PATH_YMARCH3 : LSF_PATH_YMARCH2);
 				a.warp = iteration % 2 == 0 ? s.warp : s.warp_alt;
 				a.warp_out = iteration % 2 == 0 ? s.warp_alt : s.warp;
 				TmaMaps& maps = iteration % 2 == 0 ? s.maps : s.maps_alt;
@@ -256,6 +301,7 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 				}
 				return status < 0 ? status : 2;
 			}
+			g_last_path = LSF_PATH_TMA_STAGE1 | (ymarch3_supported(s.g, s.scratch_a, s.g_post, s.warp) ? LSF_PATH_YMARCH3 : LSF_PATH_YMARCH2);
 			int status;
 			switch (plan.taps.radius) {
 			case 1:
@@ -446,7 +492,11 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 	if (plan.use_kernel) LSF_TRY(arena.alloc(&scratch_b, (size_t) finest.N * 3));
 	const int slot_count = std::max(plan.max_iterations, 1);
 	LSF_TRY(arena.alloc(&max_sq_bits, (size_t) slot_count));
-	std::vector<unsigned> host_bits((size_t) slot_count);
+	PollState& poll = poll_state();
+	LSF_TRY(poll.reserve((size_t) slot_count));
+	unsigned* host_bits = poll.host_bits;
+	const char* pipeline_env = getenv("LSF_PIPELINE_POLL");  // A/B: 0 = drain the stream at every poll
+	const bool pipelined = !(pipeline_env && pipeline_env[0] == '0');
 	float* warp_pong = nullptr;  // second warp buffer of the deferred update
 	if (plan.tikhonov && plan.use_kernel) LSF_TRY(arena.alloc(&warp_pong, (size_t) finest.N * 3));
 
@@ -470,27 +520,48 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 		LSF_CUDA(cudaMemsetAsync(g_post, 0, (size_t) s.g.N * 3 * sizeof(float), stream));
 		LSF_CUDA(cudaMemsetAsync(max_sq_bits, 0, (size_t) slot_count * sizeof(unsigned), stream));
 		const bool capturing = capture && capture->level == level && capture_dev != nullptr;
-		// per-iteration captures want the updated warp after every iteration: keep the update in the filter kernel there
-		if (!capturing && warp_pong != nullptr && deferred_update_applies(plan, s)) s.warp_alt = warp_pong;
+		if (warp_pong != nullptr && deferred_update_applies(plan, s)) s.warp_alt = warp_pong;
+		// Per-iteration captures (reference optimizer_with_telemetry.tpp:153-159) on the deferred path: the warp after
+		// iteration i is materialised by stage 1 of iteration i + 1 (its warp_out planes), so capture slot i is copied
+		// after iteration i + 1 has been enqueued; the slot of the last executed iteration is filled after
+		// finish_deferred(). Kernels of iterations beyond the converged one return early: their slots are never counted.
+		auto capture_slot = [&](const float* planes, int slot) {
+			k_planes_to_aos<<<counted(div_up(s.g.N, 256)), 256, 0, stream>>>(planes, capture_dev + (size_t) slot * s.g.N * 3,
+					s.g.N, 3);
+		};
 
+		// The termination test (reference optimizer.tpp:166-171) runs on the device at the head of every kernel; the host
+		// only has to learn the iteration count. Chunks of POLL_CHUNK iterations are enqueued one ahead of the chunk
+		// whose slots the host is waiting for (pinned staging buffer, one event per chunk), so the stream never drains
+		// while the host looks at the results. Kernels enqueued beyond the converged iteration return at once.
 		int executed = 0;      // iterations known to have run
 		int enqueued = 0;
 		bool converged = false;
 		float last_max = FLT_MAX;
-		while (!converged && enqueued < plan.max_iterations) {
-			const int chunk_end = std::min(plan.max_iterations, enqueued + POLL_CHUNK);
-			for (int it = enqueued; it < chunk_end; it++) {
+		auto enqueue_chunk = [&](int begin, int end, cudaEvent_t done) -> int {
+			for (int it = begin; it < end; it++) {
 				LSF_TRY(enqueue_iteration(plan, s, it, true, stream));
-				if (capturing && it < capture->max_iterations) {
-					k_planes_to_aos<<<counted(div_up(s.g.N, 256)), 256, 0, stream>>>(s.warp,
-							capture_dev + (size_t) it * s.g.N * 3, s.g.N, 3);
-				}
+				if (capturing && s.warp_alt == nullptr && it < capture->max_iterations) capture_slot(s.warp, it);
+				if (capturing && s.warp_alt != nullptr && it >= 1 && it - 1 < capture->max_iterations)
+					capture_slot(it % 2 == 0 ? s.warp_alt : s.warp, it - 1);  // the buffer stage 1 of iteration `it` wrote
 			}
 			LSF_CUDA(cudaGetLastError());
-			LSF_CUDA(cudaMemcpyAsync(host_bits.data() + enqueued, max_sq_bits + enqueued,
-					(size_t) (chunk_end - enqueued) * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-			LSF_CUDA(cudaStreamSynchronize(stream));
-			for (int it = enqueued; it < chunk_end; it++) {
+			LSF_CUDA(cudaMemcpyAsync(host_bits + begin, max_sq_bits + begin, (size_t) (end - begin) * sizeof(unsigned),
+					cudaMemcpyDeviceToHost, stream));
+			LSF_CUDA(cudaEventRecord(done, stream));
+			return LSF_OK;
+		};
+		int pending_begin = 0, pending_end = std::min(plan.max_iterations, POLL_CHUNK);
+		int parity = 0;
+		if (pending_end > 0) LSF_TRY(enqueue_chunk(0, pending_end, poll.events[parity]));
+		enqueued = pending_end;
+		while (!converged && pending_begin < pending_end) {
+			// keep one more chunk in flight behind the one being polled
+			const int next_end = std::min(plan.max_iterations, enqueued + POLL_CHUNK);
+			const bool has_next = pipelined && next_end > enqueued;
+			if (has_next) LSF_TRY(enqueue_chunk(enqueued, next_end, poll.events[parity ^ 1]));
+			LSF_CUDA(cudaEventSynchronize(poll.events[parity]));
+			for (int it = pending_begin; it < pending_end; it++) {
 				float sq;
 				std::memcpy(&sq, &host_bits[it], sizeof(float));
 				last_max = std::sqrt(sq);
@@ -500,9 +571,20 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 					break;
 				}
 			}
-			enqueued = chunk_end;
+			pending_begin = pending_end;
+			if (has_next) {
+				pending_end = next_end;
+				enqueued = next_end;
+				parity ^= 1;
+			} else if (!converged && !pipelined && enqueued < plan.max_iterations) {
+				pending_end = next_end;
+				LSF_TRY(enqueue_chunk(enqueued, next_end, poll.events[parity]));
+				enqueued = next_end;
+			}
 		}
 		finish_deferred(plan, s, executed, stream);
+		if (capturing && s.warp_alt != nullptr && executed >= 1 && executed - 1 < capture->max_iterations)
+			capture_slot(s.warp, executed - 1);
 		if (reports) {
 			lsf_level_report& r = reports[level];
 			std::memset(&r, 0, sizeof(r));
@@ -576,6 +658,10 @@ extern "C" int lsf_hier_optimize_3d(const lsf_hier_params* params, const float* 
 		LSF_TRY(from_device(out_dev, warp_out, N * 3, LSF_HOST, stream));
 	}
 	return plan.level_count;
+}
+
+extern "C" int lsf_debug_last_path(void) {
+	return lsf::g_last_path.load();
 }
 
 extern "C" int lsf_hier_optimize_3d_batch(const lsf_hier_params* params, const float* canonical, const float* live,

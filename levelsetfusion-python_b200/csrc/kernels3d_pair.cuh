@@ -508,6 +508,14 @@ void launch_ymarch2(const Taps& taps, const HierIterArgs& a, const float* h, flo
 }
 #endif  // __CUDACC__
 
+// best available kernel for the axis-1 / axis-2 passes: k_sobolev_ymarch3 (kernels3d_ymarch3.cuh) where it applies, else
+// k_sobolev_ymarch2 (defined in kernels3d_ymarch3.cuh, which includes this header)
+#ifdef __CUDACC__
+template<int R>
+void launch_ymarch_auto(const Taps& taps, const HierIterArgs& a, const float* h, float* filtered, float* warp, int y_chunk,
+		cudaStream_t stream, int x_begin = 0, int planes = -1);
+#endif
+
 // ---------------------------------------------------------------------------------------------- axis-0 pass alone
 // Slab mode (slab.py) exchanges the halo planes of the unfiltered gradient between stage 1 and the filter, so the
 // axis-0 pass cannot ride on stage 1 there: this kernel does it on its own (reference convolution.cpp:240-267), a thread
@@ -609,7 +617,7 @@ void launch_slab_filter(const Taps& taps, const HierIterArgs& a, const float* in
 	k_hier_xmarch<R> <<<counted(dim3(plane_blocks, (unsigned) div_up(planes, f.chunk))), 256, 0, stream>>>(f);
 	const int tiles = (int) div_up(a.g.Z, 512);
 	const int y_chunk = marching_chunk(a.g.Y, tiles * planes, 2 * R, 6);
-	launch_ymarch2<R>(taps, a, h, filtered, warp, y_chunk, stream, a.x_begin, planes);
+	launch_ymarch_auto<R>(taps, a, h, filtered, warp, y_chunk, stream, a.x_begin, planes);
 }
 #endif  // __CUDACC__
 
@@ -633,7 +641,7 @@ int launch_iteration_deferred(TmaMaps& maps, HierIterArgs a, const Taps& taps, f
 		int y_chunk, cudaStream_t stream, cudaEvent_t* events) {
 	LSF_TRY((launch_stage1_tma<true, R, true, true>(maps, a, taps, h, x_chunk, stream)));
 	if (events) cudaEventRecord(events[1], stream);
-	launch_ymarch2<R>(taps, a, h, filtered, nullptr, y_chunk, stream);
+	launch_ymarch_auto<R>(taps, a, h, filtered, nullptr, y_chunk, stream);
 	if (events) cudaEventRecord(events[2], stream);
 	return LSF_OK;
 }
@@ -653,7 +661,7 @@ int launch_iteration_v4(bool tikhonov, TmaMaps& maps, HierIterArgs a, const Taps
 	else LSF_TRY((launch_stage1_pair<false, R, 4, false>(maps, a, taps, h, x_chunk, 0, X, X, stream)));
 	if (events) cudaEventRecord(events[1], stream);
 	const bool scalar_filter = getenv("LSF_YMARCH2") && getenv("LSF_YMARCH2")[0] == '0';  // A/B: one voxel per thread
-	if (!scalar_filter && ymarch2_supported(a.g, h, filtered, warp)) launch_ymarch2<R>(taps, a, h, filtered, warp, y_chunk, stream);
+	if (!scalar_filter && ymarch2_supported(a.g, h, filtered, warp)) launch_ymarch_auto<R>(taps, a, h, filtered, warp, y_chunk, stream);
 	else launch_ymarch<R>(taps, a, h, filtered, warp, y_chunk, stream);
 	if (events) cudaEventRecord(events[2], stream);
 	return LSF_OK;

@@ -29,6 +29,7 @@ struct XPassArgs {
 	float k[7];   // flipped taps: k[q] multiplies in[i - R + q]
 	int x_chunk;  // output planes per block along axis 0
 	unsigned long long one2;  // {1.0f, 1.0f}: opaque multiplier of the packed adds (kernels3d_tma.cuh)
+	unsigned long long k2[7]; // the taps duplicated into both lanes of an f32x2 (k_hier_stage1_tma's packed chain)
 };
 
 // one axis of the replicated-border Laplacian without branches (reference gradients.tpp:28-35,114-171):

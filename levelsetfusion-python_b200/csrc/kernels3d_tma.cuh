@@ -259,7 +259,10 @@ struct Stage1Tile {
 // kernel reads the warp BEFORE that update from a.warp, applies `warp - g_prev * rate` (reference optimizer.tpp:207,
 // the same two roundings, one kernel later) for the gather and writes the updated warp of its own planes to
 // a.warp_out (a different buffer: neighbouring x-chunks still read the old planes). One warp read less per iteration.
-template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false, int PD = 0, bool APPLY = false, bool SLAB = false>
+// SYM: the filter kernel is symmetric (k[q] == k[K-1-q] bit for bit, true of every Sobolev kernel): the axis-0 chain
+// multiplies each gradient once per distinct tap (the two products are the same rounded value).
+template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false, int PD = 0, bool APPLY = false, bool SLAB = false,
+		bool SYM = false>
 static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_constant__ CUtensorMap map_g,
 		const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
 		const __grid_constant__ CUtensorMap map_p, HierIterArgs a, XPassArgs t) {
@@ -318,11 +321,14 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 	const uint32_t off_c = T::GP_BYTES + T::WP_BYTES + (ty * T::TZ + tz) * 4;
 	constexpr uint32_t G_COMP = T::GY * T::GZ * 4, W_COMP = T::TY * T::TZ * 4, G_ROW = T::GZ * 4;
 
-	float acc[3][K];
+	// axis-0 chain: components 0 and 1 as one packed f32x2 accumulator per tap, component 2 scalar
+	f32x2 acc01[K];
+	float acc2[K];
 #pragma unroll
-	for (int c = 0; c < 3; c++)
-#pragma unroll
-		for (int q = 0; q < K; q++) acc[c][q] = 0.0f;
+	for (int q = 0; q < K; q++) {
+		acc01[q] = 0ull;
+		acc2[q] = 0.0f;
+	}
 
 	// the Laplacian's border rules (reference gradients.tpp:28-35) apply on the faces of the volume only
 	const bool yz_border = y0 == 0 || y0 + T::TY >= Y || z0 == 0 || z0 + T::TZ >= Z;
@@ -457,16 +463,27 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 		if (!FUSE) {
 			// axis-0 filter pass: plane x is tap q of output plane x + R - q; acc[c][q] holds the partial sum (taps 0..q)
 			// of output x + R - q, so adding in place from the oldest output down reproduces sum_{q ascending} in[.]*k[q]
+			const f32x2 g01 = pack2(g[0], g[1]);
+			f32x2 p01[K];
+			float p2[K];
 #pragma unroll
-			for (int c = 0; c < 3; c++) {
-#pragma unroll
-				for (int q = K - 1; q >= 1; q--) acc[c][q] = acc[c][q - 1] + g[c] * t.k[q];
-				acc[c][0] = g[c] * t.k[0];
+			for (int q = 0; q < K; q++) {
+				p01[q] = (SYM && q > R) ? p01[K - 1 - q] : mul2(g01, t.k2[q]);
+				p2[q] = (SYM && q > R) ? p2[K - 1 - q] : g[2] * t.k[q];
 			}
+#pragma unroll
+			for (int q = K - 1; q >= 1; q--) {
+				acc01[q] = add2(acc01[q - 1], p01[q], t.one2);
+				acc2[q] = acc2[q - 1] + p2[q];
+			}
+			acc01[0] = p01[0];
+			acc2[0] = p2[0];
 			if (x - R >= xs && valid) {
-				a.g_out[out] = acc[0][K - 1];
-				a.g_out[N + out] = acc[1][K - 1];
-				a.g_out[2 * N + out] = acc[2][K - 1];
+				float h0, h1;
+				unpack2(acc01[K - 1], h0, h1);
+				a.g_out[out] = h0;
+				a.g_out[N + out] = h1;
+				a.g_out[2 * N + out] = acc2[K - 1];
 			}
 		}
 		if (!DEC) {
@@ -645,14 +662,32 @@ inline bool l2_prefetch_enabled(bool fused_update) {
 	return fused_update;
 }
 
-template<bool TIKHONOV, int R, bool DEC = true, bool APPLY = false>
+inline unsigned long long dup2_bits(float v) {
+	unsigned bits;
+	memcpy(&bits, &v, 4);
+	return ((unsigned long long) bits << 32) | bits;
+}
+
+inline bool taps_are_symmetric(const Taps& taps) {
+	for (int q = 0; q < taps.size; q++)
+		if (memcmp(&taps.k[q], &taps.k[taps.size - 1 - q], sizeof(float)) != 0) return false;
+	const char* e = getenv("LSF_SYM");  // A/B: LSF_SYM=0 multiplies every tap
+	return !(e && e[0] == '0');
+}
+
+template<bool TIKHONOV, int R, bool DEC = true, bool APPLY = false, bool SYM = false>
 int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h, int x_chunk, cudaStream_t stream) {
 	typedef Stage1Tile<TIKHONOV> T;
 	constexpr int NS = 4;
+	if (APPLY && !SYM && taps_are_symmetric(taps))
+		return launch_stage1_tma<TIKHONOV, R, DEC, APPLY, APPLY>(maps, a, taps, h, x_chunk, stream);
 	LSF_TRY(ensure_maps<TIKHONOV>(maps, a.g, a.warp, a.canonical, a.g_prev));
 	LSF_TRY(ensure_pack_map<T>(maps, a));
 	XPassArgs t;
-	for (int q = 0; q < 7; q++) t.k[q] = q < 2 * R + 1 ? taps.k[q] : 0.0f;
+	for (int q = 0; q < 7; q++) {
+		t.k[q] = q < 2 * R + 1 ? taps.k[q] : 0.0f;
+		t.k2[q] = dup2_bits(t.k[q]);
+	}
 	t.x_chunk = x_chunk;
 	t.one2 = F32X2_ONE;
 	a.g_out = h;
@@ -660,18 +695,18 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 	const size_t shared = (size_t) NS * T::STAGE_BYTES;
 	static bool configured = false;
 	if (!configured) {
-		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY>,
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY, false, SYM>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
-		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY>,
+		LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY, false, SYM>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
 		configured = true;
 	}
 	if (DEC && l2_prefetch_enabled(false))
-		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
-				maps.canonical, maps.pack, a, t);
+		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY, false, SYM> <<<counted(grid), block, shared, stream>>>(maps.g_prev,
+				maps.warp, maps.canonical, maps.pack, a, t);
 	else
-		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
-				maps.canonical, maps.pack, a, t);
+		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY, false, SYM> <<<counted(grid), block, shared, stream>>>(maps.g_prev,
+				maps.warp, maps.canonical, maps.pack, a, t);
 	return LSF_OK;
 }
 
@@ -683,7 +718,10 @@ int launch_stage1_fused_update(TmaMaps& maps, HierIterArgs a, int x_chunk, cudaS
 	constexpr int NS = 4;
 	LSF_TRY(ensure_maps<TIKHONOV>(maps, a.g, a.warp, a.canonical, a.g_prev));
 	XPassArgs t;
-	for (int q = 0; q < 7; q++) t.k[q] = 0.0f;
+	for (int q = 0; q < 7; q++) {
+		t.k[q] = 0.0f;
+		t.k2[q] = 0ull;
+	}
 	t.x_chunk = x_chunk;
 	t.one2 = F32X2_ONE;
 	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), div_up(a.x_end - a.x_begin, x_chunk));

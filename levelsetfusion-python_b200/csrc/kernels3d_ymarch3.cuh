@@ -1,0 +1,294 @@
+// kernels3d_ymarch3.cuh -- fifth generation of the axis-1 / axis-2 filter passes of the 3D hierarchical iteration.
+//
+// SASS audit of k_sobolev_ymarch2<3> (profiles/r2_sass_audit.md): 240 issued instructions per thread and row for 123 that
+// do the work -- 64-bit address arithmetic for every global access (LEA / LEA.HI.X / IADD3.X chains per component),
+// register rotation MOVs of the prefetched row, shared-memory addresses re-derived from the toggling buffer index,
+// CS2R zeroing, a three-way run-time branch over the store variants. The issue slots of that kernel are 54 % busy
+// with 6 warps per scheduler, i.e. the instruction stream is what a row costs. This generation keeps the algorithm
+// (thread = z pair of one x plane marching along y; axis-1 pass as a register chain of partial sums, reference
+// convolution.cpp:268-299; axis-2 pass from a double-buffered shared row kept as is and shifted by one column,
+// convolution.cpp:300-331; warp update and max-norm, optimizer.tpp:207-211) and removes the overhead:
+//
+//   * component planes arrive as three pointers in the kernel parameters; a thread addresses them with one 32-bit
+//     float2 index (one IMAD.WIDE per access);
+//   * the row loop is unrolled by two: the two shared-memory buffers and the two prefetch register sets are named at
+//     compile time (no rotation, every LDS / STS is one base register + immediate), and every row is requested two rows
+//     ahead of its use;
+//   * the store variants (gradient only | gradient + warp update) are template parameters;
+//   * symmetric kernels (every Sobolev kernel is: k[q] == k[K-1-q] bit for bit) multiply each input once per distinct
+//     tap in the axis-1 chain: v * k[q] and v * k[K-1-q] are the same rounded product.
+//
+// Arithmetic per output is unchanged (float32, reference order, separate multiply and add), so results stay bit-identical.
+#pragma once
+
+#include "kernels3d_pair.cuh"
+
+namespace lsf {
+
+struct YMarch3Args {
+	const float* in[3];   // component planes after the axis-0 pass
+	float* out[3];        // component planes of the filtered gradient (HAS_OUT)
+	float* warp[3];       // component planes of the warp, updated in place: warp -= out * rate (HAS_WARP)
+	int X, Y, Z;
+	unsigned long long k2[7];  // flipped taps duplicated into both lanes
+	unsigned long long one2, neg2, rate2;
+	float threshold;
+	unsigned* max_sq_bits;
+	int iteration;
+	int check_convergence;
+	int y_chunk;          // output rows per block
+	int x_begin;          // first plane (blockIdx.y counts from here)
+};
+
+#ifdef __CUDACC__
+
+template<int R, bool SYM, bool HAS_OUT, bool HAS_WARP>
+static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const __grid_constant__ YMarch3Args a) {
+	constexpr int K = 2 * R + 1;
+	constexpr int H = 4;             // halo columns kept either side of the tile (>= R, even)
+	constexpr int TZ = 256;          // output columns per block
+	constexpr int W = TZ + 2 * H;    // columns of a shared row
+	constexpr int NT = TZ / 2;       // owner threads
+	constexpr uint32_t ROW_BYTES = 2 * W * 4;          // one component: A | B (B[i] = A[i + 1])
+	constexpr uint32_t BUFFER_BYTES = 3 * ROW_BYTES;
+	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
+	__shared__ __align__(16) float row_memory3[2 * 3 * 2 * W];
+	const int Y = a.Y, Z = a.Z;
+	const int tid = threadIdx.x;
+	const int z0 = blockIdx.x * TZ;
+	const int x = a.x_begin + blockIdx.y;
+	const int ys = blockIdx.z * a.y_chunk;
+	const int ye = min(Y, ys + a.y_chunk);
+	// column pair of this thread in the row buffer: owners hold H .. H + TZ - 1, the halo threads H columns either side
+	const bool owner = tid < NT;
+	const int j = tid - NT;
+	const int il = owner ? H + 2 * tid : (j < H / 2 ? 2 * j : TZ + H + 2 * (j - H / 2));
+	const int z = z0 - H + il;
+	const bool active = (owner || j < H) && z >= 0 && z < Z;  // Z is even: a pair is inside or outside as a whole
+	const bool writes = owner && active;
+	for (int i = tid; i < 2 * 3 * 2 * W; i += blockDim.x) row_memory3[i] = 0.0f;  // columns outside the volume stay zero
+	__syncthreads();
+	const uint32_t mine = smem_addr(row_memory3) + il * 4;  // A[il] of component 0, buffer 0
+	const f32x2 one = a.one2, neg = a.neg2;
+	const float2* __restrict__ in0 = reinterpret_cast<const float2*>(a.in[0]);
+	const float2* __restrict__ in1 = reinterpret_cast<const float2*>(a.in[1]);
+	const float2* __restrict__ in2 = reinterpret_cast<const float2*>(a.in[2]);
+	const int ZP = Z >> 1;  // float2 elements per row
+
+	f32x2 acc[3][K];
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int q = 0; q < K; q++) acc[c][q] = 0ull;
+	const int r_first = max(ys - R, 0);
+	const int r_stop = ye + R;
+	const int r_load_end = min(r_stop, Y);
+	// float2 index of the next row to request; threads without a column pair of their own keep re-reading element 0
+	// (their values are never stored), so that the steady-state loads need no predicate
+	int ld = active ? ((x * Y + r_first) * Z + z) >> 1 : 0;
+	const int ld_step = active ? ZP : 0;
+	int ld_row = r_first;
+	int st = ((x * Y + ys) * Z + z) >> 1;                    // float2 index of the next output row
+
+	auto request = [&](f32x2 (&v)[3]) {
+		if (active && ld_row < r_load_end) {
+			const float2 v0 = __ldg(in0 + ld), v1 = __ldg(in1 + ld), v2 = __ldg(in2 + ld);
+			v[0] = pack2(v0.x, v0.y);
+			v[1] = pack2(v1.x, v1.y);
+			v[2] = pack2(v2.x, v2.y);
+		} else {
+			v[0] = v[1] = v[2] = 0ull;
+		}
+		ld += ld_step;
+		ld_row++;
+	};
+	// the same for rows known to lie inside the volume
+	auto request_inside = [&](f32x2 (&v)[3]) {
+		const float2 v0 = __ldg(in0 + ld), v1 = __ldg(in1 + ld), v2 = __ldg(in2 + ld);
+		v[0] = pack2(v0.x, v0.y);
+		v[1] = pack2(v1.x, v1.y);
+		v[2] = pack2(v2.x, v2.y);
+		ld += ld_step;
+		ld_row++;
+	};
+	// axis-1 pass: the row is tap q of output row (row + R - q); acc[c][q] holds the partial sum (taps 0..q) of that
+	// output, so adding in place from the oldest output down reproduces sum_{q ascending} in[.] * k[q]
+	auto chain = [&](const f32x2 (&v)[3]) {
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			f32x2 p[K];
+#pragma unroll
+			for (int q = 0; q < K; q++) p[q] = (SYM && q > R) ? p[K - 1 - q] : mul2(v[c], a.k2[q]);
+#pragma unroll
+			for (int q = K - 1; q >= 1; q--) acc[c][q] = add2(acc[c][q - 1], p[q], one);
+			acc[c][0] = p[0];
+		}
+	};
+	float best = 0.0f;
+	// finishes the output row `st` from the chain's oldest partial sums through shared buffer BUF
+	auto emit = [&](auto buffer_tag) {
+		constexpr uint32_t BUF = decltype(buffer_tag)::value * BUFFER_BYTES;
+		if (active) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const uint32_t pa = mine + BUF + c * ROW_BYTES;  // A[il], A[il + 1]
+				float lo, hi;
+				unpack2(acc[c][K - 1], lo, hi);
+				sts_f32x2(pa, acc[c][K - 1]);
+				if (il > 0) sts_f32(pa + (W - 1) * 4, lo);  // B[il - 1] = A[il]
+				sts_f32(pa + W * 4, hi);                    // B[il] = A[il + 1]
+			}
+		}
+		f32x2 w[3] = { 0ull, 0ull, 0ull };
+		if (HAS_WARP && writes) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const float2 v = reinterpret_cast<const float2*>(a.warp[c])[st];
+				w[c] = pack2(v.x, v.y);
+			}
+		}
+		__syncthreads();
+		if (writes) {
+			// axis-2 pass: tap q multiplies the pair (A[il - R + q], A[il - R + q + 1])
+			f32x2 gq[3];
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const uint32_t pa = mine + BUF + c * ROW_BYTES - R * 4;
+				f32x2 sum = 0ull;
+#pragma unroll
+				for (int q = 0; q < K; q++) {
+					// il is even: the pair starts on an even column when (q - R) is even, else take it from the shifted copy
+					const f32x2 v = ((q - R) % 2 == 0) ? lds_f32x2(pa + q * 4) : lds_f32x2(pa + (W + q - 1) * 4);
+					sum = q == 0 ? mul2(v, a.k2[0]) : add2(sum, mul2(v, a.k2[q]), one);
+				}
+				gq[c] = sum;
+			}
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				float2 v;
+				if (HAS_OUT) {
+					unpack2(gq[c], v.x, v.y);
+					reinterpret_cast<float2*>(a.out[c])[st] = v;
+				}
+				if (HAS_WARP) {
+					unpack2(sub2(w[c], mul2(gq[c], a.rate2), neg), v.x, v.y);
+					reinterpret_cast<float2*>(a.warp[c])[st] = v;
+				}
+			}
+			f32x2 sq = mul2(gq[0], gq[0]);
+			sq = add2(sq, mul2(gq[1], gq[1]), one);
+			sq = add2(sq, mul2(gq[2], gq[2]), one);
+			float sq_lo, sq_hi;
+			unpack2(sq, sq_lo, sq_hi);
+			best = fmaxf(best, fmaxf(sq_lo, sq_hi));  // NaNs are ignored, like `if (sq > best)` (statistics.tpp:65)
+		}
+		st += ZP;
+	};
+
+	f32x2 va[3], vb[3];
+	request(va);
+	request(vb);
+	int r = r_first;
+	// priming: rows whose consumption completes no output row of this block yet (at most 2R of them)
+#pragma unroll 1
+	for (; r < ys + R; r++) {
+		chain(va);
+#pragma unroll
+		for (int c = 0; c < 3; c++) va[c] = vb[c];
+		request(vb);
+	}
+	// steady state, two rows per trip: consuming row r completes output row r - R. First the trips whose two requests
+	// (rows r + 2 and r + 3) lie inside the volume, then the last ones, whose requests may fall behind the last row.
+#pragma unroll 1
+	for (; r + 3 < r_load_end; r += 2) {
+		chain(va);
+		request_inside(va);
+		emit(std::integral_constant<int, 0>());
+		chain(vb);
+		request_inside(vb);
+		emit(std::integral_constant<int, 1>());
+	}
+#pragma unroll 1
+	for (; r + 1 < r_stop; r += 2) {
+		chain(va);
+		request(va);
+		emit(std::integral_constant<int, 0>());
+		chain(vb);
+		request(vb);
+		emit(std::integral_constant<int, 1>());
+	}
+	if (r < r_stop) {
+		chain(va);
+		emit(std::integral_constant<int, 0>());
+	}
+	if (a.max_sq_bits != nullptr) block_atomic_max(best, a.max_sq_bits + a.iteration);
+}
+
+inline bool taps_symmetric(const Taps& taps) {
+	for (int q = 0; q < taps.size; q++)
+		if (memcmp(&taps.k[q], &taps.k[taps.size - 1 - q], sizeof(float)) != 0) return false;
+	return true;
+}
+
+// LSF_YMARCH3=0 keeps the fourth-generation filter kernel (A/B parity tests)
+inline bool ymarch3_enabled() {
+	const char* e = getenv("LSF_YMARCH3");
+	return !(e && e[0] == '0');
+}
+
+inline bool ymarch3_supported(const Grid3& g, const float* h, const float* filtered, const float* warp) {
+	return ymarch3_enabled() && g.Z >= 256 && ymarch2_supported(g, h, filtered, warp) && g.N * 3 < (1ll << 31);
+}
+
+template<int R>
+void launch_ymarch3(const Taps& taps, const HierIterArgs& a, const float* h, float* filtered, float* warp, int y_chunk,
+		cudaStream_t stream, int x_begin = 0, int planes = -1) {
+	const Grid3& g = a.g;
+	YMarch3Args f;
+	for (int c = 0; c < 3; c++) {
+		f.in[c] = h + c * g.N;
+		f.out[c] = filtered ? filtered + c * g.N : nullptr;
+		f.warp[c] = warp ? warp + c * g.N : nullptr;
+	}
+	f.X = g.X;
+	f.Y = g.Y;
+	f.Z = g.Z;
+	for (int q = 0; q < 7; q++) f.k2[q] = dup2(q < 2 * R + 1 ? taps.k[q] : 0.0f);
+	f.one2 = dup2(1.0f);
+	f.neg2 = dup2(-1.0f);
+	f.rate2 = dup2(a.rate);
+	f.threshold = a.threshold;
+	f.max_sq_bits = a.max_sq_bits;
+	f.iteration = a.iteration;
+	f.check_convergence = a.check_convergence;
+	f.y_chunk = y_chunk;
+	f.x_begin = x_begin;
+	const int tiles = div_up(g.Z, 256);
+	const dim3 grid(tiles, planes < 0 ? g.X : planes, div_up(g.Y, y_chunk));
+	const int threads = 128 + (tiles > 1 ? 32 : 0);
+	const bool sym = taps_symmetric(taps);
+#define LSF_YM3(SYM, OUT, WARP) k_sobolev_ymarch3<R, SYM, OUT, WARP> <<<counted(grid), threads, 0, stream>>>(f)
+	if (filtered && warp) {
+		if (sym) LSF_YM3(true, true, true);
+		else LSF_YM3(false, true, true);
+	} else if (filtered) {
+		if (sym) LSF_YM3(true, true, false);
+		else LSF_YM3(false, true, false);
+	} else {
+		if (sym) LSF_YM3(true, false, true);
+		else LSF_YM3(false, false, true);
+	}
+#undef LSF_YM3
+}
+
+template<int R>
+void launch_ymarch_auto(const Taps& taps, const HierIterArgs& a, const float* h, float* filtered, float* warp, int y_chunk,
+		cudaStream_t stream, int x_begin, int planes) {
+	if (ymarch3_supported(a.g, h, filtered ? filtered : h, warp ? warp : h))
+		launch_ymarch3<R>(taps, a, h, filtered, warp, y_chunk, stream, x_begin, planes);
+	else launch_ymarch2<R>(taps, a, h, filtered, warp, y_chunk, stream, x_begin, planes);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lsf

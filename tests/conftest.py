@@ -22,3 +22,15 @@ def literals():
 def python_runs():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "reference_python_runs.npz"))
+
+
+@pytest.fixture(scope="session")
+def lsf():
+    """The product package with its CUDA library loaded. Without a CUDA device the GPU tests are skipped (so a plain
+    `pytest tests` passes on a CPU-only machine); with one, a missing or unloadable liblsf_b200.so is an error."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import lsf_b200
+    lsf_b200._lib.load()
+    return lsf_b200

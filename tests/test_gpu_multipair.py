@@ -8,15 +8,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def lsf():
-    import torch
-    if not torch.cuda.is_available():
-        pytest.skip("needs a CUDA device")
-    import lsf_b200
-    return lsf_b200
-
-
 def test_streams_match_serial_loop(lsf):
     import torch
     from lsf_b200 import multigpu, synthetic

@@ -14,15 +14,6 @@ import oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def lsf():
-    import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    import lsf_b200
-    lsf_b200._lib.load()
-    return lsf_b200
-
-
 def random_fields_3d(seed, shape=(12, 10, 14), warp_scale=1.5):
     rng = np.random.default_rng(seed)
     field = (rng.random(shape) * 2 - 1).astype(np.float32)

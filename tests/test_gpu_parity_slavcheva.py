@@ -20,15 +20,6 @@ KERNEL3 = np.array([0.06742075, 0.99544406, 0.06742075], np.float32)
 
 
 @pytest.fixture(scope="module")
-def lsf():
-    import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    import lsf_b200
-    lsf_b200._lib.load()
-    return lsf_b200
-
-
-@pytest.fixture(scope="module")
 def runs():
     return np.load(os.path.join(ROOT, "tests", "golden", "reference_slavcheva_runs.npz"))
 

@@ -15,15 +15,6 @@ MODES = {
 }
 
 
-@pytest.fixture(scope="module")
-def lsf():
-    import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    import lsf_b200
-    lsf_b200._lib.load()
-    return lsf_b200
-
-
 def make_optimizer(lsf, mode, iterations=12, threshold=0.01):
     from lsf_b200 import synthetic
     return lsf.HierarchicalOptimizer3d(maximum_chunk_size=4, maximum_iteration_count=iterations,

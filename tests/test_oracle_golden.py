@@ -278,3 +278,21 @@ def test_3d_optimizer_reduces_to_2d_planewise():
     for i in (0, 7, 15):
         assert np.allclose(r3["warp"][i, :, :, 2], r2["warp"][..., 0], atol=1e-5)
         assert np.allclose(r3["warp"][i, :, :, 1], r2["warp"][..., 1], atol=1e-5)
+
+
+def test_tikhonov_strength_0_2_diverges_in_3d_and_0_1_does_not():
+    """Why bench.py and the 3D parity tests run tikhonov_strength = 0.1 instead of the reference default 0.2
+    (optimizer.hpp:51-65): the hierarchical "Tikhonov" term is the Laplacian of the PREVIOUS gradient
+    (optimizer.tpp:195-196), so g_i = data - s * Lap(g_{i-1}) is a recurrence whose high-frequency gain is
+    s * 12 * |K(pi)|^3 in 3D (12 = largest eigenvalue magnitude of the 7-point Laplacian, K = the Sobolev kernel's
+    response): about 1.6 for s = 0.2, below 1 for s = 0.1. With 0.2 the reference's own algorithm blows up on the
+    coarsest level -- the restatement shows it, so the setting cannot be benchmarked or parity-tested meaningfully."""
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(32)
+    common = dict(tikhonov_term_enabled=True, gradient_kernel_enabled=True, maximum_chunk_size=4, rate=0.1,
+                  maximum_iteration_count=100, maximum_warp_update_threshold=0.01, kernel=synthetic.sobolev_kernel_1d())
+    stable = oracle.hier_optimize(canonical, live, tikhonov_strength=0.1, **common)
+    assert float(np.abs(stable["warp"]).max()) < 5.0 and float(stable["max_updates"].max()) < 1.0
+    diverged = oracle.hier_optimize(canonical, live, tikhonov_strength=0.2, **common)
+    assert float(diverged["max_updates"][0]) > 1e6
+    assert not float(np.nanmax(np.abs(diverged["warp"]))) < 1e6
