@@ -15,6 +15,9 @@
 //     compile time (no rotation, every LDS / STS is one base register + immediate), and every row is requested two rows
 //     ahead of its use;
 //   * the store variants (gradient only | gradient + warp update) are template parameters;
+//   * the axis-2 pass reads the row as aligned pairs and builds the odd-aligned operand pairs in registers instead of
+//     keeping a shifted copy of the row: 30 instead of 54 shared-memory wavefronts per warp and row -- ncu showed the
+//     shared-memory pipe 70 % busy and the kernel bound by it (0.099 -> 0.083 ms per 256^3 iteration);
 //   * symmetric kernels (every Sobolev kernel is: k[q] == k[K-1-q] bit for bit) multiply each input once per distinct
 //     tap in the axis-1 chain: v * k[q] and v * k[K-1-q] are the same rounded product.
 //
@@ -49,10 +52,10 @@ static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const _
 	constexpr int TZ = 256;          // output columns per block
 	constexpr int W = TZ + 2 * H;    // columns of a shared row
 	constexpr int NT = TZ / 2;       // owner threads
-	constexpr uint32_t ROW_BYTES = 2 * W * 4;          // one component: A | B (B[i] = A[i + 1])
+	constexpr uint32_t ROW_BYTES = W * 4;              // one component of one row
 	constexpr uint32_t BUFFER_BYTES = 3 * ROW_BYTES;
 	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
-	__shared__ __align__(16) float row_memory3[2 * 3 * 2 * W];
+	__shared__ __align__(16) float row_memory3[2 * 3 * W];  // [2 buffers][3 components][W]
 	const int Y = a.Y, Z = a.Z;
 	const int tid = threadIdx.x;
 	const int z0 = blockIdx.x * TZ;
@@ -66,7 +69,7 @@ static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const _
 	const int z = z0 - H + il;
 	const bool active = (owner || j < H) && z >= 0 && z < Z;  // Z is even: a pair is inside or outside as a whole
 	const bool writes = owner && active;
-	for (int i = tid; i < 2 * 3 * 2 * W; i += blockDim.x) row_memory3[i] = 0.0f;  // columns outside the volume stay zero
+	for (int i = tid; i < 2 * 3 * W; i += blockDim.x) row_memory3[i] = 0.0f;  // columns outside the volume stay zero
 	__syncthreads();
 	const uint32_t mine = smem_addr(row_memory3) + il * 4;  // A[il] of component 0, buffer 0
 	const f32x2 one = a.one2, neg = a.neg2;
@@ -132,11 +135,7 @@ static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const _
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
 				const uint32_t pa = mine + BUF + c * ROW_BYTES;  // A[il], A[il + 1]
-				float lo, hi;
-				unpack2(acc[c][K - 1], lo, hi);
 				sts_f32x2(pa, acc[c][K - 1]);
-				if (il > 0) sts_f32(pa + (W - 1) * 4, lo);  // B[il - 1] = A[il]
-				sts_f32(pa + W * 4, hi);                    // B[il] = A[il + 1]
 			}
 		}
 		f32x2 w[3] = { 0ull, 0ull, 0ull };
@@ -155,10 +154,18 @@ static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const _
 			for (int c = 0; c < 3; c++) {
 				const uint32_t pa = mine + BUF + c * ROW_BYTES - R * 4;
 				f32x2 sum = 0ull;
+				// the K + 1 values A[il - R .. il + R + 1] arrive as aligned pairs (il is even; for an odd radius the first
+				// pair starts one column early); operand pairs that start on an odd column are put together in registers.
+				// A shifted copy of the row in shared memory (k_sobolev_ymarch2) saves those moves but costs 6 stores and
+				// 12 more loads per row: the shared-memory pipe, not the ALU, bounds this kernel (profiles/r2_ncu_headline.md)
+				constexpr int OFF = R % 2;
+				constexpr int PAIRS = (K + 1 + 2 * OFF) / 2;
+				float window[2 * PAIRS];
+#pragma unroll
+				for (int j = 0; j < PAIRS; j++) unpack2(lds_f32x2(pa + (2 * j - OFF) * 4), window[2 * j], window[2 * j + 1]);
 #pragma unroll
 				for (int q = 0; q < K; q++) {
-					// il is even: the pair starts on an even column when (q - R) is even, else take it from the shifted copy
-					const f32x2 v = ((q - R) % 2 == 0) ? lds_f32x2(pa + q * 4) : lds_f32x2(pa + (W + q - 1) * 4);
+					const f32x2 v = pack2(window[q + OFF], window[q + OFF + 1]);  // (A[il - R + q], A[il - R + q + 1])
 					sum = q == 0 ? mul2(v, a.k2[0]) : add2(sum, mul2(v, a.k2[q]), one);
 				}
 				gq[c] = sum;
@@ -224,12 +231,6 @@ static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const _
 	if (a.max_sq_bits != nullptr) block_atomic_max(best, a.max_sq_bits + a.iteration);
 }
 
-inline bool taps_symmetric(const Taps& taps) {
-	for (int q = 0; q < taps.size; q++)
-		if (memcmp(&taps.k[q], &taps.k[taps.size - 1 - q], sizeof(float)) != 0) return false;
-	return true;
-}
-
 // LSF_YMARCH3=0 keeps the fourth-generation filter kernel (A/B parity tests)
 inline bool ymarch3_enabled() {
 	const char* e = getenv("LSF_YMARCH3");
@@ -261,12 +262,15 @@ void launch_ymarch3(const Taps& taps, const HierIterArgs& a, const float* h, flo
 	f.max_sq_bits = a.max_sq_bits;
 	f.iteration = a.iteration;
 	f.check_convergence = a.check_convergence;
-	f.y_chunk = y_chunk;
 	f.x_begin = x_begin;
 	const int tiles = div_up(g.Z, 256);
+	// the variants that update the warp need 96 registers: 5 resident blocks per SM instead of the 6 the caller's chunk
+	// was sized for (768 blocks on 740 slots would run a second, almost empty wave: measured 0.18 instead of 0.13 ms)
+	if (warp != nullptr) y_chunk = marching_chunk(g.Y, tiles * (planes < 0 ? g.X : planes), 2 * R, 5);
+	f.y_chunk = y_chunk;
 	const dim3 grid(tiles, planes < 0 ? g.X : planes, div_up(g.Y, y_chunk));
 	const int threads = 128 + (tiles > 1 ? 32 : 0);
-	const bool sym = taps_symmetric(taps);
+	const bool sym = taps_are_symmetric(taps);  // LSF_SYM=0: full chain (A/B)
 #define LSF_YM3(SYM, OUT, WARP) k_sobolev_ymarch3<R, SYM, OUT, WARP> <<<counted(grid), threads, 0, stream>>>(f)
 	if (filtered && warp) {
 		if (sym) LSF_YM3(true, true, true);

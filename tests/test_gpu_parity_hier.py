@@ -405,3 +405,32 @@ def test_deferred_update_with_early_termination(lsf, threshold):
     assert np.array_equal(warp, expected["warp"])
     reports = optimizer.get_per_level_convergence_reports()
     assert np.allclose([r.max_update_length for r in reports], expected["max_updates"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("mode", ["tikhonov_kernel", "kernel"])
+@pytest.mark.parametrize("taps", [3, 5, 7])
+def test_ymarch3_filter_matches_previous_generations(lsf, mode, taps, monkeypatch):
+    """A/B: the fifth-generation filter kernel k_sobolev_ymarch3 (rows of >= 256 voxels; unrolled row loop, symmetric-tap
+    chain, aligned-pair window for the axis-2 operands; full-tap chain LSF_SYM=0) against k_sobolev_ymarch2
+    (LSF_YMARCH3=0) and the first-generation kernels, on volumes with one z tile, with two z tiles (halo threads) and
+    with a ragged last tile, odd chunk sizes along y -- bit-identical. The non-symmetric kernel exercises the full chain."""
+    from lsf_b200 import synthetic
+    rng = np.random.default_rng(11)
+    for shape in ((24, 40, 256), (16, 24, 512), (12, 20, 328)):
+        base_c, base_l = synthetic.sphere_plane_pair_3d(64)
+        reps = [int(np.ceil(s / 64)) for s in shape]
+        canonical = np.tile(base_c, reps)[:shape[0], :shape[1], :shape[2]].copy()
+        live = np.tile(base_l, reps)[:shape[0], :shape[1], :shape[2]].copy()
+        for kernel in (synthetic.sobolev_kernel_1d(taps), rng.random(taps).astype(np.float32) * 0.3):
+            kwargs = dict(HIER_MODES[mode])
+            kwargs.update(maximum_chunk_size=2, maximum_iteration_count=6, kernel=kernel)
+            fast = lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live)
+            assert np.abs(fast).max() > 0
+            assert lsf._lib.load().lsf_debug_last_path() & 32, "k_sobolev_ymarch3 did not run"
+            for switches in ({"LSF_SYM": "0"}, {"LSF_YCHUNK_T": "7"}, {"LSF_DEFER": "0"},
+                             {"LSF_YMARCH3": "0"}, {"LSF_LEGACY_KERNELS": "1"}):
+                for name, value in switches.items():
+                    monkeypatch.setenv(name, value)
+                assert np.array_equal(lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live), fast), (shape, switches)
+                for name in switches:
+                    monkeypatch.delenv(name)
