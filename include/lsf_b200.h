@@ -109,6 +109,45 @@ int lsf_hier_optimize_2d(const lsf_hier_params* params, const float* canonical, 
 		int H, int W, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
 		lsf_iteration_capture* capture, void* stream);
 
+/* Per-iteration telemetry (reference OptimizerWithTelemetry::optimize_iteration / optimize_level,
+ * cpp/src/nonrigid_optimization/hierarchical/optimizer_with_telemetry.tpp:83-182): with a sink the optimizer runs one
+ * iteration at a time and calls `callback` after every iteration with
+ *   - the numbers behind the reference's VerbosityParameters prints (max update length, mean / standard deviation of
+ *     diff = warped live - canonical, normalised data energy 1e6 * mean(diff^2), normalised Tikhonov energy
+ *     1e6 * 0.5 * mean((sum of the Jacobian entries of the previous gradient)^2)), computed by GPU reductions, and
+ *   - when want_fields != 0, what the reference's OptimizationIterationData stores per iteration
+ *     (cpp/src/telemetry/optimization_iteration_data.tpp; LoggingParameters.collect_per_level_iteration_data): the live
+ *     pyramid level, the warp field after the iteration, the data-term gradient (before the amplifier) and the
+ *     Tikhonov-term gradient (before the strength; NULL when the term is off) as HOST arrays in numpy layout
+ *     ([dims] / [dims][D]) that are valid during the callback only.
+ * iteration == -1 marks the reference's initial frame of hierarchy level 0 (tpp:90-99: zero fields).
+ * The result of optimize() is the same as without a sink (bit for bit); only the speed is not. */
+typedef struct {
+	int level;                       /* 0 = coarsest */
+	int iteration;                   /* 0-based; -1 = initial frame of level 0 */
+	int dims[3];                     /* level dimensions (2D: H, W, 1) */
+	float max_update_length;
+	float mean_tsdf_difference, std_tsdf_difference;
+	float normalized_data_energy, normalized_tikhonov_energy;
+	const float* live_field;
+	const float* warp_field;
+	const float* data_term_gradient;
+	const float* tikhonov_term_gradient;
+} lsf_iteration_record;
+typedef void (*lsf_iteration_callback)(void* user, const lsf_iteration_record* record);
+typedef struct {
+	lsf_iteration_callback callback;
+	void* user;
+	int want_fields;
+	int want_statistics;
+} lsf_iteration_sink;
+int lsf_hier_optimize_3d_telemetry(const lsf_hier_params* params, const float* canonical, const float* live,
+		int X, int Y, int Z, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
+		const lsf_iteration_sink* sink, void* stream);
+int lsf_hier_optimize_2d_telemetry(const lsf_hier_params* params, const float* canonical, const float* live,
+		int H, int W, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
+		const lsf_iteration_sink* sink, void* stream);
+
 /* Batched form for independent frame pairs (reference loop run_hierarchical_optimizer3d_multipair.py:403-406):
  * pair p uses canonical + p*X*Y*Z etc. iteration_counts: [pair_count][LSF_MAX_LEVELS] or NULL. */
 int lsf_hier_optimize_3d_batch(const lsf_hier_params* params, const float* canonical, const float* live,

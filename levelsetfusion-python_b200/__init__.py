@@ -12,7 +12,8 @@ Host-side mirror of the reference API for this path:
 backed by liblsf_b200.so (csrc/, C-ABI in include/lsf_b200.h). No CPU fallback exists.
 """
 from . import _lib
-from .hierarchical import HierarchicalOptimizer2d, HierarchicalOptimizer3d
+from .hierarchical import (HierarchicalOptimizer2d, HierarchicalOptimizer3d, OptimizationIterationData2d,
+                           OptimizationIterationData3d)
 from . import ops
 from . import telemetry
 from .telemetry import (Vector2i, Vector3i, Vector2f, WarpDeltaStatistics2d, WarpDeltaStatistics3d,
@@ -25,7 +26,14 @@ from .slavcheva import (SobolevOptimizer2d, SharedParameters, SobolevParameters,
                         SmoothingTermMethod, warp_field_advanced, warp_field_advanced_no_warp_change,
                         data_term_at_location)
 
-__all__ = ["HierarchicalOptimizer2d", "HierarchicalOptimizer3d", "SobolevOptimizer2d", "SharedParameters",
+# reference python_export/telemetry.tpp:113-145 exports std::vector wrappers of the report / iteration-data types; plain
+# Python lists play that role here
+ConvergenceReportVector2d = ConvergenceReportVector3d = list
+OptimizationIterationDataVector2d = OptimizationIterationDataVector3d = list
+
+__all__ = ["HierarchicalOptimizer2d", "HierarchicalOptimizer3d", "OptimizationIterationData2d",
+           "OptimizationIterationData3d", "ConvergenceReportVector2d", "ConvergenceReportVector3d",
+           "OptimizationIterationDataVector2d", "OptimizationIterationDataVector3d", "SobolevOptimizer2d", "SharedParameters",
            "SobolevParameters", "SlavchevaOptimizer2d", "SlavchevaOptimizer3d", "ComputeMethod",
            "AdaptiveLearningRateMethod", "DataTermMethod", "SmoothingTermMethod", "warp_field_advanced",
            "warp_field_advanced_no_warp_change", "data_term_at_location", "Vector2i", "Vector3i", "Vector2f",

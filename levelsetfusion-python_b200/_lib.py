@@ -69,6 +69,37 @@ class IterationCapture(ctypes.Structure):
     ]
 
 
+class IterationRecord(ctypes.Structure):
+    """lsf_iteration_record (include/lsf_b200.h)"""
+    _fields_ = [
+        ("level", ctypes.c_int),
+        ("iteration", ctypes.c_int),
+        ("dims", ctypes.c_int * 3),
+        ("max_update_length", ctypes.c_float),
+        ("mean_tsdf_difference", ctypes.c_float),
+        ("std_tsdf_difference", ctypes.c_float),
+        ("normalized_data_energy", ctypes.c_float),
+        ("normalized_tikhonov_energy", ctypes.c_float),
+        ("live_field", c_float_p),
+        ("warp_field", c_float_p),
+        ("data_term_gradient", c_float_p),
+        ("tikhonov_term_gradient", c_float_p),
+    ]
+
+
+ITERATION_CALLBACK = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(IterationRecord))
+
+
+class IterationSink(ctypes.Structure):
+    """lsf_iteration_sink (include/lsf_b200.h)"""
+    _fields_ = [
+        ("callback", ITERATION_CALLBACK),
+        ("user", ctypes.c_void_p),
+        ("want_fields", ctypes.c_int),
+        ("want_statistics", ctypes.c_int),
+    ]
+
+
 class SlabLevel(ctypes.Structure):
     """lsf_slab_level"""
     _fields_ = [
@@ -149,7 +180,7 @@ EXPORTED_SYMBOLS = [
     "lsf_convolve_3d", "lsf_convolve_2d", "lsf_downsample_3d", "lsf_upsample_3d", "lsf_downsample_2d",
     "lsf_upsample_2d", "lsf_max_norm",
     "lsf_hier_slab_iteration", "lsf_slab_pack_finest", "lsf_slab_restrict", "lsf_slab_prolong_nearest",
-    "lsf_debug_last_path",
+    "lsf_debug_last_path", "lsf_hier_optimize_3d_telemetry", "lsf_hier_optimize_2d_telemetry",
     "lsf_slavcheva_optimize", "lsf_warp_advanced", "lsf_warp_delta_statistics", "lsf_tsdf_difference_statistics",
 ]
 

@@ -4,6 +4,7 @@
 // hier3d.cu.
 #include "kernels2d.cuh"
 #include "slavcheva.cuh"  // statistics_on_device
+#include "hier_telemetry.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -134,15 +135,64 @@ static __global__ void k_unpack_live2d(const float4* __restrict__ pack, float* _
 	out[idx] = pack[g.padded_index(row, col)].x;
 }
 
-}  // namespace
+// diff = warped live - canonical and the data-term gradient of the current warp (reference optimizer.tpp:186-194)
+static __global__ void k_telemetry_terms2d(const float4* __restrict__ pack, const float* __restrict__ canonical,
+		const float* __restrict__ warp, float* __restrict__ diff, float* __restrict__ data_planes, Grid2 g) {
+	LSF_PIXEL_2D(g);
+	if (!in_grid) return;
+	const float4 s = gather4_2d(pack, g, row, col, warp[idx], warp[g.N + idx]);
+	const float d = s.x - canonical[idx];
+	diff[idx] = d;
+	data_planes[idx] = s.y * d;
+	data_planes[g.N + idx] = s.z * d;
+}
 
-}  // namespace lsf
+// One level with per-iteration telemetry (see lsf_iteration_sink in include/lsf_b200.h and hier3d.cu)
+int run_level_with_telemetry(const Plan2& plan, LevelState2& s, int level, const lsf_iteration_sink* sink,
+		TelemetryScratch& t, cudaStream_t stream, int* executed_out, float* last_max_out) {
+	const long long N = s.g.N;
+	const int dims[3] = { s.g.H, s.g.W, 1 };
+	lsf_iteration_record record;
+	std::memset(&record, 0, sizeof(record));
+	record.level = level;
+	for (int i = 0; i < 3; i++) record.dims[i] = dims[i];
+	k_unpack_live2d<<<counted(grid2(s.g)), block3(), 0, stream>>>(s.pack, t.live_level, s.g);
+	if (level == 0 && sink->want_fields) {
+		LSF_CUDA(cudaMemsetAsync(t.data_planes, 0, (size_t) N * 2 * sizeof(float), stream));
+		if (plan.tikhonov) LSF_CUDA(cudaMemsetAsync(t.tikhonov_planes, 0, (size_t) N * 2 * sizeof(float), stream));
+		record.iteration = -1;
+		LSF_TRY(telemetry_fields(t, N, 2, t.data_planes, plan.tikhonov, &record, stream));
+		sink->callback(sink->user, &record);
+	}
+	int executed = 0;
+	float last_max = FLT_MAX;
+	unsigned bits = 0;
+	for (int it = 0; it < plan.max_iterations; it++) {
+		if (last_max < plan.threshold) break;  // reference optimizer.tpp:149,166-171
+		k_telemetry_terms2d<<<counted(grid2(s.g)), block3(), 0, stream>>>(s.pack, s.canonical, s.warp, t.diff, t.data_planes, s.g);
+		if (plan.tikhonov)
+			k_laplacian_planes2d<<<counted(grid2(s.g)), block3(), 0, stream>>>(s.g_post, t.tikhonov_planes, 2, s.g);
+		record.iteration = it;
+		if (sink->want_statistics) LSF_TRY(telemetry_statistics(t, N, 2, dims, s.g_post, plan.tikhonov, &record, stream));
+		enqueue_iteration(plan, s, it, stream);
+		LSF_CUDA(cudaMemcpyAsync(&bits, s.max_sq_bits + it, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+		LSF_CUDA(cudaStreamSynchronize(stream));
+		float sq;
+		std::memcpy(&sq, &bits, sizeof(float));
+		last_max = std::sqrt(sq);
+		executed = it + 1;
+		record.max_update_length = last_max;
+		if (sink->want_fields) LSF_TRY(telemetry_fields(t, N, 2, s.warp, plan.tikhonov, &record, stream));
+		sink->callback(sink->user, &record);
+	}
+	*executed_out = executed;
+	*last_max_out = last_max;
+	return LSF_OK;
+}
 
-using namespace lsf;
-
-extern "C" int lsf_hier_optimize_2d(const lsf_hier_params* params, const float* canonical, const float* live, int H,
+int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, const float* live, int H,
 		int W, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
-		lsf_iteration_capture* capture, void* stream_handle) {
+		lsf_iteration_capture* capture, const lsf_iteration_sink* sink, void* stream_handle) {
 	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
 	Plan2 plan;
 	LSF_TRY(make_plan(params, H, W, &plan));
@@ -198,6 +248,8 @@ extern "C" int lsf_hier_optimize_2d(const lsf_hier_params* params, const float* 
 	LSF_TRY(arena.alloc(&max_sq_bits, (size_t) slot_count));
 	std::vector<unsigned> host_bits((size_t) slot_count);
 	LSF_CUDA(cudaMemsetAsync(warp_current, 0, (size_t) plan.level_grid[0].N * 2 * sizeof(float), stream));
+	TelemetryScratch telemetry;
+	if (sink != nullptr) LSF_TRY(telemetry.allocate(arena, N, 2, plan.tikhonov, sink->want_fields != 0));
 
 	float* capture_dev = nullptr;
 	if (capture) {
@@ -224,6 +276,10 @@ extern "C" int lsf_hier_optimize_2d(const lsf_hier_params* params, const float* 
 		int executed = 0, enqueued = 0;
 		bool converged = false;
 		float last_max = FLT_MAX;
+		if (sink != nullptr) {
+			LSF_TRY(run_level_with_telemetry(plan, s, level, sink, telemetry, stream, &executed, &last_max));
+			converged = true;  // the level is done
+		}
 		while (!converged && enqueued < plan.max_iterations) {
 			const int chunk_end = std::min(plan.max_iterations, enqueued + POLL_CHUNK);
 			for (int it = enqueued; it < chunk_end; it++) {
@@ -300,4 +356,25 @@ extern "C" int lsf_hier_optimize_2d(const lsf_hier_params* params, const float* 
 		LSF_TRY(from_device(out_dev, warp_out, N * 2, LSF_HOST, stream));
 	}
 	return L;
+}
+
+}  // namespace
+
+}  // namespace lsf
+
+using namespace lsf;
+
+extern "C" int lsf_hier_optimize_2d(const lsf_hier_params* params, const float* canonical, const float* live, int H,
+		int W, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
+		lsf_iteration_capture* capture, void* stream_handle) {
+	return hier_optimize_2d(params, canonical, live, H, W, warp_out, memory_kind, reports, collect_reports, capture, nullptr,
+			stream_handle);
+}
+
+extern "C" int lsf_hier_optimize_2d_telemetry(const lsf_hier_params* params, const float* canonical, const float* live,
+		int H, int W, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
+		const lsf_iteration_sink* sink, void* stream_handle) {
+	LSF_REQUIRE(sink == nullptr || sink->callback != nullptr, "the iteration sink has no callback");
+	return hier_optimize_2d(params, canonical, live, H, W, warp_out, memory_kind, reports, collect_reports, nullptr, sink,
+			stream_handle);
 }

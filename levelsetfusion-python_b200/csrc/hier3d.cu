@@ -10,6 +10,7 @@
 #include "kernels3d_pair.cuh"
 #include "kernels3d_ymarch3.cuh"
 #include "slavcheva.cuh"  // statistics_on_device
+#include "hier_telemetry.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -453,6 +454,65 @@ void fill_report_statistics(lsf_level_report& r, const lsf_warp_delta_statistics
 	for (int i = 0; i < 3; i++) r.diff_biggest_location[i] = d.biggest_difference_location[i];
 }
 
+// diff = warped live - canonical and the data-term gradient (resampled live gradient * diff) of the current warp
+// (reference optimizer.tpp:186-194), for the telemetry path
+static __global__ void k_telemetry_terms3d(const float4* __restrict__ pack, const float* __restrict__ canonical,
+		const float* __restrict__ warp, float* __restrict__ diff, float* __restrict__ data_planes, Grid3 g) {
+	LSF_VOXEL_3D(g);
+	if (!in_grid) return;
+	const float4 s = gather4(pack, g, x, y, z, warp[idx], warp[g.N + idx], warp[2 * g.N + idx]);
+	const float d = s.x - canonical[idx];
+	diff[idx] = d;
+	data_planes[idx] = s.y * d;
+	data_planes[g.N + idx] = s.z * d;
+	data_planes[2 * g.N + idx] = s.w * d;
+}
+
+// One level with per-iteration telemetry (see lsf_iteration_sink): one iteration at a time, first-in-line kernels of the
+// production path for the iteration itself (no deferred update: the warp after every iteration is wanted).
+int run_level_with_telemetry(const Plan3& plan, LevelState& s, int level, const lsf_iteration_sink* sink,
+		TelemetryScratch& t, cudaStream_t stream, int* executed_out, float* last_max_out) {
+	const long long N = s.g.N;
+	const int dims[3] = { s.g.X, s.g.Y, s.g.Z };
+	lsf_iteration_record record;
+	std::memset(&record, 0, sizeof(record));
+	record.level = level;
+	for (int i = 0; i < 3; i++) record.dims[i] = dims[i];
+	k_unpack_live3d<<<counted(grid3(s.g)), block3(), 0, stream>>>(s.pack, t.live_level, s.g);
+	if (level == 0 && sink->want_fields) {
+		// reference optimizer_with_telemetry.tpp:90-99: the first frame of level 0 holds the live level and zero fields
+		LSF_CUDA(cudaMemsetAsync(t.data_planes, 0, (size_t) N * 3 * sizeof(float), stream));
+		if (plan.tikhonov) LSF_CUDA(cudaMemsetAsync(t.tikhonov_planes, 0, (size_t) N * 3 * sizeof(float), stream));
+		record.iteration = -1;
+		LSF_TRY(telemetry_fields(t, N, 3, t.data_planes, plan.tikhonov, &record, stream));
+		sink->callback(sink->user, &record);
+	}
+	int executed = 0;
+	float last_max = FLT_MAX;
+	unsigned bits = 0;
+	for (int it = 0; it < plan.max_iterations; it++) {
+		if (last_max < plan.threshold) break;  // reference optimizer.tpp:149,166-171
+		k_telemetry_terms3d<<<counted(grid3(s.g)), block3(), 0, stream>>>(s.pack, s.canonical, s.warp, t.diff, t.data_planes, s.g);
+		if (plan.tikhonov)
+			k_laplacian_planes3d<<<counted(grid3(s.g)), block3(), 0, stream>>>(s.g_post, t.tikhonov_planes, 3, s.g);
+		record.iteration = it;
+		if (sink->want_statistics) LSF_TRY(telemetry_statistics(t, N, 3, dims, s.g_post, plan.tikhonov, &record, stream));
+		LSF_TRY(enqueue_iteration(plan, s, it, false, stream));
+		LSF_CUDA(cudaMemcpyAsync(&bits, s.max_sq_bits + it, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+		LSF_CUDA(cudaStreamSynchronize(stream));
+		float sq;
+		std::memcpy(&sq, &bits, sizeof(float));
+		last_max = std::sqrt(sq);
+		executed = it + 1;
+		record.max_update_length = last_max;
+		if (sink->want_fields) LSF_TRY(telemetry_fields(t, N, 3, s.warp, plan.tikhonov, &record, stream));
+		sink->callback(sink->user, &record);
+	}
+	*executed_out = executed;
+	*last_max_out = last_max;
+	return LSF_OK;
+}
+
 // Deferred warp update (k_hier_stage1_tma APPLY): usable when the level runs the TMA generation with both the Tikhonov
 // term and a Sobolev kernel, on the whole volume.
 bool deferred_update_applies(const Plan3& plan, const LevelState& s) {
@@ -475,7 +535,7 @@ void finish_deferred(const Plan3& plan, LevelState& s, int executed, cudaStream_
 
 int optimize_device(const Plan3& plan, const float* canonical_dev, const float* live_dev, float* warp_out_dev,
 		lsf_level_report* reports, int collect_reports, lsf_iteration_capture* capture, float* capture_dev,
-		cudaStream_t stream) {
+		cudaStream_t stream, const lsf_iteration_sink* sink = nullptr) {
 	Arena arena(stream);
 	const int L = plan.level_count;
 	const Grid3& finest = plan.level_grid[L - 1];
@@ -498,7 +558,9 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 	const char* pipeline_env = getenv("LSF_PIPELINE_POLL");  // A/B: 0 = drain the stream at every poll
 	const bool pipelined = !(pipeline_env && pipeline_env[0] == '0');
 	float* warp_pong = nullptr;  // second warp buffer of the deferred update
-	if (plan.tikhonov && plan.use_kernel) LSF_TRY(arena.alloc(&warp_pong, (size_t) finest.N * 3));
+	if (plan.tikhonov && plan.use_kernel && sink == nullptr) LSF_TRY(arena.alloc(&warp_pong, (size_t) finest.N * 3));
+	TelemetryScratch telemetry;
+	if (sink != nullptr) LSF_TRY(telemetry.allocate(arena, (size_t) finest.N, 3, plan.tikhonov, sink->want_fields != 0));
 
 	// the finest level lives in warp_a (3N floats), the level below it in warp_b (3N/8), and so on alternating
 	float* warp_current = ((L - 1) % 2 == 0) ? warp_a : warp_b;
@@ -553,6 +615,10 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 		};
 		int pending_begin = 0, pending_end = std::min(plan.max_iterations, POLL_CHUNK);
 		int parity = 0;
+		if (sink != nullptr) {
+			LSF_TRY(run_level_with_telemetry(plan, s, level, sink, telemetry, stream, &executed, &last_max));
+			pending_end = 0;
+		}
 		if (pending_end > 0) LSF_TRY(enqueue_chunk(0, pending_end, poll.events[parity]));
 		enqueued = pending_end;
 		while (!converged && pending_begin < pending_end) {
@@ -657,6 +723,26 @@ extern "C" int lsf_hier_optimize_3d(const lsf_hier_params* params, const float* 
 		}
 		LSF_TRY(from_device(out_dev, warp_out, N * 3, LSF_HOST, stream));
 	}
+	return plan.level_count;
+}
+
+extern "C" int lsf_hier_optimize_3d_telemetry(const lsf_hier_params* params, const float* canonical, const float* live,
+		int X, int Y, int Z, float* warp_out, int memory_kind, lsf_level_report* reports, int collect_reports,
+		const lsf_iteration_sink* sink, void* stream_handle) {
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
+	Plan3 plan;
+	LSF_TRY(make_plan(params, X, Y, Z, &plan));
+	LSF_REQUIRE(canonical && live && warp_out, "canonical, live and warp_out must not be NULL");
+	LSF_REQUIRE(sink == nullptr || sink->callback != nullptr, "the iteration sink has no callback");
+	const size_t N = (size_t) X * Y * Z;
+	Arena arena(stream);
+	const float *canonical_dev, *live_dev;
+	LSF_TRY(to_device(arena, canonical, N, memory_kind, stream, &canonical_dev));
+	LSF_TRY(to_device(arena, live, N, memory_kind, stream, &live_dev));
+	float* out_dev = warp_out;
+	if (memory_kind == LSF_HOST) LSF_TRY(arena.alloc(&out_dev, N * 3));
+	LSF_TRY(optimize_device(plan, canonical_dev, live_dev, out_dev, reports, collect_reports, nullptr, nullptr, stream, sink));
+	if (memory_kind == LSF_HOST) LSF_TRY(from_device(out_dev, warp_out, N * 3, LSF_HOST, stream));
 	return plan.level_count;
 }
 

@@ -36,6 +36,49 @@ def _report_from_raw(nd, raw, with_statistics):
     return report
 
 
+class OptimizationIterationData:
+    """reference telemetry::OptimizationIterationData (cpp/src/telemetry/optimization_iteration_data.tpp, exported as
+    OptimizationIterationData2d / 3d, python_export/telemetry.tpp:136-145): what one pyramid level's iterations left
+    behind when LoggingParameters.collect_per_level_iteration_data is set. Frame i of a level holds the live pyramid
+    level, the warp field after iteration i, and the data-term / Tikhonov-term gradients of that iteration (level 0
+    starts with one extra frame of zero fields, optimizer_with_telemetry.tpp:90-99)."""
+
+    def __init__(self):
+        self._live_fields = []
+        self._warp_fields = []
+        self._data_term_gradients = []
+        self._tikhonov_term_gradients = []
+
+    def add_iteration_result(self, live_field, warp_field, data_term_gradients, tikhonov_term_gradients):
+        self._live_fields.append(live_field)
+        self._warp_fields.append(warp_field)
+        self._data_term_gradients.append(data_term_gradients)
+        self._tikhonov_term_gradients.append(tikhonov_term_gradients)
+
+    def get_live_fields(self):
+        return list(self._live_fields)
+
+    def get_warp_fields(self):
+        return list(self._warp_fields)
+
+    def get_data_term_gradients(self):
+        return list(self._data_term_gradients)
+
+    def get_tikhonov_term_gradients(self):
+        return list(self._tikhonov_term_gradients)
+
+    def get_frame_count(self):
+        return len(self._live_fields)
+
+
+class OptimizationIterationData2d(OptimizationIterationData):
+    pass
+
+
+class OptimizationIterationData3d(OptimizationIterationData):
+    pass
+
+
 class _HierarchicalOptimizer:
     _nd = 0
 
@@ -168,17 +211,95 @@ class _HierarchicalOptimizer:
             if capture_level >= 0 and capture_iterations > 0:
                 capture_buffer = np.zeros((capture_iterations,) + level_shape + (nd,), dtype=np.float32)
                 capture.buffer = ptr(capture_buffer)
-        fn = lib.lsf_hier_optimize_2d if nd == 2 else lib.lsf_hier_optimize_3d
         collect = int(self.logging_parameters.collect_per_level_convergence_reports)
-        levels = _lib.check(fn(ctypes.byref(params), ptr(canonical), ptr(live), *[ctypes.c_int(d) for d in shape],
-                               ptr(warp), kind, reports, collect, ctypes.byref(capture), stream))
+        want_fields = bool(self.logging_parameters.collect_per_level_iteration_data)
+        want_prints = bool(self.verbosity_parameters.print_per_iteration_info)
+        self._iteration_data = []
+        if want_fields or want_prints:
+            # reference OptimizerWithTelemetry (optimizer_with_telemetry.tpp:83-182): the library runs one iteration at a
+            # time and reports every iteration through a callback
+            levels = self._optimize_with_telemetry(lib, params, ptr, canonical, live, shape, warp, kind, reports, collect,
+                                                   stream, want_fields, want_prints)
+            self._captured = None
+        else:
+            fn = lib.lsf_hier_optimize_2d if nd == 2 else lib.lsf_hier_optimize_3d
+            levels = _lib.check(fn(ctypes.byref(params), ptr(canonical), ptr(live), *[ctypes.c_int(d) for d in shape],
+                                   ptr(warp), kind, reports, collect, ctypes.byref(capture), stream))
+            self._captured = None if capture_buffer is None else capture_buffer[:capture.count]
         self._reports = [_report_from_raw(nd, reports[i], bool(collect)) for i in range(levels)]
-        self._captured = None if capture_buffer is None else capture_buffer[:capture.count]
-        if self.verbosity_parameters.print_per_level_info:
-            for level, report in enumerate(self._reports):
-                print("[LEVEL %d COMPLETED] iterations: %d max upd. l.: %g"
-                      % (level, report.iteration_count, report.max_update_length))
         return warp
+
+    def _optimize_with_telemetry(self, lib, params, ptr, canonical, live, shape, warp, kind, reports, collect, stream,
+                                 want_fields, want_prints):
+        nd = self._nd
+        verbosity = self.verbosity_parameters
+        data_class = OptimizationIterationData2d if nd == 2 else OptimizationIterationData3d
+        per_level = self._iteration_data
+        state = {"level": -1}
+
+        def level_done(level):
+            if verbosity.print_per_level_info:
+                print("[LEVEL %d COMPLETED]" % level)  # reference optimizer_with_telemetry.tpp:102-105
+
+        def on_iteration(_user, record_pointer):
+            record = record_pointer.contents
+            if record.level != state["level"]:
+                if state["level"] >= 0:
+                    level_done(state["level"])
+                state["level"] = record.level
+                if want_fields:
+                    per_level.append(data_class())
+            if want_fields:
+                dims = tuple(record.dims[:nd])
+                count = int(np.prod(dims))
+
+                def field(pointer, channels):
+                    if not pointer:
+                        return np.zeros((0,) * (nd + 1), np.float32)  # the reference stores an empty container
+                    flat = np.ctypeslib.as_array(pointer, shape=(count * channels,))
+                    return flat.reshape(dims + ((channels,) if channels > 1 else ())).copy()
+
+                per_level[-1].add_iteration_result(field(record.live_field, 1), field(record.warp_field, nd),
+                                                   field(record.data_term_gradient, nd),
+                                                   field(record.tikhonov_term_gradient, nd))
+            if want_prints and record.iteration >= 0:
+                # reference optimizer_with_telemetry.tpp:161-181 (current_iteration is printed before its increment)
+                line = "[ITERATION %d COMPLETED]" % record.iteration
+                if verbosity.print_iteration_max_warp_update:
+                    line += " [max upd. l.: %g]" % record.max_update_length
+                if verbosity.print_iteration_mean_tsdf_difference:
+                    line += " [mean diff.: %g]" % record.mean_tsdf_difference
+                if verbosity.print_iteration_std_tsdf_difference:
+                    line += " [std diff.: %g]" % record.std_tsdf_difference
+                if verbosity.print_iteration_data_energy:
+                    line += " [norm. data energy: %g]" % record.normalized_data_energy
+                if verbosity.print_iteration_tikhonov_energy and self.tikhonov_term_enabled:
+                    line += " [norm. tikhonov energy: %g]" % record.normalized_tikhonov_energy
+                print(line)
+            self._last_iteration_statistics = (record.max_update_length, record.mean_tsdf_difference,
+                                               record.std_tsdf_difference, record.normalized_data_energy,
+                                               record.normalized_tikhonov_energy)
+            self._iteration_statistics.append((record.level, record.iteration) + self._last_iteration_statistics)
+
+        self._iteration_statistics = []
+        sink = _lib.IterationSink()
+        callback = _lib.ITERATION_CALLBACK(on_iteration)
+        sink.callback = callback
+        sink.user = None
+        sink.want_fields = int(want_fields)
+        sink.want_statistics = 1
+        fn = lib.lsf_hier_optimize_2d_telemetry if nd == 2 else lib.lsf_hier_optimize_3d_telemetry
+        levels = _lib.check(fn(ctypes.byref(params), ptr(canonical), ptr(live), *[ctypes.c_int(d) for d in shape],
+                               ptr(warp), kind, reports, collect, ctypes.byref(sink), stream))
+        if state["level"] >= 0:
+            level_done(state["level"])
+        return levels
+
+    def get_per_iteration_statistics(self):
+        """(extension) the numbers behind the reference's per-iteration prints, one tuple per iteration of the last
+        optimize() call that ran with telemetry: (level, iteration, max update length, mean diff, std diff, normalised
+        data energy, normalised Tikhonov energy)."""
+        return list(getattr(self, "_iteration_statistics", []))
 
     def get_per_level_convergence_reports(self):
         return list(self._reports)

@@ -416,7 +416,7 @@ def test_ymarch3_filter_matches_previous_generations(lsf, mode, taps, monkeypatc
     with a ragged last tile, odd chunk sizes along y -- bit-identical. The non-symmetric kernel exercises the full chain."""
     from lsf_b200 import synthetic
     rng = np.random.default_rng(11)
-    for shape in ((24, 40, 256), (16, 24, 512), (12, 20, 328)):
+    for shape in ((40, 40, 256), (26, 24, 512), (26, 20, 328)):
         base_c, base_l = synthetic.sphere_plane_pair_3d(64)
         reps = [int(np.ceil(s / 64)) for s in shape]
         canonical = np.tile(base_c, reps)[:shape[0], :shape[1], :shape[2]].copy()
@@ -427,7 +427,7 @@ def test_ymarch3_filter_matches_previous_generations(lsf, mode, taps, monkeypatc
             fast = lsf.HierarchicalOptimizer3d(**kwargs).optimize(canonical, live)
             assert np.abs(fast).max() > 0
             assert lsf._lib.load().lsf_debug_last_path() & 32, "k_sobolev_ymarch3 did not run"
-            for switches in ({"LSF_SYM": "0"}, {"LSF_YCHUNK_T": "7"}, {"LSF_DEFER": "0"},
+            for switches in ({"LSF_SYM": "0"}, {"LSF_YCHUNK_T": "7"}, {"LSF_DEFER": "0"}, {"LSF_XCHUNK_T": "13"},
                              {"LSF_YMARCH3": "0"}, {"LSF_LEGACY_KERNELS": "1"}):
                 for name, value in switches.items():
                     monkeypatch.setenv(name, value)
