@@ -279,7 +279,8 @@ class _HierarchicalOptimizer:
             self._last_iteration_statistics = (record.max_update_length, record.mean_tsdf_difference,
                                                record.std_tsdf_difference, record.normalized_data_energy,
                                                record.normalized_tikhonov_energy)
-            self._iteration_statistics.append((record.level, record.iteration) + self._last_iteration_statistics)
+            if record.iteration >= 0:
+                self._iteration_statistics.append((record.level, record.iteration) + self._last_iteration_statistics)
 
         self._iteration_statistics = []
         sink = _lib.IterationSink()
