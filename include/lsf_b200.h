@@ -149,7 +149,11 @@ int lsf_hier_optimize_2d_telemetry(const lsf_hier_params* params, const float* c
 		const lsf_iteration_sink* sink, void* stream);
 
 /* Batched form for independent frame pairs (reference loop run_hierarchical_optimizer3d_multipair.py:403-406):
- * pair p uses canonical + p*X*Y*Z etc. iteration_counts: [pair_count][LSF_MAX_LEVELS] or NULL. */
+ * pair p uses canonical + p*X*Y*Z etc. iteration_counts: [pair_count][LSF_MAX_LEVELS] or NULL. The pairs advance in
+ * lockstep through the pyramid levels and every iteration kernel covers all pairs of a sub-batch (one launch sequence
+ * per iteration for the whole batch: the coarse levels are launch-bound otherwise), with per-pair termination on the
+ * device; results per pair are bit-identical to lsf_hier_optimize_3d. Settings the batched kernels do not cover
+ * (LINEAR resampling, kernels wider than 7 taps, Z not a multiple of 4) fall back to a loop over the pairs. */
 int lsf_hier_optimize_3d_batch(const lsf_hier_params* params, const float* canonical, const float* live,
 		int pair_count, int X, int Y, int Z, float* warp_out, int memory_kind, int* iteration_counts, void* stream);
 

@@ -172,6 +172,9 @@ struct LevelState {
 	TmaMaps maps_alt;            // the same with the gradient's other ping-pong buffer (iterations without a Sobolev kernel)
 	                             // or the warp's other ping-pong buffer (deferred update)
 	float* scratch_h = nullptr;  // planes: slab mode, the gradient after the axis-0 pass (fast filter phase)
+	// batch of pairs (HierIterArgs::batch_X): g.X = pairs * batch_X planes
+	int batch_pairs = 0, batch_X = 0, batch_slot_stride = 0;
+	long long batch_pack_stride = 0;
 	float* warp_alt = nullptr;   // planes: second warp buffer. Non-null = deferred warp update (Tikhonov + Sobolev kernel):
 	                             // iteration i reads warp (i even) / warp_alt (i odd) and writes the other one; after E
 	                             // executed iterations finish_deferred() leaves the final warp in `warp`
@@ -202,6 +205,14 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 	a.iteration = iteration;
 	a.check_convergence = check_convergence ? 1 : 0;
 	whole_volume(a);
+	if (s.batch_pairs > 0) {
+		a.batch_X = s.batch_X;
+		a.batch_pack_stride = s.batch_pack_stride;
+		a.batch_slot_stride = s.batch_slot_stride;
+		a.pack_X = s.batch_X;
+	}
+	const int volumes = s.batch_pairs > 0 ? s.batch_pairs : 1;       // tiles of the wave model: per plane x volumes
+	const int planes_per_volume = s.batch_pairs > 0 ? s.batch_X : s.g.X;
 	if (s.slab) {
 		a.x_begin = s.x_begin;
 		a.x_end = s.x_end;
@@ -242,8 +253,8 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 				&& (!plan.tikhonov || aligned16(s.scratch_a))) {
 			// TMA-fed stage 1 with the warp update and the max-norm fused (one launch per iteration)
 			g_last_path = LSF_PATH_TMA_STAGE1 | LSF_PATH_FUSED_UPDATE;
-			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8));
-			const int planes = x_end - x_begin;
+			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8)) * volumes;
+			const int planes = s.batch_pairs > 0 ? planes_per_volume : x_end - x_begin;
 			const int chunk_x = plan.x_chunk_tma > 0 ? std::min(plan.x_chunk_tma, planes) : marching_chunk(planes, tiles, 0, 3);
 			int status;
 			if (plan.tikhonov) {
@@ -276,9 +287,9 @@ int enqueue_iteration(const Plan3& plan, LevelState& s, int iteration, bool chec
 		// second-generation cut: stage 1 + axis-0 pass, then axis-1/2 passes + update (kernels3d_split.cuh)
 		float* filtered = plan.tikhonov ? s.g_post : nullptr;
 		if (plan.tma && tma_supported(s.g, s.warp, s.canonical, s.g_post) && aligned16(s.scratch_a)) {
-			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8));
-			const int chunk_x = plan.x_chunk_tma > 0 ? std::min(plan.x_chunk_tma, s.g.X)
-					: marching_chunk(s.g.X, tiles, 2 * plan.taps.radius, 3);
+			const int tiles = (int) (div_up(s.g.Z, 32) * div_up(s.g.Y, 8)) * volumes;
+			const int chunk_x = plan.x_chunk_tma > 0 ? std::min(plan.x_chunk_tma, planes_per_volume)
+					: marching_chunk(planes_per_volume, tiles, 2 * plan.taps.radius, 3);
 			const int filter_tiles = (int) (div_up(s.g.Z, 512) * s.g.X);
 			const int chunk_y = plan.y_chunk_tma > 0 ? std::min(plan.y_chunk_tma, s.g.Y)
 					: marching_chunk(s.g.Y, filter_tiles, 2 * plan.taps.radius, 6);
@@ -687,6 +698,179 @@ int optimize_device(const Plan3& plan, const float* canonical_dev, const float* 
 	return LSF_OK;
 }
 
+// Pending update of a deferred level for a batch of pairs: pair p stopped after executed[p] iterations, so its warp
+// before the last update sits in `even` (executed[p] even) or `odd`; out = that - g * rate (out may alias even).
+static __global__ void k_apply_update3d_batch(const float* __restrict__ even, const float* __restrict__ odd,
+		const float* __restrict__ g, float* __restrict__ out, float rate, long long pair_voxels, long long batch_voxels,
+		const int* __restrict__ executed) {
+	const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 3 * batch_voxels) return;
+	const int pair = (int) ((i % batch_voxels) / pair_voxels);
+	const float w = (executed[pair] % 2 == 0) ? even[i] : odd[i];
+	out[i] = w - g[i] * rate;
+}
+
+// Can the batched level loop run this plan on `pairs` pairs at once? (else the caller loops over the pairs)
+bool batch_supported(const Plan3& plan, int pairs) {
+	const char* e = getenv("LSF_BATCH");  // A/B: LSF_BATCH=0 optimises the pairs one after the other
+	if (e && e[0] == '0') return false;
+	if (pairs < 2 || plan.linear || !plan.allow_fast_kernels || !plan.tma || !plan.split_x || plan.pair_tile_y != 0) return false;
+	if (plan.use_kernel && (plan.taps.radius < 1 || plan.taps.radius > 3)) return false;
+	for (int level = 0; level < plan.level_count; level++) {
+		const Grid3& g = plan.level_grid[level];
+		if (g.Z % 4 != 0 || g.N % 2 != 0) return false;
+		if ((long long) pairs * g.N * 3 >= (1ll << 31)) return false;
+		if ((long long) (g.X + 4) * (g.Y + 4) * (g.Z + 4) >= (1ll << 31)) return false;
+	}
+	return true;
+}
+
+// Batched optimize() (reference loop run_hierarchical_optimizer3d_multipair.py:403-406 over independent pairs; SURVEY
+// 8e): the pairs advance in lockstep through the pyramid levels and every iteration kernel covers all of them
+// (HierIterArgs::batch_X), so the launch-bound coarse levels cost one launch sequence for the whole batch. Termination
+// is per pair: each pair has its own row of convergence slots, its kernels' blocks return once it has converged, and
+// the level ends when every pair has. Results per pair are bit-identical to lsf_hier_optimize_3d.
+int optimize_batch_device(const Plan3& plan, int pairs, const float* canonical_dev, const float* live_dev,
+		float* warp_out_dev, int* iteration_counts, cudaStream_t stream) {
+	Arena arena(stream);
+	const int L = plan.level_count;
+	const Grid3& finest = plan.level_grid[L - 1];
+	const size_t P = (size_t) pairs;
+	const float4 border = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+	// pyramids: one padded pack per pair and level, canonical levels one pair after the other
+	std::vector<float4*> packs(L, nullptr);
+	std::vector<const float*> canonicals(L, nullptr);
+	for (int level = L - 1; level >= 0; level--) {
+		const Grid3& g = plan.level_grid[level];
+		const long long padded = g.padded_count();
+		LSF_TRY(arena.alloc(&packs[level], (size_t) padded * P));
+		k_fill4<<<counted(div_up(padded * pairs, 256)), 256, 0, stream>>>(packs[level], padded * pairs, border);
+		float* canonical_level = nullptr;
+		if (level == L - 1) canonicals[level] = canonical_dev;
+		else {
+			LSF_TRY(arena.alloc(&canonical_level, (size_t) g.N * P));
+			canonicals[level] = canonical_level;
+		}
+		for (int pair = 0; pair < pairs; pair++) {
+			if (level == L - 1) {
+				k_gradient_pack3d<<<counted(grid3(g)), block3(), 0, stream>>>(live_dev + (size_t) pair * g.N,
+						packs[level] + (size_t) pair * padded, g);
+			} else {
+				const Grid3& src = plan.level_grid[level + 1];
+				launch_downsample(false, PackAccess { packs[level + 1] + (size_t) pair * src.padded_count(),
+						packs[level] + (size_t) pair * padded }, src, g, stream);
+				launch_downsample(false, PlainAccess { canonicals[level + 1] + (size_t) pair * src.N,
+						canonical_level + (size_t) pair * g.N }, src, g, stream);
+			}
+		}
+	}
+	LSF_CUDA(cudaGetLastError());
+
+	float *warp_a, *warp_b, *g_post, *scratch_a = nullptr, *warp_pong = nullptr;
+	unsigned* max_sq_bits;
+	int* executed_dev;
+	LSF_TRY(arena.alloc(&warp_a, (size_t) finest.N * 3 * P));
+	LSF_TRY(arena.alloc(&warp_b, ((size_t) finest.N * 3 / 8 + 16) * P));
+	LSF_TRY(arena.alloc(&g_post, (size_t) finest.N * 3 * P));
+	if (plan.use_kernel || plan.tikhonov) LSF_TRY(arena.alloc(&scratch_a, (size_t) finest.N * 3 * P));
+	if (plan.tikhonov && plan.use_kernel) LSF_TRY(arena.alloc(&warp_pong, (size_t) finest.N * 3 * P));
+	const int slot_count = std::max(plan.max_iterations, 1);
+	LSF_TRY(arena.alloc(&max_sq_bits, (size_t) slot_count * P));
+	LSF_TRY(arena.alloc(&executed_dev, P));
+	PollState& poll = poll_state();
+	LSF_TRY(poll.reserve((size_t) slot_count * P));
+	unsigned* host_bits = poll.host_bits;  // [pair][slot]
+
+	float* warp_current = ((L - 1) % 2 == 0) ? warp_a : warp_b;
+	float* warp_next = ((L - 1) % 2 == 0) ? warp_b : warp_a;
+	LSF_CUDA(cudaMemsetAsync(warp_current, 0, (size_t) plan.level_grid[0].N * 3 * P * sizeof(float), stream));
+	std::vector<int> executed(P), done(P);
+	std::vector<float> last_max(P);
+
+	for (int level = 0; level < L; level++) {
+		const Grid3& lg = plan.level_grid[level];
+		LevelState s;
+		s.g = Grid3(lg.X * pairs, lg.Y, lg.Z);
+		s.batch_pairs = pairs;
+		s.batch_X = lg.X;
+		s.batch_pack_stride = lg.padded_count();
+		s.batch_slot_stride = slot_count;
+		s.pack = packs[level];
+		s.canonical = canonicals[level];
+		s.warp = warp_current;
+		s.g_post = g_post;
+		s.scratch_a = scratch_a;
+		s.scratch_b = nullptr;
+		s.max_sq_bits = max_sq_bits;
+		LSF_CUDA(cudaMemsetAsync(g_post, 0, (size_t) s.g.N * 3 * sizeof(float), stream));
+		LSF_CUDA(cudaMemsetAsync(max_sq_bits, 0, (size_t) slot_count * P * sizeof(unsigned), stream));
+		LSF_REQUIRE(tma_supported(s.g, s.warp, s.canonical, s.g_post) && ymarch2_supported(s.g, s.scratch_a, s.g_post, s.warp),
+				"internal: the batched level loop does not apply to level %d", level);
+		if (warp_pong != nullptr && deferred_update_applies(plan, s)) s.warp_alt = warp_pong;
+		std::fill(executed.begin(), executed.end(), 0);
+		std::fill(done.begin(), done.end(), 0);
+		std::fill(last_max.begin(), last_max.end(), FLT_MAX);
+		int remaining = pairs;
+		auto enqueue_chunk = [&](int begin, int end, cudaEvent_t finished) -> int {
+			for (int it = begin; it < end; it++) LSF_TRY(enqueue_iteration(plan, s, it, true, stream));
+			LSF_CUDA(cudaGetLastError());
+			LSF_CUDA(cudaMemcpy2DAsync(host_bits + begin, (size_t) slot_count * sizeof(unsigned), max_sq_bits + begin,
+					(size_t) slot_count * sizeof(unsigned), (size_t) (end - begin) * sizeof(unsigned), P,
+					cudaMemcpyDeviceToHost, stream));
+			LSF_CUDA(cudaEventRecord(finished, stream));
+			return LSF_OK;
+		};
+		int pending_begin = 0, pending_end = std::min(plan.max_iterations, POLL_CHUNK), enqueued = pending_end, parity = 0;
+		if (pending_end > 0) LSF_TRY(enqueue_chunk(0, pending_end, poll.events[parity]));
+		while (remaining > 0 && pending_begin < pending_end) {
+			const int next_end = std::min(plan.max_iterations, enqueued + POLL_CHUNK);
+			const bool has_next = next_end > enqueued;
+			if (has_next) LSF_TRY(enqueue_chunk(enqueued, next_end, poll.events[parity ^ 1]));
+			LSF_CUDA(cudaEventSynchronize(poll.events[parity]));
+			for (int pair = 0; pair < pairs; pair++) {
+				if (done[pair]) continue;
+				for (int it = pending_begin; it < pending_end; it++) {
+					float sq;
+					std::memcpy(&sq, &host_bits[(size_t) pair * slot_count + it], sizeof(float));
+					last_max[pair] = std::sqrt(sq);
+					executed[pair] = it + 1;
+					if (last_max[pair] < plan.threshold) {  // reference optimizer.tpp:166-171
+						done[pair] = 1;
+						remaining--;
+						break;
+					}
+				}
+			}
+			pending_begin = pending_end;
+			if (has_next) {
+				pending_end = next_end;
+				enqueued = next_end;
+				parity ^= 1;
+			}
+		}
+		if (s.warp_alt != nullptr) {
+			LSF_CUDA(cudaMemcpyAsync(executed_dev, executed.data(), P * sizeof(int), cudaMemcpyHostToDevice, stream));
+			const long long count = s.g.N * 3;
+			k_apply_update3d_batch<<<counted(div_up(count, 256)), 256, 0, stream>>>(s.warp, s.warp_alt, s.g_post, s.warp,
+					plan.rate, lg.N, s.g.N, executed_dev);
+			LSF_CUDA(cudaStreamSynchronize(stream));  // `executed` is re-used by the next level
+		}
+		if (iteration_counts) {
+			for (int pair = 0; pair < pairs; pair++) iteration_counts[pair * LSF_MAX_LEVELS + level] = executed[pair];
+		}
+		if (level != L - 1) {
+			const Grid3& dl = plan.level_grid[level + 1];
+			const Grid3 dg(dl.X * pairs, dl.Y, dl.Z);
+			// reference optimizer.tpp:124-126 (nearest: every voxel's parent lies in the same pair)
+			k_upsample_nearest3d<<<counted(grid3(dg)), block3(), 0, stream>>>(warp_current, warp_next, 3, s.g, dg);
+			std::swap(warp_current, warp_next);
+		}
+	}
+	k_planes_to_aos<<<counted(div_up(finest.N * pairs, 256)), 256, 0, stream>>>(warp_current, warp_out_dev, finest.N * pairs, 3);
+	LSF_CUDA(cudaGetLastError());
+	return LSF_OK;
+}
+
 }  // namespace
 
 }  // namespace lsf
@@ -753,25 +937,51 @@ extern "C" int lsf_debug_last_path(void) {
 extern "C" int lsf_hier_optimize_3d_batch(const lsf_hier_params* params, const float* canonical, const float* live,
 		int pair_count, int X, int Y, int Z, float* warp_out, int memory_kind, int* iteration_counts,
 		void* stream_handle) {
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
 	LSF_REQUIRE(pair_count >= 0, "pair_count must be non-negative");
+	Plan3 plan;
+	LSF_TRY(make_plan(params, X, Y, Z, &plan));
 	const size_t N = (size_t) X * Y * Z;
-	int levels = 0;
-	std::vector<lsf_level_report> reports(LSF_MAX_LEVELS);
-	for (int pair = 0; pair < pair_count; pair++) {
-		levels = lsf_hier_optimize_3d(params, canonical + pair * N, live + pair * N, X, Y, Z, warp_out + pair * N * 3,
-				memory_kind, reports.data(), 0, nullptr, stream_handle);
-		if (levels < 0) return levels;
-		if (iteration_counts) {
-			for (int level = 0; level < LSF_MAX_LEVELS; level++)
-				iteration_counts[pair * LSF_MAX_LEVELS + level] = level < levels ? reports[level].iteration_count : 0;
+	if (pair_count == 0) return plan.level_count;
+	LSF_REQUIRE(canonical && live && warp_out, "canonical, live and warp_out must not be NULL");
+	if (iteration_counts) std::memset(iteration_counts, 0, sizeof(int) * (size_t) pair_count * LSF_MAX_LEVELS);
+	// sub-batches: 32-bit voxel indices inside the kernels (3 * pairs * N < 2^31) and a bound on the scratch memory
+	// (about 17 fields of N floats per pair; LSF_BATCH_BYTES overrides the 24 GB default)
+	const char* budget_env = getenv("LSF_BATCH_BYTES");
+	const double budget = budget_env ? atof(budget_env) : 24e9;
+	long long group = std::min<long long>(((1ll << 31) - 1) / (3 * (long long) N), (long long) (budget / (17.0 * 4.0 * N)));
+	group = std::max<long long>(1, std::min<long long>(group, pair_count));
+	for (int first = 0; first < pair_count; first += (int) group) {
+		const int pairs = (int) std::min<long long>(group, pair_count - first);
+		const float* canonical_group = canonical + (size_t) first * N;
+		const float* live_group = live + (size_t) first * N;
+		float* warp_group = warp_out + (size_t) first * N * 3;
+		int* counts_group = iteration_counts ? iteration_counts + (size_t) first * LSF_MAX_LEVELS : nullptr;
+		if (batch_supported(plan, pairs)) {
+			Arena arena(stream);
+			const float *canonical_dev, *live_dev;
+			LSF_TRY(to_device(arena, canonical_group, N * pairs, memory_kind, stream, &canonical_dev));
+			LSF_TRY(to_device(arena, live_group, N * pairs, memory_kind, stream, &live_dev));
+			float* out_dev = warp_group;
+			if (memory_kind == LSF_HOST) LSF_TRY(arena.alloc(&out_dev, N * 3 * pairs));
+			LSF_TRY(optimize_batch_device(plan, pairs, canonical_dev, live_dev, out_dev, counts_group, stream));
+			if (memory_kind == LSF_HOST) LSF_TRY(from_device(out_dev, warp_group, N * 3 * pairs, LSF_HOST, stream));
+			else LSF_CUDA(cudaStreamSynchronize(stream));  // the arena's blocks are released in stream order anyway
+			continue;
+		}
+		// shapes or settings outside the batched kernels: one pair after the other
+		std::vector<lsf_level_report> reports(LSF_MAX_LEVELS);
+		for (int pair = 0; pair < pairs; pair++) {
+			const int levels = lsf_hier_optimize_3d(params, canonical_group + pair * N, live_group + pair * N, X, Y, Z,
+					warp_group + pair * N * 3, memory_kind, reports.data(), 0, nullptr, stream_handle);
+			if (levels < 0) return levels;
+			if (counts_group) {
+				for (int level = 0; level < levels; level++)
+					counts_group[pair * LSF_MAX_LEVELS + level] = reports[level].iteration_count;
+			}
 		}
 	}
-	if (pair_count == 0) {
-		Plan3 plan;
-		LSF_TRY(make_plan(params, X, Y, Z, &plan));
-		levels = plan.level_count;
-	}
-	return levels;
+	return plan.level_count;
 }
 
 extern "C" int lsf_hier_iterate_3d(const lsf_hier_params* params, const float* canonical_dev, const float* live_dev,

@@ -228,6 +228,15 @@ struct HierIterArgs {
 	int x_begin, x_end, x_origin, X_global;
 	int pack_X, pack_origin, pack_interior_low, pack_interior_high;
 	int* violation;          // set to 1 when a gather would leave the rank's pack region (nullptr: whole volume)
+	// batch of independent pairs (lsf_hier_optimize_3d_batch; the reference's multi-pair loop,
+	// run_hierarchical_optimizer3d_multipair.py:403-406): the plane fields hold the pairs one after the other along
+	// axis 0 (g.X = pairs * batch_X planes, component stride g.N), every pair has its own padded pack
+	// (pack + pair * batch_pack_stride) and its own row of convergence slots (max_sq_bits + pair * batch_slot_stride).
+	// Border rules, gather clamps and the filter's zero padding apply per pair. batch_X == 0: one volume.
+	int batch_X;
+	int batch_chunks;        // x-chunks per pair (stage-1 kernels: blockIdx.z = pair * batch_chunks + chunk)
+	long long batch_pack_stride;
+	int batch_slot_stride;
 };
 
 inline void whole_volume(HierIterArgs& a) {
@@ -239,6 +248,10 @@ inline void whole_volume(HierIterArgs& a) {
 	a.pack_origin = 0;
 	a.pack_interior_low = a.pack_interior_high = 0;
 	a.violation = nullptr;
+	a.batch_X = 0;
+	a.batch_chunks = 1;
+	a.batch_pack_stride = 0;
+	a.batch_slot_stride = 0;
 }
 
 template<bool TIKHONOV, bool FUSE_UPDATE>

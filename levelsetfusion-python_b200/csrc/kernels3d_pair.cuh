@@ -334,6 +334,8 @@ struct YMarch2Args {
 	int y_chunk;       // output rows per block
 	int x_begin;       // first plane (blockIdx.y counts from here)
 	int tile_z;        // output columns per block (even); blockDim.x = tile_z / 2 (+ 32 halo threads when gridDim.x > 1)
+	int batch_X;       // batch of pairs (HierIterArgs::batch_X): planes per pair, 0 = one volume
+	int batch_slot_stride;  // convergence slots per pair
 };
 
 #ifdef __CUDACC__
@@ -348,7 +350,9 @@ template<int R>
 static __global__ void __launch_bounds__(288) k_sobolev_ymarch2(const __grid_constant__ YMarch2Args a) {
 	constexpr int K = 2 * R + 1;
 	constexpr int H = 4;  // halo columns kept either side of the tile (>= R, even)
-	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
+	unsigned* slots = a.max_sq_bits;
+	if (a.batch_X > 0 && slots != nullptr) slots += ((a.x_begin + blockIdx.y) / a.batch_X) * a.batch_slot_stride;
+	if (a.check_convergence && level_converged(slots, a.iteration, a.threshold)) return;
 	extern __shared__ __align__(16) float row_memory2[];  // [2 buffers][3 components][A: W | B: W]
 	const int Y = a.g.Y, Z = a.g.Z;
 	const int NT = a.tile_z / 2;   // owner threads
@@ -472,7 +476,7 @@ static __global__ void __launch_bounds__(288) k_sobolev_ymarch2(const __grid_con
 		}
 		buffer ^= 1;  // the row written two steps from now is read by nobody after the next barrier
 	}
-	if (a.max_sq_bits != nullptr) block_atomic_max(best, a.max_sq_bits + a.iteration);
+	if (slots != nullptr) block_atomic_max(best, slots + a.iteration);
 }
 
 inline bool ymarch2_supported(const Grid3& g, const float* h, const float* filtered, const float* warp) {
@@ -499,6 +503,8 @@ void launch_ymarch2(const Taps& taps, const HierIterArgs& a, const float* h, flo
 	f.check_convergence = a.check_convergence;
 	f.y_chunk = y_chunk;
 	f.x_begin = x_begin;
+	f.batch_X = a.batch_X;
+	f.batch_slot_stride = a.batch_slot_stride;
 	f.tile_z = std::min(512, (int) div_up(g.Z, 64) * 64);
 	const int tiles = div_up(g.Z, f.tile_z);
 	const dim3 grid(tiles, planes < 0 ? g.X : planes, div_up(g.Y, y_chunk));

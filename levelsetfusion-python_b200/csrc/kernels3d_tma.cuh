@@ -268,12 +268,24 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 		const __grid_constant__ CUtensorMap map_p, HierIterArgs a, XPassArgs t) {
 	typedef Stage1Tile<TIKHONOV> T;
 	constexpr int K = 2 * R + 1;
-	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
+	// batch of pairs (HierIterArgs::batch_X): this block's pair owns planes [x_lo, x_hi) of the allocation
+	int x_lo = 0, x_hi = a.g.X, chunk_index = blockIdx.z;
+	const float4* pack = a.pack;
+	unsigned* slots = a.max_sq_bits;
+	if (!SLAB && a.batch_X > 0) {
+		const int pair = blockIdx.z / a.batch_chunks;
+		chunk_index = blockIdx.z - pair * a.batch_chunks;
+		x_lo = pair * a.batch_X;
+		x_hi = x_lo + a.batch_X;
+		pack += pair * a.batch_pack_stride;
+		if (slots != nullptr) slots += pair * a.batch_slot_stride;
+	}
+	if (a.check_convergence && level_converged(slots, a.iteration, a.threshold)) return;
 	extern __shared__ __align__(128) unsigned char stage_memory[];
 	__shared__ uint64_t full[NS];
 	__shared__ uint64_t empty[NS];  // DEC: one arrival per warp once it has read the slot
 
-	const int X = a.g.X, Y = a.g.Y, Z = a.g.Z;
+	const int X = x_hi, Y = a.g.Y, Z = a.g.Z;  // X: end of this volume's planes in the allocation
 	const int tz = threadIdx.x, ty = threadIdx.y;
 	const int z0 = blockIdx.x * T::TZ, y0 = blockIdx.y * T::TY;
 	const int z = z0 + tz, y = y0 + ty;
@@ -282,12 +294,12 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 	const int N = (int) a.g.N;
 	// SLAB (slab decomposition, slab.py): the fields are an allocation of X planes of which [x_begin, x_end) are processed;
 	// allocation plane p is plane p + x_origin of a level of X_global planes (border rules, gather look-ups)
-	const int xs = (SLAB ? a.x_begin : 0) + blockIdx.z * t.x_chunk;
+	const int xs = (SLAB ? a.x_begin : x_lo) + chunk_index * t.x_chunk;
 	const int xe = min(SLAB ? a.x_end : X, xs + t.x_chunk);
-	const int origin = SLAB ? a.x_origin : 0, Xg = SLAB ? a.X_global : X;
+	const int origin = SLAB ? a.x_origin : -x_lo, Xg = SLAB ? a.X_global : X - x_lo;
 	// FUSE (no Sobolev kernel configured): no filter pass, the warp update and the max-norm (reference
 	// optimizer.tpp:207-211) happen here and the kernel is the whole iteration
-	const int x_first = FUSE ? xs : max(xs - R, 0);  // planes below 0 contribute zeros to accumulators that are still zero
+	const int x_first = FUSE ? xs : max(xs - R, x_lo);  // planes below the volume contribute zeros to accumulators that are still zero
 	const int x_stop = FUSE ? xe : xe + R;           // planes >= X contribute zeros
 	const int p_last = min(x_stop, X - 1);  // last plane fetched (the Tikhonov term looks one plane ahead)
 	const bool leader = tz == 0 && ty == 0;
@@ -342,7 +354,7 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 #pragma unroll
 		for (int c = 0; c < 3; c++) {
 			cur[c] = lds_f32(stage_base + off_g + c * G_COMP);
-			if (x_first > 0 && valid) prev[c] = __ldg(a.g_prev + c * N + (x_first - 1) * YZ + y * Z + z);
+			if (x_first > x_lo && valid) prev[c] = __ldg(a.g_prev + c * N + (x_first - 1) * YZ + y * Z + z);
 		}
 	}
 	int out = (x_first - R) * YZ + y * Z + z;  // index of the plane completed by the current step
@@ -432,7 +444,7 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 				}
 			}
 			const float4 s = SLAB ? gather4q<true>(a, (Y + 4) * (Z + 4), Z + 4, (float) (x + origin), (float) y, (float) z, wx, wy,
-					wz, t.one2) : gather4p(a.pack, X, Y, Z, x, y, z, wx, wy, wz, t.one2);
+					wz, t.one2) : gather4p(pack, Xg, Y, Z, x + origin, y, z, wx, wy, wz, t.one2);
 			const float diff = s.x - cn;
 			g[0] = (s.y * diff) * a.amplifier;
 			g[1] = (s.z * diff) * a.amplifier;
@@ -497,7 +509,7 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 			phase ^= 1u;
 		}
 	}
-	if (FUSE && a.warp_out != nullptr) block_atomic_max(best, a.max_sq_bits + a.iteration);
+	if (FUSE && a.warp_out != nullptr) block_atomic_max(best, slots + a.iteration);
 }
 
 // ---------------------------------------------------------------------------------------------- axis-1 / axis-2 passes
@@ -691,7 +703,9 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 	t.x_chunk = x_chunk;
 	t.one2 = F32X2_ONE;
 	a.g_out = h;
-	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), div_up(a.g.X, x_chunk));
+	const int pairs = a.batch_X > 0 ? a.g.X / a.batch_X : 1;
+	a.batch_chunks = div_up(a.batch_X > 0 ? a.batch_X : a.g.X, x_chunk);
+	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), pairs * a.batch_chunks);
 	const size_t shared = (size_t) NS * T::STAGE_BYTES;
 	static bool configured = false;
 	if (!configured) {
@@ -701,7 +715,7 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
 		configured = true;
 	}
-	if (DEC && l2_prefetch_enabled(false))
+	if (DEC && a.batch_X == 0 && l2_prefetch_enabled(false))
 		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY, false, SYM> <<<counted(grid), block, shared, stream>>>(maps.g_prev,
 				maps.warp, maps.canonical, maps.pack, a, t);
 	else
@@ -724,7 +738,9 @@ int launch_stage1_fused_update(TmaMaps& maps, HierIterArgs a, int x_chunk, cudaS
 	}
 	t.x_chunk = x_chunk;
 	t.one2 = F32X2_ONE;
-	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), div_up(a.x_end - a.x_begin, x_chunk));
+	const int pairs = (!SLAB && a.batch_X > 0) ? a.g.X / a.batch_X : 1;
+	a.batch_chunks = div_up(pairs > 1 || a.batch_X > 0 ? a.batch_X : a.x_end - a.x_begin, x_chunk);
+	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), pairs * a.batch_chunks);
 	const size_t shared = (size_t) NS * T::STAGE_BYTES;
 	LSF_TRY(ensure_pack_map<T>(maps, a));
 	static bool configured = false;
@@ -735,7 +751,7 @@ int launch_stage1_fused_update(TmaMaps& maps, HierIterArgs a, int x_chunk, cudaS
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
 		configured = true;
 	}
-	if (!SLAB && l2_prefetch_enabled(true))
+	if (!SLAB && a.batch_X == 0 && l2_prefetch_enabled(true))
 		k_hier_stage1_tma<TIKHONOV, 0, NS, true, true, 2, false, SLAB> <<<counted(grid), block, shared, stream>>>(maps.g_prev, maps.warp,
 				maps.canonical, maps.pack, a, t);
 	else

@@ -41,20 +41,24 @@ struct YMarch3Args {
 	int check_convergence;
 	int y_chunk;          // output rows per block
 	int x_begin;          // first plane (blockIdx.y counts from here)
+	int batch_X;          // batch of pairs (HierIterArgs::batch_X): planes per pair, 0 = one volume
+	int batch_slot_stride;  // convergence slots per pair
 };
 
 #ifdef __CUDACC__
 
-template<int R, bool SYM, bool HAS_OUT, bool HAS_WARP>
+template<int R, bool SYM, bool HAS_OUT, bool HAS_WARP, int TZ = 256>
 static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const __grid_constant__ YMarch3Args a) {
 	constexpr int K = 2 * R + 1;
 	constexpr int H = 4;             // halo columns kept either side of the tile (>= R, even)
-	constexpr int TZ = 256;          // output columns per block
+	// TZ: output columns per block (256; 128 for rows of 128 .. 255 voxels: the 128^3 pyramid level)
 	constexpr int W = TZ + 2 * H;    // columns of a shared row
 	constexpr int NT = TZ / 2;       // owner threads
 	constexpr uint32_t ROW_BYTES = W * 4;              // one component of one row
 	constexpr uint32_t BUFFER_BYTES = 3 * ROW_BYTES;
-	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
+	unsigned* slots = a.max_sq_bits;
+	if (a.batch_X > 0 && slots != nullptr) slots += ((a.x_begin + blockIdx.y) / a.batch_X) * a.batch_slot_stride;
+	if (a.check_convergence && level_converged(slots, a.iteration, a.threshold)) return;
 	__shared__ __align__(16) float row_memory3[2 * 3 * W];  // [2 buffers][3 components][W]
 	const int Y = a.Y, Z = a.Z;
 	const int tid = threadIdx.x;
@@ -228,7 +232,7 @@ static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const _
 		chain(va);
 		emit(std::integral_constant<int, 0>());
 	}
-	if (a.max_sq_bits != nullptr) block_atomic_max(best, a.max_sq_bits + a.iteration);
+	if (slots != nullptr) block_atomic_max(best, slots + a.iteration);
 }
 
 // LSF_YMARCH3=0 keeps the fourth-generation filter kernel (A/B parity tests)
@@ -238,7 +242,7 @@ inline bool ymarch3_enabled() {
 }
 
 inline bool ymarch3_supported(const Grid3& g, const float* h, const float* filtered, const float* warp) {
-	return ymarch3_enabled() && g.Z >= 256 && ymarch2_supported(g, h, filtered, warp) && g.N * 3 < (1ll << 31);
+	return ymarch3_enabled() && g.Z >= 128 && ymarch2_supported(g, h, filtered, warp) && g.N * 3 < (1ll << 31);
 }
 
 template<int R>
@@ -263,15 +267,24 @@ void launch_ymarch3(const Taps& taps, const HierIterArgs& a, const float* h, flo
 	f.iteration = a.iteration;
 	f.check_convergence = a.check_convergence;
 	f.x_begin = x_begin;
-	const int tiles = div_up(g.Z, 256);
-	// the variants that update the warp need 96 registers: 5 resident blocks per SM instead of the 6 the caller's chunk
-	// was sized for (768 blocks on 740 slots would run a second, almost empty wave: measured 0.18 instead of 0.13 ms)
-	if (warp != nullptr) y_chunk = marching_chunk(g.Y, tiles * (planes < 0 ? g.X : planes), 2 * R, 5);
+	f.batch_X = a.batch_X;
+	f.batch_slot_stride = a.batch_slot_stride;
+	const int tile_z = g.Z < 256 ? 128 : 256;
+	const int tiles = div_up(g.Z, tile_z);
+	const int plane_count = planes < 0 ? g.X : planes;
+	// resident blocks per SM (register-bound): 6 of 128 threads, 12 of 64; the variants that update the warp need 96
+	// registers: 5 and 10 (768 blocks on 740 slots would run a second, almost empty wave: measured 0.18 against 0.13 ms)
+	const int per_sm = (warp != nullptr ? 5 : 6) * (256 / tile_z);
+	if (warp != nullptr || tile_z != 256) y_chunk = marching_chunk(g.Y, tiles * plane_count, 2 * R, per_sm);
 	f.y_chunk = y_chunk;
-	const dim3 grid(tiles, planes < 0 ? g.X : planes, div_up(g.Y, y_chunk));
-	const int threads = 128 + (tiles > 1 ? 32 : 0);
+	const dim3 grid(tiles, plane_count, div_up(g.Y, y_chunk));
+	const int threads = tile_z / 2 + (tiles > 1 ? 32 : 0);
 	const bool sym = taps_are_symmetric(taps);  // LSF_SYM=0: full chain (A/B)
-#define LSF_YM3(SYM, OUT, WARP) k_sobolev_ymarch3<R, SYM, OUT, WARP> <<<counted(grid), threads, 0, stream>>>(f)
+#define LSF_YM3(SYM, OUT, WARP)                                                                          \
+	do {                                                                                                 \
+		if (tile_z == 256) k_sobolev_ymarch3<R, SYM, OUT, WARP, 256> <<<counted(grid), threads, 0, stream>>>(f); \
+		else k_sobolev_ymarch3<R, SYM, OUT, WARP, 128> <<<counted(grid), threads, 0, stream>>>(f);             \
+	} while (0)
 	if (filtered && warp) {
 		if (sym) LSF_YM3(true, true, true);
 		else LSF_YM3(false, true, true);

@@ -296,6 +296,55 @@ class _HierarchicalOptimizer:
             level_done(state["level"])
         return levels
 
+    def optimize_batch(self, canonical_fields, live_fields):
+        """(extension; 3D) optimize() for a batch of independent pairs in one call -- the reference's multi-pair loop
+        (run_hierarchical_optimizer3d_multipair.py:403-406): `canonical_fields` / `live_fields` are [P, X, Y, Z] arrays or
+        CUDA tensors, the result is the [P, X, Y, Z, 3] warp fields. The pairs move through the pyramid levels together
+        (one kernel launch sequence per iteration for the whole batch, per-pair termination); every pair's result equals
+        optimize() of that pair bit for bit. Iteration counts: get_per_pair_iteration_counts()."""
+        if self._nd != 3:
+            raise ValueError("optimize_batch exists for 3D pairs only")
+        on_device = _lib.is_torch_cuda(canonical_fields) or _lib.is_torch_cuda(live_fields)
+        if on_device:
+            import torch
+            if not (_lib.is_torch_cuda(canonical_fields) and _lib.is_torch_cuda(live_fields)):
+                raise ValueError("canonical_fields and live_fields must live on the same device")
+            if canonical_fields.device != live_fields.device:
+                raise ValueError("canonical_fields and live_fields must live on the same device")
+            canonical = canonical_fields.contiguous().float()
+            live = live_fields.contiguous().float()
+        else:
+            canonical = _lib.as_f32(canonical_fields)
+            live = _lib.as_f32(live_fields)
+        shape = tuple(int(d) for d in canonical.shape)
+        if len(shape) != 4 or tuple(live.shape) != shape:
+            raise ValueError("expected two [P, X, Y, Z] batches of equal shape, got %s and %s"
+                             % (tuple(canonical.shape), tuple(live.shape)))
+        lib = _lib.load()
+        params = self._params()
+        pairs = shape[0]
+        counts = (ctypes.c_int * (max(pairs, 1) * _lib.LSF_MAX_LEVELS))()
+        if on_device:
+            import torch
+            with torch.cuda.device(canonical.device):
+                warp = torch.empty(shape + (3,), dtype=torch.float32, device=canonical.device)
+                ptr = lambda t: ctypes.cast(ctypes.c_void_p(t.data_ptr()), _lib.c_float_p)
+                stream = ctypes.c_void_p(torch.cuda.current_stream(canonical.device).cuda_stream)
+                levels = _lib.check(lib.lsf_hier_optimize_3d_batch(ctypes.byref(params), ptr(canonical), ptr(live), pairs,
+                                                                   shape[1], shape[2], shape[3], ptr(warp),
+                                                                   _lib.LSF_DEVICE, counts, stream))
+        else:
+            warp = np.empty(shape + (3,), dtype=np.float32)
+            levels = _lib.check(lib.lsf_hier_optimize_3d_batch(ctypes.byref(params), _lib.fptr(canonical), _lib.fptr(live),
+                                                               pairs, shape[1], shape[2], shape[3], _lib.fptr(warp),
+                                                               _lib.LSF_HOST, counts, ctypes.c_void_p(0)))
+        self._pair_iteration_counts = [[counts[p * _lib.LSF_MAX_LEVELS + l] for l in range(levels)] for p in range(pairs)]
+        return warp
+
+    def get_per_pair_iteration_counts(self):
+        """(extension) per-level iteration counts of every pair of the last optimize_batch() call"""
+        return [list(c) for c in getattr(self, "_pair_iteration_counts", [])]
+
     def get_per_iteration_statistics(self):
         """(extension) the numbers behind the reference's per-iteration prints, one tuple per iteration of the last
         optimize() call that ran with telemetry: (level, iteration, max update length, mean diff, std diff, normalised

@@ -70,3 +70,42 @@ def test_run_multipair_matches_serial_reports(lsf, tmp_path):
     assert table.equals(expected)
     assert os.path.exists(os.path.join(out_path, "convergence_reports.pk"))
     assert os.path.exists(os.path.join(out_path, "analysis.txt"))
+
+
+@pytest.mark.parametrize("mode", ["tikhonov_kernel", "kernel", "tikhonov", "data_only"])
+def test_batched_optimize_matches_pair_by_pair(lsf, mode, monkeypatch):
+    """lsf_hier_optimize_3d_batch: the pairs of a batch advance through the pyramid together (every iteration kernel
+    covers all pairs; per-pair convergence slots and termination). Every pair's warp field and iteration counts must be
+    those of its own optimize() call bit for bit -- with pairs that terminate after different numbers of iterations
+    (odd and even: the deferred update's ping-pong buffers), from host arrays and from device tensors, and for the
+    serial fallback (LSF_BATCH=0)."""
+    import torch
+    from lsf_b200 import synthetic
+    modes = {
+        "data_only": dict(tikhonov_term_enabled=False, gradient_kernel_enabled=False),
+        "tikhonov": dict(tikhonov_term_enabled=True, gradient_kernel_enabled=False, tikhonov_strength=0.05),
+        "kernel": dict(tikhonov_term_enabled=False, gradient_kernel_enabled=True),
+        "tikhonov_kernel": dict(tikhonov_term_enabled=True, gradient_kernel_enabled=True, tikhonov_strength=0.1),
+    }
+    shifts = [(2.5, -1.5, 1.0), (0.4, 0.2, -0.3), (1.5, 0.5, 0.7), (-2.0, 1.0, 0.5), (0.1, 0.05, 0.02)]
+    pairs = [synthetic.sphere_plane_pair_3d(48, shift=shift) for shift in shifts]
+    canonical = np.stack([p[0][:, :40, :].copy() for p in pairs])   # 48 x 40 x 48: ragged tiles
+    live = np.stack([p[1][:, :40, :].copy() for p in pairs])
+    threshold = 0.02 if "kernel" in mode else 0.016  # levels of different pairs end after 1 .. 37 iterations
+    kwargs = dict(modes[mode], maximum_chunk_size=4, maximum_iteration_count=37, maximum_warp_update_threshold=threshold,
+                  kernel=synthetic.sobolev_kernel_1d())
+    optimizer = lsf.HierarchicalOptimizer3d(**kwargs)
+    expected, expected_counts = [], []
+    for index in range(len(pairs)):
+        expected.append(optimizer.optimize(canonical[index], live[index]))
+        expected_counts.append(optimizer.get_per_level_iteration_counts())
+    assert len({tuple(c) for c in expected_counts}) > 1, expected_counts  # the pairs really stop at different iterations
+    batch = optimizer.optimize_batch(canonical, live)
+    assert optimizer.get_per_pair_iteration_counts() == expected_counts
+    for index in range(len(pairs)):
+        assert np.array_equal(batch[index], expected[index]), index
+    device_batch = optimizer.optimize_batch(torch.from_numpy(canonical).cuda(), torch.from_numpy(live).cuda())
+    assert device_batch.is_cuda and np.array_equal(device_batch.cpu().numpy(), batch)
+    monkeypatch.setenv("LSF_BATCH", "0")
+    serial = optimizer.optimize_batch(canonical, live)
+    assert np.array_equal(serial, batch) and optimizer.get_per_pair_iteration_counts() == expected_counts

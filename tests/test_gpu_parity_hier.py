@@ -416,7 +416,7 @@ def test_ymarch3_filter_matches_previous_generations(lsf, mode, taps, monkeypatc
     with a ragged last tile, odd chunk sizes along y -- bit-identical. The non-symmetric kernel exercises the full chain."""
     from lsf_b200 import synthetic
     rng = np.random.default_rng(11)
-    for shape in ((40, 40, 256), (26, 24, 512), (26, 20, 328)):
+    for shape in ((40, 40, 256), (26, 24, 512), (26, 20, 328), (26, 24, 128), (26, 20, 200)):
         base_c, base_l = synthetic.sphere_plane_pair_3d(64)
         reps = [int(np.ceil(s / 64)) for s in shape]
         canonical = np.tile(base_c, reps)[:shape[0], :shape[1], :shape[2]].copy()

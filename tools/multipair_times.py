@@ -63,6 +63,29 @@ def main():
             print(json.dumps({"workload": "multipair_%dx%d^3" % (args.pairs, args.size), "n_gpus": world_size,
                               "streams_per_gpu": streams, "seconds": best, "pairs_per_s": args.pairs / best,
                               "voxel_updates_per_s": updates / best}))
+    # the same batch through lsf_hier_optimize_3d_batch: one call per rank, no Python threads
+    indices = multigpu.pair_indices_of_rank(args.pairs, rank, world_size)
+    if indices:
+        canonical = torch.stack([pairs[i][0] for i in indices])
+        live = torch.stack([pairs[i][1] for i in indices])
+        optimizer = lsf_b200.HierarchicalOptimizer3d(**kwargs)
+        best = None
+        for _ in range(3):
+            if world_size > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            optimizer.optimize_batch(canonical, live)
+            torch.cuda.synchronize()
+            seconds = multigpu.max_over_ranks(time.perf_counter() - t0, device)
+            best = seconds if best is None else min(best, seconds)
+        counts = optimizer.get_per_pair_iteration_counts()
+        level_voxels = [(args.size >> (len(counts[0]) - 1 - level)) ** 3 for level in range(len(counts[0]))]
+        updates = multigpu.sum_over_ranks(sum(c * v for pair in counts for c, v in zip(pair, level_voxels)), device)
+        if rank == 0:
+            print(json.dumps({"workload": "multipair_%dx%d^3" % (args.pairs, args.size), "n_gpus": world_size,
+                              "mode": "lsf_hier_optimize_3d_batch", "seconds": best, "pairs_per_s": args.pairs / best,
+                              "voxel_updates_per_s": updates / best}))
     if world_size > 1:
         dist.destroy_process_group()
 
