@@ -11,8 +11,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",  # bit-exact with the reference's non-contracted float32 arithmetic
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(HERE, "_obj")  # git-ignored object files: one per translation unit, compiled in parallel
 
 
 def sources():
@@ -30,15 +31,32 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     env = dict(os.environ)
     env.pop("CXX", None)  # the image's CXX points at a compiler without OpenMP specs; let nvcc pick g++ from PATH
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "lsf_b200.h")]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_unit(source):
+        obj = os.path.join(OBJ_DIR, os.path.basename(source)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(source), newest_header):
+            return obj, ""
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, source]
+        result = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if result.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), result.stderr))
+        return obj, result.stderr
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        compiled = list(pool.map(compile_unit, sources()))
+    if verbose:
+        print("".join(log for _, log in compiled))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + [obj for obj, _ in compiled]
     result = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if result.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), result.stderr))
-    if verbose:
-        print(result.stderr)
+        raise RuntimeError("nvcc link failed:\n%s\n%s" % (" ".join(cmd), result.stderr))
     return LIB
 
 

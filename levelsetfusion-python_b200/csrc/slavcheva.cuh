@@ -147,38 +147,49 @@ __device__ __forceinline__ int slav_axis(const SlavGeom& g, int component) {
 	return D == 3 ? component : g.comp_axis[component];
 }
 
-template<int D, bool IN = false>
+// SM = true: the field pointers of the argument block address a tile staged in shared memory (its own strides in g)
+template<bool SM>
+__device__ __forceinline__ float slav_ld(const float* p) {
+	if (SM) {
+		__builtin_assume(__isShared(p));
+		return *p;
+	}
+	return __ldg(p);
+}
+
+template<int D, bool IN = false, bool SM = false>
 __device__ __forceinline__ float slav_live_or_one(const SlavGeom& g, const float* __restrict__ live, const int (&q)[3]) {
-	return (IN || slav_inside<D>(g, q)) ? __ldg(live + slav_index<D>(g, q)) : 1.0f;
+	return (IN || slav_inside<D>(g, q)) ? slav_ld<SM>(live + slav_index<D>(g, q)) : 1.0f;
 }
 
 // ---------------------------------------------------------------------------------------------- gradient terms
 // data term: reference data_term.cpp:63-84 (C++), data_term.py:169-227 (Python basic / thresholded FDM)
-template<int D, bool IN = false>
-__device__ __forceinline__ void slav_data_term(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
+template<int D, bool IN = false, bool SM = false>
+__device__ __forceinline__ void slav_data_term_given(const SlavGradientArgs& a, int idx, const int (&pos)[3],
+		float canonical_value, float (&out)[3]) {
 	const SlavGeom& g = a.g;
-	const float centre = __ldg(a.live + idx);
+	const float centre = slav_ld<SM>(a.live + idx);
 	float grad[3] = { 0.f, 0.f, 0.f };
 #pragma unroll
 	for (int c = 0; c < D; c++) {
 		const int ax = slav_axis<D>(g, c), i = pos[ax], n = g.n[ax], s = g.stride[ax];
 		if (IN) {
-			grad[c] = 0.5f * (__ldg(a.live + idx + s) - __ldg(a.live + idx - s));
+			grad[c] = 0.5f * (slav_ld<SM>(a.live + idx + s) - slav_ld<SM>(a.live + idx - s));
 		} else if (n >= 2) {
-			if (i == 0) grad[c] = __ldg(a.live + idx + s) - centre;
-			else if (i == n - 1) grad[c] = centre - __ldg(a.live + idx - s);
-			else grad[c] = 0.5f * (__ldg(a.live + idx + s) - __ldg(a.live + idx - s));
+			if (i == 0) grad[c] = slav_ld<SM>(a.live + idx + s) - centre;
+			else if (i == n - 1) grad[c] = centre - slav_ld<SM>(a.live + idx - s);
+			else grad[c] = 0.5f * (slav_ld<SM>(a.live + idx + s) - slav_ld<SM>(a.live + idx - s));
 		}
 		if (a.p.data_term_method == LSF_DATA_TERM_THRESHOLDED_FDM && fabsf(grad[c]) > 0.5f) {
-			const float minus = (IN || i > 0) ? __ldg(a.live + idx - s) : 1.0f;
-			const float plus = (IN || i < n - 1) ? __ldg(a.live + idx + s) : 1.0f;
+			const float minus = (IN || i > 0) ? slav_ld<SM>(a.live + idx - s) : 1.0f;
+			const float plus = (IN || i < n - 1) ? slav_ld<SM>(a.live + idx + s) : 1.0f;
 			const float forward = plus - centre, backward = centre - minus;
 			float value = fabsf(forward) < fabsf(backward) ? forward : backward;
 			if (fabsf(value) > 0.5f) value = 0.0f;
 			grad[c] = value;
 		}
 	}
-	const float diff = centre - __ldg(a.canonical + idx);
+	const float diff = centre - canonical_value;
 	if (a.p.semantics == LSF_SEMANTICS_CPP) {
 		const float scaled = 10.0f * diff;
 #pragma unroll
@@ -190,27 +201,32 @@ __device__ __forceinline__ void slav_data_term(const SlavGradientArgs& a, int id
 }
 
 template<int D, bool IN = false>
+__device__ __forceinline__ void slav_data_term(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
+	slav_data_term_given<D, IN, false>(a, idx, pos, __ldg(a.canonical + idx), out);
+}
+
+template<int D, bool IN = false, bool SM = false>
 __device__ __forceinline__ float slav_warp_or_centre(const SlavGradientArgs& a, const int (&q)[3], int c, int centre_idx) {
 	const int at = (IN || slav_inside<D>(a.g, q)) ? slav_index<D>(a.g, q) : centre_idx;
-	return __ldg(a.warp + c * a.g.N + at);
+	return slav_ld<SM>(a.warp + c * a.g.N + at);
 }
 
 // C++ Tikhonov term: reference smoothing_term.cpp:43-108 (array axis 0 assigned, further axes added)
-template<int D, bool IN = false>
+template<int D, bool IN = false, bool SM = false>
 __device__ __forceinline__ void slav_tikhonov_cpp(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
 #pragma unroll
 	for (int c = 0; c < D; c++) {
 		const float* w = a.warp + c * a.g.N + idx;
-		const float centre = __ldg(w);
+		const float centre = slav_ld<SM>(w);
 		float total = 0.0f;
 #pragma unroll
 		for (int ax = 0; ax < D; ax++) {
 			const int i = pos[ax], n = a.g.n[ax], s = a.g.stride[ax];
 			float term;
 			if (!IN && n < 2) term = 0.0f;
-			else if (!IN && i == 0) term = -__ldg(w + s) + centre;
-			else if (!IN && i == n - 1) term = -__ldg(w - s) + centre;
-			else term = (-__ldg(w + s) + 2.0f * centre) - __ldg(w - s);
+			else if (!IN && i == 0) term = -slav_ld<SM>(w + s) + centre;
+			else if (!IN && i == n - 1) term = -slav_ld<SM>(w - s) + centre;
+			else term = (-slav_ld<SM>(w + s) + 2.0f * centre) - slav_ld<SM>(w - s);
 			if (ax == 0) total = term;
 			else total += term;
 		}
@@ -247,7 +263,7 @@ __device__ __forceinline__ void slav_tikhonov_py(const SlavGradientArgs& a, int 
 
 // Killing term: reference smoothing_term.py:50-100 (copy_if_zero=False), quirks kept; 3D form = the
 // same expression pattern
-template<int D, bool IN = false>
+template<int D, bool IN = false, bool SM = false>
 __device__ __forceinline__ void slav_killing(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
 	const float lambda = a.p.lambda;
 	const float c0 = (float) (-2.0 * (1.0 + (double) lambda));
@@ -255,18 +271,18 @@ __device__ __forceinline__ void slav_killing(const SlavGradientArgs& a, int idx,
 #pragma unroll
 	for (int ca = 0; ca < D; ca++) {
 		int q[3] = { pos[0], pos[1], pos[2] };
-		const float w = __ldg(a.warp + ca * a.g.N + idx);
+		const float w = slav_ld<SM>(a.warp + ca * a.g.N + idx);
 		q[ax0] = pos[ax0] + 1;
-		const float xp = slav_warp_or_centre<D, IN>(a, q, ca, idx);
+		const float xp = slav_warp_or_centre<D, IN, SM>(a, q, ca, idx);
 		q[ax0] = pos[ax0] - 1;
-		const float xm = slav_warp_or_centre<D, IN>(a, q, ca, idx);
+		const float xm = slav_warp_or_centre<D, IN, SM>(a, q, ca, idx);
 		q[ax0] = pos[ax0];
 		float acc = c0 * ((xp - 2.0f * w) + xm);
 #pragma unroll
 		for (int k = 1; k < D; k++) {
 			const int ax = slav_axis<D>(a.g, k);
 			q[ax] = pos[ax] + 1;
-			const float yp = slav_warp_or_centre<D, IN>(a, q, ca, idx);
+			const float yp = slav_warp_or_centre<D, IN, SM>(a, q, ca, idx);
 			q[ax] = pos[ax];
 			acc = acc + ((yp - 2.0f * w) + yp);
 		}
@@ -282,7 +298,7 @@ __device__ __forceinline__ void slav_killing(const SlavGradientArgs& a, int idx,
 				for (int s2 = 1; s2 >= -1; s2 -= 2) {
 					q[first] = pos[first] + s1;
 					q[second] = pos[second] + s2;
-					v[k++] = slav_warp_or_centre<D, IN>(a, q, cb, idx);
+					v[k++] = slav_warp_or_centre<D, IN, SM>(a, q, cb, idx);
 				}
 			q[first] = pos[first];
 			q[second] = pos[second];
@@ -294,19 +310,19 @@ __device__ __forceinline__ void slav_killing(const SlavGradientArgs& a, int idx,
 }
 
 // level-set term: reference level_set_term.py:28-64 (out-of-bounds -> 1, quirks kept)
-template<int D, bool IN = false>
+template<int D, bool IN = false, bool SM = false>
 __device__ __forceinline__ void slav_level_set(const SlavGradientArgs& a, int idx, const int (&pos)[3], float (&out)[3]) {
 	const SlavGeom& g = a.g;
-	const float centre = __ldg(a.live + idx);
+	const float centre = slav_ld<SM>(a.live + idx);
 	float grad[3] = { 0.f, 0.f, 0.f }, hessian[3][3];
 	int q[3] = { pos[0], pos[1], pos[2] };
 #pragma unroll
 	for (int c = 0; c < D; c++) {
 		const int ax = slav_axis<D>(g, c);
 		q[ax] = pos[ax] + 1;
-		const float plus = slav_live_or_one<D, IN>(g, a.live, q);
+		const float plus = slav_live_or_one<D, IN, SM>(g, a.live, q);
 		q[ax] = pos[ax] - 1;
-		const float minus = slav_live_or_one<D, IN>(g, a.live, q);
+		const float minus = slav_live_or_one<D, IN, SM>(g, a.live, q);
 		q[ax] = pos[ax];
 		grad[c] = (0.5f * (plus - minus)) * 10.0f;
 		hessian[c][c] = ((plus - 2.0f * centre) + plus) * 10.0f;
@@ -324,7 +340,7 @@ __device__ __forceinline__ void slav_level_set(const SlavGradientArgs& a, int id
 				for (int s1 = 1; s1 >= -1; s1 -= 2) {
 					q[a1] = pos[a1] + s1;
 					q[a2] = pos[a2] + s2;
-					v[k++] = slav_live_or_one<D, IN>(g, a.live, q);
+					v[k++] = slav_live_or_one<D, IN, SM>(g, a.live, q);
 				}
 			q[a1] = pos[a1];
 			q[a2] = pos[a2];
@@ -588,9 +604,18 @@ static __global__ void __launch_bounds__(256) k_slav_filter_axis(SlavFilterArgs 
 // maximum warp length (statistics.tpp:57-100; slavcheva_optimizer2d.py:309-318 measures BEFORE the re-warp).
 // one voxel of the re-warp: `update` = its filtered update vector, live_value / canonical_value = the fields at the voxel;
 // returns the new live value, the voxel's new warp vector and its contribution to the maximum warp length
-template<int D>
+// a box of the live field staged in shared memory: voxel q sits at data[((q0 - lo0) * ext1 + (q1 - lo1)) * ext2 + (q2 - lo2)]
+struct SlavLiveTile {
+	const float* data;
+	int lo[3], ext[3];
+};
+
+// TILE: the eight taps are read from `tile` when the whole 2 x 2 x 2 cell lies inside it and inside the field (3D,
+// float32 semantics only); other voxels take the global path
+template<int D, bool TILE = false>
 __device__ __forceinline__ void slav_resample_voxel(const SlavResampleArgs& a, int idx, const float (&update)[3],
-		float live_value, float canonical_value, float& new_value, float (&w)[3], float& sq_report) {
+		float live_value, float canonical_value, float& new_value, float (&w)[3], float& sq_report,
+		const SlavLiveTile* tile = nullptr) {
 	const SlavGeom& g = a.g;
 	const bool python = a.p.semantics != LSF_SEMANTICS_CPP;
 	const bool float64 = a.p.semantics == LSF_SEMANTICS_PY_DIRECT;
@@ -650,12 +675,28 @@ __device__ __forceinline__ void slav_resample_voxel(const SlavResampleArgs& a, i
 				ratio[ax] = lookup - (float) base[ax];
 			}
 			float value[1 << D];
+			bool staged = TILE;
+			if (TILE) {
 #pragma unroll
-			for (int corner = 0; corner < (1 << D); corner++) {
-				int q[3] = { 0, 0, 0 };
+				for (int ax = 0; ax < D; ax++)
+					staged = staged && base[ax] >= tile->lo[ax] && base[ax] + 1 < tile->lo[ax] + tile->ext[ax] && base[ax] >= 0
+							&& base[ax] + 1 < g.n[ax];
+			}
+			if (TILE && staged) {
+				const float* cell = tile->data
+						+ ((base[0] - tile->lo[0]) * tile->ext[1] + (base[1] - tile->lo[1])) * tile->ext[2] + (base[2] - tile->lo[2]);
+				__builtin_assume(__isShared(cell));
 #pragma unroll
-				for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
-				value[corner] = slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob;
+				for (int corner = 0; corner < (1 << D); corner++)
+					value[corner] = cell[((corner & 1) * tile->ext[1] + ((corner >> 1) & 1)) * tile->ext[2] + ((corner >> 2) & 1)];
+			} else {
+#pragma unroll
+				for (int corner = 0; corner < (1 << D); corner++) {
+					int q[3] = { 0, 0, 0 };
+#pragma unroll
+					for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
+					value[corner] = slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob;
+				}
 			}
 			// interpolation along the last component's axis first (reference field_warping.tpp:126-134,187-189)
 #pragma unroll

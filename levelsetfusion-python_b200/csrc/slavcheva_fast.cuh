@@ -366,83 +366,91 @@ static __global__ void __launch_bounds__(256) k_slav_band_scan(SlavGradientArgs 
 	}
 }
 
+// the gradient terms at one listed band voxel (packed = its coordinates, 10 bits per axis)
+__device__ __forceinline__ void slav_band_terms_voxel(const SlavGradientArgs& a, int idx, int packed) {
+	const SlavParams& p = a.p;
+	const bool killing = p.smoothing_term_method == LSF_SMOOTHING_KILLING;
+	const int q[3] = { packed & 1023, (packed >> 10) & 1023, (packed >> 20) & 1023 };
+	const float live_value = __ldg(a.live + idx);
+	if (slav_truncated(live_value) && slav_truncated(__ldg(a.canonical + idx))) {
+		// the list is re-used for several iterations: this voxel has left the band since the last scan
+#pragma unroll
+		for (int c = 0; c < 3; c++) a.out[c * a.g.N + idx] = (0.0f + 0.0f * p.smoothing_weight) * -p.rate;
+		return;
+	}
+	float data[3], smooth[3], ls[3];
+	const bool ls_here = p.level_set && !slav_truncated(live_value);
+	const bool interior = q[0] >= 1 && q[0] < a.g.n[0] - 1 && q[1] >= 1 && q[1] < a.g.n[1] - 1 && q[2] >= 1
+			&& q[2] < a.g.n[2] - 1;
+	if (interior) {
+		slav_data_term<3, true>(a, idx, q, data);
+		if (killing) slav_killing<3, true>(a, idx, q, smooth);
+		else slav_tikhonov_cpp<3, true>(a, idx, q, smooth);
+		if (ls_here) slav_level_set<3, true>(a, idx, q, ls);
+	} else {
+		slav_data_term<3>(a, idx, q, data);
+		if (killing) slav_killing<3>(a, idx, q, smooth);
+		else slav_tikhonov_cpp<3>(a, idx, q, smooth);
+		if (ls_here) slav_level_set<3>(a, idx, q, ls);
+	}
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		float total = data[c] * p.data_weight;
+		if (ls_here) total = total + ls[c] * p.level_set_weight;
+		total = total + smooth[c] * p.smoothing_weight;
+		a.out[c * a.g.N + idx] = total * -p.rate;  // reference sobolev_optimizer2d.cpp:131-132
+	}
+}
+
 // the gradient terms at the listed band voxels (full warps: the list is dense)
 static __global__ void __launch_bounds__(256) k_slav_band_terms(SlavGradientArgs a, SlavBandArgs b) {
 	if (a.status[a.iteration]) return;
-	const SlavParams& p = a.p;
 	const int count = *b.count;
-	const bool killing = p.smoothing_term_method == LSF_SMOOTHING_KILLING;
-	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
-		const int idx = b.list[j];
-		const int packed = b.positions[j];
-		const int q[3] = { packed & 1023, (packed >> 10) & 1023, (packed >> 20) & 1023 };
-		const float live_value = __ldg(a.live + idx);
-		if (slav_truncated(live_value) && slav_truncated(__ldg(a.canonical + idx))) {
-			// the list is re-used for several iterations: this voxel has left the band since the last scan
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x)
+		slav_band_terms_voxel(a, b.list[j], b.positions[j]);
+}
+
+// one pass of convolve_with_kernel_preserve_zeros (C++ zero rule) at one band voxel (i = its position along the pass
+// axis); `in` is zero outside the band
+template<int R>
+__device__ __forceinline__ void slav_band_filter_voxel(const SlavFilterArgs& a, int idx, int i, float (&acc)[3]) {
+	const int n = a.g.n[a.axis], s = a.g.stride[a.axis];
+	const int N = (int) a.g.N;
+	bool all_zero = true;
 #pragma unroll
-			for (int c = 0; c < 3; c++) a.out[c * a.g.N + idx] = (0.0f + 0.0f * p.smoothing_weight) * -p.rate;
-			continue;
-		}
-		float data[3], smooth[3], ls[3];
-		const bool ls_here = p.level_set && !slav_truncated(live_value);
-		const bool interior = q[0] >= 1 && q[0] < a.g.n[0] - 1 && q[1] >= 1 && q[1] < a.g.n[1] - 1 && q[2] >= 1
-				&& q[2] < a.g.n[2] - 1;
-		if (interior) {
-			slav_data_term<3, true>(a, idx, q, data);
-			if (killing) slav_killing<3, true>(a, idx, q, smooth);
-			else slav_tikhonov_cpp<3, true>(a, idx, q, smooth);
-			if (ls_here) slav_level_set<3, true>(a, idx, q, ls);
-		} else {
-			slav_data_term<3>(a, idx, q, data);
-			if (killing) slav_killing<3>(a, idx, q, smooth);
-			else slav_tikhonov_cpp<3>(a, idx, q, smooth);
-			if (ls_here) slav_level_set<3>(a, idx, q, ls);
-		}
+	for (int c = 0; c < 3; c++) all_zero = all_zero && __ldg(a.in + c * N + idx) == 0.0f;
+	acc[0] = acc[1] = acc[2] = 0.0f;
+	if (all_zero) return;
+	if (i >= R && i < n - R) {  // every tap inside the field
 #pragma unroll
 		for (int c = 0; c < 3; c++) {
-			float total = data[c] * p.data_weight;
-			if (ls_here) total = total + ls[c] * p.level_set_weight;
-			total = total + smooth[c] * p.smoothing_weight;
-			a.out[c * a.g.N + idx] = total * -p.rate;  // reference sobolev_optimizer2d.cpp:131-132
+			const float* line = a.in + c * N + idx;
+#pragma unroll
+			for (int t = 0; t < 2 * R + 1; t++) acc[c] += __ldg(line + (t - R) * s) * a.k[t];
+		}
+	} else {
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			const float* line = a.in + c * N + idx;
+#pragma unroll
+			for (int t = 0; t < 2 * R + 1; t++) {
+				const int src = i - R + t;
+				const float value = (src >= 0 && src < n) ? __ldg(line + (t - R) * s) : 0.0f;
+				acc[c] += value * a.k[t];
+			}
 		}
 	}
 }
 
-// one pass of convolve_with_kernel_preserve_zeros (C++ zero rule) at the band voxels; `in` is zero outside the band
 template<int R>
 static __global__ void __launch_bounds__(256) k_slav_band_filter_axis(SlavFilterArgs a, SlavBandArgs b) {
 	if (a.status[a.iteration]) return;
 	const int count = *b.count;
-	const int n = a.g.n[a.axis], s = a.g.stride[a.axis];
+	const int N = (int) a.g.N;
 	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
 		const int idx = b.list[j];
-		const int i = (b.positions[j] >> (10 * a.axis)) & 1023;
-		const int N = (int) a.g.N;
-		bool all_zero = true;
-#pragma unroll
-		for (int c = 0; c < 3; c++) all_zero = all_zero && __ldg(a.in + c * N + idx) == 0.0f;
-		float acc[3] = { 0.0f, 0.0f, 0.0f };
-		if (!all_zero) {
-			if (i >= R && i < n - R) {  // every tap inside the field
-#pragma unroll
-				for (int c = 0; c < 3; c++) {
-					const float* line = a.in + c * N + idx;
-#pragma unroll
-					for (int t = 0; t < 2 * R + 1; t++) acc[c] += __ldg(line + (t - R) * s) * a.k[t];
-				}
-			} else {
-#pragma unroll
-				for (int c = 0; c < 3; c++) {
-					const float* line = a.in + c * N + idx;
-#pragma unroll
-					for (int t = 0; t < 2 * R + 1; t++) {
-						const int src = i - R + t;
-						const float value = (src >= 0 && src < n) ? __ldg(line + (t - R) * s) : 0.0f;
-						acc[c] += value * a.k[t];
-					}
-				}
-			}
-		}
+		float acc[3];
+		slav_band_filter_voxel<R>(a, idx, (b.positions[j] >> (10 * a.axis)) & 1023, acc);
 #pragma unroll
 		for (int c = 0; c < 3; c++) a.out[c * N + idx] = acc[c];
 	}
@@ -485,6 +493,437 @@ static __global__ void __launch_bounds__(256) k_slav_band_leave(SlavBandArgs b, 
 			field_f[c * b.g.N + idx] = 0.0f;
 		}
 	}
+}
+
+// ---------------------------------------------------------------------------------------------- brick-ordered narrow band
+// Fifth generation of the sparse iteration. ncu of the list kernels above (profiles/r1_killing_v4.md): the filter passes
+// along axes 0 and 1 fetch 21 taps per voxel that no neighbouring thread shares (the list is in memory order, the
+// x / y neighbours of a voxel sit in other blocks on other SMs): 7x the pass input crosses from L2 to the SMs, L1 hit rate
+// 14 %, 30 long-scoreboard stalls per issue. Here the band is organised in bricks of 8 x 8 x 32 voxels:
+//   * k_slav_brick_scan: one block per brick classifies its 2048 voxels (128-bit loads) and writes the brick's band
+//     voxels, rows of z-adjacent voxels in order, into the brick's own segment of the list (list + brick * 2048: no
+//     global counter, no ordering between bricks needed); bricks without band voxels are dead for good;
+//   * every list kernel runs one block per brick, so the stencil and filter taps of a brick's voxels along all three axes
+//     are shared through the SM's L1 (a brick with its halo is 43 KB per pass) and every row is a coalesced run;
+//   * the axis-2 pass and the masked re-warp run in one kernel (the filtered update of a voxel is all its re-warp
+//     needs), the patch-up of the voxels that left the band and the termination test in another: 5 launches per
+//     iteration instead of 7.
+// Per-voxel arithmetic: the same device functions as the list kernels and the dense kernels.
+constexpr int SLAV_BRICK_X = 8, SLAV_BRICK_Y = 8, SLAV_BRICK_Z = 32;
+constexpr int SLAV_BRICK_VOXELS = SLAV_BRICK_X * SLAV_BRICK_Y * SLAV_BRICK_Z;
+
+struct SlavBrickArgs {
+	int* list;            // [bricks][2048]: band voxels of the brick (voxel index)
+	int* positions;       // their coordinates, 10 bits per axis
+	int* brick_count;     // listed voxels per brick
+	unsigned char* dead;  // brick holds no band voxel (the band only shrinks: never scanned again)
+	int bricks_y, bricks_z;
+	int* leave_list;      // voxels that left the band in this iteration's re-warp
+	int* leave_count;
+	const int* status;
+	int iteration;
+};
+
+// exclusive prefix sum of `mine` over the 256 threads of the block; *total = sum (needs two barriers)
+__device__ __forceinline__ int slav_block_exclusive_scan(int mine, int* warp_totals, int* total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int inclusive = mine;
+#pragma unroll
+	for (int offset = 1; offset < 32; offset <<= 1) {
+		const int other = __shfl_up_sync(0xffffffffu, inclusive, offset);
+		if (lane >= offset) inclusive += other;
+	}
+	__syncthreads();  // warp_totals may still be read from a previous call
+	if (lane == 31) warp_totals[warp] = inclusive;
+	__syncthreads();
+	int before = inclusive - mine, sum = 0;
+	for (int w = 0; w < 8; w++) {
+		if (w < warp) before += warp_totals[w];
+		sum += warp_totals[w];
+	}
+	*total = sum;
+	return before;
+}
+
+static __global__ void __launch_bounds__(256) k_slav_brick_scan(SlavGradientArgs a, SlavBrickArgs b) {
+	const int brick = blockIdx.x;
+	if (a.status[a.iteration] || b.dead[brick]) return;
+	__shared__ int warp_totals[8];
+	const int bz = brick % b.bricks_z, by = (brick / b.bricks_z) % b.bricks_y, bx = brick / (b.bricks_z * b.bricks_y);
+	const int z = bz * SLAV_BRICK_Z + (threadIdx.x & 7) * 4;
+	int listed = 0;
+	const int base = brick * SLAV_BRICK_VOXELS;
+#pragma unroll
+	for (int half = 0; half < 2; half++) {
+		const int row = (threadIdx.x >> 3) + 32 * half;  // row of the brick: x-major
+		const int x = bx * SLAV_BRICK_X + (row >> 3), y = by * SLAV_BRICK_Y + (row & 7);
+		unsigned in_band = 0;
+		int first = 0;
+		if (x < a.g.n[0] && y < a.g.n[1] && z < a.g.n[2]) {
+			first = (x * a.g.n[1] + y) * a.g.n[2] + z;
+			const float4 live4 = __ldg(reinterpret_cast<const float4*>(a.live + first));
+			const float4 canonical4 = __ldg(reinterpret_cast<const float4*>(a.canonical + first));
+			const float live_v[4] = { live4.x, live4.y, live4.z, live4.w };
+			const float canonical_v[4] = { canonical4.x, canonical4.y, canonical4.z, canonical4.w };
+#pragma unroll
+			for (int v = 0; v < 4; v++)
+				if (!(slav_truncated(live_v[v]) && slav_truncated(canonical_v[v]))) in_band |= 1u << v;
+		}
+		int total;
+		int at = base + listed + slav_block_exclusive_scan(__popc(in_band), warp_totals, &total);
+#pragma unroll
+		for (int v = 0; v < 4; v++) {
+			if (in_band & (1u << v)) {
+				b.list[at] = first + v;
+				b.positions[at] = x | (y << 10) | ((z + v) << 20);
+				at++;
+			}
+		}
+		listed += total;
+	}
+	if (threadIdx.x == 0) {
+		b.brick_count[brick] = listed;
+		if (listed == 0) b.dead[brick] = 1;
+	}
+}
+
+static __global__ void __launch_bounds__(256) k_slav_brick_terms(SlavGradientArgs a, SlavBrickArgs b) {
+	if (a.status[a.iteration]) return;
+	const int count = b.brick_count[blockIdx.x];
+	const int base = blockIdx.x * SLAV_BRICK_VOXELS;
+	for (int j = threadIdx.x; j < count; j += 256) slav_band_terms_voxel(a, b.list[base + j], b.positions[base + j]);
+}
+
+template<int R>
+static __global__ void __launch_bounds__(256) k_slav_brick_filter_axis(SlavFilterArgs a, SlavBrickArgs b) {
+	if (a.status[a.iteration]) return;
+	const int count = b.brick_count[blockIdx.x];
+	const int base = blockIdx.x * SLAV_BRICK_VOXELS;
+	const int N = (int) a.g.N;
+	for (int j = threadIdx.x; j < count; j += 256) {
+		const int idx = b.list[base + j];
+		float acc[3];
+		slav_band_filter_voxel<R>(a, idx, (b.positions[base + j] >> (10 * a.axis)) & 1023, acc);
+#pragma unroll
+		for (int c = 0; c < 3; c++) a.out[c * N + idx] = acc[c];
+	}
+}
+
+// last filter pass (a.axis) fused with the masked re-warp and the maximum warp length (k_slav_band_resample's body)
+template<int R>
+static __global__ void __launch_bounds__(256) k_slav_brick_filter_resample(SlavFilterArgs a, SlavResampleArgs ra, SlavBrickArgs b) {
+	if (a.status[a.iteration]) return;
+	const int count = b.brick_count[blockIdx.x];
+	const int base = blockIdx.x * SLAV_BRICK_VOXELS;
+	const int N = (int) a.g.N;
+	float sq_report = 0.0f;
+	for (int j = threadIdx.x; j < count; j += 256) {
+		const int idx = b.list[base + j];
+		float update[3], w[3], new_value;
+		slav_band_filter_voxel<R>(a, idx, (b.positions[base + j] >> (10 * a.axis)) & 1023, update);
+		const float canonical_value = __ldg(ra.canonical + idx);
+		slav_resample_voxel<3>(ra, idx, update, __ldg(ra.live + idx), canonical_value, new_value, w, sq_report);
+		ra.new_live[idx] = new_value;
+#pragma unroll
+		for (int c = 0; c < 3; c++) ra.warp[c * N + idx] = w[c];
+		if (slav_truncated(new_value) && slav_truncated(canonical_value)) b.leave_list[atomicAdd(b.leave_count, 1)] = idx;
+	}
+	if (ra.max_sq_bits != nullptr) block_atomic_max(sq_report, ra.max_sq_bits);
+}
+
+// restores the invariants at the voxels that left the band (k_slav_band_leave) and evaluates the termination test
+// (k_slav_decide) in one launch
+static __global__ void __launch_bounds__(256) k_slav_brick_leave_decide(SlavBrickArgs b, long long N, const float* new_live,
+		float* old_live, float* field_a, float* field_b, float* field_f, SlavParams p, const unsigned* max_sq_bits,
+		int* status, int max_iterations) {
+	if (status[b.iteration]) {
+		if (blockIdx.x == 0 && threadIdx.x == 0) status[b.iteration + 1] = 1;
+		return;
+	}
+	const int count = *b.leave_count;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+		const int idx = b.leave_list[j];
+		old_live[idx] = new_live[idx];
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			field_a[c * N + idx] = 0.0f;
+			field_b[c * N + idx] = 0.0f;
+			field_f[c * N + idx] = 0.0f;
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		const float max_warp = sqrtf(__uint_as_float(max_sq_bits[b.iteration]));
+		status[b.iteration + 1] = slav_finished(p, b.iteration + 1, max_iterations, max_warp) ? 1 : 0;
+	}
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------- TMA-staged brick kernels
+// Sixth generation: the brick kernels above with their operands staged in shared memory. One block per brick; one elected
+// thread fetches the brick's box of every input field with its halo (1 voxel for the term stencils, R voxels along the
+// pass axis for a filter pass) by TMA (cp.async.bulk.tensor.4d, zero fill outside the volume = the filter's zero
+// padding), the block waits on the mbarrier and then works through the brick's band list: every stencil / filter tap is
+// an LDS with a compile-time offset from one base address. Voxels on the faces of the volume (one-sided stencils) take
+// the global path of the list kernels. Arithmetic: the same device functions, the same order.
+constexpr int SLAV_STAGE_Z = SLAV_BRICK_Z + 8;  // staged rows start 4 voxels before the brick (16-byte aligned rows)
+
+struct SlavBrickMaps {
+	CUtensorMap live[2];  // [buffer parity] box 40 x 10 x 10 (z, y, x)
+	CUtensorMap warp;     // box 40 x 10 x 10 x 3
+	CUtensorMap pass[3];  // input field of filter pass `axis`: brick + R-voxel halo along the axis (z rows of 40 for axis 2)
+};
+
+// box extents (x, y, z) of the staged input of filter pass AXIS
+template<int R, int AXIS> struct SlavPassBox {
+	static constexpr int X = SLAV_BRICK_X + (AXIS == 0 ? 2 * R : 0);
+	static constexpr int Y = SLAV_BRICK_Y + (AXIS == 1 ? 2 * R : 0);
+	static constexpr int Z = AXIS == 2 ? SLAV_STAGE_Z : SLAV_BRICK_Z;
+	static constexpr int LO_X = AXIS == 0 ? R : 0, LO_Y = AXIS == 1 ? R : 0, LO_Z = AXIS == 2 ? 4 : 0;
+	static constexpr int VOXELS = X * Y * Z;
+	static constexpr int STRIDE = AXIS == 0 ? Y * Z : (AXIS == 1 ? Z : 1);
+};
+
+inline int make_brick_box_map(CUtensorMap* map, const float* base, int channels, long long channel_stride, const SlavGeom& g,
+		int box_x, int box_y, int box_z) {
+	EncodeTiledFn encode = encode_tiled_fn();
+	LSF_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+	const cuuint64_t dims[4] = { (cuuint64_t) g.n[2], (cuuint64_t) g.n[1], (cuuint64_t) g.n[0], (cuuint64_t) channels };
+	const cuuint64_t strides[3] = { (cuuint64_t) g.n[2] * 4, (cuuint64_t) g.n[1] * g.n[2] * 4, (cuuint64_t) channel_stride * 4 };
+	const cuuint32_t box[4] = { (cuuint32_t) box_z, (cuuint32_t) box_y, (cuuint32_t) box_x, (cuuint32_t) channels };
+	const cuuint32_t element_strides[4] = { 1, 1, 1, 1 };
+	const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box,
+			element_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+			CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	LSF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (brick box %d x %d x %d)", (int) r, box_x, box_y,
+			box_z);
+	return LSF_OK;
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void slav_brick_origin(const SlavBrickArgs& b, int brick, int& x0, int& y0, int& z0) {
+	z0 = (brick % b.bricks_z) * SLAV_BRICK_Z;
+	y0 = ((brick / b.bricks_z) % b.bricks_y) * SLAV_BRICK_Y;
+	x0 = (brick / (b.bricks_z * b.bricks_y)) * SLAV_BRICK_X;
+}
+
+constexpr int SLAV_TERMS_TILE = (SLAV_BRICK_X + 2) * (SLAV_BRICK_Y + 2) * SLAV_STAGE_Z;  // voxels of one staged field
+constexpr int SLAV_TERMS_SMEM = 4 * SLAV_TERMS_TILE * (int) sizeof(float) + 128;
+
+static __global__ void __launch_bounds__(256) k_slav_brick_terms_tma(SlavGradientArgs a, SlavBrickArgs b,
+		const __grid_constant__ CUtensorMap live_map, const __grid_constant__ CUtensorMap warp_map) {
+	if (a.status[a.iteration]) return;
+	const int brick = blockIdx.x;
+	const int count = b.brick_count[brick];
+	if (count == 0) return;
+	extern __shared__ __align__(128) unsigned char slav_smem[];
+	float* tile = reinterpret_cast<float*>(slav_smem);  // live [10][10][40], warp [3][10][10][40]
+	uint64_t* bar = reinterpret_cast<uint64_t*>(slav_smem + 4 * SLAV_TERMS_TILE * sizeof(float));
+	int x0, y0, z0;
+	slav_brick_origin(b, brick, x0, y0, z0);
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		mbar_fence_init();
+		mbar_expect_tx(bar, 4 * SLAV_TERMS_TILE * sizeof(float));
+		tma_load_4d(tile, &live_map, z0 - 4, y0 - 1, x0 - 1, 0, bar);
+		tma_load_4d(tile + SLAV_TERMS_TILE, &warp_map, z0 - 4, y0 - 1, x0 - 1, 0, bar);
+	}
+	__syncthreads();
+	// the argument block of the staged fields: component stride and strides of the tile
+	SlavGradientArgs sa = a;
+	sa.live = tile;
+	sa.warp = tile + SLAV_TERMS_TILE;
+	sa.g.N = SLAV_TERMS_TILE;
+	sa.g.stride[0] = (SLAV_BRICK_Y + 2) * SLAV_STAGE_Z;
+	sa.g.stride[1] = SLAV_STAGE_Z;
+	sa.g.stride[2] = 1;
+	const SlavParams& p = a.p;
+	const bool killing = p.smoothing_term_method == LSF_SMOOTHING_KILLING;
+	const int base = brick * SLAV_BRICK_VOXELS;
+	const int N = (int) a.g.N;
+	// list entries and the canonical values do not depend on the staged data: fetch the first ones before waiting
+	int j = threadIdx.x;
+	int idx = j < count ? b.list[base + j] : 0, packed = j < count ? b.positions[base + j] : 0;
+	mbar_wait(bar, 0);
+	for (; j < count; j += 256) {
+		const int next = j + 256;
+		const int next_idx = next < count ? b.list[base + next] : 0, next_packed = next < count ? b.positions[base + next] : 0;
+		const int q[3] = { packed & 1023, (packed >> 10) & 1023, (packed >> 20) & 1023 };
+		const bool interior = q[0] >= 1 && q[0] < a.g.n[0] - 1 && q[1] >= 1 && q[1] < a.g.n[1] - 1 && q[2] >= 1
+				&& q[2] < a.g.n[2] - 1;
+		if (!interior) {
+			slav_band_terms_voxel(a, idx, packed);
+		} else {
+			const int s[3] = { q[0] - x0 + 1, q[1] - y0 + 1, q[2] - z0 + 4 };
+			const int at = (s[0] * (SLAV_BRICK_Y + 2) + s[1]) * SLAV_STAGE_Z + s[2];
+			const float live_value = tile[at];
+			const float canonical_value = __ldg(a.canonical + idx);
+			if (slav_truncated(live_value) && slav_truncated(canonical_value)) {
+				// the list is re-used for several iterations: this voxel has left the band since the last scan
+#pragma unroll
+				for (int c = 0; c < 3; c++) a.out[c * N + idx] = (0.0f + 0.0f * p.smoothing_weight) * -p.rate;
+			} else {
+				float data[3], smooth[3], ls[3];
+				const bool ls_here = p.level_set && !slav_truncated(live_value);
+				slav_data_term_given<3, true, true>(sa, at, s, canonical_value, data);
+				if (killing) slav_killing<3, true, true>(sa, at, s, smooth);
+				else slav_tikhonov_cpp<3, true, true>(sa, at, s, smooth);
+				if (ls_here) slav_level_set<3, true, true>(sa, at, s, ls);
+#pragma unroll
+				for (int c = 0; c < 3; c++) {
+					float total = data[c] * p.data_weight;
+					if (ls_here) total = total + ls[c] * p.level_set_weight;
+					total = total + smooth[c] * p.smoothing_weight;
+					a.out[c * N + idx] = total * -p.rate;  // reference sobolev_optimizer2d.cpp:131-132
+				}
+			}
+		}
+		idx = next_idx;
+		packed = next_packed;
+	}
+}
+
+// one pass of convolve_with_kernel_preserve_zeros (C++ zero rule) at a band voxel from the staged box of the pass input
+// (`at` = the voxel inside component 0 of the box); same tap order as slav_band_filter_voxel
+template<int R, int AXIS>
+__device__ __forceinline__ void slav_staged_filter_voxel(const float* box, int at, const float (&k)[LSF_MAX_KERNEL_SIZE],
+		float (&acc)[3]) {
+	typedef SlavPassBox<R, AXIS> Box;
+	bool all_zero = true;
+#pragma unroll
+	for (int c = 0; c < 3; c++) all_zero = all_zero && box[c * Box::VOXELS + at] == 0.0f;
+	acc[0] = acc[1] = acc[2] = 0.0f;
+	if (all_zero) return;
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+#pragma unroll
+		for (int t = 0; t < 2 * R + 1; t++) acc[c] += box[c * Box::VOXELS + at + (t - R) * Box::STRIDE] * k[t];
+	}
+}
+
+template<int R, int AXIS>
+__device__ __forceinline__ int slav_staged_filter_offset(int packed, int x0, int y0, int z0) {
+	typedef SlavPassBox<R, AXIS> Box;
+	const int sx = (packed & 1023) - x0 + Box::LO_X, sy = ((packed >> 10) & 1023) - y0 + Box::LO_Y,
+			sz = ((packed >> 20) & 1023) - z0 + Box::LO_Z;
+	return (sx * Box::Y + sy) * Box::Z + sz;
+}
+
+template<int R, int AXIS>
+static __global__ void __launch_bounds__(256) k_slav_brick_filter_tma(SlavFilterArgs a, SlavBrickArgs b,
+		const __grid_constant__ CUtensorMap in_map) {
+	typedef SlavPassBox<R, AXIS> Box;
+	if (a.status[a.iteration]) return;
+	const int brick = blockIdx.x;
+	const int count = b.brick_count[brick];
+	if (count == 0) return;
+	extern __shared__ __align__(128) unsigned char slav_smem[];
+	float* box = reinterpret_cast<float*>(slav_smem);
+	uint64_t* bar = reinterpret_cast<uint64_t*>(slav_smem + 3 * Box::VOXELS * sizeof(float));
+	int x0, y0, z0;
+	slav_brick_origin(b, brick, x0, y0, z0);
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		mbar_fence_init();
+		mbar_expect_tx(bar, 3 * Box::VOXELS * sizeof(float));
+		tma_load_4d(box, &in_map, z0 - Box::LO_Z, y0 - Box::LO_Y, x0 - Box::LO_X, 0, bar);
+	}
+	__syncthreads();
+	const int base = brick * SLAV_BRICK_VOXELS;
+	const int N = (int) a.g.N;
+	int j = threadIdx.x;
+	int idx = j < count ? b.list[base + j] : 0, packed = j < count ? b.positions[base + j] : 0;
+	mbar_wait(bar, 0);
+	for (; j < count; j += 256) {
+		const int next = j + 256;
+		const int next_idx = next < count ? b.list[base + next] : 0, next_packed = next < count ? b.positions[base + next] : 0;
+		float acc[3];
+		slav_staged_filter_voxel<R, AXIS>(box, slav_staged_filter_offset<R, AXIS>(packed, x0, y0, z0), a.k, acc);
+#pragma unroll
+		for (int c = 0; c < 3; c++) a.out[c * N + idx] = acc[c];
+		idx = next_idx;
+		packed = next_packed;
+	}
+}
+
+// axis-2 pass from the staged box + masked re-warp (taps from the staged live box) + maximum warp length
+template<int R>
+static __global__ void __launch_bounds__(256) k_slav_brick_filter_resample_tma(SlavFilterArgs a, SlavResampleArgs ra,
+		SlavBrickArgs b, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap live_map) {
+	typedef SlavPassBox<R, 2> Box;
+	if (a.status[a.iteration]) return;
+	const int brick = blockIdx.x;
+	const int count = b.brick_count[brick];
+	if (count == 0) return;
+	extern __shared__ __align__(128) unsigned char slav_smem[];
+	float* box = reinterpret_cast<float*>(slav_smem);
+	float* live_tile = box + 3 * Box::VOXELS;
+	uint64_t* bar = reinterpret_cast<uint64_t*>(slav_smem + (3 * Box::VOXELS + SLAV_TERMS_TILE) * sizeof(float));
+	int x0, y0, z0;
+	slav_brick_origin(b, brick, x0, y0, z0);
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		mbar_fence_init();
+		mbar_expect_tx(bar, (3 * Box::VOXELS + SLAV_TERMS_TILE) * sizeof(float));
+		tma_load_4d(box, &in_map, z0 - Box::LO_Z, y0, x0, 0, bar);
+		tma_load_4d(live_tile, &live_map, z0 - 4, y0 - 1, x0 - 1, 0, bar);
+	}
+	__syncthreads();
+	SlavLiveTile tile;
+	tile.data = live_tile;
+	tile.lo[0] = x0 - 1;
+	tile.lo[1] = y0 - 1;
+	tile.lo[2] = z0 - 4;
+	tile.ext[0] = SLAV_BRICK_X + 2;
+	tile.ext[1] = SLAV_BRICK_Y + 2;
+	tile.ext[2] = SLAV_STAGE_Z;
+	const int base = brick * SLAV_BRICK_VOXELS;
+	const int N = (int) a.g.N;
+	float sq_report = 0.0f;
+	int j = threadIdx.x;
+	int idx = j < count ? b.list[base + j] : 0, packed = j < count ? b.positions[base + j] : 0;
+	float canonical_value = j < count ? __ldg(ra.canonical + idx) : 0.0f;
+	mbar_wait(bar, 0);
+	for (; j < count; j += 256) {
+		const int next = j + 256;
+		const int next_idx = next < count ? b.list[base + next] : 0, next_packed = next < count ? b.positions[base + next] : 0;
+		const float next_canonical = next < count ? __ldg(ra.canonical + next_idx) : 0.0f;
+		float update[3], w[3], new_value;
+		slav_staged_filter_voxel<R, 2>(box, slav_staged_filter_offset<R, 2>(packed, x0, y0, z0), a.k, update);
+		const int sx = (packed & 1023) - x0 + 1, sy = ((packed >> 10) & 1023) - y0 + 1, sz = ((packed >> 20) & 1023) - z0 + 4;
+		const float live_value = live_tile[(sx * (SLAV_BRICK_Y + 2) + sy) * SLAV_STAGE_Z + sz];
+		slav_resample_voxel<3, true>(ra, idx, update, live_value, canonical_value, new_value, w, sq_report, &tile);
+		ra.new_live[idx] = new_value;
+#pragma unroll
+		for (int c = 0; c < 3; c++) ra.warp[c * N + idx] = w[c];
+		if (slav_truncated(new_value) && slav_truncated(canonical_value)) b.leave_list[atomicAdd(b.leave_count, 1)] = idx;
+		idx = next_idx;
+		packed = next_packed;
+		canonical_value = next_canonical;
+	}
+	if (ra.max_sq_bits != nullptr) block_atomic_max(sq_report, ra.max_sq_bits);
+}
+
+template<int R, int AXIS>
+inline void launch_slav_brick_filter_tma(const SlavFilterArgs& fa, const SlavBrickArgs& brick, const CUtensorMap& map,
+		unsigned bricks, cudaStream_t stream) {
+	constexpr int bytes = 3 * SlavPassBox<R, AXIS>::VOXELS * (int) sizeof(float) + 128;
+	static const bool configured = cudaFuncSetAttribute(k_slav_brick_filter_tma<R, AXIS>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+	(void) configured;
+	k_slav_brick_filter_tma<R, AXIS> <<<counted(bricks), 256, bytes, stream>>>(fa, brick, map);
+}
+
+template<int R>
+inline void launch_slav_brick_filter_resample_tma(const SlavFilterArgs& fa, const SlavResampleArgs& ra,
+		const SlavBrickArgs& brick, const CUtensorMap& in_map, const CUtensorMap& live_map, unsigned bricks,
+		cudaStream_t stream) {
+	constexpr int bytes = (3 * SlavPassBox<R, 2>::VOXELS + SLAV_TERMS_TILE) * (int) sizeof(float) + 128;
+	static const bool configured = cudaFuncSetAttribute(k_slav_brick_filter_resample_tma<R>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+	(void) configured;
+	k_slav_brick_filter_resample_tma<R> <<<counted(bricks), 256, bytes, stream>>>(fa, ra, brick, in_map, live_map);
 }
 
 #endif  // __CUDACC__
