@@ -173,38 +173,44 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			&& taps.radius >= 1 && taps.radius <= 3 && g.n[0] <= 1024 && g.n[1] <= 1024 && g.n[2] <= 1024 && g.n[2] % 4 == 0
 			&& g.N * 3 < (1ll << 31) && aligned_16(live_a)
 			&& aligned_16(canonical) && !finished;
-	// brick-ordered band (fifth generation, slavcheva_fast.cuh): LSF_SLAV_BRICK=0 keeps the memory-ordered global list
+	// brick-ordered band with TMA-staged persistent kernels (fifth generation, slavcheva_fast.cuh); LSF_SLAV_BRICK=0 keeps
+	// the memory-ordered global list
 	const char* brick_env = getenv("LSF_SLAV_BRICK");
-	const bool bricked = sparse && !(brick_env && brick_env[0] == '0');
+	const bool bricked = sparse && !(brick_env && brick_env[0] == '0') && g.n[2] >= SLAV_STAGE_Z;
 	const int bricks_x = (g.n[0] + SLAV_BRICK_X - 1) / SLAV_BRICK_X, bricks_y = (g.n[1] + SLAV_BRICK_Y - 1) / SLAV_BRICK_Y,
 			bricks_z = (g.n[2] + SLAV_BRICK_Z - 1) / SLAV_BRICK_Z;
 	const size_t bricks = (size_t) bricks_x * bricks_y * bricks_z;
-	int* brick_counts = nullptr;
-	// TMA-staged brick kernels (sixth generation): LSF_SLAV_TMA=0 keeps the L1-fed brick kernels
-	const char* staged_env = getenv("LSF_SLAV_TMA");
-	const bool staged = bricked && !(staged_env && staged_env[0] == '0') && g.n[2] >= SLAV_STAGE_Z;
 	SlavBrickMaps maps;
+	unsigned short* brick_list = nullptr;
+	int *brick_counts = nullptr, *active_bricks = nullptr, *active_counts = nullptr, *cursors = nullptr;
 	if (sparse) {
-		const size_t list_capacity = bricked ? bricks * SLAV_BRICK_VOXELS : N;
 		const size_t dead_flags = bricked ? bricks : (N + 1023) / 1024;
-		LSF_TRY(arena.alloc(&band_list, list_capacity));
-		LSF_TRY(arena.alloc(&band_positions, list_capacity));
 		LSF_TRY(arena.alloc(&leave_list, N));
 		LSF_TRY(arena.alloc(&band_dead, dead_flags));
 		LSF_CUDA(cudaMemsetAsync(band_dead, 0, dead_flags, stream));
 		if (bricked) {
+			// list segments, active-brick list (one count per scan), one work cursor per launch
+			const size_t generations = (size_t) bound / rescan_period + 1;
+			LSF_TRY(arena.alloc(&brick_list, bricks * SLAV_BRICK_VOXELS));
 			LSF_TRY(arena.alloc(&brick_counts, bricks));
+			LSF_TRY(arena.alloc(&active_bricks, bricks));
+			LSF_TRY(arena.alloc(&active_counts, generations));
+			LSF_TRY(arena.alloc(&cursors, ((size_t) bound + 1) * 4));
 			LSF_CUDA(cudaMemsetAsync(brick_counts, 0, bricks * sizeof(int), stream));
-		}
-		if (staged) {
-			// tensor maps of the staged brick kernels (the three update fields keep their roles in this mode)
+			LSF_CUDA(cudaMemsetAsync(active_counts, 0, generations * sizeof(int), stream));
+			LSF_CUDA(cudaMemsetAsync(cursors, 0, ((size_t) bound + 1) * 4 * sizeof(int), stream));
+			// tensor maps of the staged boxes (the three update fields keep their roles in this mode)
 			const int R = taps.radius;
 			LSF_TRY(make_brick_box_map(&maps.live[0], live_a, 1, (long long) N, g, SLAV_BRICK_X + 2, SLAV_BRICK_Y + 2, SLAV_STAGE_Z));
 			LSF_TRY(make_brick_box_map(&maps.live[1], live_b, 1, (long long) N, g, SLAV_BRICK_X + 2, SLAV_BRICK_Y + 2, SLAV_STAGE_Z));
+			LSF_TRY(make_brick_box_map(&maps.canonical, canonical, 1, (long long) N, g, SLAV_BRICK_X, SLAV_BRICK_Y, SLAV_BRICK_Z));
 			LSF_TRY(make_brick_box_map(&maps.warp, warp, 3, (long long) N, g, SLAV_BRICK_X + 2, SLAV_BRICK_Y + 2, SLAV_STAGE_Z));
 			LSF_TRY(make_brick_box_map(&maps.pass[0], field_a, 3, (long long) N, g, SLAV_BRICK_X + 2 * R, SLAV_BRICK_Y, SLAV_BRICK_Z));
 			LSF_TRY(make_brick_box_map(&maps.pass[1], field_f, 3, (long long) N, g, SLAV_BRICK_X, SLAV_BRICK_Y + 2 * R, SLAV_BRICK_Z));
 			LSF_TRY(make_brick_box_map(&maps.pass[2], field_b, 3, (long long) N, g, SLAV_BRICK_X, SLAV_BRICK_Y, SLAV_STAGE_Z));
+		} else {
+			LSF_TRY(arena.alloc(&band_list, N));
+			LSF_TRY(arena.alloc(&band_positions, N));
 		}
 		LSF_TRY(arena.alloc(&band_counts, (size_t) bound + 1));
 		LSF_TRY(arena.alloc(&leave_counts, (size_t) bound + 1));
@@ -243,27 +249,22 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			band.iteration = it;
 			const unsigned band_blocks = 148 * 8;
 			SlavBrickArgs brick;
-			brick.list = band_list;
-			brick.positions = band_positions;
+			brick.list = brick_list;
 			brick.brick_count = brick_counts;
 			brick.dead = band_dead;
 			brick.bricks_y = bricks_y;
 			brick.bricks_z = bricks_z;
 			brick.leave_list = leave_list;
 			brick.leave_count = band.leave_count;
+			brick.active = active_bricks;
+			brick.active_count = active_counts ? active_counts + it / rescan_period : nullptr;
+			brick.cursor = cursors ? cursors + (size_t) it * 4 : nullptr;
 			brick.status = status;
 			brick.iteration = it;
 			const int live_parity = it & 1;  // the live buffers swap once per enqueued iteration
 			if (bricked) {
 				if (rescan) k_slav_brick_scan<<<counted((unsigned) bricks), 256, 0, stream>>>(ga, brick);
-				if (staged) {
-					static const bool configured = cudaFuncSetAttribute(k_slav_brick_terms_tma,
-							cudaFuncAttributeMaxDynamicSharedMemorySize, SLAV_TERMS_SMEM) == cudaSuccess;
-					(void) configured;
-					k_slav_brick_terms_tma<<<counted((unsigned) bricks), 256, SLAV_TERMS_SMEM, stream>>>(ga, brick,
-							maps.live[live_parity], maps.warp);
-				} else
-					k_slav_brick_terms<<<counted((unsigned) bricks), 256, 0, stream>>>(ga, brick);
+				launch_slav_brick_terms_tma(ga, brick, maps, live_parity, stream);
 			} else if (sparse) {
 				if (rescan) k_slav_band_scan<<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ga, band);
 				k_slav_band_terms<<<counted(band_blocks), 256, 0, stream>>>(ga, band);
@@ -308,46 +309,29 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 				float* outs[3] = { field_b, field_f, field_b };
 				if (bricked) {
 					// a -> f (axis 0) -> b (axis 1); the axis-2 pass runs in the re-warp kernel, its result is not stored
-					float* brick_outs[2] = { field_f, field_b };
-					for (int axis = 0; axis < 2 && !staged; axis++) {
-						fa.in = in;
-						fa.out = brick_outs[axis];
-						fa.axis = axis;
-						if (taps.radius == 1) k_slav_brick_filter_axis<1> <<<counted((unsigned) bricks), 256, 0, stream>>>(fa, brick);
-						else if (taps.radius == 2) k_slav_brick_filter_axis<2> <<<counted((unsigned) bricks), 256, 0, stream>>>(fa, brick);
-						else k_slav_brick_filter_axis<3> <<<counted((unsigned) bricks), 256, 0, stream>>>(fa, brick);
-						in = brick_outs[axis];
-					}
 					ra.update = nullptr;
 					ra.gradient_field = nullptr;
-					if (staged) {
-						fa.in = field_a;
-						fa.out = field_f;
-						fa.axis = 0;
-						if (taps.radius == 1) launch_slav_brick_filter_tma<1, 0>(fa, brick, maps.pass[0], (unsigned) bricks, stream);
-						else if (taps.radius == 2) launch_slav_brick_filter_tma<2, 0>(fa, brick, maps.pass[0], (unsigned) bricks, stream);
-						else launch_slav_brick_filter_tma<3, 0>(fa, brick, maps.pass[0], (unsigned) bricks, stream);
-						fa.in = field_f;
-						fa.out = field_b;
-						fa.axis = 1;
-						if (taps.radius == 1) launch_slav_brick_filter_tma<1, 1>(fa, brick, maps.pass[1], (unsigned) bricks, stream);
-						else if (taps.radius == 2) launch_slav_brick_filter_tma<2, 1>(fa, brick, maps.pass[1], (unsigned) bricks, stream);
-						else launch_slav_brick_filter_tma<3, 1>(fa, brick, maps.pass[1], (unsigned) bricks, stream);
-					}
+					fa.in = field_a;
+					fa.out = field_f;
+					fa.axis = 0;
+					brick.cursor++;
+					if (taps.radius == 1) launch_slav_brick_filter_tma<1, 0>(fa, brick, maps.pass[0], stream);
+					else if (taps.radius == 2) launch_slav_brick_filter_tma<2, 0>(fa, brick, maps.pass[0], stream);
+					else launch_slav_brick_filter_tma<3, 0>(fa, brick, maps.pass[0], stream);
+					fa.in = field_f;
+					fa.out = field_b;
+					fa.axis = 1;
+					brick.cursor++;
+					if (taps.radius == 1) launch_slav_brick_filter_tma<1, 1>(fa, brick, maps.pass[1], stream);
+					else if (taps.radius == 2) launch_slav_brick_filter_tma<2, 1>(fa, brick, maps.pass[1], stream);
+					else launch_slav_brick_filter_tma<3, 1>(fa, brick, maps.pass[1], stream);
 					fa.in = field_b;
 					fa.out = nullptr;
 					fa.axis = 2;
-					if (staged) {
-						if (taps.radius == 1)
-							launch_slav_brick_filter_resample_tma<1>(fa, ra, brick, maps.pass[2], maps.live[live_parity], (unsigned) bricks, stream);
-						else if (taps.radius == 2)
-							launch_slav_brick_filter_resample_tma<2>(fa, ra, brick, maps.pass[2], maps.live[live_parity], (unsigned) bricks, stream);
-						else
-							launch_slav_brick_filter_resample_tma<3>(fa, ra, brick, maps.pass[2], maps.live[live_parity], (unsigned) bricks, stream);
-					}
-					else if (taps.radius == 1) k_slav_brick_filter_resample<1> <<<counted((unsigned) bricks), 256, 0, stream>>>(fa, ra, brick);
-					else if (taps.radius == 2) k_slav_brick_filter_resample<2> <<<counted((unsigned) bricks), 256, 0, stream>>>(fa, ra, brick);
-					else k_slav_brick_filter_resample<3> <<<counted((unsigned) bricks), 256, 0, stream>>>(fa, ra, brick);
+					brick.cursor++;
+					if (taps.radius == 1) launch_slav_brick_filter_resample_tma<1>(fa, ra, brick, maps, live_parity, stream);
+					else if (taps.radius == 2) launch_slav_brick_filter_resample_tma<2>(fa, ra, brick, maps, live_parity, stream);
+					else launch_slav_brick_filter_resample_tma<3>(fa, ra, brick, maps, live_parity, stream);
 					k_slav_brick_leave_decide<<<counted(64u), 256, 0, stream>>>(brick, g.N, live_b, live_a, field_a, field_b, field_f, p,
 							max_sq_bits, status, max_iterations);
 					rewarped = true;

@@ -615,7 +615,7 @@ struct SlavLiveTile {
 template<int D, bool TILE = false>
 __device__ __forceinline__ void slav_resample_voxel(const SlavResampleArgs& a, int idx, const float (&update)[3],
 		float live_value, float canonical_value, float& new_value, float (&w)[3], float& sq_report,
-		const SlavLiveTile* tile = nullptr) {
+		const SlavLiveTile* tile = nullptr, const int* known_pos = nullptr) {
 	const SlavGeom& g = a.g;
 	const bool python = a.p.semantics != LSF_SEMANTICS_CPP;
 	const bool float64 = a.p.semantics == LSF_SEMANTICS_PY_DIRECT;
@@ -632,7 +632,11 @@ __device__ __forceinline__ void slav_resample_voxel(const SlavResampleArgs& a, i
 	new_value = live_value;
 	if (!skip) {
 		int pos[3];
-		slav_coords<D>(g, idx, pos);
+		if (known_pos != nullptr) {
+#pragma unroll
+			for (int ax = 0; ax < 3; ax++) pos[ax] = known_pos[ax];
+		} else
+			slav_coords<D>(g, idx, pos);
 		int base[3] = { 0, 0, 0 };
 		const float oob = a.substitute_original ? live_value : 1.0f;
 		double result;

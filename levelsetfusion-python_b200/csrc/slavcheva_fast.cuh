@@ -495,183 +495,52 @@ static __global__ void __launch_bounds__(256) k_slav_band_leave(SlavBandArgs b, 
 	}
 }
 
+#endif  // __CUDACC__
+
 // ---------------------------------------------------------------------------------------------- brick-ordered narrow band
-// Fifth generation of the sparse iteration. ncu of the list kernels above (profiles/r1_killing_v4.md): the filter passes
-// along axes 0 and 1 fetch 21 taps per voxel that no neighbouring thread shares (the list is in memory order, the
+// Fifth generation of the sparse iteration (default). ncu of the list kernels above (profiles/r1_killing_v4.md): every
+// band voxel issues 21 - 60 dependent 4-byte loads that no neighbouring thread shares (the list is in memory order, the
 // x / y neighbours of a voxel sit in other blocks on other SMs): 7x the pass input crosses from L2 to the SMs, L1 hit rate
-// 14 %, 30 long-scoreboard stalls per issue. Here the band is organised in bricks of 8 x 8 x 32 voxels:
+// 14 %, 30 long-scoreboard stalls per issue. Here the band is organised in bricks of 8 x 8 x 32 voxels and every operand
+// of a brick is staged in shared memory by the TMA unit:
 //   * k_slav_brick_scan: one block per brick classifies its 2048 voxels (128-bit loads) and writes the brick's band
-//     voxels, rows of z-adjacent voxels in order, into the brick's own segment of the list (list + brick * 2048: no
-//     global counter, no ordering between bricks needed); bricks without band voxels are dead for good;
-//   * every list kernel runs one block per brick, so the stencil and filter taps of a brick's voxels along all three axes
-//     are shared through the SM's L1 (a brick with its halo is 43 KB per pass) and every row is a coalesced run;
+//     voxels (16-bit offsets inside the brick, rows of z-adjacent voxels in order) into the brick's own segment of the
+//     list; bricks with band voxels are appended to the active list, bricks without are dead for good;
+//   * the iteration kernels are persistent (one block per SM): a producer warp claims the next active brick from a
+//     device-side cursor and fetches the brick's box of every input field with its halo (1 voxel for the term stencils,
+//     R voxels along the pass axis for a filter pass; cp.async.bulk.tensor.4d, zero fill outside the volume = the
+//     filter's zero padding), the canonical box and the brick's list segment (cp.async.bulk) into a ring of stages; the
+//     consumer warps wait on a stage's `full` mbarrier, work through the list -- every stencil / filter tap is an LDS with
+//     a compile-time offset from one base address, no global load is left -- and release the stage on its `empty`
+//     mbarrier warp by warp (no block-wide barrier). The boxes of the next bricks are in flight while a brick is computed;
 //   * the axis-2 pass and the masked re-warp run in one kernel (the filtered update of a voxel is all its re-warp
 //     needs), the patch-up of the voxels that left the band and the termination test in another: 5 launches per
 //     iteration instead of 7.
-// Per-voxel arithmetic: the same device functions as the list kernels and the dense kernels.
+// Voxels on the faces of the volume (one-sided stencils) take the global path of the list kernels.
+// Per-voxel arithmetic: the same device functions as the list kernels and the dense kernels, in the same order.
 constexpr int SLAV_BRICK_X = 8, SLAV_BRICK_Y = 8, SLAV_BRICK_Z = 32;
 constexpr int SLAV_BRICK_VOXELS = SLAV_BRICK_X * SLAV_BRICK_Y * SLAV_BRICK_Z;
+constexpr int SLAV_STAGE_Z = SLAV_BRICK_Z + 8;  // staged rows start 4 voxels before the brick (16-byte aligned rows)
 
 struct SlavBrickArgs {
-	int* list;            // [bricks][2048]: band voxels of the brick (voxel index)
-	int* positions;       // their coordinates, 10 bits per axis
-	int* brick_count;     // listed voxels per brick
-	unsigned char* dead;  // brick holds no band voxel (the band only shrinks: never scanned again)
+	unsigned short* list;  // [bricks][2048]: band voxels of the brick as offsets inside it ((x * 8 + y) * 32 + z)
+	int* brick_count;      // listed voxels per brick
+	unsigned char* dead;   // brick holds no band voxel (the band only shrinks: never scanned again)
 	int bricks_y, bricks_z;
-	int* leave_list;      // voxels that left the band in this iteration's re-warp
+	int* leave_list;       // voxels that left the band in this iteration's re-warp
 	int* leave_count;
+	int* active;           // bricks with band voxels, appended by the scan (arbitrary order)
+	int* active_count;
+	int* cursor;           // next entry of `active` to claim (zero at launch; one cursor per launch)
 	const int* status;
 	int iteration;
 };
 
-// exclusive prefix sum of `mine` over the 256 threads of the block; *total = sum (needs two barriers)
-__device__ __forceinline__ int slav_block_exclusive_scan(int mine, int* warp_totals, int* total) {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int inclusive = mine;
-#pragma unroll
-	for (int offset = 1; offset < 32; offset <<= 1) {
-		const int other = __shfl_up_sync(0xffffffffu, inclusive, offset);
-		if (lane >= offset) inclusive += other;
-	}
-	__syncthreads();  // warp_totals may still be read from a previous call
-	if (lane == 31) warp_totals[warp] = inclusive;
-	__syncthreads();
-	int before = inclusive - mine, sum = 0;
-	for (int w = 0; w < 8; w++) {
-		if (w < warp) before += warp_totals[w];
-		sum += warp_totals[w];
-	}
-	*total = sum;
-	return before;
-}
-
-static __global__ void __launch_bounds__(256) k_slav_brick_scan(SlavGradientArgs a, SlavBrickArgs b) {
-	const int brick = blockIdx.x;
-	if (a.status[a.iteration] || b.dead[brick]) return;
-	__shared__ int warp_totals[8];
-	const int bz = brick % b.bricks_z, by = (brick / b.bricks_z) % b.bricks_y, bx = brick / (b.bricks_z * b.bricks_y);
-	const int z = bz * SLAV_BRICK_Z + (threadIdx.x & 7) * 4;
-	int listed = 0;
-	const int base = brick * SLAV_BRICK_VOXELS;
-#pragma unroll
-	for (int half = 0; half < 2; half++) {
-		const int row = (threadIdx.x >> 3) + 32 * half;  // row of the brick: x-major
-		const int x = bx * SLAV_BRICK_X + (row >> 3), y = by * SLAV_BRICK_Y + (row & 7);
-		unsigned in_band = 0;
-		int first = 0;
-		if (x < a.g.n[0] && y < a.g.n[1] && z < a.g.n[2]) {
-			first = (x * a.g.n[1] + y) * a.g.n[2] + z;
-			const float4 live4 = __ldg(reinterpret_cast<const float4*>(a.live + first));
-			const float4 canonical4 = __ldg(reinterpret_cast<const float4*>(a.canonical + first));
-			const float live_v[4] = { live4.x, live4.y, live4.z, live4.w };
-			const float canonical_v[4] = { canonical4.x, canonical4.y, canonical4.z, canonical4.w };
-#pragma unroll
-			for (int v = 0; v < 4; v++)
-				if (!(slav_truncated(live_v[v]) && slav_truncated(canonical_v[v]))) in_band |= 1u << v;
-		}
-		int total;
-		int at = base + listed + slav_block_exclusive_scan(__popc(in_band), warp_totals, &total);
-#pragma unroll
-		for (int v = 0; v < 4; v++) {
-			if (in_band & (1u << v)) {
-				b.list[at] = first + v;
-				b.positions[at] = x | (y << 10) | ((z + v) << 20);
-				at++;
-			}
-		}
-		listed += total;
-	}
-	if (threadIdx.x == 0) {
-		b.brick_count[brick] = listed;
-		if (listed == 0) b.dead[brick] = 1;
-	}
-}
-
-static __global__ void __launch_bounds__(256) k_slav_brick_terms(SlavGradientArgs a, SlavBrickArgs b) {
-	if (a.status[a.iteration]) return;
-	const int count = b.brick_count[blockIdx.x];
-	const int base = blockIdx.x * SLAV_BRICK_VOXELS;
-	for (int j = threadIdx.x; j < count; j += 256) slav_band_terms_voxel(a, b.list[base + j], b.positions[base + j]);
-}
-
-template<int R>
-static __global__ void __launch_bounds__(256) k_slav_brick_filter_axis(SlavFilterArgs a, SlavBrickArgs b) {
-	if (a.status[a.iteration]) return;
-	const int count = b.brick_count[blockIdx.x];
-	const int base = blockIdx.x * SLAV_BRICK_VOXELS;
-	const int N = (int) a.g.N;
-	for (int j = threadIdx.x; j < count; j += 256) {
-		const int idx = b.list[base + j];
-		float acc[3];
-		slav_band_filter_voxel<R>(a, idx, (b.positions[base + j] >> (10 * a.axis)) & 1023, acc);
-#pragma unroll
-		for (int c = 0; c < 3; c++) a.out[c * N + idx] = acc[c];
-	}
-}
-
-// last filter pass (a.axis) fused with the masked re-warp and the maximum warp length (k_slav_band_resample's body)
-template<int R>
-static __global__ void __launch_bounds__(256) k_slav_brick_filter_resample(SlavFilterArgs a, SlavResampleArgs ra, SlavBrickArgs b) {
-	if (a.status[a.iteration]) return;
-	const int count = b.brick_count[blockIdx.x];
-	const int base = blockIdx.x * SLAV_BRICK_VOXELS;
-	const int N = (int) a.g.N;
-	float sq_report = 0.0f;
-	for (int j = threadIdx.x; j < count; j += 256) {
-		const int idx = b.list[base + j];
-		float update[3], w[3], new_value;
-		slav_band_filter_voxel<R>(a, idx, (b.positions[base + j] >> (10 * a.axis)) & 1023, update);
-		const float canonical_value = __ldg(ra.canonical + idx);
-		slav_resample_voxel<3>(ra, idx, update, __ldg(ra.live + idx), canonical_value, new_value, w, sq_report);
-		ra.new_live[idx] = new_value;
-#pragma unroll
-		for (int c = 0; c < 3; c++) ra.warp[c * N + idx] = w[c];
-		if (slav_truncated(new_value) && slav_truncated(canonical_value)) b.leave_list[atomicAdd(b.leave_count, 1)] = idx;
-	}
-	if (ra.max_sq_bits != nullptr) block_atomic_max(sq_report, ra.max_sq_bits);
-}
-
-// restores the invariants at the voxels that left the band (k_slav_band_leave) and evaluates the termination test
-// (k_slav_decide) in one launch
-static __global__ void __launch_bounds__(256) k_slav_brick_leave_decide(SlavBrickArgs b, long long N, const float* new_live,
-		float* old_live, float* field_a, float* field_b, float* field_f, SlavParams p, const unsigned* max_sq_bits,
-		int* status, int max_iterations) {
-	if (status[b.iteration]) {
-		if (blockIdx.x == 0 && threadIdx.x == 0) status[b.iteration + 1] = 1;
-		return;
-	}
-	const int count = *b.leave_count;
-	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
-		const int idx = b.leave_list[j];
-		old_live[idx] = new_live[idx];
-#pragma unroll
-		for (int c = 0; c < 3; c++) {
-			field_a[c * N + idx] = 0.0f;
-			field_b[c * N + idx] = 0.0f;
-			field_f[c * N + idx] = 0.0f;
-		}
-	}
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		const float max_warp = sqrtf(__uint_as_float(max_sq_bits[b.iteration]));
-		status[b.iteration + 1] = slav_finished(p, b.iteration + 1, max_iterations, max_warp) ? 1 : 0;
-	}
-}
-
-#endif  // __CUDACC__
-
-// ---------------------------------------------------------------------------------------------- TMA-staged brick kernels
-// Sixth generation: the brick kernels above with their operands staged in shared memory. One block per brick; one elected
-// thread fetches the brick's box of every input field with its halo (1 voxel for the term stencils, R voxels along the
-// pass axis for a filter pass) by TMA (cp.async.bulk.tensor.4d, zero fill outside the volume = the filter's zero
-// padding), the block waits on the mbarrier and then works through the brick's band list: every stencil / filter tap is
-// an LDS with a compile-time offset from one base address. Voxels on the faces of the volume (one-sided stencils) take
-// the global path of the list kernels. Arithmetic: the same device functions, the same order.
-constexpr int SLAV_STAGE_Z = SLAV_BRICK_Z + 8;  // staged rows start 4 voxels before the brick (16-byte aligned rows)
-
 struct SlavBrickMaps {
-	CUtensorMap live[2];  // [buffer parity] box 40 x 10 x 10 (z, y, x)
-	CUtensorMap warp;     // box 40 x 10 x 10 x 3
-	CUtensorMap pass[3];  // input field of filter pass `axis`: brick + R-voxel halo along the axis (z rows of 40 for axis 2)
+	CUtensorMap live[2];    // [buffer parity] box 40 x 10 x 10 (z, y, x)
+	CUtensorMap canonical;  // box 32 x 8 x 8
+	CUtensorMap warp;       // box 40 x 10 x 10 x 3
+	CUtensorMap pass[3];    // input field of filter pass `axis`: brick + R-voxel halo along the axis (z rows of 40 for axis 2)
 };
 
 // box extents (x, y, z) of the staged input of filter pass AXIS
@@ -702,34 +571,164 @@ inline int make_brick_box_map(CUtensorMap* map, const float* base, int channels,
 
 #ifdef __CUDACC__
 
+// exclusive prefix sum of `mine` over the 256 threads of the block; *total = sum (needs two barriers)
+__device__ __forceinline__ int slav_block_exclusive_scan(int mine, int* warp_totals, int* total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int inclusive = mine;
+#pragma unroll
+	for (int offset = 1; offset < 32; offset <<= 1) {
+		const int other = __shfl_up_sync(0xffffffffu, inclusive, offset);
+		if (lane >= offset) inclusive += other;
+	}
+	__syncthreads();  // warp_totals may still be read from a previous call
+	if (lane == 31) warp_totals[warp] = inclusive;
+	__syncthreads();
+	int before = inclusive - mine, sum = 0;
+	for (int w = 0; w < 8; w++) {
+		if (w < warp) before += warp_totals[w];
+		sum += warp_totals[w];
+	}
+	*total = sum;
+	return before;
+}
+
 __device__ __forceinline__ void slav_brick_origin(const SlavBrickArgs& b, int brick, int& x0, int& y0, int& z0) {
 	z0 = (brick % b.bricks_z) * SLAV_BRICK_Z;
 	y0 = ((brick / b.bricks_z) % b.bricks_y) * SLAV_BRICK_Y;
 	x0 = (brick / (b.bricks_z * b.bricks_y)) * SLAV_BRICK_X;
 }
 
-constexpr int SLAV_TERMS_TILE = (SLAV_BRICK_X + 2) * (SLAV_BRICK_Y + 2) * SLAV_STAGE_Z;  // voxels of one staged field
-constexpr int SLAV_TERMS_SMEM = 4 * SLAV_TERMS_TILE * (int) sizeof(float) + 128;
-
-static __global__ void __launch_bounds__(256) k_slav_brick_terms_tma(SlavGradientArgs a, SlavBrickArgs b,
-		const __grid_constant__ CUtensorMap live_map, const __grid_constant__ CUtensorMap warp_map) {
-	if (a.status[a.iteration]) return;
+static __global__ void __launch_bounds__(256) k_slav_brick_scan(SlavGradientArgs a, SlavBrickArgs b) {
 	const int brick = blockIdx.x;
-	const int count = b.brick_count[brick];
-	if (count == 0) return;
-	extern __shared__ __align__(128) unsigned char slav_smem[];
-	float* tile = reinterpret_cast<float*>(slav_smem);  // live [10][10][40], warp [3][10][10][40]
-	uint64_t* bar = reinterpret_cast<uint64_t*>(slav_smem + 4 * SLAV_TERMS_TILE * sizeof(float));
+	if (a.status[a.iteration] || b.dead[brick]) return;
+	__shared__ int warp_totals[8];
 	int x0, y0, z0;
 	slav_brick_origin(b, brick, x0, y0, z0);
+	const int lz = (threadIdx.x & 7) * 4;
+	int listed = 0;
+	const int base = brick * SLAV_BRICK_VOXELS;
+#pragma unroll
+	for (int half = 0; half < 2; half++) {
+		const int row = (threadIdx.x >> 3) + 32 * half;  // row of the brick: x-major
+		const int x = x0 + (row >> 3), y = y0 + (row & 7), z = z0 + lz;
+		unsigned in_band = 0;
+		if (x < a.g.n[0] && y < a.g.n[1] && z < a.g.n[2]) {
+			const int first = (x * a.g.n[1] + y) * a.g.n[2] + z;
+			const float4 live4 = __ldg(reinterpret_cast<const float4*>(a.live + first));
+			const float4 canonical4 = __ldg(reinterpret_cast<const float4*>(a.canonical + first));
+			const float live_v[4] = { live4.x, live4.y, live4.z, live4.w };
+			const float canonical_v[4] = { canonical4.x, canonical4.y, canonical4.z, canonical4.w };
+#pragma unroll
+			for (int v = 0; v < 4; v++)
+				if (!(slav_truncated(live_v[v]) && slav_truncated(canonical_v[v]))) in_band |= 1u << v;
+		}
+		int total;
+		int at = base + listed + slav_block_exclusive_scan(__popc(in_band), warp_totals, &total);
+#pragma unroll
+		for (int v = 0; v < 4; v++)
+			if (in_band & (1u << v)) b.list[at++] = (unsigned short) (row * SLAV_BRICK_Z + lz + v);
+		listed += total;
+	}
 	if (threadIdx.x == 0) {
-		mbar_init(bar, 1);
+		b.brick_count[brick] = listed;
+		if (listed == 0) b.dead[brick] = 1;
+		else b.active[atomicAdd(b.active_count, 1)] = brick;
+	}
+}
+
+// restores the invariants at the voxels that left the band (k_slav_band_leave) and evaluates the termination test
+// (k_slav_decide) in one launch
+static __global__ void __launch_bounds__(256) k_slav_brick_leave_decide(SlavBrickArgs b, long long N, const float* new_live,
+		float* old_live, float* field_a, float* field_b, float* field_f, SlavParams p, const unsigned* max_sq_bits,
+		int* status, int max_iterations) {
+	if (status[b.iteration]) {
+		if (blockIdx.x == 0 && threadIdx.x == 0) status[b.iteration + 1] = 1;
+		return;
+	}
+	const int count = *b.leave_count;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+		const int idx = b.leave_list[j];
+		old_live[idx] = new_live[idx];
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			field_a[c * N + idx] = 0.0f;
+			field_b[c * N + idx] = 0.0f;
+			field_f[c * N + idx] = 0.0f;
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		const float max_warp = sqrtf(__uint_as_float(max_sq_bits[b.iteration]));
+		status[b.iteration + 1] = slav_finished(p, b.iteration + 1, max_iterations, max_warp) ? 1 : 0;
+	}
+}
+
+// plain bulk copy global -> shared (bytes: multiple of 16, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// ring of stages shared by the producer warp and the consumer warps of a persistent block
+template<int STAGES>
+struct SlavPipe {
+	uint64_t full[STAGES];   // the stage's boxes have landed (or: no brick left)
+	uint64_t empty[STAGES];  // every consumer warp is done with the stage
+	int brick[STAGES];       // brick staged there; -1 = the list is exhausted
+	int count[STAGES];       // its listed voxels
+};
+
+template<int STAGES>
+__device__ __forceinline__ void slav_pipe_init(SlavPipe<STAGES>& pipe, int consumer_warps) {
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < STAGES; s++) {
+			mbar_init(&pipe.full[s], 1);
+			mbar_init(&pipe.empty[s], consumer_warps);
+		}
 		mbar_fence_init();
-		mbar_expect_tx(bar, 4 * SLAV_TERMS_TILE * sizeof(float));
-		tma_load_4d(tile, &live_map, z0 - 4, y0 - 1, x0 - 1, 0, bar);
-		tma_load_4d(tile + SLAV_TERMS_TILE, &warp_map, z0 - 4, y0 - 1, x0 - 1, 0, bar);
 	}
 	__syncthreads();
+}
+
+// producer: waits until stage n % STAGES is free and claims the next active brick; returns it (-1 at the end of the list:
+// the stage is then completed so that the consumers see the end marker). The brick's list segment is requested here.
+template<int STAGES>
+__device__ __forceinline__ int slav_pipe_claim(SlavPipe<STAGES>& pipe, const SlavBrickArgs& b, int total, int n,
+		unsigned short* stage_list, uint32_t box_bytes) {
+	const int s = n % STAGES;
+	if (n >= STAGES) mbar_wait(&pipe.empty[s], ((n / STAGES) - 1) & 1);
+	const int k = atomicAdd(b.cursor, 1);
+	const int brick = k < total ? b.active[k] : -1;
+	pipe.brick[s] = brick;
+	if (brick < 0) {
+		mbar_arrive(&pipe.full[s]);
+		return brick;
+	}
+	const int count = b.brick_count[brick];
+	pipe.count[s] = count;
+	const uint32_t list_bytes = ((uint32_t) count * 2u + 15u) & ~15u;
+	mbar_expect_tx(&pipe.full[s], box_bytes + list_bytes);
+	bulk_load(stage_list, b.list + (size_t) brick * SLAV_BRICK_VOXELS, list_bytes, &pipe.full[s]);
+	return brick;
+}
+
+template<int STAGES>
+__device__ __forceinline__ void slav_pipe_release(SlavPipe<STAGES>& pipe, int s) {
+	__syncwarp();
+	if ((threadIdx.x & 31) == 0) mbar_arrive(&pipe.empty[s]);
+}
+
+constexpr int SLAV_LIST_BYTES = SLAV_BRICK_VOXELS * 2;                                    // staged list segment
+constexpr int SLAV_TERMS_TILE = (SLAV_BRICK_X + 2) * (SLAV_BRICK_Y + 2) * SLAV_STAGE_Z;  // voxels of one staged field
+// stage of the terms kernel: live [10][10][40], warp [3][10][10][40], canonical [8][8][32], list
+constexpr int SLAV_TERMS_BOX_BYTES = (4 * SLAV_TERMS_TILE + SLAV_BRICK_VOXELS) * 4;
+constexpr int SLAV_TERMS_STAGE_BYTES = SLAV_TERMS_BOX_BYTES + SLAV_LIST_BYTES;
+constexpr int SLAV_TERMS_STAGES = 3, SLAV_CONSUMERS = 768;
+
+// gradient terms of one staged brick, `workers` threads
+__device__ __forceinline__ void slav_terms_brick(const SlavGradientArgs& a, const SlavBrickArgs& b, const float* tile,
+		const float* canonical_box, const unsigned short* list, int count, int brick, int worker, int workers) {
+	int x0, y0, z0;
+	slav_brick_origin(b, brick, x0, y0, z0);
 	// the argument block of the staged fields: component stride and strides of the tile
 	SlavGradientArgs sa = a;
 	sa.live = tile;
@@ -740,47 +739,80 @@ static __global__ void __launch_bounds__(256) k_slav_brick_terms_tma(SlavGradien
 	sa.g.stride[2] = 1;
 	const SlavParams& p = a.p;
 	const bool killing = p.smoothing_term_method == LSF_SMOOTHING_KILLING;
-	const int base = brick * SLAV_BRICK_VOXELS;
 	const int N = (int) a.g.N;
-	// list entries and the canonical values do not depend on the staged data: fetch the first ones before waiting
-	int j = threadIdx.x;
-	int idx = j < count ? b.list[base + j] : 0, packed = j < count ? b.positions[base + j] : 0;
-	mbar_wait(bar, 0);
-	for (; j < count; j += 256) {
-		const int next = j + 256;
-		const int next_idx = next < count ? b.list[base + next] : 0, next_packed = next < count ? b.positions[base + next] : 0;
-		const int q[3] = { packed & 1023, (packed >> 10) & 1023, (packed >> 20) & 1023 };
+	for (int j = worker; j < count; j += workers) {
+		const int local = list[j];
+		const int lx = local >> 8, ly = (local >> 5) & 7, lz = local & 31;
+		const int q[3] = { x0 + lx, y0 + ly, z0 + lz };
+		const int idx = (q[0] * a.g.n[1] + q[1]) * a.g.n[2] + q[2];
 		const bool interior = q[0] >= 1 && q[0] < a.g.n[0] - 1 && q[1] >= 1 && q[1] < a.g.n[1] - 1 && q[2] >= 1
 				&& q[2] < a.g.n[2] - 1;
 		if (!interior) {
-			slav_band_terms_voxel(a, idx, packed);
-		} else {
-			const int s[3] = { q[0] - x0 + 1, q[1] - y0 + 1, q[2] - z0 + 4 };
-			const int at = (s[0] * (SLAV_BRICK_Y + 2) + s[1]) * SLAV_STAGE_Z + s[2];
-			const float live_value = tile[at];
-			const float canonical_value = __ldg(a.canonical + idx);
-			if (slav_truncated(live_value) && slav_truncated(canonical_value)) {
-				// the list is re-used for several iterations: this voxel has left the band since the last scan
+			slav_band_terms_voxel(a, idx, q[0] | (q[1] << 10) | (q[2] << 20));
+			continue;
+		}
+		const int s[3] = { lx + 1, ly + 1, lz + 4 };
+		const int at = (s[0] * (SLAV_BRICK_Y + 2) + s[1]) * SLAV_STAGE_Z + s[2];
+		const float live_value = tile[at];
+		const float canonical_value = canonical_box[local];
+		if (slav_truncated(live_value) && slav_truncated(canonical_value)) {
+			// the list is re-used for several iterations: this voxel has left the band since the last scan
 #pragma unroll
-				for (int c = 0; c < 3; c++) a.out[c * N + idx] = (0.0f + 0.0f * p.smoothing_weight) * -p.rate;
-			} else {
-				float data[3], smooth[3], ls[3];
-				const bool ls_here = p.level_set && !slav_truncated(live_value);
-				slav_data_term_given<3, true, true>(sa, at, s, canonical_value, data);
-				if (killing) slav_killing<3, true, true>(sa, at, s, smooth);
-				else slav_tikhonov_cpp<3, true, true>(sa, at, s, smooth);
-				if (ls_here) slav_level_set<3, true, true>(sa, at, s, ls);
+			for (int c = 0; c < 3; c++) a.out[c * N + idx] = (0.0f + 0.0f * p.smoothing_weight) * -p.rate;
+			continue;
+		}
+		float data[3], smooth[3], ls[3];
+		const bool ls_here = p.level_set && !slav_truncated(live_value);
+		slav_data_term_given<3, true, true>(sa, at, s, canonical_value, data);
+		if (killing) slav_killing<3, true, true>(sa, at, s, smooth);
+		else slav_tikhonov_cpp<3, true, true>(sa, at, s, smooth);
+		if (ls_here) slav_level_set<3, true, true>(sa, at, s, ls);
 #pragma unroll
-				for (int c = 0; c < 3; c++) {
-					float total = data[c] * p.data_weight;
-					if (ls_here) total = total + ls[c] * p.level_set_weight;
-					total = total + smooth[c] * p.smoothing_weight;
-					a.out[c * N + idx] = total * -p.rate;  // reference sobolev_optimizer2d.cpp:131-132
-				}
+		for (int c = 0; c < 3; c++) {
+			float total = data[c] * p.data_weight;
+			if (ls_here) total = total + ls[c] * p.level_set_weight;
+			total = total + smooth[c] * p.smoothing_weight;
+			a.out[c * N + idx] = total * -p.rate;  // reference sobolev_optimizer2d.cpp:131-132
+		}
+	}
+}
+
+static __global__ void __launch_bounds__(SLAV_CONSUMERS + 32, 1) k_slav_brick_terms_tma(SlavGradientArgs a, SlavBrickArgs b,
+		const __grid_constant__ CUtensorMap live_map, const __grid_constant__ CUtensorMap warp_map,
+		const __grid_constant__ CUtensorMap canonical_map) {
+	if (a.status[a.iteration]) return;
+	extern __shared__ __align__(128) unsigned char slav_smem[];
+	__shared__ SlavPipe<SLAV_TERMS_STAGES> pipe;
+	slav_pipe_init(pipe, SLAV_CONSUMERS / 32);
+	if (threadIdx.x >= SLAV_CONSUMERS) {
+		if (threadIdx.x == SLAV_CONSUMERS) {
+			const int total = *b.active_count;
+			for (int n = 0;; n++) {
+				const int s = n % SLAV_TERMS_STAGES;
+				unsigned char* stage = slav_smem + s * SLAV_TERMS_STAGE_BYTES;
+				const int brick = slav_pipe_claim(pipe, b, total, n, reinterpret_cast<unsigned short*>(stage + SLAV_TERMS_BOX_BYTES),
+						SLAV_TERMS_BOX_BYTES);
+				if (brick < 0) break;
+				int x0, y0, z0;
+				slav_brick_origin(b, brick, x0, y0, z0);
+				float* tile = reinterpret_cast<float*>(stage);
+				tma_load_4d(tile, &live_map, z0 - 4, y0 - 1, x0 - 1, 0, &pipe.full[s]);
+				tma_load_4d(tile + SLAV_TERMS_TILE, &warp_map, z0 - 4, y0 - 1, x0 - 1, 0, &pipe.full[s]);
+				tma_load_4d(tile + 4 * SLAV_TERMS_TILE, &canonical_map, z0, y0, x0, 0, &pipe.full[s]);
 			}
 		}
-		idx = next_idx;
-		packed = next_packed;
+		return;
+	}
+	for (int n = 0;; n++) {
+		const int s = n % SLAV_TERMS_STAGES;
+		mbar_wait(&pipe.full[s], (n / SLAV_TERMS_STAGES) & 1);
+		const int brick = pipe.brick[s];
+		if (brick < 0) break;
+		const unsigned char* stage = slav_smem + s * SLAV_TERMS_STAGE_BYTES;
+		const float* tile = reinterpret_cast<const float*>(stage);
+		slav_terms_brick(a, b, tile, tile + 4 * SLAV_TERMS_TILE, reinterpret_cast<const unsigned short*>(stage + SLAV_TERMS_BOX_BYTES),
+				pipe.count[s], brick, threadIdx.x, SLAV_CONSUMERS);
+		slav_pipe_release(pipe, s);
 	}
 }
 
@@ -803,127 +835,176 @@ __device__ __forceinline__ void slav_staged_filter_voxel(const float* box, int a
 }
 
 template<int R, int AXIS>
-__device__ __forceinline__ int slav_staged_filter_offset(int packed, int x0, int y0, int z0) {
+__device__ __forceinline__ int slav_staged_filter_offset(int lx, int ly, int lz) {
 	typedef SlavPassBox<R, AXIS> Box;
-	const int sx = (packed & 1023) - x0 + Box::LO_X, sy = ((packed >> 10) & 1023) - y0 + Box::LO_Y,
-			sz = ((packed >> 20) & 1023) - z0 + Box::LO_Z;
-	return (sx * Box::Y + sy) * Box::Z + sz;
+	return ((lx + Box::LO_X) * Box::Y + (ly + Box::LO_Y)) * Box::Z + (lz + Box::LO_Z);
 }
 
+constexpr int SLAV_FILTER_STAGES = 4, SLAV_RESAMPLE_STAGES = 3;
+
 template<int R, int AXIS>
-static __global__ void __launch_bounds__(256) k_slav_brick_filter_tma(SlavFilterArgs a, SlavBrickArgs b,
+static __global__ void __launch_bounds__(SLAV_CONSUMERS + 32, 1) k_slav_brick_filter_tma(SlavFilterArgs a, SlavBrickArgs b,
 		const __grid_constant__ CUtensorMap in_map) {
 	typedef SlavPassBox<R, AXIS> Box;
+	constexpr int BOX_BYTES = 3 * Box::VOXELS * 4, STAGE_BYTES = BOX_BYTES + SLAV_LIST_BYTES;
 	if (a.status[a.iteration]) return;
-	const int brick = blockIdx.x;
-	const int count = b.brick_count[brick];
-	if (count == 0) return;
 	extern __shared__ __align__(128) unsigned char slav_smem[];
-	float* box = reinterpret_cast<float*>(slav_smem);
-	uint64_t* bar = reinterpret_cast<uint64_t*>(slav_smem + 3 * Box::VOXELS * sizeof(float));
-	int x0, y0, z0;
-	slav_brick_origin(b, brick, x0, y0, z0);
-	if (threadIdx.x == 0) {
-		mbar_init(bar, 1);
-		mbar_fence_init();
-		mbar_expect_tx(bar, 3 * Box::VOXELS * sizeof(float));
-		tma_load_4d(box, &in_map, z0 - Box::LO_Z, y0 - Box::LO_Y, x0 - Box::LO_X, 0, bar);
+	__shared__ SlavPipe<SLAV_FILTER_STAGES> pipe;
+	slav_pipe_init(pipe, SLAV_CONSUMERS / 32);
+	if (threadIdx.x >= SLAV_CONSUMERS) {
+		if (threadIdx.x == SLAV_CONSUMERS) {
+			const int total = *b.active_count;
+			for (int n = 0;; n++) {
+				const int s = n % SLAV_FILTER_STAGES;
+				unsigned char* stage = slav_smem + s * STAGE_BYTES;
+				const int brick = slav_pipe_claim(pipe, b, total, n, reinterpret_cast<unsigned short*>(stage + BOX_BYTES), BOX_BYTES);
+				if (brick < 0) break;
+				int x0, y0, z0;
+				slav_brick_origin(b, brick, x0, y0, z0);
+				tma_load_4d(stage, &in_map, z0 - Box::LO_Z, y0 - Box::LO_Y, x0 - Box::LO_X, 0, &pipe.full[s]);
+			}
+		}
+		return;
 	}
-	__syncthreads();
-	const int base = brick * SLAV_BRICK_VOXELS;
 	const int N = (int) a.g.N;
-	int j = threadIdx.x;
-	int idx = j < count ? b.list[base + j] : 0, packed = j < count ? b.positions[base + j] : 0;
-	mbar_wait(bar, 0);
-	for (; j < count; j += 256) {
-		const int next = j + 256;
-		const int next_idx = next < count ? b.list[base + next] : 0, next_packed = next < count ? b.positions[base + next] : 0;
-		float acc[3];
-		slav_staged_filter_voxel<R, AXIS>(box, slav_staged_filter_offset<R, AXIS>(packed, x0, y0, z0), a.k, acc);
+	for (int n = 0;; n++) {
+		const int s = n % SLAV_FILTER_STAGES;
+		mbar_wait(&pipe.full[s], (n / SLAV_FILTER_STAGES) & 1);
+		const int brick = pipe.brick[s];
+		if (brick < 0) break;
+		const unsigned char* stage = slav_smem + s * STAGE_BYTES;
+		const float* box = reinterpret_cast<const float*>(stage);
+		const unsigned short* list = reinterpret_cast<const unsigned short*>(stage + BOX_BYTES);
+		int x0, y0, z0;
+		slav_brick_origin(b, brick, x0, y0, z0);
+		const int count = pipe.count[s];
+		for (int j = threadIdx.x; j < count; j += SLAV_CONSUMERS) {
+			const int local = list[j];
+			const int lx = local >> 8, ly = (local >> 5) & 7, lz = local & 31;
+			const int idx = ((x0 + lx) * a.g.n[1] + y0 + ly) * a.g.n[2] + z0 + lz;
+			float acc[3];
+			slav_staged_filter_voxel<R, AXIS>(box, slav_staged_filter_offset<R, AXIS>(lx, ly, lz), a.k, acc);
 #pragma unroll
-		for (int c = 0; c < 3; c++) a.out[c * N + idx] = acc[c];
-		idx = next_idx;
-		packed = next_packed;
+			for (int c = 0; c < 3; c++) a.out[c * N + idx] = acc[c];
+		}
+		slav_pipe_release(pipe, s);
 	}
 }
 
 // axis-2 pass from the staged box + masked re-warp (taps from the staged live box) + maximum warp length
+// stage: pass input [3][8][8][40], live [10][10][40], canonical [8][8][32], list
 template<int R>
-static __global__ void __launch_bounds__(256) k_slav_brick_filter_resample_tma(SlavFilterArgs a, SlavResampleArgs ra,
-		SlavBrickArgs b, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap live_map) {
+static __global__ void __launch_bounds__(SLAV_CONSUMERS + 32, 1) k_slav_brick_filter_resample_tma(SlavFilterArgs a,
+		SlavResampleArgs ra, SlavBrickArgs b, const __grid_constant__ CUtensorMap in_map,
+		const __grid_constant__ CUtensorMap live_map, const __grid_constant__ CUtensorMap canonical_map) {
 	typedef SlavPassBox<R, 2> Box;
+	constexpr int BOX_BYTES = (3 * Box::VOXELS + SLAV_TERMS_TILE + SLAV_BRICK_VOXELS) * 4, STAGE_BYTES = BOX_BYTES + SLAV_LIST_BYTES;
 	if (a.status[a.iteration]) return;
-	const int brick = blockIdx.x;
-	const int count = b.brick_count[brick];
-	if (count == 0) return;
 	extern __shared__ __align__(128) unsigned char slav_smem[];
-	float* box = reinterpret_cast<float*>(slav_smem);
-	float* live_tile = box + 3 * Box::VOXELS;
-	uint64_t* bar = reinterpret_cast<uint64_t*>(slav_smem + (3 * Box::VOXELS + SLAV_TERMS_TILE) * sizeof(float));
-	int x0, y0, z0;
-	slav_brick_origin(b, brick, x0, y0, z0);
-	if (threadIdx.x == 0) {
-		mbar_init(bar, 1);
-		mbar_fence_init();
-		mbar_expect_tx(bar, (3 * Box::VOXELS + SLAV_TERMS_TILE) * sizeof(float));
-		tma_load_4d(box, &in_map, z0 - Box::LO_Z, y0, x0, 0, bar);
-		tma_load_4d(live_tile, &live_map, z0 - 4, y0 - 1, x0 - 1, 0, bar);
-	}
-	__syncthreads();
-	SlavLiveTile tile;
-	tile.data = live_tile;
-	tile.lo[0] = x0 - 1;
-	tile.lo[1] = y0 - 1;
-	tile.lo[2] = z0 - 4;
-	tile.ext[0] = SLAV_BRICK_X + 2;
-	tile.ext[1] = SLAV_BRICK_Y + 2;
-	tile.ext[2] = SLAV_STAGE_Z;
-	const int base = brick * SLAV_BRICK_VOXELS;
-	const int N = (int) a.g.N;
+	__shared__ SlavPipe<SLAV_RESAMPLE_STAGES> pipe;
+	slav_pipe_init(pipe, SLAV_CONSUMERS / 32);
 	float sq_report = 0.0f;
-	int j = threadIdx.x;
-	int idx = j < count ? b.list[base + j] : 0, packed = j < count ? b.positions[base + j] : 0;
-	float canonical_value = j < count ? __ldg(ra.canonical + idx) : 0.0f;
-	mbar_wait(bar, 0);
-	for (; j < count; j += 256) {
-		const int next = j + 256;
-		const int next_idx = next < count ? b.list[base + next] : 0, next_packed = next < count ? b.positions[base + next] : 0;
-		const float next_canonical = next < count ? __ldg(ra.canonical + next_idx) : 0.0f;
-		float update[3], w[3], new_value;
-		slav_staged_filter_voxel<R, 2>(box, slav_staged_filter_offset<R, 2>(packed, x0, y0, z0), a.k, update);
-		const int sx = (packed & 1023) - x0 + 1, sy = ((packed >> 10) & 1023) - y0 + 1, sz = ((packed >> 20) & 1023) - z0 + 4;
-		const float live_value = live_tile[(sx * (SLAV_BRICK_Y + 2) + sy) * SLAV_STAGE_Z + sz];
-		slav_resample_voxel<3, true>(ra, idx, update, live_value, canonical_value, new_value, w, sq_report, &tile);
-		ra.new_live[idx] = new_value;
+	if (threadIdx.x >= SLAV_CONSUMERS) {
+		if (threadIdx.x == SLAV_CONSUMERS) {
+			const int total = *b.active_count;
+			for (int n = 0;; n++) {
+				const int s = n % SLAV_RESAMPLE_STAGES;
+				unsigned char* stage = slav_smem + s * STAGE_BYTES;
+				const int brick = slav_pipe_claim(pipe, b, total, n, reinterpret_cast<unsigned short*>(stage + BOX_BYTES), BOX_BYTES);
+				if (brick < 0) break;
+				int x0, y0, z0;
+				slav_brick_origin(b, brick, x0, y0, z0);
+				float* box = reinterpret_cast<float*>(stage);
+				tma_load_4d(box, &in_map, z0 - Box::LO_Z, y0, x0, 0, &pipe.full[s]);
+				tma_load_4d(box + 3 * Box::VOXELS, &live_map, z0 - 4, y0 - 1, x0 - 1, 0, &pipe.full[s]);
+				tma_load_4d(box + 3 * Box::VOXELS + SLAV_TERMS_TILE, &canonical_map, z0, y0, x0, 0, &pipe.full[s]);
+			}
+		}
+	} else {
+		const int N = (int) a.g.N;
+		for (int n = 0;; n++) {
+			const int s = n % SLAV_RESAMPLE_STAGES;
+			mbar_wait(&pipe.full[s], (n / SLAV_RESAMPLE_STAGES) & 1);
+			const int brick = pipe.brick[s];
+			if (brick < 0) break;
+			const unsigned char* stage = slav_smem + s * STAGE_BYTES;
+			const float* box = reinterpret_cast<const float*>(stage);
+			const float* live_tile = box + 3 * Box::VOXELS;
+			const float* canonical_box = live_tile + SLAV_TERMS_TILE;
+			const unsigned short* list = reinterpret_cast<const unsigned short*>(stage + BOX_BYTES);
+			int x0, y0, z0;
+			slav_brick_origin(b, brick, x0, y0, z0);
+			SlavLiveTile tile;
+			tile.data = live_tile;
+			tile.lo[0] = x0 - 1;
+			tile.lo[1] = y0 - 1;
+			tile.lo[2] = z0 - 4;
+			tile.ext[0] = SLAV_BRICK_X + 2;
+			tile.ext[1] = SLAV_BRICK_Y + 2;
+			tile.ext[2] = SLAV_STAGE_Z;
+			const int count = pipe.count[s];
+			for (int j = threadIdx.x; j < count; j += SLAV_CONSUMERS) {
+				const int local = list[j];
+				const int lx = local >> 8, ly = (local >> 5) & 7, lz = local & 31;
+				const int q[3] = { x0 + lx, y0 + ly, z0 + lz };
+				const int idx = (q[0] * a.g.n[1] + q[1]) * a.g.n[2] + q[2];
+				const float canonical_value = canonical_box[local];
+				float update[3], w[3], new_value;
+				slav_staged_filter_voxel<R, 2>(box, slav_staged_filter_offset<R, 2>(lx, ly, lz), a.k, update);
+				const float live_value = live_tile[((lx + 1) * (SLAV_BRICK_Y + 2) + (ly + 1)) * SLAV_STAGE_Z + (lz + 4)];
+				slav_resample_voxel<3, true>(ra, idx, update, live_value, canonical_value, new_value, w, sq_report, &tile, q);
+				ra.new_live[idx] = new_value;
 #pragma unroll
-		for (int c = 0; c < 3; c++) ra.warp[c * N + idx] = w[c];
-		if (slav_truncated(new_value) && slav_truncated(canonical_value)) b.leave_list[atomicAdd(b.leave_count, 1)] = idx;
-		idx = next_idx;
-		packed = next_packed;
-		canonical_value = next_canonical;
+				for (int c = 0; c < 3; c++) ra.warp[c * N + idx] = w[c];
+				if (slav_truncated(new_value) && slav_truncated(canonical_value)) b.leave_list[atomicAdd(b.leave_count, 1)] = idx;
+			}
+			slav_pipe_release(pipe, s);
+		}
 	}
 	if (ra.max_sq_bits != nullptr) block_atomic_max(sq_report, ra.max_sq_bits);
 }
 
+inline unsigned slav_pipe_blocks() {
+	static int sms = 0;
+	if (sms == 0) {
+		int device = 0;
+		cudaGetDevice(&device);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+		if (sms <= 0) sms = 148;
+	}
+	return (unsigned) sms;
+}
+
+inline void launch_slav_brick_terms_tma(const SlavGradientArgs& ga, const SlavBrickArgs& brick, const SlavBrickMaps& maps,
+		int live_parity, cudaStream_t stream) {
+	constexpr int bytes = SLAV_TERMS_STAGES * SLAV_TERMS_STAGE_BYTES;
+	static const bool configured = cudaFuncSetAttribute(k_slav_brick_terms_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			bytes) == cudaSuccess;
+	(void) configured;
+	k_slav_brick_terms_tma<<<counted(slav_pipe_blocks()), SLAV_CONSUMERS + 32, bytes, stream>>>(ga, brick, maps.live[live_parity],
+			maps.warp, maps.canonical);
+}
+
 template<int R, int AXIS>
 inline void launch_slav_brick_filter_tma(const SlavFilterArgs& fa, const SlavBrickArgs& brick, const CUtensorMap& map,
-		unsigned bricks, cudaStream_t stream) {
-	constexpr int bytes = 3 * SlavPassBox<R, AXIS>::VOXELS * (int) sizeof(float) + 128;
+		cudaStream_t stream) {
+	constexpr int bytes = SLAV_FILTER_STAGES * (3 * SlavPassBox<R, AXIS>::VOXELS * 4 + SLAV_LIST_BYTES);
 	static const bool configured = cudaFuncSetAttribute(k_slav_brick_filter_tma<R, AXIS>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
 	(void) configured;
-	k_slav_brick_filter_tma<R, AXIS> <<<counted(bricks), 256, bytes, stream>>>(fa, brick, map);
+	k_slav_brick_filter_tma<R, AXIS> <<<counted(slav_pipe_blocks()), SLAV_CONSUMERS + 32, bytes, stream>>>(fa, brick, map);
 }
 
 template<int R>
 inline void launch_slav_brick_filter_resample_tma(const SlavFilterArgs& fa, const SlavResampleArgs& ra,
-		const SlavBrickArgs& brick, const CUtensorMap& in_map, const CUtensorMap& live_map, unsigned bricks,
-		cudaStream_t stream) {
-	constexpr int bytes = (3 * SlavPassBox<R, 2>::VOXELS + SLAV_TERMS_TILE) * (int) sizeof(float) + 128;
+		const SlavBrickArgs& brick, const SlavBrickMaps& maps, int live_parity, cudaStream_t stream) {
+	constexpr int bytes = SLAV_RESAMPLE_STAGES
+			* ((3 * SlavPassBox<R, 2>::VOXELS + SLAV_TERMS_TILE + SLAV_BRICK_VOXELS) * 4 + SLAV_LIST_BYTES);
 	static const bool configured = cudaFuncSetAttribute(k_slav_brick_filter_resample_tma<R>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
 	(void) configured;
-	k_slav_brick_filter_resample_tma<R> <<<counted(bricks), 256, bytes, stream>>>(fa, ra, brick, in_map, live_map);
+	k_slav_brick_filter_resample_tma<R> <<<counted(slav_pipe_blocks()), SLAV_CONSUMERS + 32, bytes, stream>>>(fa, ra, brick,
+			maps.pass[2], maps.live[live_parity], maps.canonical);
 }
 
 #endif  // __CUDACC__

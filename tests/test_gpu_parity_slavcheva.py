@@ -363,11 +363,10 @@ def test_fast_filter_matches_three_pass_filter(lsf, taps, monkeypatch):
         results = []
         # default (narrow-band sparse iteration) | dense with band-compacted gradient / re-warp and marching filter |
         # without the band compaction | re-warp in the filter kernel's epilogue | first-generation kernels
-        # (brick-ordered since round 2; LSF_SLAV_BRICK=0: memory-ordered global list)
-        # (TMA-staged brick kernels; LSF_SLAV_TMA=0: L1-fed brick kernels)
-        for switches in ({}, {"LSF_SLAV_TMA": "0"}, {"LSF_SLAV_BRICK": "0"}, {"LSF_SLAV_SPARSE": "0"}, {"LSF_SLAV_BAND": "0"},
+        # (brick-ordered, TMA-staged persistent kernels since round 2; LSF_SLAV_BRICK=0: memory-ordered global list)
+        for switches in ({}, {"LSF_SLAV_BRICK": "0"}, {"LSF_SLAV_SPARSE": "0"}, {"LSF_SLAV_BAND": "0"},
                          {"LSF_SLAV_SPARSE": "0", "LSF_SLAV_FUSE_REWARP": "1"}, {"LSF_SLAV_FAST": "0"}):
-            for name in ("LSF_SLAV_SPARSE", "LSF_SLAV_BAND", "LSF_SLAV_FUSE_REWARP", "LSF_SLAV_FAST", "LSF_SLAV_BRICK", "LSF_SLAV_TMA"):
+            for name in ("LSF_SLAV_SPARSE", "LSF_SLAV_BAND", "LSF_SLAV_FUSE_REWARP", "LSF_SLAV_FAST", "LSF_SLAV_BRICK"):
                 monkeypatch.delenv(name, raising=False)
             for name, value in switches.items():
                 monkeypatch.setenv(name, value)
@@ -395,12 +394,10 @@ def test_sparse_iteration_long_run_with_band_shrinkage(lsf, monkeypatch):
     # sparse with the default scan period (the band list is re-used for 32 iterations: voxels that leave the band in
     # between stay listed and are recognised) | list rebuilt every iteration | every 16 iterations | dense
     # the same with the memory-ordered list (LSF_SLAV_BRICK=0)
-    # and with the L1-fed brick kernels (LSF_SLAV_TMA=0)
-    for sparse, rescan, brick, tma in (("1", None, "1", "1"), ("1", "1", "1", "1"), ("1", "16", "1", "1"), ("0", None, "1", "1"),
-                                       ("1", None, "0", "1"), ("1", "16", "0", "1"), ("1", None, "1", "0"), ("1", "16", "1", "0")):
+    for sparse, rescan, brick in (("1", None, "1"), ("1", "1", "1"), ("1", "16", "1"), ("0", None, "1"), ("1", None, "0"),
+                                  ("1", "16", "0")):
         monkeypatch.setenv("LSF_SLAV_SPARSE", sparse)
         monkeypatch.setenv("LSF_SLAV_BRICK", brick)
-        monkeypatch.setenv("LSF_SLAV_TMA", tma)
         if rescan is None:
             monkeypatch.delenv("LSF_SLAV_RESCAN", raising=False)
         else:
