@@ -196,10 +196,11 @@ def load():
     """Loads liblsf_b200.so; raises if it has not been built (no fallback path exists)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("LSF_B200_LIBRARY", LIB_PATH)  # experiment builds of the same sources (build.py -D... -o ...)
+        if not os.path.exists(path):
             raise LsfError("liblsf_b200.so is missing at %s: build it with `python __graft_entry__.py` "
-                           "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-        lib = ctypes.CDLL(LIB_PATH)
+                           "(nvcc, sm_100a). There is no CPU fallback." % path)
+        lib = ctypes.CDLL(path)
         lib.lsf_last_error.restype = ctypes.c_char_p
         lib.lsf_launch_count.restype = ctypes.c_longlong
         for name in EXPORTED_SYMBOLS:

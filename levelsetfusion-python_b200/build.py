@@ -28,7 +28,11 @@ def needs_build():
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), output=None):
+    """defines / output: experiment builds (python build.py -DNAME=1 -o liblsf_exp.so; selected at run time with
+    LSF_B200_LIBRARY=<path>); the default build has neither."""
+    if defines or output:
+        return _build_experiment(list(defines), output or os.path.join(HERE, "liblsf_b200_exp.so"))
     if not force and not needs_build():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
@@ -60,6 +64,34 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def _build_experiment(defines, output):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    from concurrent.futures import ThreadPoolExecutor
+    directory = os.path.join(OBJ_DIR, "exp_" + os.path.basename(output))
+    os.makedirs(directory, exist_ok=True)
+
+    def compile_unit(source):
+        obj = os.path.join(directory, os.path.basename(source)[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + defines + ["-c", "-o", obj, source]
+        result = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if result.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), result.stderr))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        objects = list(pool.map(compile_unit, sources()))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", output] + objects
+    result = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if result.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n%s" % result.stderr)
+    return output
+
+
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defines = [a for a in sys.argv[1:] if a.startswith("-D")]
+    output = sys.argv[sys.argv.index("-o") + 1] if "-o" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defines,
+                output=os.path.abspath(output) if output else None))

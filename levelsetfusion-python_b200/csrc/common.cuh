@@ -134,6 +134,43 @@ inline int marching_chunk(int extent, int tiles, int lead, int blocks_per_sm) {
 // ---------------------------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_dependent() may be scheduled while its
+// predecessor in the stream still drains -- its blocks run their prologue (barrier set-up, shared-memory clearing)
+// and then sleep in pdl_wait() until the predecessor has completed and its writes are visible. Every kernel of the
+// iteration loop calls pdl_launch_dependents() first thing (lets the successor in) and pdl_wait() before it touches
+// global memory. Both are no-ops for plain launches. LSF_PDL=0 launches without the attribute (A/B).
+__device__ __forceinline__ void pdl_launch_dependents() {
+	asm volatile("griddepcontrol.launch_dependents;");
+}
+__device__ __forceinline__ void pdl_wait() {
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+	static int enabled = -1;
+	if (enabled < 0) {
+		const char* e = getenv("LSF_PDL");
+		enabled = (e && e[0] == '0') ? 0 : 1;
+	}
+	return enabled == 1;
+}
+
+template<typename... Params, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(Params...), dim3 grid, dim3 block, size_t shared, cudaStream_t stream,
+		Args&&... args) {
+	cudaLaunchConfig_t config = {};
+	config.gridDim = counted(grid);
+	config.blockDim = block;
+	config.dynamicSmemBytes = shared;
+	config.stream = stream;
+	cudaLaunchAttribute attribute;
+	attribute.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attribute.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+	config.attrs = &attribute;
+	config.numAttrs = 1;
+	return cudaLaunchKernelEx(&config, kernel, static_cast<Params>(args)...);
+}
+
 // Level termination test evaluated on the device so that the host never has to synchronise inside the
 // iteration loop: iteration `it` runs iff it == 0 or max||g|| of iteration it-1 is >= threshold
 // (reference optimizer.tpp:149,166-171). max_sq_bits[i] holds the bits of max ||g||^2 of iteration i.

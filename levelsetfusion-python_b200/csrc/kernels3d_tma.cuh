@@ -280,7 +280,7 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 		pack += pair * a.batch_pack_stride;
 		if (slots != nullptr) slots += pair * a.batch_slot_stride;
 	}
-	if (a.check_convergence && level_converged(slots, a.iteration, a.threshold)) return;
+	pdl_launch_dependents();
 	extern __shared__ __align__(128) unsigned char stage_memory[];
 	__shared__ uint64_t full[NS];
 	__shared__ uint64_t empty[NS];  // DEC: one arrival per warp once it has read the slot
@@ -314,6 +314,8 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 		mbar_fence_init();
 	}
 	__syncthreads();
+	pdl_wait();  // everything above is independent of the previous kernel's output
+	if (a.check_convergence && level_converged(slots, a.iteration, a.threshold)) return;
 	auto fetch = [&](int plane, int slot) {
 		unsigned char* dst = stage_memory + slot * T::STAGE_BYTES;
 		mbar_expect_tx(&full[slot], T::STAGE_TX);
@@ -716,11 +718,11 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 		configured = true;
 	}
 	if (DEC && a.batch_X == 0 && l2_prefetch_enabled(false))
-		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY, false, SYM> <<<counted(grid), block, shared, stream>>>(maps.g_prev,
-				maps.warp, maps.canonical, maps.pack, a, t);
+		LSF_CUDA(launch_dependent(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY, false, SYM>, grid, block, shared, stream,
+				maps.g_prev, maps.warp, maps.canonical, maps.pack, a, t));
 	else
-		k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY, false, SYM> <<<counted(grid), block, shared, stream>>>(maps.g_prev,
-				maps.warp, maps.canonical, maps.pack, a, t);
+		LSF_CUDA(launch_dependent(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY, false, SYM>, grid, block, shared, stream,
+				maps.g_prev, maps.warp, maps.canonical, maps.pack, a, t));
 	return LSF_OK;
 }
 

@@ -41,6 +41,8 @@ struct YMarch3Args {
 	int check_convergence;
 	int y_chunk;          // output rows per block
 	int x_begin;          // first plane (blockIdx.y counts from here)
+	int planes;           // balanced mode (y_chunk == 0): the planes x_begin .. x_begin + planes - 1 form one list of
+	                      // planes * Y rows that the gridDim.y blocks split evenly (a block's range may span two planes)
 	int batch_X;          // batch of pairs (HierIterArgs::batch_X): planes per pair, 0 = one volume
 	int batch_slot_stride;  // convergence slots per pair
 };
@@ -56,16 +58,11 @@ static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const _
 	constexpr int NT = TZ / 2;       // owner threads
 	constexpr uint32_t ROW_BYTES = W * 4;              // one component of one row
 	constexpr uint32_t BUFFER_BYTES = 3 * ROW_BYTES;
-	unsigned* slots = a.max_sq_bits;
-	if (a.batch_X > 0 && slots != nullptr) slots += ((a.x_begin + blockIdx.y) / a.batch_X) * a.batch_slot_stride;
-	if (a.check_convergence && level_converged(slots, a.iteration, a.threshold)) return;
+	pdl_launch_dependents();
 	__shared__ __align__(16) float row_memory3[2 * 3 * W];  // [2 buffers][3 components][W]
 	const int Y = a.Y, Z = a.Z;
 	const int tid = threadIdx.x;
 	const int z0 = blockIdx.x * TZ;
-	const int x = a.x_begin + blockIdx.y;
-	const int ys = blockIdx.z * a.y_chunk;
-	const int ye = min(Y, ys + a.y_chunk);
 	// column pair of this thread in the row buffer: owners hold H .. H + TZ - 1, the halo threads H columns either side
 	const bool owner = tid < NT;
 	const int j = tid - NT;
@@ -75,12 +72,40 @@ static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const _
 	const bool writes = owner && active;
 	for (int i = tid; i < 2 * 3 * W; i += blockDim.x) row_memory3[i] = 0.0f;  // columns outside the volume stay zero
 	__syncthreads();
+	pdl_wait();  // everything above is independent of the previous kernel's output
 	const uint32_t mine = smem_addr(row_memory3) + il * 4;  // A[il] of component 0, buffer 0
 	const f32x2 one = a.one2, neg = a.neg2;
 	const float2* __restrict__ in0 = reinterpret_cast<const float2*>(a.in[0]);
 	const float2* __restrict__ in1 = reinterpret_cast<const float2*>(a.in[1]);
 	const float2* __restrict__ in2 = reinterpret_cast<const float2*>(a.in[2]);
 	const int ZP = Z >> 1;  // float2 elements per row
+	// this block's rows: one y-chunk of one plane (blockIdx.y = plane, blockIdx.z = chunk), or, in balanced mode, an
+	// even share of the planes' rows taken as one list -- up to two segments (the tail of one plane, the head of the next)
+	long long flat_lo = 0, flat_hi = 0;
+	if (a.y_chunk == 0) {
+		const long long total = (long long) a.planes * Y;
+		flat_lo = total * blockIdx.y / gridDim.y;
+		flat_hi = total * (blockIdx.y + 1) / gridDim.y;
+	}
+#pragma unroll 1
+	for (int segment = 0; segment < 2; segment++) {
+	int x, ys, ye;
+	if (a.y_chunk > 0) {
+		if (segment == 1) break;
+		x = a.x_begin + blockIdx.y;
+		ys = blockIdx.z * a.y_chunk;
+		ye = min(Y, ys + a.y_chunk);
+	} else {
+		const int plane = (int) (flat_lo / Y) + segment;
+		const long long plane_lo = (long long) plane * Y;
+		if (flat_hi <= plane_lo || flat_lo >= flat_hi) break;
+		x = a.x_begin + plane;
+		ys = segment == 0 ? (int) (flat_lo - plane_lo) : 0;
+		ye = (int) min((long long) Y, flat_hi - plane_lo);
+	}
+	unsigned* slots = a.max_sq_bits;
+	if (a.batch_X > 0 && slots != nullptr) slots += (x / a.batch_X) * a.batch_slot_stride;
+	if (a.check_convergence && level_converged(slots, a.iteration, a.threshold)) continue;
 
 	f32x2 acc[3][K];
 #pragma unroll
@@ -233,6 +258,8 @@ static __global__ void __maxnreg__(HAS_WARP ? 96 : 80) k_sobolev_ymarch3(const _
 		emit(std::integral_constant<int, 0>());
 	}
 	if (slots != nullptr) block_atomic_max(best, slots + a.iteration);
+	__syncthreads();  // the next segment starts in row buffer 0 again
+	}
 }
 
 // LSF_YMARCH3=0 keeps the fourth-generation filter kernel (A/B parity tests)
@@ -277,13 +304,34 @@ void launch_ymarch3(const Taps& taps, const HierIterArgs& a, const float* h, flo
 	const int per_sm = (warp != nullptr ? 5 : 6) * (256 / tile_z);
 	if (warp != nullptr || tile_z != 256) y_chunk = marching_chunk(g.Y, tiles * plane_count, 2 * R, per_sm);
 	f.y_chunk = y_chunk;
-	const dim3 grid(tiles, plane_count, div_up(g.Y, y_chunk));
+	f.planes = plane_count;
+	dim3 grid(tiles, plane_count, div_up(g.Y, y_chunk));
+	// balanced mode: when the (plane, y-chunk) grid would leave part of the SMs one resident block short, the rows of all
+	// planes are split evenly over exactly one wave of blocks instead (LSF_YM3_BALANCE=0: always y-chunks)
+	{
+		static int sm_count = 0;
+		if (sm_count == 0) {
+			int device = 0;
+			cudaGetDevice(&device);
+			if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sm_count <= 0)
+				sm_count = 148;
+		}
+		const char* e = getenv("LSF_YM3_BALANCE");
+		const long long slots_total = (long long) sm_count * per_sm;
+		const long long blocks = (long long) grid.x * grid.y * grid.z;
+		const long long share = (long long) plane_count * g.Y * tiles / slots_total;  // rows per block
+		if (!(e && e[0] == '0') && blocks <= slots_total && blocks % sm_count != 0 && share >= 8 * R && share <= g.Y
+				&& slots_total % tiles == 0) {
+			f.y_chunk = 0;
+			grid = dim3(tiles, (unsigned) (slots_total / tiles), 1);
+		}
+	}
 	const int threads = tile_z / 2 + (tiles > 1 ? 32 : 0);
 	const bool sym = taps_are_symmetric(taps);  // LSF_SYM=0: full chain (A/B)
 #define LSF_YM3(SYM, OUT, WARP)                                                                          \
 	do {                                                                                                 \
-		if (tile_z == 256) k_sobolev_ymarch3<R, SYM, OUT, WARP, 256> <<<counted(grid), threads, 0, stream>>>(f); \
-		else k_sobolev_ymarch3<R, SYM, OUT, WARP, 128> <<<counted(grid), threads, 0, stream>>>(f);             \
+		if (tile_z == 256) launch_dependent(k_sobolev_ymarch3<R, SYM, OUT, WARP, 256>, grid, dim3(threads), 0, stream, f); \
+		else launch_dependent(k_sobolev_ymarch3<R, SYM, OUT, WARP, 128>, grid, dim3(threads), 0, stream, f);             \
 	} while (0)
 	if (filtered && warp) {
 		if (sym) LSF_YM3(true, true, true);
