@@ -30,6 +30,10 @@ struct XPassArgs {
 	int x_chunk;  // output planes per block along axis 0
 	unsigned long long one2;  // {1.0f, 1.0f}: opaque multiplier of the packed adds (kernels3d_tma.cuh)
 	unsigned long long k2[7]; // the taps duplicated into both lanes of an f32x2 (k_hier_stage1_tma's packed chain)
+	// k_hier_stage1_tma, one volume: chunks of unequal length (chunk c = planes [bounds[c], bounds[c + 1])), longest first,
+	// so that the blocks of the last wave are short ones (marching_schedule); chunk_count == 0: chunks of x_chunk planes
+	int chunk_count;
+	short chunk_bounds[13];
 };
 
 // one axis of the replicated-border Laplacian without branches (reference gradients.tpp:28-35,114-171):

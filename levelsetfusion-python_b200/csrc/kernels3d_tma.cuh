@@ -261,8 +261,10 @@ struct Stage1Tile {
 // a.warp_out (a different buffer: neighbouring x-chunks still read the old planes). One warp read less per iteration.
 // SYM: the filter kernel is symmetric (k[q] == k[K-1-q] bit for bit, true of every Sobolev kernel): the axis-0 chain
 // multiplies each gradient once per distinct tap (the two products are the same rounded value).
+// EXACT: one whole volume (no batch, no slab) whose planes the tiles cover exactly (Y % TY == 0, Z % TZ == 0): no thread
+// is outside the volume, the x-chunks come from XPassArgs::chunk_bounds.
 template<bool TIKHONOV, int R, int NS, bool DEC, bool FUSE = false, int PD = 0, bool APPLY = false, bool SLAB = false,
-		bool SYM = false>
+		bool SYM = false, bool EXACT = false>
 static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_constant__ CUtensorMap map_g,
 		const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
 		const __grid_constant__ CUtensorMap map_p, HierIterArgs a, XPassArgs t) {
@@ -272,7 +274,7 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 	int x_lo = 0, x_hi = a.g.X, chunk_index = blockIdx.z;
 	const float4* pack = a.pack;
 	unsigned* slots = a.max_sq_bits;
-	if (!SLAB && a.batch_X > 0) {
+	if (!SLAB && !EXACT && a.batch_X > 0) {
 		const int pair = blockIdx.z / a.batch_chunks;
 		chunk_index = blockIdx.z - pair * a.batch_chunks;
 		x_lo = pair * a.batch_X;
@@ -289,13 +291,14 @@ static __global__ void __launch_bounds__(256, 3) k_hier_stage1_tma(const __grid_
 	const int tz = threadIdx.x, ty = threadIdx.y;
 	const int z0 = blockIdx.x * T::TZ, y0 = blockIdx.y * T::TY;
 	const int z = z0 + tz, y = y0 + ty;
-	const bool valid = z < Z && y < Y;
+	const bool valid = EXACT || (z < Z && y < Y);
 	const int YZ = Y * Z;
 	const int N = (int) a.g.N;
 	// SLAB (slab decomposition, slab.py): the fields are an allocation of X planes of which [x_begin, x_end) are processed;
 	// allocation plane p is plane p + x_origin of a level of X_global planes (border rules, gather look-ups)
-	const int xs = (SLAB ? a.x_begin : x_lo) + chunk_index * t.x_chunk;
-	const int xe = min(SLAB ? a.x_end : X, xs + t.x_chunk);
+	// EXACT kernels (one whole volume) take their chunk from the table: chunks may have unequal lengths
+	const int xs = EXACT ? t.chunk_bounds[chunk_index] : (SLAB ? a.x_begin : x_lo) + chunk_index * t.x_chunk;
+	const int xe = EXACT ? t.chunk_bounds[chunk_index + 1] : min(SLAB ? a.x_end : X, xs + t.x_chunk);
 	const int origin = SLAB ? a.x_origin : -x_lo, Xg = SLAB ? a.X_global : X - x_lo;
 	// FUSE (no Sobolev kernel configured): no filter pass, the warp update and the max-norm (reference
 	// optimizer.tpp:207-211) happen here and the kernel is the whole iteration
@@ -704,9 +707,62 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 	}
 	t.x_chunk = x_chunk;
 	t.one2 = F32X2_ONE;
+	t.chunk_count = 0;
 	a.g_out = h;
 	const int pairs = a.batch_X > 0 ? a.g.X / a.batch_X : 1;
 	a.batch_chunks = div_up(a.batch_X > 0 ? a.batch_X : a.g.X, x_chunk);
+	const bool exact = APPLY && SYM && a.batch_X == 0 && a.g.Y % T::TY == 0 && a.g.Z % T::TZ == 0 && a.batch_chunks <= 12
+			&& a.g.X < 32768;
+	if (exact) {
+		for (int c = 0; c <= a.batch_chunks; c++) t.chunk_bounds[c] = (short) std::min(c * x_chunk, a.g.X);
+		t.chunk_count = a.batch_chunks;
+		// Long-first schedule. When one plane holds between half a wave and a whole wave of tiles (256^3 on B200: 256 tiles,
+		// 444 resident blocks) equal chunks end in a wave of equally long blocks on part of the SMs. Chunks of 55 % and 25 % of
+		// the planes followed by three short ones let the short blocks fill the machine while the long ones finish:
+		// measured 0.3432 - 0.3444 ms per 256^3 iteration against 0.3473 for five equal chunks (tools/xchunk_sweep.py,
+		// profiles/r2_experiments.md; the slot model of marching_chunk does not predict this, the sweep does).
+		// LSF_XSCHEDULE=0 keeps equal chunks.
+		{
+			static int sm_count = 0;
+			if (sm_count == 0) {
+				int device = 0;
+				cudaGetDevice(&device);
+				if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sm_count <= 0)
+					sm_count = 148;
+			}
+			const char* off = getenv("LSF_XSCHEDULE");
+			const int tiles = div_up(a.g.Z, T::TZ) * div_up(a.g.Y, T::TY), slots = 3 * sm_count;
+			const int first = a.g.X * 142 / 256, second = a.g.X * 63 / 256, piece = (a.g.X - first - second) / 3;
+			if (!(off && off[0] == '0') && tiles <= slots && slots < 2 * tiles && piece >= 2 * R + 2) {
+				t.chunk_bounds[0] = 0;
+				t.chunk_bounds[1] = (short) first;
+				t.chunk_bounds[2] = (short) (first + second);
+				t.chunk_bounds[3] = (short) (a.g.X - 2 * piece);
+				t.chunk_bounds[4] = (short) (a.g.X - piece);
+				t.chunk_bounds[5] = (short) a.g.X;
+				t.chunk_count = 5;
+				a.batch_chunks = 5;
+			}
+		}
+		// experiment: LSF_XCHUNKS="142:68:22:12:12" (plane counts, must add up to X)
+		const char* e = getenv("LSF_XCHUNKS");
+		if (e) {
+			int n = 0, at = 0;
+			short bounds[13] = { 0 };
+			const char* q = e;
+			while (*q && n < 12) {
+				at += atoi(q);
+				bounds[++n] = (short) at;
+				while (*q && *q != ',' && *q != ':') q++;
+				if (*q) q++;
+			}
+			if (at == a.g.X) {
+				for (int c = 0; c <= n; c++) t.chunk_bounds[c] = bounds[c];
+				t.chunk_count = n;
+				a.batch_chunks = n;
+			}
+		}
+	}
 	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), pairs * a.batch_chunks);
 	const size_t shared = (size_t) NS * T::STAGE_BYTES;
 	static bool configured = false;
@@ -720,7 +776,16 @@ int launch_stage1_tma(TmaMaps& maps, HierIterArgs a, const Taps& taps, float* h,
 	if (DEC && a.batch_X == 0 && l2_prefetch_enabled(false))
 		LSF_CUDA(launch_dependent(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 2, APPLY, false, SYM>, grid, block, shared, stream,
 				maps.g_prev, maps.warp, maps.canonical, maps.pack, a, t));
-	else
+	else if (exact) {
+		static bool configured_exact = false;
+		if (!configured_exact) {
+			LSF_CUDA(cudaFuncSetAttribute(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY, false, SYM, APPLY && SYM>,
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared));
+			configured_exact = true;
+		}
+		LSF_CUDA(launch_dependent(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY, false, SYM, APPLY && SYM>, grid, block,
+				shared, stream, maps.g_prev, maps.warp, maps.canonical, maps.pack, a, t));
+	} else
 		LSF_CUDA(launch_dependent(k_hier_stage1_tma<TIKHONOV, R, NS, DEC, false, 0, APPLY, false, SYM>, grid, block, shared, stream,
 				maps.g_prev, maps.warp, maps.canonical, maps.pack, a, t));
 	return LSF_OK;
@@ -740,6 +805,7 @@ int launch_stage1_fused_update(TmaMaps& maps, HierIterArgs a, int x_chunk, cudaS
 	}
 	t.x_chunk = x_chunk;
 	t.one2 = F32X2_ONE;
+	t.chunk_count = 0;
 	const int pairs = (!SLAB && a.batch_X > 0) ? a.g.X / a.batch_X : 1;
 	a.batch_chunks = div_up(pairs > 1 || a.batch_X > 0 ? a.batch_X : a.x_end - a.x_begin, x_chunk);
 	const dim3 block(T::TZ, T::TY, 1), grid(div_up(a.g.Z, T::TZ), div_up(a.g.Y, T::TY), pairs * a.batch_chunks);

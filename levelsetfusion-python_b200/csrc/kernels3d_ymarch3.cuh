@@ -317,10 +317,11 @@ void launch_ymarch3(const Taps& taps, const HierIterArgs& a, const float* h, flo
 				sm_count = 148;
 		}
 		const char* e = getenv("LSF_YM3_BALANCE");
-		const long long slots_total = (long long) sm_count * per_sm;
+		const char* forced = getenv("LSF_YM3_BLOCKS");  // experiment: blocks per SM of the balanced grid
+		const long long slots_total = (long long) sm_count * (forced && atoi(forced) > 0 ? atoi(forced) : per_sm);
 		const long long blocks = (long long) grid.x * grid.y * grid.z;
 		const long long share = (long long) plane_count * g.Y * tiles / slots_total;  // rows per block
-		if (!(e && e[0] == '0') && blocks <= slots_total && blocks % sm_count != 0 && share >= 8 * R && share <= g.Y
+		if (!(e && e[0] == '0') && (forced || blocks <= slots_total) && blocks % sm_count != 0 && share >= 8 * R && share <= g.Y
 				&& slots_total % tiles == 0) {
 			f.y_chunk = 0;
 			grid = dim3(tiles, (unsigned) (slots_total / tiles), 1);
