@@ -36,8 +36,8 @@ UNIT = "voxel-updates/s"
 ALGORITHMIC_BYTES_PER_VOXEL_UPDATE = 68  # hierarchical 3D with Tikhonov (+- kernel), see DESIGN.md
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one finest-level 256^3 iteration, from the committed
 # `ncu --set full` capture (per launch group, like `achieved`)
-NCU_DRAM_BYTES_PER_ITERATION = 1530480000
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_v4.md, final build (1162.5 MB + 368.0 MB)"
+NCU_DRAM_BYTES_PER_ITERATION = 1559500000
+NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_headline.md (stage 1 1186.0 MB + filter 373.5 MB)"
 STAGE_NAMES = {1: ("fused_iteration",), 2: ("stage1_gather_terms_axis0", "ymarch_axis12_update_max"),
                4: ("gradient_stage", "filter_axis0", "filter_axis1", "filter_axis2_update_max")}
 
@@ -55,6 +55,20 @@ def optimizer_kwargs():
 
 def workload_name(size):
     return "hierarchical3d_%d_tikhonov_sobolev7_4level" % size
+
+
+def workload_config(size, kwargs, world):
+    """The `config` object of the JSON line -- the same for both arms (the driver compares them)."""
+    return {"workload": workload_name(size), "volume": [size] * 3, "pairs_per_gpu": 1, "levels": 4,
+            "maximum_iterations_per_level": kwargs["maximum_iteration_count"],
+            "maximum_warp_update_threshold": kwargs["maximum_warp_update_threshold"],
+            "tikhonov_strength": kwargs["tikhonov_strength"],
+            "tikhonov_strength_note": "0.1, not the reference default 0.2: with the Sobolev kernel the reference's "
+                                      "Laplacian-of-previous-gradient feedback diverges in 3D at 0.2 "
+                                      "(tests/test_oracle_golden.py::test_tikhonov_strength_0p2_diverges_in_3d)",
+            "kernel_taps": 7,
+            "l2_policy": "working set ~1.1 GB per iteration >> 126 MB L2 (inputs larger than L2)",
+            "parallelism": "independent pairs, 1 per GPU" if world > 1 else "single GPU"}
 
 
 class ClockSampler:
@@ -170,37 +184,55 @@ def run_ours(args):
     iteration_counts = optimizer.get_per_level_iteration_counts()
 
     # ------------------------------------------------------------------ end to end through the public API (`e2e`)
+    # (a) the reference-shaped call: pageable numpy arrays in, a fresh numpy array out
+    host_c, host_l = canonical.cpu().numpy(), live.cpu().numpy()
+    # warm-up of the staging path; two results alive at once, as in the timed loop (the result arrays come from a cache of
+    # page-locked blocks, see _lib.result_array)
+    warm = [optimizer.optimize(host_c, host_l) for _ in range(2)]
+    del warm
+    barrier()
+    e2e_updates = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        warp_host = optimizer.optimize(host_c, host_l)  # H2D of both fields + D2H of the warp field inside
+        e2e_updates += voxel_updates(optimizer.get_per_level_convergence_reports())
+    torch.cuda.synchronize()
+    e2e_seconds = time.perf_counter() - t0
+    assert isinstance(warp_host, np.ndarray) and warp_host.shape == tuple(canonical.shape) + (3,)
+    # (b) caller-pinned buffers and the out= extension
     pinned_c = torch.empty(canonical.shape, dtype=torch.float32, pin_memory=True)
     pinned_l = torch.empty(live.shape, dtype=torch.float32, pin_memory=True)
     pinned_out = torch.empty(tuple(canonical.shape) + (3,), dtype=torch.float32, pin_memory=True)
     pinned_c.copy_(canonical)
     pinned_l.copy_(live)
-    host_c, host_l, host_out = pinned_c.numpy(), pinned_l.numpy(), pinned_out.numpy()
-    optimizer.optimize(host_c, host_l, out=host_out)  # warm-up of the staging path
+    optimizer.optimize(pinned_c.numpy(), pinned_l.numpy(), out=pinned_out.numpy())
     barrier()
-    e2e_updates = 0
+    pinned_updates = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        optimizer.optimize(host_c, host_l, out=host_out)  # H2D of both fields + D2H of the warp field inside
-        e2e_updates += voxel_updates(optimizer.get_per_level_convergence_reports())
+        optimizer.optimize(pinned_c.numpy(), pinned_l.numpy(), out=pinned_out.numpy())
+        pinned_updates += voxel_updates(optimizer.get_per_level_convergence_reports())
     torch.cuda.synchronize()
-    e2e_seconds = time.perf_counter() - t0
+    pinned_seconds = time.perf_counter() - t0
+    del pinned_c, pinned_l, pinned_out
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        stats = torch.tensor([elapsed_ms, e2e_seconds], dtype=torch.float64, device=device)
+        stats = torch.tensor([elapsed_ms, e2e_seconds, pinned_seconds], dtype=torch.float64, device=device)
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_seconds = float(stats[0]), float(stats[1])
-        sums = torch.tensor([updates, e2e_updates, launches], dtype=torch.float64, device=device)
+        elapsed_ms, e2e_seconds, pinned_seconds = float(stats[0]), float(stats[1]), float(stats[2])
+        sums = torch.tensor([updates, e2e_updates, launches, pinned_updates], dtype=torch.float64, device=device)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        updates, e2e_updates, launches = int(sums[0]), int(sums[1]), int(sums[2])
+        updates, e2e_updates, launches, pinned_updates = int(sums[0]), int(sums[1]), int(sums[2]), int(sums[3])
 
     result = None
+    roofline = other_workloads = None
+    lib.lsf_trim()  # the roofline kernels run in freshly allocated scratch, like a first optimize() call
     if rank == 0:
         # -------------------------------------------------------------- roofline of the finest-level iteration
         import ctypes
         N = size ** 3
-        iterations = 50
+        iterations = kwargs["maximum_iteration_count"]  # what a level of the workload executes (100)
         params = optimizer._params()
         ms = ctypes.c_float(0.0)
         n_launch = ctypes.c_int(0)
@@ -244,8 +276,8 @@ def run_ours(args):
             "frac": round(achieved / peak, 4), "traffic": NCU_DRAM_BYTES_PER_ITERATION if size == 256 else None,
             "traffic_source": NCU_TRAFFIC_SOURCE if size == 256 else None,
             "kernel": "finest-level iteration = k_hier_stage1_tma<APPLY> (TMA-fed: previous warp update + gather + data + "
-                      "Tikhonov + axis-0 filter pass) + k_sobolev_ymarch2 (axis-1/2 filter passes + max norm), "
-                      "%d launches/iteration"
+                      "Tikhonov + axis-0 filter pass) + k_sobolev_ymarch3 (axis-1/2 filter passes + max norm), "
+                      "%d launches/iteration, programmatic dependent launch"
                       % launches_per_iteration,
             "algorithmic_bytes_per_launch_group": ALGORITHMIC_BYTES_PER_VOXEL_UPDATE * N,
             "ms_per_iteration": round(iteration_ms, 4),
@@ -255,21 +287,36 @@ def run_ours(args):
         }
         # -------------------------------------------------------------- BASELINE.json configs[2]: 3D KillingFusion at 256^3
         other_workloads = {"killingfusion3d_%d" % size: killingfusion_iteration(lsf_b200, canonical, live, size, peak)}
+    # ------------------------------------------------------------------ BASELINE.json configs[3] and configs[4] (all ranks)
+    del canonical, live
+    torch.cuda.empty_cache()
+    lib.lsf_trim()
+    shared_workloads = {}
+    if size == 256:
+        shared_workloads["multipair_64x128"] = multipair_batch(rank, world, device)
+        if world > 1:
+            lib.lsf_trim()
+            shared_workloads["slab_1024"] = slab_volume(1024, 20, rank, world, device)
+    if rank == 0:
+        other_workloads.update(shared_workloads)
         # -------------------------------------------------------------- CPU baseline (oracle port), bounded sample
         cpu = cpu_baseline_sample(size, kwargs)
         value = updates / (elapsed_ms * 1e-3)
+        N = size ** 3
         result = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(size), "volume": [size] * 3, "pairs_per_gpu": 1,
-                       "levels": len(iteration_counts), "iterations_per_level": iteration_counts,
-                       "tikhonov_strength": kwargs["tikhonov_strength"], "kernel_taps": 7,
-                       "l2_policy": "working set ~1.1 GB per iteration >> 126 MB L2 (inputs larger than L2)",
-                       "parallelism": "independent pairs, 1 per GPU" if world > 1 else "single GPU"},
+            "config": workload_config(size, kwargs, world),
+            "iterations_per_level": iteration_counts,
+            # e2e = the reference-shaped call: pageable numpy arrays in, a fresh numpy array out (the library stages them
+            # through its pinned ring); `pinned` = the same with caller-pinned buffers and the out= extension
             "e2e": {"value": e2e_updates / e2e_seconds, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * 4 * N * world, "d2h_bytes_per_step": 3 * 4 * N * world,
-                    "ms_per_step": 1e3 * e2e_seconds / args.steps},
+                    "ms_per_step": 1e3 * e2e_seconds / args.steps,
+                    "call": "optimizer.optimize(canonical: np.ndarray, live: np.ndarray) -> np.ndarray (pageable host memory)",
+                    "pinned": {"value": pinned_updates / pinned_seconds, "ms_per_step": 1e3 * pinned_seconds / args.steps,
+                               "call": "optimize(pinned numpy views, out=pinned numpy view)"}},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "other_workloads": other_workloads,
@@ -281,6 +328,79 @@ def run_ours(args):
         dist.destroy_process_group()
     if result is not None:
         print(json.dumps(result))
+
+
+def multipair_batch(rank, world, device, pairs=64, size=128):
+    """BASELINE.json configs[3]: 64 independent 128^3 pairs, sharded round-robin over the ranks (no data-path collective),
+    each rank's share in ONE lsf_hier_optimize_3d_batch call (pairs advance in lockstep, per-pair convergence). Seconds =
+    max over ranks."""
+    import torch
+    import lsf_b200
+    from lsf_b200 import multigpu, synthetic
+    rng = np.random.default_rng(1234)
+    shifts = rng.uniform(-3, 3, size=(pairs, 3)) + np.array([2.5, -1.5, 1.0])
+    indices = multigpu.pair_indices_of_rank(pairs, rank, world)
+    fields = [synthetic.sphere_plane_pair_3d(size, shift=tuple(shifts[i]), xp=torch, device=device) for i in indices]
+    canonical = torch.stack([f[0] for f in fields])
+    live = torch.stack([f[1] for f in fields])
+    del fields
+    optimizer = lsf_b200.HierarchicalOptimizer3d(**optimizer_kwargs())
+    best = None
+    for _ in range(3):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        optimizer.optimize_batch(canonical, live)
+        stop.record()
+        torch.cuda.synchronize()
+        seconds = multigpu.max_over_ranks(start.elapsed_time(stop) * 1e-3, device)
+        best = seconds if best is None else min(best, seconds)
+    counts = optimizer.get_per_pair_iteration_counts()
+    level_voxels = [(size >> (len(counts[0]) - 1 - level)) ** 3 for level in range(len(counts[0]))]
+    updates = multigpu.sum_over_ranks(sum(c * v for pair in counts for c, v in zip(pair, level_voxels)), device)
+    return {"workload": "multipair batch: %d independent %d^3 pairs, %d per GPU, one batched call per rank" % (pairs, size, len(indices)),
+            "n_gpus": world, "seconds": best, "pairs_per_s": pairs / best, "value": updates / best, "unit": UNIT}
+
+
+def slab_volume(size, iterations, rank, world, device):
+    """BASELINE.json configs[4]: ONE size^3 pair split into slabs along axis 0 over the ranks, halo exchange of the
+    Sobolev radius per iteration over NCCL (levelsetfusion-python_b200/slab.py). Every rank generates its own planes."""
+    import torch
+    import lsf_b200
+    from lsf_b200 import multigpu, slab, synthetic
+    kwargs = dict(optimizer_kwargs(), maximum_iteration_count=iterations)
+    optimizer = lsf_b200.HierarchicalOptimizer3d(**kwargs)
+    sharded = slab.SlabHierarchicalOptimizer3d(optimizer, pack_halo=32)
+    plan = sharded.plan((size, size, size), rank, world)
+    own_lo, own_hi = plan.own_range()
+    live_lo, live_hi = plan.live_range()
+    lo, hi = min(own_lo, live_lo), max(own_hi, live_hi)
+    canonical_part, live_part = synthetic.sphere_plane_pair_3d(size, xp=torch, device=device, planes=(lo, hi))
+    canonical_slab = canonical_part[own_lo - lo:own_hi - lo].contiguous()
+    live_region = live_part[live_lo - lo:live_hi - lo].contiguous()
+    del canonical_part, live_part
+    best = None
+    for _ in range(2):
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        sharded.optimize(canonical_slab, live_region, (size, size, size))
+        stop.record()
+        torch.cuda.synchronize()
+        seconds = multigpu.max_over_ranks(start.elapsed_time(stop) * 1e-3, device)
+        best = seconds if best is None else min(best, seconds)
+    updates = sum((size >> (plan.level_count - 1 - level)) ** 3 * count
+                  for level, count in enumerate(sharded.iteration_counts))
+    counts = list(sharded.iteration_counts)
+    halo_bytes = sharded.exchanged_bytes
+    del canonical_slab, live_region, sharded
+    torch.cuda.empty_cache()
+    return {"workload": "one %d^3 pair, slabs of %d planes per GPU, at most %d iterations per level" % (size, own_hi - own_lo, iterations),
+            "n_gpus": world, "seconds": best, "value": updates / best, "unit": UNIT, "iterations_per_level": counts,
+            "halo_bytes_sent_per_rank": halo_bytes}
 
 
 def killingfusion_iteration(lsf_b200, canonical, live, size, peak, iterations=10):
@@ -352,7 +472,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(size), "volume": [size] * 3},
+        "config": workload_config(size, kwargs, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

@@ -87,6 +87,11 @@ const char* lsf_last_error(void);
 int lsf_version(void);
 /* number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches) */
 long long lsf_launch_count(void);
+/* Scratch memory comes from a memory pool owned by the library (one per device; freed blocks stay cached for the next
+ * call; LSF_POOL_KEEP_MB bounds the cache). lsf_trim() synchronises the current device and returns every cached
+ * block to the driver. The reference has no counterpart: its Eigen temporaries are heap allocations per call
+ * (cpp/src/nonrigid_optimization/hierarchical/optimizer.tpp:186-207). */
+int lsf_trim(void);
 
 /* Debug / test introspection: kernel family used by the last 3D hierarchical iteration enqueued by this process
  * (the parity tests assert that they ran the kernels bench.py measures). */

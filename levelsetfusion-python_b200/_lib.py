@@ -174,7 +174,7 @@ class SlavchevaReport(ctypes.Structure):
 
 # every symbol include/lsf_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "lsf_last_error", "lsf_version", "lsf_launch_count",
+    "lsf_last_error", "lsf_version", "lsf_launch_count", "lsf_trim",
     "lsf_hier_optimize_3d", "lsf_hier_optimize_2d", "lsf_hier_optimize_3d_batch", "lsf_hier_iterate_3d",
     "lsf_warp_3d", "lsf_warp_2d", "lsf_gradient_3d", "lsf_gradient_2d", "lsf_laplacian_3d", "lsf_laplacian_2d",
     "lsf_convolve_3d", "lsf_convolve_2d", "lsf_downsample_3d", "lsf_upsample_3d", "lsf_downsample_2d",
@@ -232,3 +232,49 @@ def is_torch_cuda(obj):
 def current_stream_handle():
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def host_stream_handle():
+    """Stream for calls with numpy (LSF_HOST) arguments: torch's current stream when torch.cuda is in use in this
+    process -- worker threads that set their own stream (multigpu.optimize_pairs, multipair.run_multipair) then really
+    run side by side -- else the default stream."""
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(0)
+
+
+PINNED_RESULT_BYTES = 8 << 20
+
+
+def result_array(shape):
+    """A fresh float32 numpy array for a result (the reference returns new arrays, SURVEY.md 8b "Ownership"). Large
+    results are backed by page-locked memory from torch's caching host allocator when torch is loaded: the device-to-host
+    copy then needs no bounce through a staging buffer and no first-touch page faults (201 MB for a 256^3 warp field),
+    and the block goes back to the allocator when the array is garbage-collected. LSF_PINNED_RESULTS=0: plain np.empty."""
+    import sys
+    count = int(np.prod(shape)) if len(shape) else 1
+    torch = sys.modules.get("torch")
+    if (count * 4 >= PINNED_RESULT_BYTES and torch is not None and os.environ.get("LSF_PINNED_RESULTS", "1") != "0"
+            and torch.cuda.is_available()):
+        try:
+            return torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True).numpy()
+        except RuntimeError:
+            pass
+    return np.empty(tuple(shape), dtype=np.float32)
+
+
+def check_device(*tensors):
+    """torch CUDA tensors of one call must live on one GPU and that GPU must be the current device: the library
+    launches on the current device's stream and allocates its scratch there. Raises ValueError otherwise (wrap the
+    call in `with torch.cuda.device(tensor.device):`)."""
+    import torch
+    devices = {t.device for t in tensors if t is not None and is_torch_cuda(t)}
+    if len(devices) != 1:
+        raise ValueError("all fields of a call must live on the same CUDA device, got %s" % sorted(map(str, devices)))
+    device = devices.pop()
+    if device.index != torch.cuda.current_device():
+        raise ValueError("the fields live on %s but the current CUDA device is cuda:%d; wrap the call in "
+                         "`with torch.cuda.device(%r):`" % (device, torch.cuda.current_device(), str(device)))
+    return device

@@ -168,6 +168,7 @@ class _HierarchicalOptimizer:
             import torch
             if not (_lib.is_torch_cuda(canonical_field) and _lib.is_torch_cuda(live_field)):
                 raise ValueError("canonical_field and live_field must live on the same device")
+            _lib.check_device(canonical_field, live_field)
             canonical = canonical_field.contiguous().float()
             live = live_field.contiguous().float()
             shape = tuple(int(d) for d in canonical.shape)
@@ -205,8 +206,8 @@ class _HierarchicalOptimizer:
                     raise ValueError("out must be a C-contiguous float32 array of shape %s" % (tuple(shape) + (nd,),))
                 warp = out
             else:
-                warp = np.empty(tuple(shape) + (nd,), dtype=np.float32)
-            kind, stream = _lib.LSF_HOST, ctypes.c_void_p(0)
+                warp = _lib.result_array(tuple(shape) + (nd,))
+            kind, stream = _lib.LSF_HOST, _lib.host_stream_handle()
             ptr = _lib.fptr
             if capture_level >= 0 and capture_iterations > 0:
                 capture_buffer = np.zeros((capture_iterations,) + level_shape + (nd,), dtype=np.float32)
@@ -334,10 +335,10 @@ class _HierarchicalOptimizer:
                                                                    shape[1], shape[2], shape[3], ptr(warp),
                                                                    _lib.LSF_DEVICE, counts, stream))
         else:
-            warp = np.empty(shape + (3,), dtype=np.float32)
+            warp = _lib.result_array(shape + (3,))
             levels = _lib.check(lib.lsf_hier_optimize_3d_batch(ctypes.byref(params), _lib.fptr(canonical), _lib.fptr(live),
                                                                pairs, shape[1], shape[2], shape[3], _lib.fptr(warp),
-                                                               _lib.LSF_HOST, counts, ctypes.c_void_p(0)))
+                                                               _lib.LSF_HOST, counts, _lib.host_stream_handle()))
         self._pair_iteration_counts = [[counts[p * _lib.LSF_MAX_LEVELS + l] for l in range(levels)] for p in range(pairs)]
         return warp
 

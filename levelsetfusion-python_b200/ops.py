@@ -18,11 +18,13 @@ from . import _lib
 def _prepare(*arrays):
     """Returns (memory_kind, stream, converted arrays, maker of outputs)."""
     if any(_lib.is_torch_cuda(a) for a in arrays):
-        import torch
+        if not all(a is None or _lib.is_torch_cuda(a) for a in arrays):
+            raise ValueError("all fields of a call must be torch CUDA tensors, or all numpy arrays")
+        _lib.check_device(*arrays)
         converted = [a.contiguous().float() if a is not None else None for a in arrays]
         return _lib.LSF_DEVICE, _lib.current_stream_handle(), converted, "torch"
     converted = [_lib.as_f32(a) if a is not None else None for a in arrays]
-    return _lib.LSF_HOST, ctypes.c_void_p(0), converted, "numpy"
+    return _lib.LSF_HOST, _lib.host_stream_handle(), converted, "numpy"
 
 
 def _ptr(a):

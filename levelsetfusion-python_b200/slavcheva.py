@@ -120,6 +120,7 @@ def _run(nd, live_field, canonical_field, semantics, data_term_method, smoothing
         import torch
         if not (_lib.is_torch_cuda(live_field) and _lib.is_torch_cuda(canonical_field)):
             raise ValueError("live_field and canonical_field must live on the same device")
+        _lib.check_device(live_field, canonical_field)
         live = live_field.contiguous().float()
         canonical = canonical_field.contiguous().float()
     else:
@@ -167,11 +168,11 @@ def _run(nd, live_field, canonical_field, semantics, data_term_method, smoothing
             capture_buffer = torch.zeros((capture_iterations,) + shape + (nd,), dtype=torch.float32, device=live.device)
         kind, stream = _lib.LSF_DEVICE, _lib.current_stream_handle()
     else:
-        live_out = np.empty(shape, dtype=np.float32)
-        warp_out = np.empty(shape + (nd,), dtype=np.float32)
+        live_out = _lib.result_array(shape)
+        warp_out = _lib.result_array(shape + (nd,))
         if capture_iterations > 0:
             capture_buffer = np.zeros((capture_iterations,) + shape + (nd,), dtype=np.float32)
-        kind, stream = _lib.LSF_HOST, ctypes.c_void_p(0)
+        kind, stream = _lib.LSF_HOST, _lib.host_stream_handle()
     if capture_buffer is not None:
         capture.buffer = _pointer(capture_buffer)
     report = _lib.SlavchevaReport()
@@ -424,7 +425,7 @@ def _warp_advanced(warped_live_field, canonical_field, warp_field_u, warp_field_
                                              int(bool(band_union_only)), int(bool(known_values_only)),
                                              int(bool(substitute_original)),
                                              ctypes.c_float(truncation_float_threshold), int(modify_warp),
-                                             _lib.fptr(out), _lib.LSF_HOST, ctypes.c_void_p(0)))
+                                             _lib.fptr(out), _lib.LSF_HOST, _lib.host_stream_handle()))
     return out, warp
 
 
@@ -458,7 +459,7 @@ def warp_advanced(live_field, canonical_field, warp_field, band_union_only=False
                                              int(bool(band_union_only)), int(bool(known_values_only)),
                                              int(bool(substitute_original)),
                                              ctypes.c_float(truncation_float_threshold), int(bool(modify_warp)),
-                                             _lib.fptr(out), _lib.LSF_HOST, ctypes.c_void_p(0)))
+                                             _lib.fptr(out), _lib.LSF_HOST, _lib.host_stream_handle()))
     return out, warp
 
 

@@ -239,13 +239,16 @@ def _fields(nd, *arrays):
     """numpy (host) or torch CUDA (device) arguments -> (memory kind, stream, pointers, dims)"""
     on_device = any(_lib.is_torch_cuda(a) for a in arrays)
     if on_device:
+        if not all(_lib.is_torch_cuda(a) for a in arrays):
+            raise ValueError("all fields of a call must be torch CUDA tensors, or all numpy arrays")
+        _lib.check_device(*arrays)
         converted = [a.contiguous().float() for a in arrays]
         pointers = [ctypes.cast(ctypes.c_void_p(a.data_ptr()), _lib.c_float_p) for a in converted]
         kind, stream = _lib.LSF_DEVICE, _lib.current_stream_handle()
     else:
         converted = [_lib.as_f32(a) for a in arrays]
         pointers = [_lib.fptr(a) for a in converted]
-        kind, stream = _lib.LSF_HOST, ctypes.c_void_p(0)
+        kind, stream = _lib.LSF_HOST, _lib.host_stream_handle()
     shape = tuple(int(d) for d in converted[-1].shape[:nd])
     return kind, stream, pointers, (ctypes.c_int * nd)(*shape), converted
 

@@ -296,3 +296,21 @@ def test_tikhonov_strength_0_2_diverges_in_3d_and_0_1_does_not():
     diverged = oracle.hier_optimize(canonical, live, tikhonov_strength=0.2, **common)
     assert float(diverged["max_updates"][0]) > 1e6
     assert not float(np.nanmax(np.abs(diverged["warp"]))) < 1e6
+
+
+def test_tikhonov_strength_0p2_diverges_in_3d():
+    """Why bench.py and the 3D parity tests run tikhonov_strength=0.1 and not the reference default 0.2: the
+    reference feeds the Laplacian of the PREVIOUS gradient back into the gradient (optimizer.tpp:191-200).
+    With the 7-tap Sobolev kernel the 3D checkerboard mode is amplified by 12 * strength * |K(pi)|^3 per iteration:
+    0.80 at strength 0.1 (decays), 1.59 at 0.2 (grows without bound). The CPU oracle (the restatement of the reference)
+    shows exactly that on the synthetic sphere/plane pair: same inputs, same 60 iterations per level."""
+    from lsf_b200 import synthetic  # numpy-only module (the package import does not load the CUDA library)
+    canonical, live = synthetic.sphere_plane_pair_3d(32)
+    results = {}
+    for strength in (0.1, 0.2):
+        r = oracle.hier_optimize(canonical, live, tikhonov_term_enabled=True, tikhonov_strength=strength,
+                                 gradient_kernel_enabled=True, kernel=synthetic.sobolev_kernel_1d(), maximum_chunk_size=4,
+                                 maximum_iteration_count=60, maximum_warp_update_threshold=0.0, rate=0.1)
+        results[strength] = float(np.abs(r["warp"]).max())
+    assert results[0.1] < 5.0, results          # a few voxels of displacement: the pair is shifted by (2.5, -1.5, 1) / 8
+    assert results[0.2] > 1e3 * results[0.1], results   # diverged
