@@ -106,7 +106,8 @@ template<int D>
 int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const Taps& taps, bool use_kernel,
 		const float* live_in, const float* canonical, float* live_out, float* warp_out_aos, lsf_slavcheva_report* report,
 		int collect_statistics, float* max_warps, int max_warps_capacity, lsf_iteration_capture* capture,
-		float* capture_dev, Arena& arena, cudaStream_t stream) {
+		float* capture_dev, Arena& arena, cudaStream_t stream, lsf_warp_delta_statistics_t* iteration_statistics = nullptr,
+		int iteration_statistics_capacity = 0) {
 	const size_t N = (size_t) g.N;
 	SlavParams p;
 	p.semantics = params->semantics;
@@ -222,7 +223,8 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 		LSF_CUDA(cudaMemcpyAsync(live_b, live_a, N * sizeof(float), cudaMemcpyDeviceToDevice, stream));
 	}
 	while (!finished) {
-		const int chunk_end = std::min(bound, enqueued + POLL_CHUNK);
+		// with per-iteration statistics requested (reference sobolev_optimizer2d.cpp:88-97) the host looks at every iteration
+		const int chunk_end = std::min(bound, enqueued + (iteration_statistics ? 1 : POLL_CHUNK));
 		for (int it = enqueued; it < chunk_end; it++) {
 			SlavGradientArgs ga;
 			ga.g = g;
@@ -413,6 +415,11 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			executed = it + 1;
 			if (host_status[it + 1]) finished = true;
 		}
+		if (iteration_statistics && executed == chunk_end && executed <= iteration_statistics_capacity) {
+			// statistics of the warp field over the band union of (canonical, warped live) after this iteration
+			LSF_TRY(statistics_device<D>(g, warp, g.N, 1, canonical, live_a, p.lower, p.upper, &iteration_statistics[executed - 1],
+					nullptr, arena, stream));
+		}
 		// live buffers were swapped once per ENQUEUED iteration; undo the swaps of the skipped ones
 		if (finished && ((chunk_end - executed) & 1)) std::swap(live_a, live_b);
 		enqueued = chunk_end;
@@ -458,10 +465,10 @@ int statistics_on_device(int nd, const int* dims, const float* field, long long 
 
 using namespace lsf;
 
-extern "C" int lsf_slavcheva_optimize(const lsf_slavcheva_params* params, const float* live, const float* canonical,
+extern "C" int lsf_slavcheva_optimize_logged(const lsf_slavcheva_params* params, const float* live, const float* canonical,
 		int nd, const int* dims, float* live_out, float* warp_out, int memory_kind, lsf_slavcheva_report* report,
 		int collect_statistics, float* max_warps, int max_warps_capacity, lsf_iteration_capture* capture,
-		void* stream_handle) {
+		lsf_warp_delta_statistics_t* iteration_statistics, int iteration_statistics_capacity, void* stream_handle) {
 	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
 	LSF_REQUIRE(params != nullptr, "params is NULL");
 	LSF_REQUIRE(live && canonical && live_out, "live, canonical and live_out must not be NULL");
@@ -494,10 +501,12 @@ extern "C" int lsf_slavcheva_optimize(const lsf_slavcheva_params* params, const 
 	}
 	if (nd == 2)
 		LSF_TRY(optimize_device<2>(params, g, taps, use_kernel, live_dev, canonical_dev, live_out_dev, warp_out_dev, report,
-				collect_statistics, max_warps, max_warps_capacity, capture, capture_dev, arena, stream));
+				collect_statistics, max_warps, max_warps_capacity, capture, capture_dev, arena, stream, iteration_statistics,
+				iteration_statistics_capacity));
 	else
 		LSF_TRY(optimize_device<3>(params, g, taps, use_kernel, live_dev, canonical_dev, live_out_dev, warp_out_dev, report,
-				collect_statistics, max_warps, max_warps_capacity, capture, capture_dev, arena, stream));
+				collect_statistics, max_warps, max_warps_capacity, capture, capture_dev, arena, stream, iteration_statistics,
+				iteration_statistics_capacity));
 	if (memory_kind == LSF_HOST) {
 		if (capture_dev && capture->count > 0)
 			LSF_CUDA(cudaMemcpyAsync(capture->buffer, capture_dev, (size_t) capture->count * N * nd * sizeof(float),
@@ -507,6 +516,14 @@ extern "C" int lsf_slavcheva_optimize(const lsf_slavcheva_params* params, const 
 		LSF_TRY(from_device(live_out_dev, live_out, N, LSF_HOST, stream));
 	}
 	return LSF_OK;
+}
+
+extern "C" int lsf_slavcheva_optimize(const lsf_slavcheva_params* params, const float* live, const float* canonical,
+		int nd, const int* dims, float* live_out, float* warp_out, int memory_kind, lsf_slavcheva_report* report,
+		int collect_statistics, float* max_warps, int max_warps_capacity, lsf_iteration_capture* capture,
+		void* stream_handle) {
+	return lsf_slavcheva_optimize_logged(params, live, canonical, nd, dims, live_out, warp_out, memory_kind, report,
+			collect_statistics, max_warps, max_warps_capacity, capture, nullptr, 0, stream_handle);
 }
 
 extern "C" int lsf_warp_advanced(const float* live, const float* canonical, float* warp, int nd, const int* dims,

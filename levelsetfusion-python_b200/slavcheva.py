@@ -113,8 +113,10 @@ class _Result:
 def _run(nd, live_field, canonical_field, semantics, data_term_method, smoothing_term_method, level_set_term_enabled,
          sobolev_smoothing_enabled, gradient_descent_rate, data_term_weight, smoothing_term_weight,
          isomorphic_enforcement_factor, level_set_term_weight, lower, upper, maximum_iteration_count,
-         minimum_iteration_count, sobolev_kernel, collect_statistics=False, capture_iterations=0):
-    """One lsf_slavcheva_optimize call. Returns an object with live, warp, report, max_warps, captured."""
+         minimum_iteration_count, sobolev_kernel, collect_statistics=False, capture_iterations=0,
+         log_iteration_statistics=False):
+    """One lsf_slavcheva_optimize[_logged] call. Returns an object with live, warp, report, max_warps, captured and
+    iteration_statistics (one WarpDeltaStatistics per iteration when log_iteration_statistics is set)."""
     on_device = _lib.is_torch_cuda(live_field) or _lib.is_torch_cuda(canonical_field)
     if on_device:
         import torch
@@ -177,11 +179,15 @@ def _run(nd, live_field, canonical_field, semantics, data_term_method, smoothing
         capture.buffer = _pointer(capture_buffer)
     report = _lib.SlavchevaReport()
     dims = (ctypes.c_int * nd)(*shape)
-    _lib.check(_lib.load().lsf_slavcheva_optimize(ctypes.byref(params), _pointer(live), _pointer(canonical), nd, dims,
-                                                  _pointer(live_out), _pointer(warp_out), kind, ctypes.byref(report),
-                                                  int(bool(collect_statistics)), _lib.fptr(max_warps), capacity,
-                                                  ctypes.byref(capture), stream))
+    iteration_statistics = (_lib.WarpDeltaStatisticsRaw * capacity)() if log_iteration_statistics else None
+    _lib.check(_lib.load().lsf_slavcheva_optimize_logged(
+        ctypes.byref(params), _pointer(live), _pointer(canonical), nd, dims, _pointer(live_out), _pointer(warp_out), kind,
+        ctypes.byref(report), int(bool(collect_statistics)), _lib.fptr(max_warps), capacity, ctypes.byref(capture),
+        iteration_statistics, capacity if log_iteration_statistics else 0, stream))
     result = _Result()
+    statistics_class = telemetry.WarpDeltaStatistics2d if nd == 2 else telemetry.WarpDeltaStatistics3d
+    result.iteration_statistics = [] if iteration_statistics is None else \
+        [statistics_class._from_raw(iteration_statistics[i]) for i in range(int(report.iteration_count))]
     result.live = live_out
     result.warp = warp_out
     result.iteration_count = int(report.iteration_count)
@@ -222,9 +228,11 @@ class SobolevOptimizer2d:
                       shared.maximum_warp_length_upper_threshold, shared.maximum_iteration_count,
                       shared.minimum_iteration_count, sobolev.get_sobolev_kernel(),
                       collect_statistics=shared.enable_convergence_reporting,
-                      capture_iterations=max(int(capture_iterations), 0))
+                      capture_iterations=max(int(capture_iterations), 0),
+                      log_iteration_statistics=shared.enable_warp_statistics_logging)
         if shared.enable_convergence_reporting:
             self._report = result.report
+        self._warp_statistics = result.iteration_statistics
         self._last = result
         return result.live
 
@@ -232,10 +240,13 @@ class SobolevOptimizer2d:
         return self._report
 
     def get_warp_statistics_as_matrix(self):
-        """reference sobolev_optimizer2d.cpp:146-160: one row of WarpDeltaStatistics2d.to_array() per iteration, filled
-        when SharedParameters.enable_warp_statistics_logging is set. Not tracked per iteration by this
-        implementation (the per-iteration live fields are not kept): returns an empty matrix."""
-        return np.zeros((0, 6), dtype=np.float32)
+        """reference sobolev_optimizer2d.cpp:144-160: one row of WarpDeltaStatistics2d.to_array() per iteration of the
+        last optimize() call, filled when SharedParameters.enable_warp_statistics_logging is set. The reference sizes the
+        matrix for 6 columns, to_array() declares 7 and streams 9 values (warp_delta_statistics.tpp:55-68): the nine
+        values are returned here -- ratio above the minimum threshold, minimum, maximum, mean and standard deviation of
+        the warp lengths, location of the longest warp (x, y), is-largest-below-minimum, is-largest-above-maximum."""
+        rows = [s.to_array() for s in self._warp_statistics]
+        return np.array(rows, dtype=np.float32).reshape(len(rows), 9)
 
     # extensions used by the parity tests
     def get_last_warp_field(self):

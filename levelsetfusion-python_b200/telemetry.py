@@ -104,10 +104,12 @@ class _WarpDeltaStatistics:
                    bool(raw.is_largest_below_min_threshold), bool(raw.is_largest_above_max_threshold))
 
     def to_array(self):
-        """reference WarpDeltaStatistics::to_array (warp_delta_statistics.tpp:55-68)"""
+        """reference WarpDeltaStatistics::to_array (warp_delta_statistics.tpp:55-68): the vector is declared with 7
+        entries and nine values are streamed into it; all nine are returned"""
         return np.array([self.ratio_above_min_threshold, self.length_min, self.length_max, self.length_mean,
                          self.length_standard_deviation, float(self.longest_warp_location.x),
-                         float(self.longest_warp_location.y)], dtype=np.float32)
+                         float(self.longest_warp_location.y), float(self.is_largest_below_min_threshold),
+                         float(self.is_largest_above_max_threshold)], dtype=np.float32)
 
     def __eq__(self, other):
         return (isinstance(other, _WarpDeltaStatistics)

@@ -46,7 +46,8 @@ class IterationDump(ctypes.Structure):
 
 def build(force=False):
     """Compile the oracle with the recipe in oracle/Makefile (g++ -O3 -fopenmp -ffp-contract=off)."""
-    sources = [os.path.join(_HERE, name) for name in ("lsf_oracle.cpp", "lsf_oracle_slavcheva.cpp", "lsf_oracle.h")]
+    sources = [os.path.join(_HERE, name) for name in ("lsf_oracle.cpp", "lsf_oracle_slavcheva.cpp", "lsf_oracle_tsdf.cpp",
+                                                          "lsf_oracle.h")]
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(map(os.path.getmtime, sources)):
         subprocess.run(["make", "-C", _HERE, "-B", "liblsf_oracle.so"], check=True, capture_output=True)
     return _LIB_PATH
@@ -393,4 +394,46 @@ def tsdf_difference_statistics(canonical, live):
     canonical, live = _f32(canonical), _f32(live)
     out = TsdfDifferenceStatistics()
     lib().orc_tsdf_difference_statistics(_p(canonical), _p(live), live.ndim, _dims(live.shape), ctypes.byref(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ TSDF generation
+class TsdfParams(ctypes.Structure):
+    """orc_tsdf_params (oracle/lsf_oracle.h)"""
+    _fields_ = [
+        ("depth_unit_ratio", ctypes.c_float),
+        ("projection_matrix", ctypes.c_float * 9),
+        ("near_clipping_distance", ctypes.c_float),
+        ("array_offset", ctypes.c_int * 3),
+        ("field_shape", ctypes.c_int * 3),
+        ("voxel_size", ctypes.c_float),
+        ("narrow_band_width_voxels", ctypes.c_int),
+        ("filtering_method", ctypes.c_int),
+        ("smoothing_factor", ctypes.c_float),
+    ]
+
+
+def tsdf_generate(depth_image, camera_pose, nd, projection_matrix, array_offset, field_shape, image_y_coordinate=0,
+                  depth_unit_ratio=0.001, near_clipping_distance=0.05, voxel_size=0.004, narrow_band_width_voxels=20):
+    """reference tsdf::Generator{2d,3d}::generate with FilteringMethod::NONE (generator_tensor.tpp:40-101,
+    generator_matrix.tpp:33-93). Returns [x][y][z] (3D) or [y][x] (2D)."""
+    depth = np.ascontiguousarray(depth_image, dtype=np.uint16)
+    pose = np.ascontiguousarray(camera_pose, dtype=np.float32).reshape(16)
+    p = TsdfParams()
+    p.depth_unit_ratio = depth_unit_ratio
+    p.projection_matrix = (ctypes.c_float * 9)(*np.asarray(projection_matrix, dtype=np.float32).reshape(9))
+    p.near_clipping_distance = near_clipping_distance
+    offset = list(array_offset) + [0] * (3 - len(array_offset))
+    shape = list(field_shape) + [1] * (3 - len(field_shape))
+    p.array_offset = (ctypes.c_int * 3)(*[int(v) for v in offset])
+    p.field_shape = (ctypes.c_int * 3)(*[int(v) for v in shape])
+    p.voxel_size = voxel_size
+    p.narrow_band_width_voxels = int(narrow_band_width_voxels)
+    p.filtering_method = 0
+    p.smoothing_factor = 1.0
+    out = np.empty((shape[0], shape[1], shape[2]) if nd == 3 else (shape[1], shape[0]), dtype=np.float32)
+    status = lib().orc_tsdf_generate(ctypes.byref(p), depth.ctypes.data_as(ctypes.POINTER(ctypes.c_ushort)),
+                                     int(depth.shape[0]), int(depth.shape[1]), _p(pose), int(image_y_coordinate), nd, _p(out))
+    if status != 0:
+        raise RuntimeError("oracle TSDF generator: unsupported parameters (status %d)" % status)
     return out

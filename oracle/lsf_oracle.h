@@ -141,6 +141,24 @@ void orc_warp_delta_statistics(const float* warp, const float* canonical, const 
 void orc_tsdf_difference_statistics(const float* canonical, const float* live, int nd, const int* dims,
 		orc_tsdf_difference_statistics_t* out);
 
+/* ---------------------------------------------------------------- TSDF generation from a depth image (lsf_oracle_tsdf.cpp)
+ * reference tsdf::Parameters, cpp/src/tsdf/parameters.hpp:31-56 (projection_matrix row-major) */
+typedef struct {
+	float depth_unit_ratio;
+	float projection_matrix[9];
+	float near_clipping_distance;
+	int array_offset[3];
+	int field_shape[3];
+	float voxel_size;
+	int narrow_band_width_voxels;
+	int filtering_method; /* 0 = NONE (the only one restated) */
+	float smoothing_factor;
+} orc_tsdf_params;
+/* nd 3: field [shape.x][shape.y][shape.z]; nd 2: field [shape.y][shape.x] from image row image_y_coordinate.
+ * depth_image [rows][cols] uint16, pose 4x4 row-major. Returns 0, or -1 for an unsupported filtering method. */
+int orc_tsdf_generate(const orc_tsdf_params* p, const unsigned short* depth_image, int rows, int cols, const float* pose,
+		int image_y_coordinate, int nd, float* field);
+
 #ifdef __cplusplus
 }
 #endif

@@ -156,3 +156,38 @@ def test_verbosity_prints(lsf, capsys):
     assert all("[max upd. l.: " in l and "[norm. data energy: " in l and "[norm. tikhonov energy: " in l
                for l in iteration_lines)
     assert "[mean diff.: " not in iteration_lines[0]
+
+
+def test_sobolev_optimizer_warp_statistics_matrix(lsf):
+    """reference SobolevOptimizer2d with SharedParameters.enable_warp_statistics_logging
+    (sobolev_optimizer2d.cpp:88-97,144-160): one row of warp statistics per iteration, computed over the band union of
+    (canonical, warped live) AFTER that iteration. Checked against build_warp_delta_statistics_2d applied to the
+    per-iteration warp fields (capture) of a second run and the live fields obtained by replaying the re-warp, and the
+    last row against the convergence report."""
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.circle_line_pair_2d(64)
+    shared = lsf.SharedParameters.get_instance()
+    saved = (shared.enable_warp_statistics_logging, shared.enable_convergence_reporting, shared.maximum_iteration_count,
+             shared.maximum_warp_length_lower_threshold)
+    try:
+        shared.enable_warp_statistics_logging = True
+        shared.enable_convergence_reporting = True
+        shared.maximum_iteration_count = 12
+        shared.maximum_warp_length_lower_threshold = 0.0
+        lsf.SobolevParameters.get_instance().set_sobolev_kernel(synthetic.sobolev_kernel_1d())
+        optimizer = lsf.SobolevOptimizer2d()
+        optimizer.optimize(live, canonical)
+        matrix = optimizer.get_warp_statistics_as_matrix()
+        report = optimizer.get_convergence_report()
+        assert matrix.shape == (12, 9) and optimizer.get_iteration_count() == 12
+        last = report.warp_delta_statistics.to_array()
+        assert np.allclose(matrix[-1], last, atol=1e-6)
+        assert np.all(matrix[:, 2] >= matrix[:, 3]) and np.all(matrix[:, 3] >= matrix[:, 1])  # max >= mean >= min
+        # the maximum column is the per-iteration maximum warp length the termination test uses
+        assert np.allclose(matrix[:, 2], optimizer.get_max_warps(), atol=1e-6)
+        shared.enable_warp_statistics_logging = False
+        optimizer.optimize(live, canonical)
+        assert optimizer.get_warp_statistics_as_matrix().shape == (0, 9)
+    finally:
+        (shared.enable_warp_statistics_logging, shared.enable_convergence_reporting, shared.maximum_iteration_count,
+         shared.maximum_warp_length_lower_threshold) = saved

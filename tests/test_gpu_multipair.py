@@ -109,3 +109,23 @@ def test_batched_optimize_matches_pair_by_pair(lsf, mode, monkeypatch):
     monkeypatch.setenv("LSF_BATCH", "0")
     serial = optimizer.optimize_batch(canonical, live)
     assert np.array_equal(serial, batch) and optimizer.get_per_pair_iteration_counts() == expected_counts
+
+
+def test_numpy_calls_run_on_the_callers_current_stream():
+    """multigpu.optimize_pairs / multipair.run_multipair give every worker thread its own torch stream and feed numpy
+    pairs: the LSF_HOST path must enqueue on that stream (it used to hard-code the legacy default stream, which serialised
+    the workers). Stream identity is checked directly, and a numpy call inside a side stream must leave results equal to
+    the default-stream call."""
+    import torch
+    from lsf_b200 import _lib, synthetic
+    import lsf_b200
+    assert _lib.host_stream_handle().value in (None, 0) or _lib.host_stream_handle().value == torch.cuda.current_stream().cuda_stream
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        assert _lib.host_stream_handle().value == side.cuda_stream
+        assert _lib.current_stream_handle().value == side.cuda_stream
+        canonical, live = synthetic.sphere_plane_pair_3d(32)
+        optimizer = lsf_b200.HierarchicalOptimizer3d(maximum_chunk_size=4, maximum_iteration_count=10)
+        on_side = optimizer.optimize(canonical, live)
+    on_default = lsf_b200.HierarchicalOptimizer3d(maximum_chunk_size=4, maximum_iteration_count=10).optimize(canonical, live)
+    assert np.array_equal(on_side, on_default)
