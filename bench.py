@@ -287,6 +287,8 @@ def run_ours(args):
         }
         # -------------------------------------------------------------- BASELINE.json configs[2]: 3D KillingFusion at 256^3
         other_workloads = {"killingfusion3d_%d" % size: killingfusion_iteration(lsf_b200, canonical, live, size, peak)}
+        # -------------------------------------------------------------- TSDF generation from depth
+        other_workloads["tsdf_generation_%d" % size] = tsdf_generation(lsf_b200, size, peak)
     # ------------------------------------------------------------------ BASELINE.json configs[3] and configs[4] (all ranks)
     del canonical, live
     torch.cuda.empty_cache()
@@ -433,6 +435,49 @@ def killingfusion_iteration(lsf_b200, canonical, live, size, peak, iterations=10
     return {"ms_per_iteration": round(per_iteration, 4), "value": updates, "unit": UNIT,
             "terms": "data + Killing + level set, 7-tap Sobolev filter, masked re-warp",
             "algorithmic_bytes_per_voxel_update": 36, "achieved": round(achieved, 1), "frac": round(achieved / peak, 4)}
+
+
+def tsdf_generation(lsf_b200, size, peak, repeats=20):
+    """tsdf.Generator3d.generate of a size^3 field from a synthetic 480 x 640 depth frame (a tilted wall with ripples at
+    about 1.5 m) that is resident on the device: ms per call (CUDA events over `repeats` calls after a warm-up), voxels/s
+    and the fraction of the HBM roofline at 4 B per voxel (the field is written once; the 0.6 MB image stays in L2),
+    for filtering NONE; ms per call of EWA_IMAGE_SPACE on (size/2)^3; the CPU oracle on all cores beside both."""
+    import time
+    import numpy as np
+    import torch
+    import oracle
+    rows, cols = 480, 640
+    v, u = np.mgrid[0:rows, 0:cols].astype(np.float32)
+    depth = (1500.0 + 0.35 * (u - 320.0) + 40.0 * np.sin(u / 23.0) * np.cos(v / 31.0)).astype(np.uint16)
+    image = torch.from_numpy(depth.view(np.int16)).cuda()
+    intrinsics = np.array([[700.0, 0.0, 320.0], [0.0, 700.0, 240.0], [0.0, 0.0, 1.0]], dtype=np.float32)
+    out = {}
+    for name, method, n in (("none", lsf_b200.tsdf.FilteringMethod.NONE, size),
+                            ("ewa_image_space", lsf_b200.tsdf.FilteringMethod.EWA_IMAGE_SPACE, size // 2)):
+        offset = (-n // 2, -n // 2, 375 - n // 2)
+        generator = lsf_b200.tsdf.Generator3d(lsf_b200.tsdf.Parameters3d(
+            projection_matrix=intrinsics, array_offset=lsf_b200.Vector3i(*offset), field_shape=lsf_b200.Vector3i(n, n, n),
+            interpolation_method=method))
+        field = generator.generate(image)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(repeats):
+            field = generator.generate(image)
+        stop.record()
+        torch.cuda.synchronize()
+        ms = start.elapsed_time(stop) / repeats
+        t0 = time.perf_counter()
+        expected = oracle.tsdf_generate(depth, np.identity(4, dtype=np.float32), 3, intrinsics, offset, (n, n, n),
+                                        filtering_method=int(method))
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        difference = float(np.abs(field.cpu().numpy() - expected).max())
+        achieved = 4 * n ** 3 / (ms * 1e-3) / 1e9
+        out[name] = {"volume": [n, n, n], "ms_per_call": round(ms, 4), "voxels_per_s": n ** 3 / (ms * 1e-3),
+                     "algorithmic_bytes_per_voxel": 4, "achieved": round(achieved, 1), "frac": round(achieved / peak, 4),
+                     "cpu_oracle_ms": round(cpu_ms, 2), "cpu_cores": os.cpu_count(), "max_abs_difference_to_oracle": difference,
+                     "band_fraction": float((np.abs(expected) < 1).mean())}
+    return out
 
 
 def cpu_baseline_sample(size, kwargs, iterations=3):

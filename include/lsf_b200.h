@@ -332,6 +332,38 @@ int lsf_warp_delta_statistics(const float* warp, const float* canonical, const f
 int lsf_tsdf_difference_statistics(const float* canonical, const float* live, int nd, const int* dims,
 		lsf_tsdf_difference_statistics_t* out, int memory_kind, void* stream);
 
+/* ---------------------------------------------------------------- TSDF generation from a depth image
+ * reference tsdf::FilteringMethod, cpp/src/tsdf/interpolation_method.hpp:39-46 (exported python_export/tsdf.cpp:44-50) */
+#define LSF_TSDF_FILTER_NONE 0
+#define LSF_TSDF_FILTER_BILINEAR_IMAGE_SPACE 1      /* reference: "Not yet implemented" -> LSF_ERR_INVALID_ARGUMENT */
+#define LSF_TSDF_FILTER_BILINEAR_VOXEL_SPACE 2      /* reference: "Not yet implemented" -> LSF_ERR_INVALID_ARGUMENT */
+#define LSF_TSDF_FILTER_EWA_IMAGE_SPACE 3
+#define LSF_TSDF_FILTER_EWA_VOXEL_SPACE 4
+#define LSF_TSDF_FILTER_EWA_VOXEL_SPACE_INCLUSIVE 5
+
+/* reference tsdf::Parameters<Container>, cpp/src/tsdf/parameters.hpp:31-56 (exported as tsdf.Parameters2d / Parameters3d,
+ * python_export/tsdf.cpp:52-82). 2D: array_offset / field_shape hold (x, y) = (image-x direction, depth direction). */
+typedef struct {
+	float depth_unit_ratio;        /* metres per depth unit, reference default 0.001 */
+	float projection_matrix[9];    /* camera intrinsics, row-major */
+	float near_clipping_distance;  /* metres, default 0.05 */
+	int array_offset[3];           /* voxels, default -64 */
+	int field_shape[3];            /* voxels, default 128 */
+	float voxel_size;              /* metres, default 0.004 */
+	int narrow_band_width_voxels;  /* default 20 */
+	int filtering_method;          /* LSF_TSDF_FILTER_*; the reference calls the member interpolation_method */
+	float smoothing_factor;        /* covariance scale of the EWA methods, default 1 */
+} lsf_tsdf_params;
+
+/* reference tsdf::Generator2d / Generator3d ::generate(depth_image, camera_pose, image_y_coordinate),
+ * cpp/src/tsdf/generator_crtp.tpp:40-71 -> generator_matrix.tpp:33-238 (2D), generator_tensor.tpp:40-270 (3D).
+ * depth_image: uint16 [rows][cols] (memory_kind says where it and field_out live); camera_pose: HOST float[16], 4x4
+ * row-major; image_y_coordinate: the image row a 2D field is generated from (ignored for nd = 3).
+ * field_out: nd = 3 float [shape.x][shape.y][shape.z]; nd = 2 float [shape.y][shape.x]. Voxels behind the near clipping
+ * distance, outside the image or without a depth reading keep the default value 1. */
+int lsf_tsdf_generate(const lsf_tsdf_params* params, const unsigned short* depth_image, int rows, int cols,
+		const float* camera_pose, int image_y_coordinate, int nd, float* field_out, int memory_kind, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,4 +2,4 @@
 cpp/CMakeLists.txt:55): reference scripts `import level_set_fusion_optimization as cpp` unchanged and get the
 B200 implementation."""
 from lsf_b200 import *  # noqa: F401,F403
-from lsf_b200 import ops, telemetry, slavcheva  # noqa: F401
+from lsf_b200 import ops, telemetry, slavcheva, tsdf  # noqa: F401

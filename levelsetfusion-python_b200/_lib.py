@@ -172,6 +172,21 @@ class SlavchevaReport(ctypes.Structure):
     ]
 
 
+class TsdfParams(ctypes.Structure):
+    """lsf_tsdf_params"""
+    _fields_ = [
+        ("depth_unit_ratio", ctypes.c_float),
+        ("projection_matrix", ctypes.c_float * 9),
+        ("near_clipping_distance", ctypes.c_float),
+        ("array_offset", ctypes.c_int * 3),
+        ("field_shape", ctypes.c_int * 3),
+        ("voxel_size", ctypes.c_float),
+        ("narrow_band_width_voxels", ctypes.c_int),
+        ("filtering_method", ctypes.c_int),
+        ("smoothing_factor", ctypes.c_float),
+    ]
+
+
 # every symbol include/lsf_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "lsf_last_error", "lsf_version", "lsf_launch_count", "lsf_trim",
@@ -182,6 +197,7 @@ EXPORTED_SYMBOLS = [
     "lsf_hier_slab_iteration", "lsf_slab_pack_finest", "lsf_slab_restrict", "lsf_slab_prolong_nearest",
     "lsf_debug_last_path", "lsf_hier_optimize_3d_telemetry", "lsf_hier_optimize_2d_telemetry",
     "lsf_slavcheva_optimize", "lsf_slavcheva_optimize_logged", "lsf_warp_advanced", "lsf_warp_delta_statistics", "lsf_tsdf_difference_statistics",
+    "lsf_tsdf_generate",
 ]
 
 _lib = None

@@ -414,9 +414,11 @@ class TsdfParams(ctypes.Structure):
 
 
 def tsdf_generate(depth_image, camera_pose, nd, projection_matrix, array_offset, field_shape, image_y_coordinate=0,
-                  depth_unit_ratio=0.001, near_clipping_distance=0.05, voxel_size=0.004, narrow_band_width_voxels=20):
-    """reference tsdf::Generator{2d,3d}::generate with FilteringMethod::NONE (generator_tensor.tpp:40-101,
-    generator_matrix.tpp:33-93). Returns [x][y][z] (3D) or [y][x] (2D)."""
+                  depth_unit_ratio=0.001, near_clipping_distance=0.05, voxel_size=0.004, narrow_band_width_voxels=20,
+                  filtering_method=0, smoothing_factor=1.0):
+    """reference tsdf::Generator{2d,3d}::generate (generator_crtp.tpp:40-71) with FilteringMethod NONE (0),
+    EWA_IMAGE_SPACE (3), EWA_VOXEL_SPACE (4) or EWA_VOXEL_SPACE_INCLUSIVE (5) (generator_tensor.tpp:40-270,
+    generator_matrix.tpp:33-238). Returns [x][y][z] (3D) or [y][x] (2D)."""
     depth = np.ascontiguousarray(depth_image, dtype=np.uint16)
     pose = np.ascontiguousarray(camera_pose, dtype=np.float32).reshape(16)
     p = TsdfParams()
@@ -429,8 +431,8 @@ def tsdf_generate(depth_image, camera_pose, nd, projection_matrix, array_offset,
     p.field_shape = (ctypes.c_int * 3)(*[int(v) for v in shape])
     p.voxel_size = voxel_size
     p.narrow_band_width_voxels = int(narrow_band_width_voxels)
-    p.filtering_method = 0
-    p.smoothing_factor = 1.0
+    p.filtering_method = int(filtering_method)
+    p.smoothing_factor = smoothing_factor
     out = np.empty((shape[0], shape[1], shape[2]) if nd == 3 else (shape[1], shape[0]), dtype=np.float32)
     status = lib().orc_tsdf_generate(ctypes.byref(p), depth.ctypes.data_as(ctypes.POINTER(ctypes.c_ushort)),
                                      int(depth.shape[0]), int(depth.shape[1]), _p(pose), int(image_y_coordinate), nd, _p(out))

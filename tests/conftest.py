@@ -46,3 +46,34 @@ def lsf():
     import lsf_b200
     lsf_b200._lib.load()
     return lsf_b200
+
+
+class TsdfCases:
+    """tests/golden/reference_tsdf.npz (made by tests/golden/make_tsdf_golden.py): the reference's own TSDF-generation
+    test cases (`cases`) and runs of the reference's Python generators (`python_runs`); every entry is
+    (parameters dict, depth image uint16, expected field)."""
+
+    def __init__(self):
+        import json
+        import numpy as np
+        data = np.load(os.path.join(ROOT, "tests", "golden", "reference_tsdf.npz"))
+        self.images = {key[len("image/"):]: data[key] for key in data.files if key.startswith("image/")}
+
+        def entries(prefix):
+            out = []
+            while "%s/%02d/expected" % (prefix, len(out)) in data.files:
+                k = len(out)
+                parameters = json.loads(str(data["%s/%02d/parameters" % (prefix, k)]))
+                image = self.images[parameters["image"]].copy()
+                if parameters["zero_depth_to_maximum"]:  # tests/test_tsdf_ewa.py:30-37 image_load_helper
+                    image[image == 0] = np.iinfo(np.uint16).max
+                out.append((parameters, image, data["%s/%02d/expected" % (prefix, k)]))
+            return out
+
+        self.cases = entries("case")
+        self.python_runs = entries("python")
+
+
+@pytest.fixture(scope="session")
+def tsdf_cases():
+    return TsdfCases()
