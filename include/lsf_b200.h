@@ -364,6 +364,20 @@ typedef struct {
 int lsf_tsdf_generate(const lsf_tsdf_params* params, const unsigned short* depth_image, int rows, int cols,
 		const float* camera_pose, int image_y_coordinate, int nd, float* field_out, int memory_kind, void* stream);
 
+/* ---------------------------------------------------------------- rigid SDF-2-SDF tracker, 2D
+ * reference rigid_optimization::Sdf2SdfOptimizer2d(rate, maximum_iteration_count, tsdf_generation_parameters,
+ * verbosity_parameters).optimize(image_y_coordinate, canonical_field, live_depth_image, eta, initial_camera_pose) -> 3 x 3
+ * twist matrix, cpp/src/rigid_optimization/sdf_2_sdf_optimizer2d.cpp:24-124 (exported
+ * python_export/sdf_2_sdf_optimizer.cpp:22-58).
+ * canonical_field float [shape.y][shape.x] and live_depth_image uint16 [rows][cols] live where memory_kind says;
+ * initial_camera_pose (host 4 x 4 or NULL) is accepted and ignored like in the reference. Host outputs:
+ * twist_matrix_out float[9] row-major; twists_out / optimal_twists_out float[maximum_iteration_count][3] and
+ * energies_out float[maximum_iteration_count] (the numbers behind the reference's verbosity prints) may be NULL. */
+int lsf_sdf2sdf_optimize_2d(const lsf_tsdf_params* tsdf_generation_parameters, float rate, int maximum_iteration_count,
+		int image_y_coordinate, const float* canonical_field, const unsigned short* live_depth_image, int rows, int cols,
+		float eta, const float* initial_camera_pose, float* twist_matrix_out, float* twists_out,
+		float* optimal_twists_out, float* energies_out, int memory_kind, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@ Host-side mirror of the reference API for this path:
   * SobolevOptimizer2d + SharedParameters / SobolevParameters, SlavchevaOptimizer2d / 3d, warp_field_advanced (slavcheva.py)
   * telemetry types and builders (telemetry.py)
   * tsdf.FilteringMethod / Parameters2d / Parameters3d / Generator2d / Generator3d: TSDF generation from depth (tsdf.py)
+  * Sdf2SdfOptimizer2d: rigid SDF-2-SDF tracker (rigid.py)
   * primitives warp / gradient / laplacian / convolution / resampling (ops.py)
 backed by liblsf_b200.so (csrc/, C-ABI in include/lsf_b200.h). No CPU fallback exists.
 """
@@ -23,6 +24,7 @@ from .telemetry import (Vector2i, Vector3i, Vector2f, WarpDeltaStatistics2d, War
                         build_tsdf_difference_statistics_2d, build_tsdf_difference_statistics_3d, mean_vector_length)
 from . import slavcheva
 from . import tsdf
+from .rigid import Sdf2SdfOptimizer2d
 from .slavcheva import (SobolevOptimizer2d, SharedParameters, SobolevParameters, SlavchevaOptimizer2d,
                         SlavchevaOptimizer3d, ComputeMethod, AdaptiveLearningRateMethod, DataTermMethod,
                         SmoothingTermMethod, warp_field_advanced, warp_field_advanced_no_warp_change,
@@ -42,4 +44,4 @@ __all__ = ["HierarchicalOptimizer2d", "HierarchicalOptimizer3d", "OptimizationIt
            "WarpDeltaStatistics2d", "WarpDeltaStatistics3d", "TsdfDifferenceStatistics2d", "TsdfDifferenceStatistics3d",
            "ConvergenceReport2d", "ConvergenceReport3d", "build_warp_delta_statistics_2d",
            "build_warp_delta_statistics_3d", "build_tsdf_difference_statistics_2d",
-           "build_tsdf_difference_statistics_3d", "mean_vector_length", "ops", "telemetry", "slavcheva", "tsdf", "_lib"]
+           "build_tsdf_difference_statistics_3d", "mean_vector_length", "ops", "telemetry", "slavcheva", "tsdf", "Sdf2SdfOptimizer2d", "_lib"]

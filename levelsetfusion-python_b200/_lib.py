@@ -197,7 +197,7 @@ EXPORTED_SYMBOLS = [
     "lsf_hier_slab_iteration", "lsf_slab_pack_finest", "lsf_slab_restrict", "lsf_slab_prolong_nearest",
     "lsf_debug_last_path", "lsf_hier_optimize_3d_telemetry", "lsf_hier_optimize_2d_telemetry",
     "lsf_slavcheva_optimize", "lsf_slavcheva_optimize_logged", "lsf_warp_advanced", "lsf_warp_delta_statistics", "lsf_tsdf_difference_statistics",
-    "lsf_tsdf_generate",
+    "lsf_tsdf_generate", "lsf_sdf2sdf_optimize_2d",
 ]
 
 _lib = None

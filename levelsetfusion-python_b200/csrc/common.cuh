@@ -92,6 +92,10 @@ int to_device(Arena& arena, const float* src, size_t count, int memory_kind, cud
 // Copies a device result to the caller's buffer (host or device).
 int from_device(const float* src_dev, float* dst, size_t count, int memory_kind, cudaStream_t stream);
 
+// TSDF generation on device buffers (tsdf.cu); camera_pose is a host 4 x 4 row-major matrix
+int tsdf_generate_device(const lsf_tsdf_params* params, const unsigned short* depth_dev, int rows, int cols,
+		const float* camera_pose, int image_y_coordinate, int nd, float* field_dev, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------- separable kernel taps
 struct Taps {
 	float k[LSF_MAX_KERNEL_SIZE];  // flipped: k[j] multiplies in[i - r + j]

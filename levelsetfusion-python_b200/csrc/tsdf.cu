@@ -284,12 +284,11 @@ cudaError_t launch(const TsdfArgs& a, int method, cudaStream_t stream) {
 }  // namespace
 }  // namespace lsf
 
-using namespace lsf;
+namespace lsf {
 
-extern "C" int lsf_tsdf_generate(const lsf_tsdf_params* params, const unsigned short* depth_image, int rows, int cols,
-		const float* camera_pose, int image_y_coordinate, int nd, float* field_out, int memory_kind, void* stream_handle) {
-	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
-	LSF_REQUIRE(params && depth_image && camera_pose && field_out, "params, depth_image, camera_pose and field_out must not be NULL");
+// the generator on device buffers (depth image and field already on the device); shared with the rigid tracker
+int tsdf_generate_device(const lsf_tsdf_params* params, const unsigned short* depth_dev, int rows, int cols,
+		const float* camera_pose, int image_y_coordinate, int nd, float* field_dev, cudaStream_t stream) {
 	LSF_REQUIRE(nd == 2 || nd == 3, "nd must be 2 or 3, got %d", nd);
 	LSF_REQUIRE(rows > 0 && cols > 0, "depth image must not be empty, got %d x %d", rows, cols);
 	const int method = params->filtering_method;
@@ -331,21 +330,36 @@ extern "C" int lsf_tsdf_generate(const lsf_tsdf_params* params, const unsigned s
 	a.rows = rows;
 	a.cols = cols;
 	a.image_y_coordinate = image_y_coordinate;
-	const size_t N = (size_t) a.shape[0] * a.shape[1] * a.shape[2];
-	const size_t pixels = (size_t) rows * cols;
-	Arena arena(stream);
-	float* field_dev = field_out;
-	if (memory_kind == LSF_HOST) {
-		unsigned short* depth_dev = nullptr;
-		LSF_TRY(arena.alloc(&depth_dev, pixels));
-		LSF_CUDA(cudaMemcpyAsync(depth_dev, depth_image, pixels * sizeof(unsigned short), cudaMemcpyHostToDevice, stream));
-		a.depth = depth_dev;
-		LSF_TRY(arena.alloc(&field_dev, N));
-	} else {
-		a.depth = depth_image;
-	}
+	a.depth = depth_dev;
 	a.field = field_dev;
 	LSF_CUDA(nd == 3 ? launch<3>(a, method, stream) : launch<2>(a, method, stream));
-	if (memory_kind == LSF_HOST) return from_device(field_dev, field_out, N, LSF_HOST, stream);
 	return LSF_OK;
+}
+
+}  // namespace lsf
+
+using namespace lsf;
+
+extern "C" int lsf_tsdf_generate(const lsf_tsdf_params* params, const unsigned short* depth_image, int rows, int cols,
+		const float* camera_pose, int image_y_coordinate, int nd, float* field_out, int memory_kind, void* stream_handle) {
+	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
+	LSF_REQUIRE(params && depth_image && camera_pose && field_out, "params, depth_image, camera_pose and field_out must not be NULL");
+	LSF_REQUIRE(nd == 2 || nd == 3, "nd must be 2 or 3, got %d", nd);
+	LSF_REQUIRE(rows > 0 && cols > 0, "depth image must not be empty, got %d x %d", rows, cols);
+	size_t N = 1;
+	for (int d = 0; d < nd; d++) {
+		LSF_REQUIRE(params->field_shape[d] > 0, "field_shape[%d] must be positive, got %d", d, params->field_shape[d]);
+		N *= (size_t) params->field_shape[d];
+	}
+	const size_t pixels = (size_t) rows * cols;
+	Arena arena(stream);
+	if (memory_kind == LSF_DEVICE)
+		return tsdf_generate_device(params, depth_image, rows, cols, camera_pose, image_y_coordinate, nd, field_out, stream);
+	unsigned short* depth_dev = nullptr;
+	float* field_dev = nullptr;
+	LSF_TRY(arena.alloc(&depth_dev, pixels));
+	LSF_CUDA(cudaMemcpyAsync(depth_dev, depth_image, pixels * sizeof(unsigned short), cudaMemcpyHostToDevice, stream));
+	LSF_TRY(arena.alloc(&field_dev, N));
+	LSF_TRY(tsdf_generate_device(params, depth_dev, rows, cols, camera_pose, image_y_coordinate, nd, field_dev, stream));
+	return from_device(field_dev, field_out, N, LSF_HOST, stream);
 }

@@ -46,7 +46,7 @@ class IterationDump(ctypes.Structure):
 
 def build(force=False):
     """Compile the oracle with the recipe in oracle/Makefile (g++ -O3 -fopenmp -ffp-contract=off)."""
-    sources = [os.path.join(_HERE, name) for name in ("lsf_oracle.cpp", "lsf_oracle_slavcheva.cpp", "lsf_oracle_tsdf.cpp",
+    sources = [os.path.join(_HERE, name) for name in ("lsf_oracle.cpp", "lsf_oracle_slavcheva.cpp", "lsf_oracle_tsdf.cpp", "lsf_oracle_rigid.cpp",
                                                           "lsf_oracle.h")]
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(map(os.path.getmtime, sources)):
         subprocess.run(["make", "-C", _HERE, "-B", "liblsf_oracle.so"], check=True, capture_output=True)
@@ -411,6 +411,47 @@ class TsdfParams(ctypes.Structure):
         ("filtering_method", ctypes.c_int),
         ("smoothing_factor", ctypes.c_float),
     ]
+
+
+def _tsdf_params(nd, projection_matrix, array_offset, field_shape, depth_unit_ratio, near_clipping_distance, voxel_size,
+                 narrow_band_width_voxels, filtering_method, smoothing_factor):
+    p = TsdfParams()
+    p.depth_unit_ratio = depth_unit_ratio
+    p.projection_matrix = (ctypes.c_float * 9)(*np.asarray(projection_matrix, dtype=np.float32).reshape(9))
+    p.near_clipping_distance = near_clipping_distance
+    offset = list(array_offset) + [0] * (3 - len(array_offset))
+    shape = list(field_shape) + [1] * (3 - len(field_shape))
+    p.array_offset = (ctypes.c_int * 3)(*[int(v) for v in offset])
+    p.field_shape = (ctypes.c_int * 3)(*[int(v) for v in shape])
+    p.voxel_size = voxel_size
+    p.narrow_band_width_voxels = int(narrow_band_width_voxels)
+    p.filtering_method = int(filtering_method)
+    p.smoothing_factor = smoothing_factor
+    return p, shape
+
+
+def sdf2sdf_optimize(canonical_field, live_depth_image, image_y_coordinate, projection_matrix, array_offset, field_shape,
+                     rate=0.5, maximum_iteration_count=60, eta=0.01, depth_unit_ratio=0.001, near_clipping_distance=0.05,
+                     voxel_size=0.004, narrow_band_width_voxels=20, filtering_method=0, smoothing_factor=1.0, double_sums=False):
+    """reference Sdf2SdfOptimizer2d(rate, maximum_iteration_count, tsdf_generation_parameters).optimize(image_y_coordinate,
+    canonical_field, live_depth_image, eta, initial_camera_pose) (sdf_2_sdf_optimizer2d.cpp:63-124). Returns a dict with the
+    3 x 3 twist matrix, the twist after every iteration and the energy of every iteration. `double_sums`: float32 terms
+    added up in double instead of the reference's sequential float32 sums (the arithmetic of the GPU reduction)."""
+    p, _ = _tsdf_params(2, projection_matrix, array_offset, field_shape, depth_unit_ratio, near_clipping_distance, voxel_size,
+                        narrow_band_width_voxels, filtering_method, smoothing_factor)
+    canonical = np.ascontiguousarray(canonical_field, dtype=np.float32)
+    depth = np.ascontiguousarray(live_depth_image, dtype=np.uint16)
+    matrix = np.zeros((3, 3), dtype=np.float32)
+    twists = np.zeros((maximum_iteration_count, 3), dtype=np.float32)
+    energies = np.zeros(maximum_iteration_count, dtype=np.float32)
+    status = lib().orc_sdf2sdf_optimize(ctypes.byref(p), ctypes.c_float(rate), int(maximum_iteration_count),
+                                        int(image_y_coordinate), _p(canonical),
+                                        depth.ctypes.data_as(ctypes.POINTER(ctypes.c_ushort)), int(depth.shape[0]),
+                                        int(depth.shape[1]), ctypes.c_float(eta), int(bool(double_sums)), _p(matrix),
+                                        _p(twists), _p(energies))
+    if status != 0:
+        raise RuntimeError("oracle rigid tracker: unsupported parameters (status %d)" % status)
+    return {"twist_matrix": matrix, "twists": twists, "energies": energies}
 
 
 def tsdf_generate(depth_image, camera_pose, nd, projection_matrix, array_offset, field_shape, image_y_coordinate=0,

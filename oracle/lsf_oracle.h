@@ -159,6 +159,14 @@ typedef struct {
 int orc_tsdf_generate(const orc_tsdf_params* p, const unsigned short* depth_image, int rows, int cols, const float* pose,
 		int image_y_coordinate, int nd, float* field);
 
+/* ---------------------------------------------------------------- rigid SDF-2-SDF tracker, 2D (lsf_oracle_rigid.cpp)
+ * reference Sdf2SdfOptimizer2d::optimize, cpp/src/rigid_optimization/sdf_2_sdf_optimizer2d.cpp:63-124.
+ * canonical_field [shape.y][shape.x]; twist_matrix_out 3x3 row-major; twists_out [maximum_iteration_count][3] and
+ * energies_out [maximum_iteration_count] may be NULL. Returns 0, or the TSDF generator's error. */
+int orc_sdf2sdf_optimize(const orc_tsdf_params* tsdf_parameters, float rate, int maximum_iteration_count,
+		int image_y_coordinate, const float* canonical_field, const unsigned short* live_depth_image, int rows, int cols,
+		float eta, int double_sums, float* twist_matrix_out, float* twists_out, float* energies_out);
+
 #ifdef __cplusplus
 }
 #endif
