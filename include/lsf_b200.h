@@ -211,6 +211,40 @@ int lsf_slab_restrict(int kind, const void* src, int src_planes, int src_origin,
 int lsf_slab_prolong_nearest(const float* src, int src_planes, int src_origin, int src_Y, int src_Z, float* dst,
 		int dst_planes, int dst_origin, int dst_begin, int dst_end, void* stream);
 
+/* ---------------------------------------------------------------- slab decomposition: halo exchange through peer memory
+ * The ranks of one NVLink / NVSwitch box (one process per GPU) exchange the halo planes of the slab decomposition and the
+ * 4-byte level-termination maximum by storing straight into each other's memory: one kernel per exchange on every rank
+ * (csrc/slab_peer.cu), no host round trip, no library collective. Replaces the per-iteration NCCL send / recv pairs and the
+ * all_reduce of the first slab driver; no reference counterpart.
+ * Every rank makes ONE allocation with lsf_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; zero-filled), publishes the
+ * 64-byte handle to the other ranks (any channel: torch.distributed.all_gather_object in slab.py) and maps theirs with
+ * lsf_peer_open. All allocations share one layout: the exchanged fields at fixed byte offsets, a mailbox of
+ * LSF_SLAB_MAILBOX_BYTES at mailbox_offset. */
+#define LSF_SLAB_MAX_PEERS 8
+#define LSF_SLAB_MAILBOX_BYTES 512
+#define LSF_PEER_HANDLE_BYTES 64
+int lsf_peer_alloc(size_t bytes, void** pointer_out, unsigned char* handle_out /* [LSF_PEER_HANDLE_BYTES] or NULL */);
+int lsf_peer_open(const unsigned char* handle, void** pointer_out);
+int lsf_peer_close(void* pointer);  /* a pointer from lsf_peer_open */
+int lsf_peer_free(void* pointer);   /* a pointer from lsf_peer_alloc */
+typedef struct {
+	int rank, world_size;               /* world_size <= LSF_SLAB_MAX_PEERS */
+	void* base[LSF_SLAB_MAX_PEERS];     /* every rank's allocation as mapped in this process (base[rank] = own) */
+	size_t mailbox_offset;              /* byte offset of the mailbox inside every allocation (16-byte aligned) */
+} lsf_slab_peers;
+/* One exchange, enqueued on `stream` of every rank in the same order with the same `sequence` (1, 2, 3, ... over the life of
+ * the allocations): copies this rank's first / last `width` owned planes of the 3-component field at `field_offset`
+ * (geometry: level->planes / Y / Z / own_begin / own_end) into the halo planes of the low / high neighbour's field at the
+ * same offset (their allocation has low_planes / high_planes planes, the halo starts at plane low_destination_plane /
+ * high_destination_plane), signals, and waits for the neighbours' planes. reduce_iteration >= 0: additionally replaces
+ * level->max_sq_bits[reduce_iteration] by the maximum over all ranks (width may be 0: reduction only). The kernel ends when
+ * everything this rank waits for has arrived; a wait of more than ~4 s sets the error flag (lsf_slab_exchange_error). */
+int lsf_slab_exchange(const lsf_slab_peers* peers, const lsf_slab_level* level, size_t field_offset, int width,
+		int low_planes, int low_destination_plane, int high_planes, int high_destination_plane, int reduce_iteration,
+		unsigned sequence, void* stream);
+/* synchronises `stream` and reports whether a wait of this rank has timed out (1) */
+int lsf_slab_exchange_error(const lsf_slab_peers* peers, int* error_out, void* stream);
+
 /* ---------------------------------------------------------------- primitives (device or host pointers)
  * reference: warp / warp_with_replacement, cpp/src/nonrigid_optimization/field_warping.tpp:68-225 */
 int lsf_warp_3d(const float* field, int channels, const float* warp, int X, int Y, int Z, float oob_value,

@@ -113,6 +113,20 @@ class SlabLevel(ctypes.Structure):
     ]
 
 
+SLAB_MAX_PEERS = 8          # LSF_SLAB_MAX_PEERS
+SLAB_MAILBOX_BYTES = 512    # LSF_SLAB_MAILBOX_BYTES
+PEER_HANDLE_BYTES = 64      # LSF_PEER_HANDLE_BYTES
+
+
+class SlabPeers(ctypes.Structure):
+    """lsf_slab_peers"""
+    _fields_ = [
+        ("rank", ctypes.c_int), ("world_size", ctypes.c_int),
+        ("base", ctypes.c_void_p * SLAB_MAX_PEERS),
+        ("mailbox_offset", ctypes.c_size_t),
+    ]
+
+
 class SlavchevaParams(ctypes.Structure):
     """lsf_slavcheva_params"""
     _fields_ = [

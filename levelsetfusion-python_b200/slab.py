@@ -11,13 +11,19 @@ the live level {TSDF, gradient} is iteration-invariant, so every rank keeps its 
 reaches beyond it. Per-voxel arithmetic is untouched, hence the sharded result is bit-identical to the whole-volume
 optimizer -- that is what the tests assert.
 
-The driver is written over a list of rank states with a pluggable exchange: `DistExchange` (one process per GPU,
-torch.distributed P2P + all_reduce, NCCL over NVLink on the GPU box, gloo in the CPU tests of the exchange logic) and
-`LocalExchange` (all virtual ranks in one process on one GPU: used to verify the decomposition on a single B200).
+The driver is written over a list of rank states with a pluggable exchange:
+  * `PeerExchange` (default with one process per GPU on one NVLink / NVSwitch box): the exchanged fields live in memory
+    every rank maps (CUDA IPC); ONE kernel per exchange (csrc/slab_peer.cu, lsf_slab_exchange) stores the boundary planes
+    straight into the neighbours' halo planes, signals through a mailbox in peer memory, carries the 4-byte maximum of
+    the termination test to all ranks and waits for the neighbours' planes -- no host round trip, no library collective;
+    also runs with virtual ranks on one GPU (one stream per rank), which is how the single-GPU tests cover the kernel;
+  * `DistExchange` (torch.distributed P2P + all_reduce: NCCL, or gloo in the CPU tests of the exchange logic);
+  * `LocalExchange` (all virtual ranks in one process on one stream, plain tensor copies).
 Restrictions of the slab mode: NEAREST_AND_AVERAGE resampling, Sobolev kernels of 3/5/7 taps, X / 2^(levels-1)
 divisible by the rank count.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -155,6 +161,151 @@ class DistExchange:
         self.dist.all_reduce(slots[0][iteration:iteration + 1], op=self.dist.ReduceOp.MAX, group=self.group)
 
 
+class _DeviceFloats:
+    """raw device memory as an object torch.as_tensor can wrap without a copy"""
+
+    def __init__(self, pointer, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4", "data": (int(pointer), False),
+                                         "version": 2}
+
+
+class PeerExchange:
+    """Halo exchange + termination maximum through peer memory (csrc/slab_peer.cu).
+
+    Every rank owns one allocation [field A | field B | mailbox] sized for the finest level; the gradient fields of every
+    level are views at offset 0 of A / B (g_pre = A, g_post = B; without a Sobolev kernel the two swap roles every
+    iteration, on all ranks alike). `exchange()` enqueues one kernel per local rank; sequence numbers count the exchanges.
+
+    Why a neighbour's stores never hit planes that are still being read (r = this rank, n = a neighbour):
+      * r stores the planes of exchange e+1 only after its wait of exchange e has ended, i.e. after n's stores of exchange e,
+        which n's stream issues after the phase kernel that last read the halo planes exchange e+1 overwrites
+        (g_pre halo: read by phase 2 of the previous iteration, followed by the g_post / maximum exchange;
+         g_post halo: read by phase 1 of this iteration, followed by the g_pre exchange; reduction-only exchanges wait for
+         all ranks' maxima, which every rank posts after its phase kernel);
+      * a level starts by zero-filling g_post ONLY (optimizer.tpp:142-143; its first delivery follows an exchange the
+        owner took part in); g_pre is never cleared: every owned plane is written by phase 1 and every halo plane by the
+        neighbour before phase 2 reads it -- a neighbour that is already in the next level may deliver g_pre planes before
+        the owner gets there;
+      * nothing reads the fields between the last exchange of a level and the first kernel of the next one.
+    """
+    fused = True
+
+    def __init__(self, group=None, virtual_ranks=None):
+        import torch
+        self.lib = _lib.load()
+        self.group = group
+        if virtual_ranks is None:
+            import torch.distributed as dist
+            self.dist = dist
+            self.rank, self.world_size = dist.get_rank(group), dist.get_world_size(group)
+            self.local_ranks = [self.rank]
+        else:
+            self.dist = None
+            self.rank, self.world_size = 0, int(virtual_ranks)
+            self.local_ranks = list(range(self.world_size))
+        if self.world_size > _lib.SLAB_MAX_PEERS:
+            raise ValueError("PeerExchange supports at most %d ranks" % _lib.SLAB_MAX_PEERS)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.region_bytes = 0
+        self.owned = {}      # rank -> pointer from lsf_peer_alloc
+        self.mapped = {}     # rank -> pointer from lsf_peer_open
+        self.sequence = 0
+
+    # ---------------------------------------------------------------- memory
+    def setup(self, field_floats):
+        """(re)allocates for fields of up to `field_floats` floats (the same number on every rank)"""
+        region_bytes = (int(field_floats) * 4 + 255) // 256 * 256
+        if region_bytes <= self.region_bytes:
+            return
+        self.close()
+        self.region_bytes = region_bytes
+        total = 2 * region_bytes + _lib.SLAB_MAILBOX_BYTES
+        handles = {}
+        for rank in self.local_ranks:
+            pointer = ctypes.c_void_p()
+            handle = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+            _lib.check(self.lib.lsf_peer_alloc(ctypes.c_size_t(total), ctypes.byref(pointer),
+                                               handle if self.dist is not None else None))
+            self.owned[rank] = pointer.value
+            handles[rank] = bytes(handle)
+        if self.dist is not None:
+            gathered = [None] * self.world_size
+            self.dist.all_gather_object(gathered, handles[self.rank], group=self.group)
+            for rank, handle in enumerate(gathered):
+                if rank == self.rank:
+                    continue
+                pointer = ctypes.c_void_p()
+                raw = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(handle)
+                _lib.check(self.lib.lsf_peer_open(raw, ctypes.byref(pointer)))
+                self.mapped[rank] = pointer.value
+        self.sequence = 0
+
+    def close(self):
+        """frees the allocations (collective with one process per GPU: nobody may still be storing into them)"""
+        if not self.owned:
+            return
+        import torch
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier(group=self.group)
+        for pointer in self.mapped.values():
+            self.lib.lsf_peer_close(ctypes.c_void_p(pointer))
+        if self.dist is not None:
+            self.dist.barrier(group=self.group)
+        for pointer in self.owned.values():
+            self.lib.lsf_peer_free(ctypes.c_void_p(pointer))
+        self.owned, self.mapped, self.region_bytes = {}, {}, 0
+
+    def _peers(self, rank):
+        peers = _lib.SlabPeers()
+        peers.rank, peers.world_size = rank, self.world_size
+        for r in range(self.world_size):
+            peers.base[r] = self.owned[r] if r in self.owned else self.mapped[r]
+        peers.mailbox_offset = 2 * self.region_bytes
+        return peers
+
+    def fields(self, rank, geometry):
+        """(g_pre, g_post) of `rank` (a local rank) at a level: views [3][planes][Y][Z] of the two exchanged fields"""
+        import torch
+        count = 3 * geometry.voxels
+        if count * 4 > self.region_bytes:
+            raise ValueError("level does not fit the peer allocation")
+        base = self.owned[rank]
+        shape = (3, geometry.planes, geometry.Y, geometry.Z)
+        views = [torch.as_tensor(_DeviceFloats(base + k * self.region_bytes, count), device=self.device).view(shape)
+                 for k in range(2)]
+        return views[0], views[1]
+
+    # ---------------------------------------------------------------- one exchange on every local rank
+    def exchange(self, states, level, which, width, reduce_iteration):
+        """which: "pre" / "post" = the field of the states whose boundary planes travel (`width` planes; 0 = none);
+        reduce_iteration >= 0: slot of the termination maximum to reduce over the ranks in the same kernel"""
+        self.sequence += 1
+        for state in states:
+            rank = state.plan.rank
+            g = state.plan.levels[level]
+            field = state.g_pre if which == "pre" else state.g_post
+            offset = field.data_ptr() - self.owned[rank]
+            low = SlabGeometry(g.X_global, g.Y, g.Z, rank - 1, self.world_size, state.plan.halo, 0) if rank > 0 else None
+            high = SlabGeometry(g.X_global, g.Y, g.Z, rank + 1, self.world_size, state.plan.halo, 0) \
+                if rank < self.world_size - 1 else None
+            peers = self._peers(rank)
+            descriptor = state.descriptor(level)
+            _lib.check(self.lib.lsf_slab_exchange(
+                ctypes.byref(peers), ctypes.byref(descriptor), ctypes.c_size_t(offset), int(width),
+                low.planes if low else 0, low.own_end if low else 0,
+                high.planes if high else 0, high.own_begin - int(width) if high else 0,
+                int(reduce_iteration), ctypes.c_uint(self.sequence), state.stream_handle()))
+
+    def check(self, states):
+        for state in states:
+            error = ctypes.c_int(0)
+            peers = self._peers(state.plan.rank)
+            _lib.check(self.lib.lsf_slab_exchange_error(ctypes.byref(peers), ctypes.byref(error), state.stream_handle()))
+            if error.value:
+                raise RuntimeError("slab exchange: rank %d waited more than 4 s for its neighbours" % state.plan.rank)
+
+
 # ------------------------------------------------------------------------------------------------ per-rank state
 def _ptr(tensor):
     return ctypes.c_void_p(tensor.data_ptr())
@@ -163,12 +314,29 @@ def _ptr(tensor):
 class _RankState:
     """Device buffers of one (virtual) rank."""
 
-    def __init__(self, plan, canonical_own, live_region, device):
+    def __init__(self, plan, canonical_own, live_region, device, stream=None):
         import torch
         self.plan = plan
         self.device = device
+        self.stream = stream  # torch.cuda.Stream of this (virtual) rank; None = the caller's current stream
+        with self.on_stream():
+            self._build(canonical_own, live_region)
+
+    def on_stream(self):
+        import contextlib
+        import torch
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
+    def stream_handle(self):
+        if self.stream is not None:
+            return ctypes.c_void_p(self.stream.cuda_stream)
+        return _lib.current_stream_handle()
+
+    def _build(self, canonical_own, live_region):
+        import torch
+        plan, device = self.plan, self.device
         lib = _lib.load()
-        stream = _lib.current_stream_handle()
+        stream = self.stream_handle()
         finest = plan.levels[-1]
         live_region = live_region.to(device=device, dtype=torch.float32).contiguous()
         canonical_own = canonical_own.to(device=device, dtype=torch.float32).contiguous()
@@ -204,14 +372,19 @@ class _RankState:
         self.warp = None
         self.g_post = self.g_pre = self.slots = None
 
-    def start_level(self, level, max_iterations):
+    def start_level(self, level, max_iterations, exchange=None):
         import torch
         g = self.plan.levels[level]
         shape = (3, g.planes, g.Y, g.Z)
         if level == 0:
             self.warp = torch.zeros(shape, dtype=torch.float32, device=self.device)
-        self.g_post = torch.zeros(shape, dtype=torch.float32, device=self.device)  # optimizer.tpp:142-143
-        self.g_pre = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        if exchange is not None and getattr(exchange, "fused", False):
+            # views of the peer-visible allocation; g_pre is NOT cleared (see PeerExchange)
+            self.g_pre, self.g_post = exchange.fields(self.plan.rank, g)
+            self.g_post.zero_()
+        else:
+            self.g_post = torch.zeros(shape, dtype=torch.float32, device=self.device)  # optimizer.tpp:142-143
+            self.g_pre = torch.zeros(shape, dtype=torch.float32, device=self.device)
         self.slots = torch.zeros(max(max_iterations, 1), dtype=torch.int32, device=self.device)
 
     def descriptor(self, level):
@@ -239,18 +412,24 @@ class _RankState:
         fine = torch.zeros((3, f.planes, f.Y, f.Z), dtype=torch.float32, device=self.device)
         fp = lambda t: ctypes.cast(_ptr(t), _lib.c_float_p)
         _lib.check(lib.lsf_slab_prolong_nearest(fp(self.warp), g.planes, g.x_origin, g.Y, g.Z, fp(fine), f.planes,
-                                                f.x_origin, f.own_begin, f.own_end, _lib.current_stream_handle()))
+                                                f.x_origin, f.own_begin, f.own_end, self.stream_handle()))
         self.warp = fine
 
 
 class SlabHierarchicalOptimizer3d:
     """HierarchicalOptimizer3d over slabs. `optimizer` is a lsf_b200.HierarchicalOptimizer3d carrying the parameters."""
 
-    def __init__(self, optimizer, pack_halo=32):
+    def __init__(self, optimizer, pack_halo=32, exchange=None):
+        """exchange: "peer" (kernels storing into the neighbours' memory; default with NCCL ranks of one box, at most 8),
+        "dist" (torch.distributed send / recv + all_reduce); the environment variable LSF_SLAB_EXCHANGE sets the default."""
         if int(optimizer.resampling_strategy) != 0:
             raise RuntimeError("the slab decomposition supports the NEAREST_AND_AVERAGE resampling strategy only")
         self.optimizer = optimizer
         self.pack_halo = int(pack_halo)
+        self.exchange_kind = exchange or os.environ.get("LSF_SLAB_EXCHANGE", "peer")
+        if self.exchange_kind not in ("peer", "dist"):
+            raise ValueError("exchange must be 'peer' or 'dist', got %r" % (self.exchange_kind,))
+        self._peer_exchange = None
         self.iteration_counts = []
         self.max_update_lengths = []
         self.exchanged_bytes = 0
@@ -273,36 +452,53 @@ class SlabHierarchicalOptimizer3d:
         o = self.optimizer
         params = o._params()
         tikhonov, use_kernel, radius = self._flags()
-        stream = _lib.current_stream_handle()
+        fused = getattr(exchange, "fused", False)
         plan0 = states[0].plan
+        if fused:
+            finest = plan0.levels[-1]
+            per_rank = finest.own_hi - finest.own_lo
+            exchange.setup(3 * (per_rank + 2 * plan0.halo) * finest.Y * finest.Z)
         self.iteration_counts, self.max_update_lengths = [], []
         self.exchanged_bytes = 0
+
+        def phase(number, it, level):
+            for s in states:
+                d = s.descriptor(level)
+                _lib.check(lib.lsf_hier_slab_iteration(ctypes.byref(params), ctypes.byref(d), it, number, s.stream_handle()))
+
         for level in range(plan0.level_count):
             geometries = [s.plan.levels[level] for s in states]
             for s in states:
-                s.start_level(level, o.maximum_iteration_count)
+                with s.on_stream():
+                    s.start_level(level, o.maximum_iteration_count, exchange)
             executed, enqueued, converged, last_max = 0, 0, False, float("inf")
             plane_bytes = geometries[0].Y * geometries[0].Z * 3 * 4
             while not converged and enqueued < o.maximum_iteration_count:
                 chunk_end = min(o.maximum_iteration_count, enqueued + POLL_CHUNK)
                 for it in range(enqueued, chunk_end):
-                    descriptors = [s.descriptor(level) for s in states]
-                    for d in descriptors:
-                        _lib.check(lib.lsf_hier_slab_iteration(ctypes.byref(params), ctypes.byref(d), it, 1, stream))
+                    phase(1, it, level)
                     if use_kernel:
-                        exchange.halos([s.g_pre for s in states], geometries, radius)
-                        for d in descriptors:
-                            _lib.check(lib.lsf_hier_slab_iteration(ctypes.byref(params), ctypes.byref(d), it, 2,
-                                                                   stream))
+                        if fused:
+                            exchange.exchange(states, level, "pre", radius, -1)
+                        else:
+                            exchange.halos([s.g_pre for s in states], geometries, radius)
+                        phase(2, it, level)
                         self.exchanged_bytes += 2 * radius * plane_bytes
                     else:
                         for s in states:  # without a filter phase 1 wrote the final gradient into g_pre
                             s.g_pre, s.g_post = s.g_post, s.g_pre
+                    if fused:  # the filtered gradient's boundary plane and the termination maximum in one kernel
+                        exchange.exchange(states, level, "post", 1 if tikhonov else 0, it)
+                    else:
+                        if tikhonov:
+                            exchange.halos([s.g_post for s in states], geometries, 1)
+                        exchange.reduce_max([s.slots for s in states], it)
                     if tikhonov:
-                        exchange.halos([s.g_post for s in states], geometries, 1)
                         self.exchanged_bytes += 2 * plane_bytes
-                    exchange.reduce_max([s.slots for s in states], it)
-                bits = states[0].slots[enqueued:chunk_end].cpu().numpy()  # synchronises once per chunk
+                with states[0].on_stream():
+                    bits = states[0].slots[enqueued:chunk_end].cpu().numpy()  # synchronises once per chunk
+                if fused:
+                    exchange.check(states)
                 for it, value in zip(range(enqueued, chunk_end), bits.view(np.float32)):
                     last_max = float(np.sqrt(value))
                     executed = it + 1
@@ -314,15 +510,18 @@ class SlabHierarchicalOptimizer3d:
             self.max_update_lengths.append(last_max)
             if level != plan0.level_count - 1:
                 for s in states:
-                    s.prolong(level)
-        for s in states:
-            if int(s.violation.item()):
-                raise RuntimeError("a warp vector reached beyond the rank's gather halo (%d planes at the finest level): "
-                                   "increase pack_halo" % self.pack_halo)
+                    with s.on_stream():
+                        s.prolong(level)
         results = []
         for s in states:
-            g = s.plan.levels[-1]
-            results.append(s.warp[:, g.own_begin:g.own_end].permute(1, 2, 3, 0).contiguous())
+            with s.on_stream():
+                if int(s.violation.item()):
+                    raise RuntimeError("a warp vector reached beyond the rank's gather halo (%d planes at the finest "
+                                       "level): increase pack_halo" % self.pack_halo)
+                g = s.plan.levels[-1]
+                results.append(s.warp[:, g.own_begin:g.own_end].permute(1, 2, 3, 0).contiguous())
+                if s.stream is not None:
+                    s.stream.synchronize()
         return results
 
     # ---------------------------------------------------------------- one process per GPU
@@ -333,28 +532,57 @@ class SlabHierarchicalOptimizer3d:
         import torch
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
-            exchange = DistExchange(group)
+            world_size = dist.get_world_size(group)
+            if (self.exchange_kind == "peer" and 1 < world_size <= _lib.SLAB_MAX_PEERS
+                    and dist.get_backend(group) == "nccl"):
+                if self._peer_exchange is None:
+                    self._peer_exchange = PeerExchange(group)
+                exchange = self._peer_exchange
+            else:
+                exchange = DistExchange(group)
             rank, world_size = exchange.rank, exchange.world_size
         else:
             exchange, rank, world_size = LocalExchange(), 0, 1
         plan = self.plan(shape, rank, world_size)
         device = torch.device("cuda", torch.cuda.current_device())
         state = _RankState(plan, torch.as_tensor(canonical_slab), torch.as_tensor(live_region), device)
+        if getattr(exchange, "fused", False):
+            dist.barrier(group=group)  # the ranks wait for each other on the device: start them together
         return self._run([state], exchange)[0]
 
     # ---------------------------------------------------------------- all ranks emulated in this process
-    def optimize_emulated(self, canonical_field, live_field, world_size):
-        """Runs `world_size` virtual ranks in lockstep on the current GPU and returns the assembled warp field
-        [X, Y, Z, 3] (numpy). Verifies the decomposition without a multi-GPU box."""
+    def optimize_emulated(self, canonical_field, live_field, world_size, exchange="local"):
+        """Runs `world_size` virtual ranks on the current GPU and returns the assembled warp field [X, Y, Z, 3] (numpy).
+        Verifies the decomposition without a multi-GPU box. exchange="local": one stream, halos copied between the ranks'
+        tensors; "peer": one stream per rank and the peer-memory exchange kernel (PeerExchange) -- the ranks wait for each
+        other on the device exactly like the GPUs of a box do."""
         import torch
         canonical = torch.as_tensor(np.ascontiguousarray(canonical_field, dtype=np.float32))
         live = torch.as_tensor(np.ascontiguousarray(live_field, dtype=np.float32))
         device = torch.device("cuda", torch.cuda.current_device())
+        if exchange not in ("local", "peer"):
+            raise ValueError("exchange must be 'local' or 'peer'")
+        peer = exchange == "peer" and world_size > 1
         states = []
+        torch.cuda.synchronize()
         for rank in range(world_size):
             plan = self.plan(tuple(canonical.shape), rank, world_size)
             own_lo, own_hi = plan.own_range()
             live_lo, live_hi = plan.live_range()
-            states.append(_RankState(plan, canonical[own_lo:own_hi], live[live_lo:live_hi], device))
-        slabs = self._run(states, LocalExchange())
+            states.append(_RankState(plan, canonical[own_lo:own_hi], live[live_lo:live_hi], device,
+                                     torch.cuda.Stream(device) if peer else None))
+        if peer:
+            link = PeerExchange(virtual_ranks=world_size)
+            try:
+                slabs = self._run(states, link)
+            finally:
+                link.close()
+        else:
+            slabs = self._run(states, LocalExchange())
         return torch.cat(slabs, dim=0).cpu().numpy()
+
+    def close(self):
+        """frees the peer-visible allocation (collective over the ranks)"""
+        if self._peer_exchange is not None:
+            self._peer_exchange.close()
+            self._peer_exchange = None

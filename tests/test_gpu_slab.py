@@ -43,6 +43,45 @@ def test_slabs_match_whole_volume(lsf, mode, world_size, slab_kernels, monkeypat
                        [r.max_update_length for r in optimizer.get_per_level_convergence_reports()], rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("mode", sorted(MODES))
+@pytest.mark.parametrize("world_size", [2, 4])
+def test_peer_memory_exchange_matches_whole_volume(lsf, mode, world_size):
+    """the peer-memory exchange kernel (csrc/slab_peer.cu: boundary planes stored into the neighbours' halo planes, mailbox
+    signals, termination maximum to all ranks, device-side wait) with one stream per virtual rank -- the ranks wait for
+    each other on the device like the GPUs of a box; bit-identical to the whole-volume optimizer in all term modes"""
+    from lsf_b200 import slab, synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(64)
+    canonical, live = canonical[:, :48, :56].copy(), live[:, :48, :56].copy()
+    optimizer = make_optimizer(lsf, mode)
+    whole = optimizer.optimize(canonical, live)
+    sharded = slab.SlabHierarchicalOptimizer3d(optimizer, pack_halo=16)
+    warp = sharded.optimize_emulated(canonical, live, world_size, exchange="peer")
+    assert sharded.iteration_counts == optimizer.get_per_level_iteration_counts()
+    assert np.array_equal(warp, whole)
+    assert np.allclose(sharded.max_update_lengths,
+                       [r.max_update_length for r in optimizer.get_per_level_convergence_reports()], rtol=0, atol=0)
+
+
+def test_peer_memory_exchange_early_termination_and_odd_plane_size(lsf):
+    """levels that converge inside a polling chunk (the remaining iterations of the chunk are no-ops on every rank, the
+    exchanges still pair up) and planes whose float count is not a multiple of 4 (scalar copy path of the exchange kernel
+    at the coarsest level: 13 x 11 voxels per plane)"""
+    from lsf_b200 import slab, synthetic
+    canonical, live = synthetic.sphere_plane_pair_3d(64)
+    optimizer = make_optimizer(lsf, "kernel", iterations=40, threshold=0.05)
+    whole = optimizer.optimize(canonical, live)
+    counts = optimizer.get_per_level_iteration_counts()
+    assert any(c < 40 for c in counts)
+    sharded = slab.SlabHierarchicalOptimizer3d(optimizer)
+    assert np.array_equal(sharded.optimize_emulated(canonical, live, 2, exchange="peer"), whole)
+    assert sharded.iteration_counts == counts
+    canonical, live = canonical[:, :52, :44].copy(), live[:, :52, :44].copy()
+    optimizer = make_optimizer(lsf, "tikhonov_kernel", iterations=6)
+    whole = optimizer.optimize(canonical, live)
+    sharded = slab.SlabHierarchicalOptimizer3d(optimizer, pack_halo=16)
+    assert np.array_equal(sharded.optimize_emulated(canonical, live, 4, exchange="peer"), whole)
+
+
 def test_slabs_early_termination_and_single_rank(lsf):
     from lsf_b200 import slab, synthetic
     canonical, live = synthetic.sphere_plane_pair_3d(64)
