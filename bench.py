@@ -368,7 +368,8 @@ def multipair_batch(rank, world, device, pairs=64, size=128):
 
 def slab_volume(size, iterations, rank, world, device):
     """BASELINE.json configs[4]: ONE size^3 pair split into slabs along axis 0 over the ranks, halo exchange of the
-    Sobolev radius per iteration over NCCL (levelsetfusion-python_b200/slab.py). Every rank generates its own planes."""
+    Sobolev radius per iteration through peer memory (levelsetfusion-python_b200/slab.py, csrc/slab_peer.cu). Every rank
+    generates its own planes."""
     import torch
     import lsf_b200
     from lsf_b200 import multigpu, slab, synthetic
@@ -398,11 +399,14 @@ def slab_volume(size, iterations, rank, world, device):
                   for level, count in enumerate(sharded.iteration_counts))
     counts = list(sharded.iteration_counts)
     halo_bytes = sharded.exchanged_bytes
+    exchange = "peer memory (lsf_slab_exchange: one kernel per exchange stores into the neighbours' halo planes over NVLink)" \
+        if sharded._peer_exchange is not None else "torch.distributed send/recv + all_reduce"
+    sharded.close()
     del canonical_slab, live_region, sharded
     torch.cuda.empty_cache()
     return {"workload": "one %d^3 pair, slabs of %d planes per GPU, at most %d iterations per level" % (size, own_hi - own_lo, iterations),
             "n_gpus": world, "seconds": best, "value": updates / best, "unit": UNIT, "iterations_per_level": counts,
-            "halo_bytes_sent_per_rank": halo_bytes}
+            "halo_bytes_sent_per_rank": halo_bytes, "exchange": exchange}
 
 
 def killingfusion_iteration(lsf_b200, canonical, live, size, peak, iterations=10):

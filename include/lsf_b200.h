@@ -242,6 +242,21 @@ typedef struct {
 int lsf_slab_exchange(const lsf_slab_peers* peers, const lsf_slab_level* level, size_t field_offset, int width,
 		int low_planes, int low_destination_plane, int high_planes, int high_destination_plane, int reduce_iteration,
 		unsigned sequence, void* stream);
+/* Geometry of the two exchanges of an iteration: byte offsets of g_pre / g_post inside every rank's allocation (they must
+ * be the level's g_pre / g_post pointers minus base[rank]) and the neighbours' allocations at this level. */
+typedef struct {
+	size_t pre_offset, post_offset;
+	int low_planes, low_own_end;       /* low neighbour: planes of its allocation, first plane of its high halo */
+	int high_planes, high_own_begin;   /* high neighbour: planes of its allocation, first owned plane (its low halo ends there) */
+} lsf_slab_link;
+/* Enqueues iterations [first_iteration, first_iteration + iteration_count) of a level on this rank: per iteration
+ * phase 1, [with a Sobolev kernel: exchange of `radius` g_pre planes, phase 2,] exchange of one g_post plane (Tikhonov term
+ * enabled) together with the reduction of the iteration's maximum. Without a Sobolev kernel g_pre / g_post swap roles after
+ * every iteration (the caller applies the parity to its own pointers). Exchanges take the sequence numbers first_sequence,
+ * first_sequence + 1, ...; *sequences_used receives their count. One call replaces 4 host calls per iteration. */
+int lsf_hier_slab_iterations(const lsf_hier_params* params, const lsf_slab_level* level, const lsf_slab_peers* peers,
+		const lsf_slab_link* link, int first_iteration, int iteration_count, unsigned first_sequence,
+		unsigned* sequences_used, void* stream);
 /* synchronises `stream` and reports whether a wait of this rank has timed out (1) */
 int lsf_slab_exchange_error(const lsf_slab_peers* peers, int* error_out, void* stream);
 

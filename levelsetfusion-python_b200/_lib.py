@@ -127,6 +127,15 @@ class SlabPeers(ctypes.Structure):
     ]
 
 
+class SlabLink(ctypes.Structure):
+    """lsf_slab_link"""
+    _fields_ = [
+        ("pre_offset", ctypes.c_size_t), ("post_offset", ctypes.c_size_t),
+        ("low_planes", ctypes.c_int), ("low_own_end", ctypes.c_int),
+        ("high_planes", ctypes.c_int), ("high_own_begin", ctypes.c_int),
+    ]
+
+
 class SlavchevaParams(ctypes.Structure):
     """lsf_slavcheva_params"""
     _fields_ = [

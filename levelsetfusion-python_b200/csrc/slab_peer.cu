@@ -251,3 +251,36 @@ extern "C" int lsf_slab_exchange_error(const lsf_slab_peers* peers, int* error_o
 	LSF_CUDA(cudaStreamSynchronize(stream));
 	return LSF_OK;
 }
+
+extern "C" int lsf_hier_slab_iterations(const lsf_hier_params* params, const lsf_slab_level* level_in,
+		const lsf_slab_peers* peers, const lsf_slab_link* link, int first_iteration, int iteration_count,
+		unsigned first_sequence, unsigned* sequences_used, void* stream) {
+	LSF_REQUIRE(params && level_in && peers && link, "params, level, peers and link must not be NULL");
+	LSF_REQUIRE(first_iteration >= 0 && iteration_count >= 0, "invalid iteration range");
+	const bool tikhonov = params->tikhonov_term_enabled && params->tikhonov_strength > 0.0f;
+	const bool use_kernel = params->gradient_kernel_enabled && params->kernel_size > 0 && params->kernel != nullptr;
+	const int radius = use_kernel ? params->kernel_size / 2 : 0;
+	lsf_slab_level level = *level_in;
+	size_t pre_offset = link->pre_offset, post_offset = link->post_offset;
+	const char* own = static_cast<const char*>(peers->base[peers->rank]);
+	LSF_REQUIRE(reinterpret_cast<const char*>(level.g_pre) == own + pre_offset
+			&& reinterpret_cast<const char*>(level.g_post) == own + post_offset,
+			"g_pre / g_post of the level are not at the link's offsets inside the rank's allocation");
+	unsigned sequence = first_sequence;
+	for (int it = first_iteration; it < first_iteration + iteration_count; it++) {
+		LSF_TRY(lsf_hier_slab_iteration(params, &level, it, 1, stream));
+		if (use_kernel) {
+			LSF_TRY(lsf_slab_exchange(peers, &level, pre_offset, radius, link->low_planes, link->low_own_end, link->high_planes,
+					link->high_own_begin - radius, -1, sequence++, stream));
+			LSF_TRY(lsf_hier_slab_iteration(params, &level, it, 2, stream));
+		} else {  // phase 1 wrote the iteration's gradient into g_pre: it is the next iteration's g_post
+			std::swap(level.g_pre, level.g_post);
+			std::swap(pre_offset, post_offset);
+		}
+		const int width = tikhonov ? 1 : 0;
+		LSF_TRY(lsf_slab_exchange(peers, &level, post_offset, width, link->low_planes, link->low_own_end, link->high_planes,
+				link->high_own_begin - width, it, sequence++, stream));
+	}
+	if (sequences_used) *sequences_used = sequence - first_sequence;
+	return LSF_OK;
+}

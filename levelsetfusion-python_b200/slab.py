@@ -297,6 +297,28 @@ class PeerExchange:
                 high.planes if high else 0, high.own_begin - int(width) if high else 0,
                 int(reduce_iteration), ctypes.c_uint(self.sequence), state.stream_handle()))
 
+    def iterations(self, params, states, level, first_iteration, count):
+        """enqueues `count` whole iterations (phases + exchanges) of every local rank with one library call per rank"""
+        used = ctypes.c_uint(0)
+        for state in states:
+            rank = state.plan.rank
+            g = state.plan.levels[level]
+            low = SlabGeometry(g.X_global, g.Y, g.Z, rank - 1, self.world_size, state.plan.halo, 0) if rank > 0 else None
+            high = SlabGeometry(g.X_global, g.Y, g.Z, rank + 1, self.world_size, state.plan.halo, 0) \
+                if rank < self.world_size - 1 else None
+            link = _lib.SlabLink()
+            link.pre_offset = state.g_pre.data_ptr() - self.owned[rank]
+            link.post_offset = state.g_post.data_ptr() - self.owned[rank]
+            link.low_planes, link.low_own_end = (low.planes, low.own_end) if low else (0, 0)
+            link.high_planes, link.high_own_begin = (high.planes, high.own_begin) if high else (0, 0)
+            peers = self._peers(rank)
+            descriptor = state.descriptor(level)
+            _lib.check(self.lib.lsf_hier_slab_iterations(
+                ctypes.byref(params), ctypes.byref(descriptor), ctypes.byref(peers), ctypes.byref(link),
+                int(first_iteration), int(count), ctypes.c_uint(self.sequence + 1), ctypes.byref(used),
+                state.stream_handle()))
+        self.sequence += used.value
+
     def check(self, states):
         for state in states:
             error = ctypes.c_int(0)
@@ -473,32 +495,57 @@ class SlabHierarchicalOptimizer3d:
                     s.start_level(level, o.maximum_iteration_count, exchange)
             executed, enqueued, converged, last_max = 0, 0, False, float("inf")
             plane_bytes = geometries[0].Y * geometries[0].Z * 3 * 4
-            while not converged and enqueued < o.maximum_iteration_count:
+            per_iteration_bytes = (2 * radius * plane_bytes if use_kernel else 0) + (2 * plane_bytes if tikhonov else 0)
+            if fused:
+                # one library call per chunk and rank; one chunk is always in flight behind the one the host waits for
+                # (iterations past the convergence point are no-ops on the device: the kernels test the previous slot)
+                in_flight = []
+                while True:
+                    if not converged and enqueued < o.maximum_iteration_count:
+                        chunk_end = min(o.maximum_iteration_count, enqueued + POLL_CHUNK)
+                        exchange.iterations(params, states, level, enqueued, chunk_end - enqueued)
+                        if not use_kernel and (chunk_end - enqueued) % 2:
+                            for s in states:  # the library swapped the roles once per iteration
+                                s.g_pre, s.g_post = s.g_post, s.g_pre
+                        with states[0].on_stream():
+                            host_bits = torch.empty(chunk_end - enqueued, dtype=torch.int32, pin_memory=True)
+                            host_bits.copy_(states[0].slots[enqueued:chunk_end], non_blocking=True)
+                            done = torch.cuda.Event()
+                            done.record()
+                        in_flight.append((enqueued, chunk_end, host_bits, done))
+                        self.exchanged_bytes += (chunk_end - enqueued) * per_iteration_bytes
+                        enqueued = chunk_end
+                        if len(in_flight) < 2 and enqueued < o.maximum_iteration_count:
+                            continue
+                    if not in_flight:
+                        break
+                    begin, end, host_bits, done = in_flight.pop(0)
+                    done.synchronize()
+                    if converged:
+                        continue
+                    for it, value in zip(range(begin, end), host_bits.numpy().view(np.float32)):
+                        last_max = float(np.sqrt(value))
+                        executed = it + 1
+                        if last_max < o.maximum_warp_update_threshold:  # optimizer.tpp:166-171
+                            converged = True
+                            break
+                exchange.check(states)
+            while not fused and not converged and enqueued < o.maximum_iteration_count:
                 chunk_end = min(o.maximum_iteration_count, enqueued + POLL_CHUNK)
                 for it in range(enqueued, chunk_end):
                     phase(1, it, level)
                     if use_kernel:
-                        if fused:
-                            exchange.exchange(states, level, "pre", radius, -1)
-                        else:
-                            exchange.halos([s.g_pre for s in states], geometries, radius)
+                        exchange.halos([s.g_pre for s in states], geometries, radius)
                         phase(2, it, level)
-                        self.exchanged_bytes += 2 * radius * plane_bytes
                     else:
                         for s in states:  # without a filter phase 1 wrote the final gradient into g_pre
                             s.g_pre, s.g_post = s.g_post, s.g_pre
-                    if fused:  # the filtered gradient's boundary plane and the termination maximum in one kernel
-                        exchange.exchange(states, level, "post", 1 if tikhonov else 0, it)
-                    else:
-                        if tikhonov:
-                            exchange.halos([s.g_post for s in states], geometries, 1)
-                        exchange.reduce_max([s.slots for s in states], it)
                     if tikhonov:
-                        self.exchanged_bytes += 2 * plane_bytes
+                        exchange.halos([s.g_post for s in states], geometries, 1)
+                    exchange.reduce_max([s.slots for s in states], it)
+                    self.exchanged_bytes += per_iteration_bytes
                 with states[0].on_stream():
                     bits = states[0].slots[enqueued:chunk_end].cpu().numpy()  # synchronises once per chunk
-                if fused:
-                    exchange.check(states)
                 for it, value in zip(range(enqueued, chunk_end), bits.view(np.float32)):
                     last_max = float(np.sqrt(value))
                     executed = it + 1

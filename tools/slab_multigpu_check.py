@@ -26,6 +26,8 @@ def main():
     parser.add_argument("--iterations", type=int, default=20)
     parser.add_argument("--check", action="store_true")
     parser.add_argument("--repeat", type=int, default=2)
+    parser.add_argument("--exchange", choices=["peer", "dist"], default="peer",
+                        help="peer: kernels storing into the neighbours' memory (csrc/slab_peer.cu); dist: NCCL send/recv + all_reduce")
     args = parser.parse_args()
     rank, world_size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -38,7 +40,7 @@ def main():
                                                  gradient_kernel_enabled=True, kernel=synthetic.sobolev_kernel_1d(),
                                                  maximum_chunk_size=8, maximum_iteration_count=args.iterations,
                                                  maximum_warp_update_threshold=0.01)
-    sharded = slab.SlabHierarchicalOptimizer3d(optimizer, pack_halo=32)
+    sharded = slab.SlabHierarchicalOptimizer3d(optimizer, pack_halo=32, exchange=args.exchange)
     plan = sharded.plan((size, size, size), rank, world_size)
     own_lo, own_hi = plan.own_range()
     live_lo, live_hi = plan.live_range()
@@ -62,7 +64,8 @@ def main():
         times.append(multigpu.max_over_ranks(start.elapsed_time(stop), device=device))
     updates = sum((size >> (plan.level_count - 1 - level)) ** 3 * count
                   for level, count in enumerate(sharded.iteration_counts))
-    result = {"workload": "hierarchical3d_%d_slab_sharded" % size, "n_gpus": world_size, "ms": times[-1],
+    result = {"workload": "hierarchical3d_%d_slab_sharded" % size, "n_gpus": world_size, "exchange": args.exchange,
+              "ms": times[-1], "ms_all_repeats": times,
               "voxel_updates_per_s": updates / (times[-1] * 1e-3), "iterations_per_level": sharded.iteration_counts,
               "halo_bytes_sent_per_rank": sharded.exchanged_bytes, "planes_per_rank": own_hi - own_lo}
     if args.check:
@@ -76,6 +79,7 @@ def main():
             result["iteration_counts_equal"] = sharded.iteration_counts == optimizer.get_per_level_iteration_counts()
     if rank == 0:
         print(json.dumps(result))
+    sharded.close()
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
