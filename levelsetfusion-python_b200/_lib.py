@@ -221,6 +221,8 @@ EXPORTED_SYMBOLS = [
     "lsf_debug_last_path", "lsf_hier_optimize_3d_telemetry", "lsf_hier_optimize_2d_telemetry",
     "lsf_slavcheva_optimize", "lsf_slavcheva_optimize_logged", "lsf_warp_advanced", "lsf_warp_delta_statistics", "lsf_tsdf_difference_statistics",
     "lsf_tsdf_generate", "lsf_sdf2sdf_optimize_2d",
+    "lsf_peer_alloc", "lsf_peer_open", "lsf_peer_close", "lsf_peer_free", "lsf_slab_exchange", "lsf_slab_exchange_error",
+    "lsf_hier_slab_iterations",
 ]
 
 _lib = None
