@@ -222,9 +222,19 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 		LSF_CUDA(cudaMemsetAsync(field_b, 0, N * D * sizeof(float), stream));
 		LSF_CUDA(cudaMemcpyAsync(live_b, live_a, N * sizeof(float), cudaMemcpyDeviceToDevice, stream));
 	}
+	// small 2D fields: a polling chunk of iterations in one cooperative launch (slavcheva_persistent.cu); LSF_SLAV_PERSISTENT=0
+	// keeps one launch per kernel (A/B)
+	const char* persistent_env = getenv("LSF_SLAV_PERSISTENT");
+	const bool persistent = D == 2 && !sparse && capture_dev == nullptr && !(persistent_env && persistent_env[0] == '0')
+			&& g.N <= slav_persistent_capacity();
+	// the launch ends by itself at the first finished iteration, so a long chunk costs nothing: the host looks once
+	constexpr int PERSISTENT_CHUNK = 128;
+	std::vector<SlavIterationCommand> commands(persistent ? PERSISTENT_CHUNK : 0);
+	SlavIterationCommand* commands_dev = nullptr;
+	if (persistent) LSF_TRY(arena.alloc(&commands_dev, (size_t) PERSISTENT_CHUNK));
 	while (!finished) {
 		// with per-iteration statistics requested (reference sobolev_optimizer2d.cpp:88-97) the host looks at every iteration
-		const int chunk_end = std::min(bound, enqueued + (iteration_statistics ? 1 : POLL_CHUNK));
+		const int chunk_end = std::min(bound, enqueued + (iteration_statistics ? 1 : (persistent ? PERSISTENT_CHUNK : POLL_CHUNK)));
 		for (int it = enqueued; it < chunk_end; it++) {
 			SlavGradientArgs ga;
 			ga.g = g;
@@ -277,8 +287,10 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 				if (band_compaction) k_slav_gradient_cpp3_band<<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ga);
 				else k_slav_gradient_cpp3_v4<<<counted(blocks_for(g.N / 4)), 256, 0, stream>>>(ga);  // four voxels per thread
 			}
+			else if (persistent) commands[it - enqueued].gradient = ga;
 			else
 				k_slav_gradient<D> <<<counted(blocks), 256, 0, stream>>>(ga);
+			if (persistent) commands[it - enqueued].passes = 0;
 			float* final_field = field_a;
 			SlavResampleArgs ra;
 			ra.g = g;
@@ -366,7 +378,8 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 						fa.in = in;
 						fa.out = outs[axis];
 						fa.axis = axis;
-						k_slav_filter_axis<D> <<<counted(blocks), 256, 0, stream>>>(fa);
+						if (persistent) commands[it - enqueued].pass[commands[it - enqueued].passes++] = fa;
+						else k_slav_filter_axis<D> <<<counted(blocks), 256, 0, stream>>>(fa);
 						in = outs[axis];
 					}
 				}
@@ -387,9 +400,10 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 					k_slav_resample_band<D> <<<counted((unsigned) ((g.N + 1023) / 1024)), 256, 0, stream>>>(ra);
 				else k_slav_resample_v4<D> <<<counted(blocks_for(g.N / 4)), 256, 0, stream>>>(ra);  // four voxels per thread
 			}
+			else if (persistent) commands[it - enqueued].resample = ra;
 			else
 				k_slav_resample<D> <<<counted(blocks), 256, 0, stream>>>(ra);
-			if (!bricked) k_slav_decide<<<counted(1u), 1, 0, stream>>>(p, max_sq_bits, status, it, max_iterations);
+			if (!bricked && !persistent) k_slav_decide<<<counted(1u), 1, 0, stream>>>(p, max_sq_bits, status, it, max_iterations);
 			// the filtered field becomes the persistent gradient field read as `stale` next iteration; the live buffers
 			// swap. Both swaps also happen for iterations the device skips (status set): skipped kernels write nothing,
 			// and the results are read from the buffers of the last executed iteration (tracked below).
@@ -400,6 +414,13 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			std::swap(live_a, live_b);
 			if (capture_dev != nullptr && it < capture->max_iterations)
 				k_planes_to_aos<<<counted(blocks), 256, 0, stream>>>(warp, capture_dev + (size_t) it * N * D, g.N, D);
+		}
+		if (persistent) {
+			// pageable source: the driver has copied it out when the call returns, `commands` is free for the next chunk
+			LSF_CUDA(cudaMemcpyAsync(commands_dev, commands.data(), (size_t) (chunk_end - enqueued) * sizeof(SlavIterationCommand),
+					cudaMemcpyHostToDevice, stream));
+			LSF_TRY(launch_slav_persistent2d(commands_dev, chunk_end - enqueued, p, g.N, max_sq_bits, status, enqueued, max_iterations,
+					stream));
 		}
 		LSF_CUDA(cudaGetLastError());
 		LSF_CUDA(cudaMemcpyAsync(host_status.data() + enqueued + 1, status + enqueued + 1,

@@ -100,6 +100,21 @@ struct SlavResampleArgs {
 	int iteration;
 };
 
+// One iteration of the generic (dense, dimension-generic) kernel sequence as data: what k_slav_gradient, the
+// k_slav_filter_axis passes and k_slav_resample would be launched with. Small fields run a whole polling chunk of
+// iterations in ONE cooperative launch that reads these records (slavcheva_persistent.cu).
+struct SlavIterationCommand {
+	SlavGradientArgs gradient;
+	SlavFilterArgs pass[3];
+	int passes;
+	SlavResampleArgs resample;
+};
+// largest field (voxels) the single-launch path takes: all blocks must be resident at once
+long long slav_persistent_capacity();
+// iterations [first_iteration, first_iteration + count) from `commands_dev`; the termination test (k_slav_decide) runs inside
+int launch_slav_persistent2d(const SlavIterationCommand* commands_dev, int count, const SlavParams& p, long long N,
+		const unsigned* max_sq_bits, int* status, int first_iteration, int max_iterations, cudaStream_t stream);
+
 // Band-union warp statistics and TSDF difference statistics of device-resident fields (defined in slavcheva.cu; also
 // used by the hierarchical optimizers for their per-level convergence reports). `field` element (voxel i,
 // component c) = field[c * component_stride + i * voxel_stride]. Either output may be NULL.
@@ -362,12 +377,10 @@ __device__ __forceinline__ void slav_level_set(const SlavGradientArgs& a, int id
 	}
 }
 
+// the gradient terms at voxel idx (body of k_slav_gradient; also called by the single-launch optimizer of small fields,
+// slavcheva_persistent.cu)
 template<int D>
-static __global__ void __launch_bounds__(256) k_slav_gradient(SlavGradientArgs a) {
-	if (a.status[a.iteration]) return;
-	const long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	if (linear >= a.g.N) return;
-	const int idx = (int) linear;
+__device__ __forceinline__ void slav_gradient_at(const SlavGradientArgs& a, int idx) {
 	int pos[3];
 	slav_coords<D>(a.g, idx, pos);
 	const float live_value = __ldg(a.live + idx);
@@ -433,6 +446,14 @@ static __global__ void __launch_bounds__(256) k_slav_gradient(SlavGradientArgs a
 	}
 #pragma unroll
 	for (int c = 0; c < D; c++) a.out[c * a.g.N + idx] = result[c];
+}
+
+template<int D>
+static __global__ void __launch_bounds__(256) k_slav_gradient(SlavGradientArgs a) {
+	if (a.status[a.iteration]) return;
+	const long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (linear >= a.g.N) return;
+	slav_gradient_at<D>(a, (int) linear);
 }
 
 // The C++-semantics branch of k_slav_gradient<3> with four consecutive z voxels per thread (128-bit loads of the two
@@ -566,11 +587,7 @@ static __global__ void __launch_bounds__(256) k_slav_gradient_cpp3_band(SlavGrad
 // reference convolve_with_kernel_preserve_zeros, cpp/src/math/convolution.cpp:23-67,69-145 (C++ rule) and
 // math_utils/convolution.py:114-132 (Python rule)
 template<int D>
-static __global__ void __launch_bounds__(256) k_slav_filter_axis(SlavFilterArgs a) {
-	if (a.status[a.iteration]) return;
-	const long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	if (linear >= a.g.N) return;
-	const int idx = (int) linear;
+__device__ __forceinline__ void slav_filter_axis_at(const SlavFilterArgs& a, int idx) {
 	int pos[3];
 	slav_coords<D>(a.g, idx, pos);
 	const int i = pos[a.axis], n = a.g.n[a.axis], s = a.g.stride[a.axis];
@@ -596,6 +613,14 @@ static __global__ void __launch_bounds__(256) k_slav_filter_axis(SlavFilterArgs 
 		if (a.zero_rule == 2 && fabsf(__ldg(a.original + c * a.g.N + idx)) < 1e-6f) acc = 0.0f;
 		a.out[c * a.g.N + idx] = acc;
 	}
+}
+
+template<int D>
+static __global__ void __launch_bounds__(256) k_slav_filter_axis(SlavFilterArgs a) {
+	if (a.status[a.iteration]) return;
+	const long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (linear >= a.g.N) return;
+	slav_filter_axis_at<D>(a, (int) linear);
 }
 
 // ---------------------------------------------------------------------------------------------- re-warp of the live field
@@ -738,25 +763,27 @@ __device__ __forceinline__ void slav_resample_voxel(const SlavResampleArgs& a, i
 }
 
 template<int D>
+__device__ __forceinline__ void slav_resample_at(const SlavResampleArgs& a, int idx, float& sq_report) {
+	const SlavGeom& g = a.g;
+	float update[3] = { 0.f, 0.f, 0.f }, w[3], new_value;
+#pragma unroll
+	for (int c = 0; c < D; c++) update[c] = __ldg(a.update + c * g.N + idx);
+	const float live_value = __ldg(a.live + idx);
+	const float canonical_value = a.band_union_only ? __ldg(a.canonical + idx) : 0.0f;
+	slav_resample_voxel<D>(a, idx, update, live_value, canonical_value, new_value, w, sq_report);
+	a.new_live[idx] = new_value;
+	if (a.warp != nullptr) {
+#pragma unroll
+		for (int c = 0; c < D; c++) a.warp[c * g.N + idx] = w[c];
+	}
+}
+
+template<int D>
 static __global__ void __launch_bounds__(256) k_slav_resample(SlavResampleArgs a) {
 	if (a.status != nullptr && a.status[a.iteration]) return;
-	const SlavGeom& g = a.g;
 	const long long linear = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	float sq_report = 0.0f;
-	if (linear < g.N) {
-		const int idx = (int) linear;
-		float update[3] = { 0.f, 0.f, 0.f }, w[3], new_value;
-#pragma unroll
-		for (int c = 0; c < D; c++) update[c] = __ldg(a.update + c * g.N + idx);
-		const float live_value = __ldg(a.live + idx);
-		const float canonical_value = a.band_union_only ? __ldg(a.canonical + idx) : 0.0f;
-		slav_resample_voxel<D>(a, idx, update, live_value, canonical_value, new_value, w, sq_report);
-		a.new_live[idx] = new_value;
-		if (a.warp != nullptr) {
-#pragma unroll
-			for (int c = 0; c < D; c++) a.warp[c * g.N + idx] = w[c];
-		}
-	}
+	if (linear < a.g.N) slav_resample_at<D>(a, (int) linear, sq_report);
 	if (a.max_sq_bits != nullptr) block_atomic_max(sq_report, a.max_sq_bits);
 }
 

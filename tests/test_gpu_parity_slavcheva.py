@@ -167,6 +167,62 @@ def test_slavcheva2d_vs_oracle(lsf, semantics, terms):
     run_both(lsf, 2, semantics, live, canonical, sobolev=False, iterations=6, **TERM_CASES[terms])
 
 
+def run_single_launch(lsf, semantics, live, canonical, iterations=12, lower=0.01, sobolev=True, **terms):
+    """2D runs WITHOUT a per-iteration capture take the single-launch path (csrc/slavcheva_persistent.cu: all iterations of
+    a polling chunk in one cooperative kernel); compared with the oracle bit for bit and, through LSF_SLAV_PERSISTENT=0, with
+    the one-launch-per-kernel path, whose launch count it must undercut"""
+    from lsf_b200 import _lib, slavcheva, synthetic
+    kernel = synthetic.sobolev_kernel_1d()
+    expected = oracle.slavcheva_optimize(live, canonical, semantics=semantics, max_iterations=iterations,
+                                         maximum_warp_length_lower_threshold=lower, sobolev_smoothing_enabled=sobolev,
+                                         sobolev_kernel=kernel, **terms)
+
+    def run():
+        before = _lib.load().lsf_launch_count()
+        result = slavcheva._run(2, live, canonical, semantics, terms.get("data_term_method", 0),
+                                terms.get("smoothing_term_method", 0), terms.get("level_set_term_enabled", False), sobolev,
+                                0.1, 1.0, 0.2, 0.1, terms.get("level_set_term_weight", 0.2), lower, 10000.0, iterations, 1,
+                                kernel, collect_statistics=False, capture_iterations=0)
+        return result, _lib.load().lsf_launch_count() - before
+
+    result, launches = run()
+    assert result.iteration_count == expected["iterations"]
+    assert np.array_equal(result.max_warps, expected["max_warps"])
+    assert np.array_equal(result.warp, expected["warp"])
+    assert np.array_equal(result.live, expected["live"])
+    os.environ["LSF_SLAV_PERSISTENT"] = "0"
+    try:
+        plain, plain_launches = run()
+    finally:
+        del os.environ["LSF_SLAV_PERSISTENT"]
+    assert plain.iteration_count == result.iteration_count
+    assert np.array_equal(plain.live, result.live) and np.array_equal(plain.warp, result.warp)
+    if result.iteration_count >= 4:
+        assert launches < plain_launches / 2, (launches, plain_launches)
+    return result
+
+
+@pytest.mark.parametrize("terms", sorted(TERM_CASES))
+@pytest.mark.parametrize("semantics", [0, 1, 2])
+def test_single_launch_2d_vs_oracle(lsf, semantics, terms):
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.circle_line_pair_2d(64)
+    result = run_single_launch(lsf, semantics, live, canonical, **TERM_CASES[terms])
+    assert result.iteration_count >= 2
+    run_single_launch(lsf, semantics, live, canonical, sobolev=False, iterations=6, **TERM_CASES[terms])
+
+
+def test_single_launch_2d_config1_and_odd_shape(lsf):
+    """BASELINE.json configs[0] (128 x 128, terminates through the threshold after 52 iterations, i.e. inside the launch) and
+    a 90 x 90 field (last block with idle threads; the reference's 2D code is only defined for square fields)"""
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.circle_line_pair_2d(128, shift=(5.0, -3.0), line_shift=-4.0)
+    result = run_single_launch(lsf, 0, live, canonical, iterations=100, lower=0.05)
+    assert result.iteration_count == 52
+    result = run_single_launch(lsf, 0, live[:90, :90].copy(), canonical[:90, :90].copy(), iterations=150, lower=0.0)
+    assert result.iteration_count == 150  # more iterations than one launch takes (chunks of 128)
+
+
 def test_slavcheva2d_128_config1(lsf):
     """BASELINE.json configs[0]: 2D SobolevFusion on a 128x128 pair with the reference experiment's parameters
     (experiment/singleframe_experiment.py:91-116: rate 0.1, weights 1.0 / 0.2, lower threshold 0.05, 100 iterations,
