@@ -131,13 +131,90 @@ def write_reports(data_frame, out_path, reports_file_name="convergence_reports")
     return written
 
 
+# ------------------------------------------------------------------------------------------------ telemetry_log.npz
+def get_telemetry_subfolder_path(telemetry_folder, frame_number, pixel_row):
+    """reference run_hierarchical_optimizer3d_multipair.py:214-215"""
+    return os.path.join(telemetry_folder, "pair_{:d}-{:d}_{:d}".format(frame_number, frame_number + 1, pixel_row))
+
+
+class TelemetryMetadata:
+    """reference hierarchical_optimization_visualizer.py:150-157"""
+
+    def __init__(self, has_warp_fields, has_data_term_gradients, has_tikhonov_term_gradients, field_size):
+        self.has_warp_fields = has_warp_fields
+        self.has_data_term_gradients = has_data_term_gradients
+        self.has_tikhonov_term_gradients = has_tikhonov_term_gradients
+        self.field_size = field_size
+
+
+def get_telemetry_metadata(telemetry_log):
+    """what the first level of a per-level iteration-data list holds (reference
+    hierarchical_optimization_visualizer.py:182-208; that code files a non-empty Tikhonov list under
+    has_data_term_gradients -- here it sets has_tikhonov_term_gradients)"""
+    first = telemetry_log[0]
+
+    def probe(fields):
+        if fields is not None and len(fields) > 0 and fields[0] is not None and np.asarray(fields[0]).size > 0:
+            return True, np.asarray(fields[0]).shape[0]
+        return False, 0
+
+    has_warp, size_warp = probe(first.get_warp_fields())
+    has_data, size_data = probe(first.get_data_term_gradients())
+    has_tikhonov, size_tikhonov = probe(first.get_tikhonov_term_gradients())
+    return TelemetryMetadata(has_warp, has_data, has_tikhonov, size_warp or size_data or size_tikhonov)
+
+
+def save_telemetry_log(telemetry_log, telemetry_metadata, output_folder):
+    """`telemetry_log.npz` of one pair in the reference's layout (hierarchical_optimization_visualizer.py:210-227): per
+    level i the keys l<i>_warp_fields, l<i>_data_term_gradients, l<i>_tikhonov_term_gradients, each the fields of all
+    iterations stacked along axis 2 (np.dstack) or an empty array. `telemetry_log` = get_per_level_iteration_data()."""
+    telemetry_dict = {}
+    for i_level, level_data in enumerate(telemetry_log):
+        telemetry_dict["l{:d}_warp_fields".format(i_level)] = np.dstack(level_data.get_warp_fields())
+        telemetry_dict["l{:d}_data_term_gradients".format(i_level)] = \
+            np.array([]) if not telemetry_metadata.has_data_term_gradients else np.dstack(
+                level_data.get_data_term_gradients())
+        telemetry_dict["l{:d}_tikhonov_term_gradients".format(i_level)] = \
+            np.array([]) if not telemetry_metadata.has_tikhonov_term_gradients else np.dstack(
+                level_data.get_tikhonov_term_gradients())
+    os.makedirs(output_folder, exist_ok=True)
+    np.savez_compressed(os.path.join(output_folder, "telemetry_log.npz"), **telemetry_dict)
+
+
+def load_telemetry_log(output_folder, components=2):
+    """inverse of save_telemetry_log (reference :230-250, which splits the stacks into 2-component fields: written for 2D
+    runs -- 3D fields [X][Y][Z][3] are stacked along their Z axis by np.dstack and split back with components = Z). Returns
+    a list of OptimizationIterationData2d (the live fields are not part of the file)."""
+    from .hierarchical import OptimizationIterationData2d
+    telemetry_dict = np.load(os.path.join(output_folder, "telemetry_log.npz"))
+    level_count = len(telemetry_dict.files) // 3
+    telemetry_log = []
+    for i_level in range(level_count):
+        def split(key):
+            stack = telemetry_dict["l{:d}_{:s}".format(i_level, key)]
+            if stack.ndim < 3 or stack.size == 0:
+                return []
+            return [np.ascontiguousarray(part) for part in np.dsplit(stack, stack.shape[2] // components)]
+        warp_fields, data_term_gradients = split("warp_fields"), split("data_term_gradients")
+        tikhonov_term_gradients = split("tikhonov_term_gradients")
+        level_data = OptimizationIterationData2d()
+        for i, warp_field in enumerate(warp_fields):
+            level_data.add_iteration_result(None, warp_field, data_term_gradients[i] if data_term_gradients else None,
+                                            tikhonov_term_gradients[i] if tikhonov_term_gradients else None)
+        telemetry_log.append(level_data)
+    return telemetry_log
+
+
 def run_multipair(data_path, out_path, optimizer_factory, streams=1, start_from_index=0, stop_before_index=10000000,
-                  save_warps=False, group=None):
+                  save_warps=False, group=None, save_telemetry=False):
     """Optimises every cached pair (reference :403-436) over the ranks / streams and writes the report table.
 
     optimizer_factory -- callable() -> HierarchicalOptimizer3d with
                          LoggingParameters(collect_per_level_convergence_reports=True) (one object per worker thread)
     save_warps        -- also write `warp_<frame>_<row>.npy` next to the reports (this rank's pairs)
+    save_telemetry    -- reference --save_telemetry (:395-411,443-453): the optimizers must be built with
+                         LoggingParameters(collect_per_level_iteration_data=True); every pair's per-level iteration data
+                         goes to <out_path>/telemetry/pair_<f>-<f+1>_<row>/telemetry_log.npz (written by the pair's rank)
     Returns the DataFrame (all ranks)."""
     entries = list_pair_cache(data_path, start_from_index, stop_before_index)
     rank, world_size, _ = multigpu.world()
@@ -146,7 +223,8 @@ def run_multipair(data_path, out_path, optimizer_factory, streams=1, start_from_
 
     def call(optimizer, canonical, live, entry=None):
         warp = optimizer.optimize(canonical, live)
-        return warp, optimizer.get_per_level_convergence_reports()
+        telemetry_log = optimizer.get_per_level_iteration_data() if save_telemetry else None
+        return warp, optimizer.get_per_level_convergence_reports(), telemetry_log
 
     def one_pair(optimizer, canonical, live):
         return call(optimizer, canonical, live)
@@ -158,10 +236,13 @@ def run_multipair(data_path, out_path, optimizer_factory, streams=1, start_from_
         return load_pair(entries[index][2])
 
     results = multigpu.optimize_pairs(worker, len(entries), load, rank, world_size, gather=False, streams=streams)
-    for index, (warp, reports) in results.items():
+    for index, (warp, reports, telemetry_log) in results.items():
+        frame, row, _ = entries[index]
         if save_warps:
-            frame, row, _ = entries[index]
             np.save(os.path.join(out_path, "warp_{:d}_{:d}.npy".format(frame, row)), np.asarray(warp))
+        if save_telemetry and telemetry_log:
+            save_telemetry_log(telemetry_log, get_telemetry_metadata(telemetry_log),
+                               get_telemetry_subfolder_path(os.path.join(out_path, "telemetry"), frame, row))
         local[index] = reports
     if world_size > 1:
         import torch.distributed as dist

@@ -70,6 +70,23 @@ def test_run_multipair_matches_serial_reports(lsf, tmp_path):
     assert table.equals(expected)
     assert os.path.exists(os.path.join(out_path, "convergence_reports.pk"))
     assert os.path.exists(os.path.join(out_path, "analysis.txt"))
+    # reference --save_telemetry: per-level iteration data of every pair in telemetry/pair_<f>-<f+1>_<row>/telemetry_log.npz
+    kwargs["logging_parameters"] = lsf.HierarchicalOptimizer3d.LoggingParameters(
+        collect_per_level_convergence_reports=True, collect_per_level_iteration_data=True)
+    telemetry_table = multipair.run_multipair(data_path, out_path, factory, streams=1, save_telemetry=True)
+    assert telemetry_table.equals(expected)  # collecting the iteration data does not change the result
+    optimizer = factory()
+    for frame, row, path in entries:
+        canonical, live = multipair.load_pair(path)
+        optimizer.optimize(canonical, live)
+        log = optimizer.get_per_level_iteration_data()
+        stored = np.load(os.path.join(multipair.get_telemetry_subfolder_path(os.path.join(out_path, "telemetry"), frame, row),
+                                      "telemetry_log.npz"))
+        assert len(stored.files) == 3 * len(log)
+        for level, level_data in enumerate(log):
+            assert np.array_equal(stored["l%d_warp_fields" % level], np.dstack(level_data.get_warp_fields()))
+            assert np.array_equal(stored["l%d_data_term_gradients" % level], np.dstack(level_data.get_data_term_gradients()))
+            assert stored["l%d_tikhonov_term_gradients" % level].size == 0  # the Tikhonov term is off in this run
 
 
 @pytest.mark.parametrize("mode", ["tikhonov_kernel", "kernel", "tikhonov", "data_only"])

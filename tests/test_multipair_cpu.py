@@ -64,3 +64,39 @@ def test_report_table_columns_and_analysis(tmp_path):
     log = multipair.analyze_convergence_data(frame, str(tmp_path))
     text = open(log).read()
     assert "Per-level convergence ratios" in text and "level 1" in text
+
+
+def test_telemetry_log_file_layout_and_round_trip(tmp_path):
+    """`telemetry_log.npz` in the reference's layout (hierarchical_optimization_visualizer.py:210-250): per level the keys
+    l<i>_warp_fields / l<i>_data_term_gradients / l<i>_tikhonov_term_gradients holding the iterations' [H][W][2] fields
+    stacked along axis 2, an empty array where a kind was not collected; the folder name of a pair
+    (run_hierarchical_optimizer3d_multipair.py:214-215)"""
+    from lsf_b200.hierarchical import OptimizationIterationData2d
+    rng = np.random.default_rng(5)
+    log = []
+    for size, frames in ((4, 3), (8, 2)):
+        level = OptimizationIterationData2d()
+        for _ in range(frames):
+            level.add_iteration_result(rng.random((size, size), dtype=np.float32), rng.random((size, size, 2), dtype=np.float32),
+                                       rng.random((size, size, 2), dtype=np.float32), None)
+        log.append(level)
+    metadata = multipair.get_telemetry_metadata(log)
+    assert (metadata.has_warp_fields, metadata.has_data_term_gradients, metadata.has_tikhonov_term_gradients,
+            metadata.field_size) == (True, True, False, 4)
+    folder = multipair.get_telemetry_subfolder_path(str(tmp_path / "telemetry"), 12, 214)
+    assert os.path.basename(folder) == "pair_12-13_214"
+    multipair.save_telemetry_log(log, metadata, folder)
+    stored = np.load(os.path.join(folder, "telemetry_log.npz"))
+    assert sorted(stored.files) == sorted("l%d_%s" % (i, kind) for i in (0, 1)
+                                          for kind in ("warp_fields", "data_term_gradients", "tikhonov_term_gradients"))
+    assert stored["l0_warp_fields"].shape == (4, 4, 6) and stored["l1_warp_fields"].shape == (8, 8, 4)
+    assert stored["l0_tikhonov_term_gradients"].size == 0
+    assert np.array_equal(stored["l0_warp_fields"][:, :, 2:4], log[0].get_warp_fields()[1])
+    loaded = multipair.load_telemetry_log(folder)
+    assert [level.get_frame_count() for level in loaded] == [3, 2]
+    for level, original in zip(loaded, log):
+        for a, b in zip(level.get_warp_fields(), original.get_warp_fields()):
+            assert np.array_equal(a, b)
+        for a, b in zip(level.get_data_term_gradients(), original.get_data_term_gradients()):
+            assert np.array_equal(a, b)
+        assert all(t is None for t in level.get_tikhonov_term_gradients())

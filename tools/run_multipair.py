@@ -38,6 +38,8 @@ def main():
     parser.add_argument("--start-from-index", type=int, default=0)
     parser.add_argument("--stop-before-index", type=int, default=10000000)
     parser.add_argument("--save-warps", action="store_true")
+    parser.add_argument("--save-telemetry", action="store_true",
+                        help="reference --save_telemetry: per-level iteration data of every pair -> telemetry/pair_*/telemetry_log.npz")
     args = parser.parse_args()
     rank, world_size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
@@ -52,7 +54,8 @@ def main():
             multipair.save_pair(args.data, i, 214, canonical, live)
     if world_size > 1:
         dist.barrier()
-    logging = lsf_b200.HierarchicalOptimizer3d.LoggingParameters(collect_per_level_convergence_reports=True)
+    logging = lsf_b200.HierarchicalOptimizer3d.LoggingParameters(collect_per_level_convergence_reports=True,
+                                                                 collect_per_level_iteration_data=args.save_telemetry)
     factory = lambda: lsf_b200.HierarchicalOptimizer3d(
         tikhonov_term_enabled=args.tikhonov, gradient_kernel_enabled=not args.no_kernel, maximum_chunk_size=8,
         rate=args.rate, maximum_iteration_count=args.maximum_iteration_count,
@@ -60,7 +63,7 @@ def main():
         kernel=synthetic.sobolev_kernel_1d(args.kernel_size, args.kernel_strength), logging_parameters=logging)
     t0 = time.perf_counter()
     table = multipair.run_multipair(args.data, args.out, factory, args.streams, args.start_from_index,
-                                    args.stop_before_index, args.save_warps)
+                                    args.stop_before_index, args.save_warps, save_telemetry=args.save_telemetry)
     torch.cuda.synchronize()
     seconds = multigpu.max_over_ranks(time.perf_counter() - t0, torch.device("cuda", torch.cuda.current_device()))
     if rank == 0:
