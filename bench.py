@@ -146,6 +146,12 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=device)
+        # one process per GPU: keep this rank's host buffers and staging threads on the GPU's NUMA node
+        from lsf_b200 import multigpu
+        full_affinity = os.sched_getaffinity(0)
+        numa_cpus = multigpu.bind_to_gpu_numa_node(local_rank)
+    else:
+        full_affinity = numa_cpus = None
     lib = lsf_b200._lib.load()
     size = args.size
     kwargs = optimizer_kwargs()
@@ -302,6 +308,8 @@ def run_ours(args):
     if rank == 0:
         other_workloads.update(shared_workloads)
         # -------------------------------------------------------------- CPU baseline (oracle port), bounded sample
+        if numa_cpus:
+            os.sched_setaffinity(0, full_affinity)  # the CPU baseline may use every host core
         cpu = cpu_baseline_sample(size, kwargs)
         value = updates / (elapsed_ms * 1e-3)
         N = size ** 3
@@ -316,6 +324,7 @@ def run_ours(args):
             "e2e": {"value": e2e_updates / e2e_seconds, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * 4 * N * world, "d2h_bytes_per_step": 3 * 4 * N * world,
                     "ms_per_step": 1e3 * e2e_seconds / args.steps,
+                    "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else 0,
                     "call": "optimizer.optimize(canonical: np.ndarray, live: np.ndarray) -> np.ndarray (pageable host memory)",
                     "pinned": {"value": pinned_updates / pinned_seconds, "ms_per_step": 1e3 * pinned_seconds / args.steps,
                                "call": "optimize(pinned numpy views, out=pinned numpy view)"}},
