@@ -121,7 +121,17 @@ bool is_pageable(const void* host) {
 
 // memcpy on several threads (first-touch page faults of a fresh destination array are spread over the threads too)
 void parallel_copy(void* dst, const void* src, size_t bytes) {
-	static const unsigned workers = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+	// up to 8 threads; with several ranks on the host (torchrun exports LOCAL_WORLD_SIZE) each rank takes its share of the
+	// cores -- all ranks stage their inputs at the same time; LSF_COPY_THREADS overrides
+	static const unsigned workers = []() {
+		unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+		const char* local_world = getenv("LOCAL_WORLD_SIZE");
+		if (local_world && atoi(local_world) > 1) cores = std::max(1u, cores / (unsigned) atoi(local_world));
+		unsigned n = std::min(8u, cores);
+		const char* fixed = getenv("LSF_COPY_THREADS");
+		if (fixed && atoi(fixed) >= 1) n = std::min(64u, (unsigned) atoi(fixed));
+		return n;
+	}();
 	if (bytes < (4u << 20) || workers == 1) {
 		std::memcpy(dst, src, bytes);
 		return;

@@ -77,6 +77,39 @@ struct LevelState2 {
 	unsigned* max_sq_bits = nullptr;
 };
 
+// iterations [first, first + count) of a level in one cooperative launch (small fields)
+int enqueue_level_persistent(const Plan2& plan, LevelState2& s, int first, int count, cudaStream_t stream) {
+	HierIterArgs2 a;
+	a.pack = s.pack;
+	a.canonical = s.canonical;
+	a.warp = s.warp;
+	a.warp_out = s.warp;
+	a.g_prev = s.g_post;
+	a.g_out = nullptr;
+	a.g = s.g;
+	a.amplifier = plan.amplifier;
+	a.strength = plan.strength;
+	a.rate = plan.rate;
+	a.threshold = plan.threshold;
+	a.max_sq_bits = s.max_sq_bits;
+	a.iteration = first;
+	a.check_convergence = 1;
+	ConvArgs2 c;
+	c.in = nullptr;
+	c.out = nullptr;
+	c.warp = s.warp;
+	c.g = s.g;
+	c.taps = plan.taps;
+	c.rate = plan.rate;
+	c.threshold = plan.threshold;
+	c.max_sq_bits = s.max_sq_bits;
+	c.iteration = first;
+	c.check_convergence = 1;
+	c.channels = 2;
+	c.preserve_zeros = 0;
+	return launch_hier2d_persistent(a, c, plan.tikhonov, plan.use_kernel, s.g_post, s.scratch_a, first, count, stream);
+}
+
 void enqueue_iteration(const Plan2& plan, LevelState2& s, int iteration, cudaStream_t stream) {
 	HierIterArgs2 a;
 	a.pack = s.pack;
@@ -280,9 +313,16 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 			LSF_TRY(run_level_with_telemetry(plan, s, level, sink, telemetry, stream, &executed, &last_max));
 			converged = true;  // the level is done
 		}
+		// small fields: the whole level in one cooperative launch (hier2d_persistent.cu); LSF_HIER2D_PERSISTENT=0 keeps one
+		// launch per kernel (A/B)
+		const char* persistent_env = getenv("LSF_HIER2D_PERSISTENT");
+		const bool persistent = !capturing && sink == nullptr && !(persistent_env && persistent_env[0] == '0')
+				&& s.g.N <= hier2d_persistent_capacity();
 		while (!converged && enqueued < plan.max_iterations) {
-			const int chunk_end = std::min(plan.max_iterations, enqueued + POLL_CHUNK);
-			for (int it = enqueued; it < chunk_end; it++) {
+			// the launch ends by itself at the first converged iteration: the host looks once per level
+			const int chunk_end = persistent ? plan.max_iterations : std::min(plan.max_iterations, enqueued + POLL_CHUNK);
+			if (persistent) LSF_TRY(enqueue_level_persistent(plan, s, enqueued, chunk_end - enqueued, stream));
+			for (int it = enqueued; it < chunk_end && !persistent; it++) {
 				enqueue_iteration(plan, s, it, stream);
 				if (capturing && it < capture->max_iterations)
 					k_planes_to_aos<<<counted(div_up(s.g.N, 256)), 256, 0, stream>>>(s.warp, capture_dev + (size_t) it * s.g.N * 2,

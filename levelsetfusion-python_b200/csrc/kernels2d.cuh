@@ -133,33 +133,39 @@ struct HierIterArgs2 {
 };
 
 // reference optimizer.tpp:186-211 instantiated for MatrixXf / MatrixXv2f (see k_hier_gradient3d)
+// one pixel of the gradient stage (body of k_hier_gradient2d; also called by the single-launch level kernel of small
+// fields, hier2d_persistent.cu); sq = the pixel's ||g||^2 when FUSE_UPDATE
+template<bool TIKHONOV, bool FUSE_UPDATE>
+__device__ __forceinline__ void hier_gradient2d_at(const HierIterArgs2& a, int row, int col, long long idx, float& sq) {
+	const Grid2& g = a.g;
+	const float u = a.warp[idx], v = a.warp[g.N + idx];
+	const float4 s = gather4_2d(a.pack, g, row, col, u, v);
+	const float diff = s.x - a.canonical[idx];
+	float gx = (s.y * diff) * a.amplifier;
+	float gy = (s.z * diff) * a.amplifier;
+	if (TIKHONOV) {
+		gx = gx - laplacian2d_at(a.g_prev, idx, row, col, g) * a.strength;
+		gy = gy - laplacian2d_at(a.g_prev + g.N, idx, row, col, g) * a.strength;
+	}
+	if (a.g_out != nullptr) {
+		a.g_out[idx] = gx;
+		a.g_out[g.N + idx] = gy;
+	}
+	if (FUSE_UPDATE) {
+		a.warp_out[idx] = u - gx * a.rate;
+		a.warp_out[g.N + idx] = v - gy * a.rate;
+		sq = 0.0f + gx * gx;
+		sq += gy * gy;
+	}
+}
+
 template<bool TIKHONOV, bool FUSE_UPDATE>
 static __global__ void __launch_bounds__(BLOCK_Z * BLOCK_Y) k_hier_gradient2d(HierIterArgs2 a) {
 	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
 	const Grid2 g = a.g;
 	LSF_PIXEL_2D(g);
 	float sq = 0.0f;
-	if (in_grid) {
-		const float u = a.warp[idx], v = a.warp[g.N + idx];
-		const float4 s = gather4_2d(a.pack, g, row, col, u, v);
-		const float diff = s.x - a.canonical[idx];
-		float gx = (s.y * diff) * a.amplifier;
-		float gy = (s.z * diff) * a.amplifier;
-		if (TIKHONOV) {
-			gx = gx - laplacian2d_at(a.g_prev, idx, row, col, g) * a.strength;
-			gy = gy - laplacian2d_at(a.g_prev + g.N, idx, row, col, g) * a.strength;
-		}
-		if (a.g_out != nullptr) {
-			a.g_out[idx] = gx;
-			a.g_out[g.N + idx] = gy;
-		}
-		if (FUSE_UPDATE) {
-			a.warp_out[idx] = u - gx * a.rate;
-			a.warp_out[g.N + idx] = v - gy * a.rate;
-			sq = 0.0f + gx * gx;
-			sq += gy * gy;
-		}
-	}
+	if (in_grid) hier_gradient2d_at<TIKHONOV, FUSE_UPDATE>(a, row, col, idx, sq);
 	if (FUSE_UPDATE) block_atomic_max(sq, a.max_sq_bits + a.iteration);
 }
 
@@ -181,41 +187,53 @@ struct ConvArgs2 {
 	int preserve_zeros;
 };
 
+// one pixel of a filter pass (body of k_convolve_axis2d); sq accumulates the pixel's ||out||^2 when FINAL
+template<int AXIS, bool FINAL>
+__device__ __forceinline__ void convolve_axis2d_at(const ConvArgs2& a, int row, int col, long long idx, float& sq) {
+	const Grid2& g = a.g;
+	const int i = AXIS == 0 ? row : col;
+	const int n = AXIS == 0 ? g.H : g.W;
+	const long long stride = AXIS == 0 ? g.W : 1;
+	const int r = a.taps.radius;
+	bool keep_zero = false;
+	if (a.preserve_zeros) {
+		keep_zero = true;
+		for (int c = 0; c < a.channels; c++) keep_zero = keep_zero && (a.in[c * g.N + idx] == 0.0f);
+	}
+	for (int c = 0; c < a.channels; c++) {
+		float acc = 0.0f;
+		if (!keep_zero) {
+			const float* line = a.in + c * g.N + idx;
+			for (int j = 0; j < a.taps.size; j++) {
+				const int src = i - r + j;
+				const float value = (src >= 0 && src < n) ? __ldg(line + (long long) (j - r) * stride) : 0.0f;
+				acc += value * a.taps.k[j];
+			}
+		}
+		a.out[c * g.N + idx] = acc;
+		if (FINAL) {
+			a.warp[c * g.N + idx] = a.warp[c * g.N + idx] - acc * a.rate;
+			sq += acc * acc;
+		}
+	}
+}
+
 template<int AXIS, bool FINAL>
 static __global__ void __launch_bounds__(BLOCK_Z * BLOCK_Y) k_convolve_axis2d(ConvArgs2 a) {
 	if (a.check_convergence && level_converged(a.max_sq_bits, a.iteration, a.threshold)) return;
 	const Grid2 g = a.g;
 	LSF_PIXEL_2D(g);
 	float sq = 0.0f;
-	if (in_grid) {
-		const int i = AXIS == 0 ? row : col;
-		const int n = AXIS == 0 ? g.H : g.W;
-		const long long stride = AXIS == 0 ? g.W : 1;
-		const int r = a.taps.radius;
-		bool keep_zero = false;
-		if (a.preserve_zeros) {
-			keep_zero = true;
-			for (int c = 0; c < a.channels; c++) keep_zero = keep_zero && (a.in[c * g.N + idx] == 0.0f);
-		}
-		for (int c = 0; c < a.channels; c++) {
-			float acc = 0.0f;
-			if (!keep_zero) {
-				const float* line = a.in + c * g.N + idx;
-				for (int j = 0; j < a.taps.size; j++) {
-					const int src = i - r + j;
-					const float value = (src >= 0 && src < n) ? __ldg(line + (long long) (j - r) * stride) : 0.0f;
-					acc += value * a.taps.k[j];
-				}
-			}
-			a.out[c * g.N + idx] = acc;
-			if (FINAL) {
-				a.warp[c * g.N + idx] = a.warp[c * g.N + idx] - acc * a.rate;
-				sq += acc * acc;
-			}
-		}
-	}
+	if (in_grid) convolve_axis2d_at<AXIS, FINAL>(a, row, col, idx, sq);
 	if (FINAL) block_atomic_max(sq, a.max_sq_bits + a.iteration);
 }
+
+// Small fields: all iterations of a level in one cooperative launch (hier2d_persistent.cu). `gradient` / `filter` are the
+// arguments of iteration `first_iteration` (gradient.g_prev = the level's g_post, gradient.g_out = its scratch field with a
+// Sobolev kernel or the Tikhonov term, else nullptr); the kernel rotates the two fields like enqueue_iteration does.
+long long hier2d_persistent_capacity();
+int launch_hier2d_persistent(const HierIterArgs2& gradient, const ConvArgs2& filter, bool tikhonov, bool use_kernel,
+		float* g_post, float* scratch, int first_iteration, int count, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------- restrict x2
 struct PlainAccess2 {

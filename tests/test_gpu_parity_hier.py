@@ -6,6 +6,8 @@ optimizer runs are compared BIT-EXACTLY (np.array_equal) with the oracle; the no
 (per-iteration warp <= 1e-5 over the first 10 iterations, final warped live <= 1e-4, identical iteration counts)
 are asserted on top, and golden vectors use the reference tests' own atol (1e-6 / 10e-6).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -220,6 +222,42 @@ def test_hier2d_vs_oracle(lsf, mode):
     canonical, live = synthetic.circle_line_pair_2d(128)
     check_against_oracle(lsf, canonical, live, 2, mode, chunk=8)
     check_against_oracle(lsf, canonical, live, 2, mode, chunk=8, linear=True)
+
+
+@pytest.mark.parametrize("mode", sorted(HIER_MODES))
+def test_hier2d_single_launch_levels_vs_oracle(lsf, mode):
+    """without a per-iteration capture every level of a 2D run takes the single-launch path (csrc/hier2d_persistent.cu: all
+    iterations of a level in one cooperative kernel, termination test inside): bit-identical to the oracle and to the
+    one-launch-per-kernel path (LSF_HIER2D_PERSISTENT=0), identical iteration counts -- also where levels terminate early,
+    on a non-square field and with LINEAR resampling -- with far fewer launches"""
+    from lsf_b200 import _lib, synthetic
+    canonical, live = synthetic.circle_line_pair_2d(128)
+    cases = [(canonical, live, 30, 0.01, 0), (canonical, live, 60, 0.05, 1),
+             (canonical[:64, :].copy(), live[:64, :].copy(), 25, 0.02, 0)]
+    for c, l, iterations, threshold, linear in cases:
+        kwargs = dict(HIER_MODES[mode])
+        kwargs.update(maximum_chunk_size=8, rate=0.1, maximum_iteration_count=iterations,
+                      maximum_warp_update_threshold=threshold, data_term_amplifier=1.0,
+                      kernel=synthetic.sobolev_kernel_1d(), resampling_strategy=linear)
+        expected = oracle.hier_optimize(c, l, **kwargs)
+        optimizer = lsf.HierarchicalOptimizer2d(**kwargs)
+        before = _lib.load().lsf_launch_count()
+        warp = optimizer.optimize(c, l)
+        launches = _lib.load().lsf_launch_count() - before
+        assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
+        assert np.array_equal(warp, expected["warp"])
+        reports = optimizer.get_per_level_convergence_reports()
+        assert np.allclose([r.max_update_length for r in reports], expected["max_updates"], rtol=0, atol=0)
+        os.environ["LSF_HIER2D_PERSISTENT"] = "0"
+        try:
+            before = _lib.load().lsf_launch_count()
+            plain = optimizer.optimize(c, l)
+            plain_launches = _lib.load().lsf_launch_count() - before
+        finally:
+            del os.environ["LSF_HIER2D_PERSISTENT"]
+        assert np.array_equal(plain, warp)
+        assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
+        assert launches < plain_launches / 2, (launches, plain_launches)
 
 
 def test_hier2d_python_reference_runs(lsf, python_runs):
