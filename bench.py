@@ -295,6 +295,8 @@ def run_ours(args):
         other_workloads = {"killingfusion3d_%d" % size: killingfusion_iteration(lsf_b200, canonical, live, size, peak)}
         # -------------------------------------------------------------- TSDF generation from depth
         other_workloads["tsdf_generation_%d" % size] = tsdf_generation(lsf_b200, size, peak)
+        # -------------------------------------------------------------- BASELINE.json configs[0]: the 2D optimizers at 128 x 128
+        other_workloads.update(optimizers_2d(lsf_b200))
     # ------------------------------------------------------------------ BASELINE.json configs[3] and configs[4] (all ranks)
     del canonical, live
     torch.cuda.empty_cache()
@@ -490,6 +492,64 @@ def tsdf_generation(lsf_b200, size, peak, repeats=20):
                      "algorithmic_bytes_per_voxel": 4, "achieved": round(achieved, 1), "frac": round(achieved / peak, 4),
                      "cpu_oracle_ms": round(cpu_ms, 2), "cpu_cores": os.cpu_count(), "max_abs_difference_to_oracle": difference,
                      "band_fraction": float((np.abs(expected) < 1).mean())}
+    return out
+
+
+def optimizers_2d(lsf_b200, size=128, repeats=5):
+    """BASELINE.json configs[0] and the reference's 2D class: one size x size pair from numpy arrays (host staging inside),
+    ms per optimize() of SobolevOptimizer2d with the reference experiment's parameters (experiment/
+    singleframe_experiment.py:91-116) and of HierarchicalOptimizer2d (4 levels x 100 iterations, data term), the CPU
+    oracle beside them, results compared bit for bit. 2D fields are launch-bound: both run one cooperative launch per
+    iteration loop (csrc/slavcheva_persistent.cu, csrc/hier2d_persistent.cu)."""
+    import time
+    import numpy as np
+    import torch
+    import oracle
+    from lsf_b200 import synthetic
+    canonical, live = synthetic.circle_line_pair_2d(size, shift=(5.0, -3.0), line_shift=-4.0)
+    kernel = synthetic.sobolev_kernel_1d()
+
+    def best_of(call):
+        call()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            result = call()
+            torch.cuda.synchronize()
+            seconds = time.perf_counter() - t0
+            best = seconds if best is None else min(best, seconds)
+        return 1e3 * best, result
+
+    shared, sobolev = lsf_b200.SharedParameters.get_instance(), lsf_b200.SobolevParameters.get_instance()
+    saved = dict(vars(shared)), dict(vars(sobolev))
+    try:
+        shared.maximum_iteration_count = 100
+        shared.maximum_warp_length_lower_threshold = 0.05
+        sobolev.set_sobolev_kernel(kernel)
+        optimizer = lsf_b200.SobolevOptimizer2d()
+        ms, result = best_of(lambda: optimizer.optimize(live.copy(), canonical))
+        iterations = optimizer.get_iteration_count()
+    finally:
+        vars(shared).update(saved[0])
+        vars(sobolev).update(saved[1])
+    t0 = time.perf_counter()
+    expected = oracle.slavcheva_optimize(live, canonical, semantics=0, max_iterations=100,
+                                         maximum_warp_length_lower_threshold=0.05, sobolev_kernel=kernel)
+    cpu_ms = 1e3 * (time.perf_counter() - t0)
+    out = {"sobolevfusion2d_%d" % size: {
+        "ms_per_optimize": round(ms, 3), "iterations": int(iterations), "cpu_oracle_ms": round(cpu_ms, 3),
+        "identical_to_oracle": bool(np.array_equal(result, expected["live"])) and iterations == expected["iterations"]}}
+    kwargs = dict(tikhonov_term_enabled=False, gradient_kernel_enabled=False, maximum_chunk_size=8, rate=0.2,
+                  maximum_iteration_count=100, maximum_warp_update_threshold=0.001)
+    hierarchical = lsf_b200.HierarchicalOptimizer2d(**kwargs)
+    ms, warp = best_of(lambda: hierarchical.optimize(canonical, live))
+    t0 = time.perf_counter()
+    expected = oracle.hier_optimize(canonical, live, **kwargs)
+    cpu_ms = 1e3 * (time.perf_counter() - t0)
+    out["hierarchical2d_%d" % size] = {
+        "ms_per_optimize": round(ms, 3), "iterations_per_level": hierarchical.get_per_level_iteration_counts(),
+        "cpu_oracle_ms": round(cpu_ms, 3), "identical_to_oracle": bool(np.array_equal(warp, expected["warp"]))}
     return out
 
 
