@@ -22,6 +22,7 @@ from .telemetry import (Vector2i, Vector3i, Vector2f, WarpDeltaStatistics2d, War
                         TsdfDifferenceStatistics2d, TsdfDifferenceStatistics3d, ConvergenceReport2d, ConvergenceReport3d,
                         build_warp_delta_statistics_2d, build_warp_delta_statistics_3d,
                         build_tsdf_difference_statistics_2d, build_tsdf_difference_statistics_3d, mean_vector_length)
+from ._lib import set_strict_inputs
 from . import slavcheva
 from . import tsdf
 from .rigid import Sdf2SdfOptimizer2d
@@ -44,4 +45,4 @@ __all__ = ["HierarchicalOptimizer2d", "HierarchicalOptimizer3d", "OptimizationIt
            "WarpDeltaStatistics2d", "WarpDeltaStatistics3d", "TsdfDifferenceStatistics2d", "TsdfDifferenceStatistics3d",
            "ConvergenceReport2d", "ConvergenceReport3d", "build_warp_delta_statistics_2d",
            "build_warp_delta_statistics_3d", "build_tsdf_difference_statistics_2d",
-           "build_tsdf_difference_statistics_3d", "mean_vector_length", "ops", "telemetry", "slavcheva", "tsdf", "Sdf2SdfOptimizer2d", "_lib"]
+           "build_tsdf_difference_statistics_3d", "mean_vector_length", "ops", "telemetry", "slavcheva", "tsdf", "Sdf2SdfOptimizer2d", "set_strict_inputs", "_lib"]

@@ -256,9 +256,31 @@ def check(status):
     return status
 
 
+# The reference's Boost.Python converters only accept float32, C-contiguous, aligned numpy arrays
+# (python_export/eigen_numpy_tensor.cpp:120-156, eigen_numpy_matrix.cpp): any other argument fails overload resolution with
+# Boost.Python.ArgumentError, a TypeError. By default this package is lenient and converts; set_strict_inputs(True) (or
+# LSF_STRICT_INPUTS=1) reproduces the reference's refusal, e.g. to find silent float64 copies in a pipeline.
+_strict_inputs = os.environ.get("LSF_STRICT_INPUTS", "0") == "1"
+
+
+def set_strict_inputs(enabled):
+    """True: field arguments must be float32 C-contiguous aligned numpy arrays, as for the reference's extension module
+    (TypeError otherwise); False (default): anything array-like is converted. Returns the previous setting."""
+    global _strict_inputs
+    previous, _strict_inputs = _strict_inputs, bool(enabled)
+    return previous
+
+
 def as_f32(array, name="array"):
-    """The reference's converters only accept float32 C-contiguous arrays
-    (python_export/eigen_numpy_tensor.cpp:120-156); be a little more lenient and convert."""
+    """float32 C-contiguous view or copy of a field argument (see set_strict_inputs)"""
+    if _strict_inputs:
+        if not isinstance(array, np.ndarray):
+            raise TypeError("%s must be a numpy array, got %s" % (name, type(array).__name__))
+        if array.dtype != np.float32 or not array.flags.c_contiguous or not array.flags.aligned:
+            raise TypeError("%s must be a float32, C-contiguous, aligned numpy array (got dtype %s, C-contiguous %s): the "
+                            "reference's converters accept nothing else (python_export/eigen_numpy_tensor.cpp:120-156)"
+                            % (name, array.dtype, array.flags.c_contiguous))
+        return array
     return np.ascontiguousarray(array, dtype=np.float32)
 
 

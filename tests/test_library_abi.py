@@ -82,3 +82,25 @@ def test_product_never_imports_oracle():
             if name.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, name)).read()
                 assert "import oracle" not in text and "lsf_oracle" not in text, name
+
+
+def test_strict_inputs_refuse_what_the_reference_refuses():
+    """reference python_export/eigen_numpy_tensor.cpp:120-156: float32, C-contiguous, aligned arrays only (TypeError through
+    Boost.Python's overload resolution); lenient conversion is this package's default"""
+    import numpy as np
+    import pytest
+    field = np.zeros((4, 6), dtype=np.float64)
+    assert _lib.as_f32(field).dtype == np.float32
+    previous = lsf_b200.set_strict_inputs(True)
+    try:
+        with pytest.raises(TypeError):
+            _lib.as_f32(field)
+        with pytest.raises(TypeError):
+            _lib.as_f32(np.zeros((4, 6), dtype=np.float32).T)
+        with pytest.raises(TypeError):
+            _lib.as_f32([[0.0, 1.0]])
+        good = np.zeros((4, 6), dtype=np.float32)
+        assert _lib.as_f32(good) is good
+    finally:
+        lsf_b200.set_strict_inputs(previous)
+    assert _lib.as_f32(field).dtype == np.float32
