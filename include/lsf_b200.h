@@ -361,11 +361,17 @@ int lsf_slavcheva_optimize(const lsf_slavcheva_params* params, const float* live
 /* the same with the reference's per-iteration log (SharedParameters.enable_warp_statistics_logging,
  * cpp/src/nonrigid_optimization/slavcheva/sobolev_optimizer2d.cpp:88-97): iteration_statistics[i] (host array of
  * iteration_statistics_capacity entries, or NULL) receives the warp statistics over the band union of (canonical,
- * warped live) after iteration i; the rows of get_warp_statistics_as_matrix() (:144-160). */
+ * warped live) after iteration i; the rows of get_warp_statistics_as_matrix() (:144-160).
+ * iteration_energies (host array [iteration_energies_capacity][3] of doubles, or NULL) receives what the reference's Python
+ * optimizer appends to its OptimizationLog every iteration (nonrigid_opt/slavcheva/slavcheva_optimizer2d.py:370-374:
+ * data_energies, smoothing_energies, level_set_energies, each times its weight; GPU reductions over the band union of the
+ * state the iteration starts from). 2D fields with the Python semantics; zeros otherwise (the C++ optimizer drops its
+ * energies, sobolev_optimizer2d.cpp:121-138). */
 int lsf_slavcheva_optimize_logged(const lsf_slavcheva_params* params, const float* live, const float* canonical, int nd,
 		const int* dims, float* live_out, float* warp_out, int memory_kind, lsf_slavcheva_report* report,
 		int collect_statistics, float* max_warps, int max_warps_capacity, lsf_iteration_capture* capture,
-		lsf_warp_delta_statistics_t* iteration_statistics, int iteration_statistics_capacity, void* stream);
+		lsf_warp_delta_statistics_t* iteration_statistics, int iteration_statistics_capacity, double* iteration_energies,
+		int iteration_energies_capacity, void* stream);
 
 /* reference warp_2d_advanced / warp_2d_advanced_warp_unchanged, cpp/src/nonrigid_optimization/field_warping.cpp:64-154
  * (exported as warp_field_advanced[_no_warp_change], python_export/slavcheva_optimizer.cpp:64-89) and its 3D form.

@@ -107,7 +107,7 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 		const float* live_in, const float* canonical, float* live_out, float* warp_out_aos, lsf_slavcheva_report* report,
 		int collect_statistics, float* max_warps, int max_warps_capacity, lsf_iteration_capture* capture,
 		float* capture_dev, Arena& arena, cudaStream_t stream, lsf_warp_delta_statistics_t* iteration_statistics = nullptr,
-		int iteration_statistics_capacity = 0) {
+		int iteration_statistics_capacity = 0, double* iteration_energies = nullptr, int iteration_energies_capacity = 0) {
 	const size_t N = (size_t) g.N;
 	SlavParams p;
 	p.semantics = params->semantics;
@@ -225,8 +225,15 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	// small 2D fields: a polling chunk of iterations in one cooperative launch (slavcheva_persistent.cu); LSF_SLAV_PERSISTENT=0
 	// keeps one launch per kernel (A/B)
 	const char* persistent_env = getenv("LSF_SLAV_PERSISTENT");
-	const bool persistent = D == 2 && !sparse && capture_dev == nullptr && !(persistent_env && persistent_env[0] == '0')
-			&& g.N <= slav_persistent_capacity();
+	// energy log of the reference's Python optimizer (2D): one kernel per iteration in front of the gradient kernel
+	const bool log_energies = D == 2 && !cpp && iteration_energies != nullptr && iteration_energies_capacity > 0;
+	double* energies_dev = nullptr;
+	if (log_energies) {
+		LSF_TRY(arena.alloc(&energies_dev, 3 * (size_t) (bound + 1)));
+		LSF_CUDA(cudaMemsetAsync(energies_dev, 0, 3 * (size_t) (bound + 1) * sizeof(double), stream));
+	}
+	const bool persistent = D == 2 && !sparse && capture_dev == nullptr && !log_energies
+			&& !(persistent_env && persistent_env[0] == '0') && g.N <= slav_persistent_capacity();
 	// the launch ends by itself at the first finished iteration, so a long chunk costs nothing: the host looks once
 	constexpr int PERSISTENT_CHUNK = 128;
 	std::vector<SlavIterationCommand> commands(persistent ? PERSISTENT_CHUNK : 0);
@@ -273,6 +280,7 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			brick.cursor = cursors ? cursors + (size_t) it * 4 : nullptr;
 			brick.status = status;
 			brick.iteration = it;
+			if (log_energies) k_slav_energies2d<<<counted(blocks), 256, 0, stream>>>(ga, energies_dev + 3 * (size_t) it);
 			const int live_parity = it & 1;  // the live buffers swap once per enqueued iteration
 			if (bricked) {
 				if (rescan) k_slav_brick_scan<<<counted((unsigned) bricks), 256, 0, stream>>>(ga, brick);
@@ -450,6 +458,15 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	LSF_CUDA(cudaMemcpyAsync(live_out, live_a, N * sizeof(float), cudaMemcpyDeviceToDevice, stream));
 	if (warp_out_aos) k_planes_to_aos<<<counted(blocks), 256, 0, stream>>>(warp, warp_out_aos, g.N, D);
 	if (capture) capture->count = capture_dev ? std::min(executed, capture->max_iterations) : 0;
+	if (iteration_energies != nullptr && iteration_energies_capacity > 0) {
+		const int rows = std::min(executed, iteration_energies_capacity);
+		std::memset(iteration_energies, 0, 3 * (size_t) iteration_energies_capacity * sizeof(double));
+		if (log_energies && rows > 0) {
+			LSF_CUDA(cudaMemcpyAsync(iteration_energies, energies_dev, 3 * (size_t) rows * sizeof(double), cudaMemcpyDeviceToHost,
+					stream));
+			LSF_CUDA(cudaStreamSynchronize(stream));
+		}
+	}
 	if (report) {
 		std::memset(report, 0, sizeof(*report));
 		report->iteration_count = executed;
@@ -489,7 +506,8 @@ using namespace lsf;
 extern "C" int lsf_slavcheva_optimize_logged(const lsf_slavcheva_params* params, const float* live, const float* canonical,
 		int nd, const int* dims, float* live_out, float* warp_out, int memory_kind, lsf_slavcheva_report* report,
 		int collect_statistics, float* max_warps, int max_warps_capacity, lsf_iteration_capture* capture,
-		lsf_warp_delta_statistics_t* iteration_statistics, int iteration_statistics_capacity, void* stream_handle) {
+		lsf_warp_delta_statistics_t* iteration_statistics, int iteration_statistics_capacity, double* iteration_energies,
+		int iteration_energies_capacity, void* stream_handle) {
 	cudaStream_t stream = static_cast<cudaStream_t>(stream_handle);
 	LSF_REQUIRE(params != nullptr, "params is NULL");
 	LSF_REQUIRE(live && canonical && live_out, "live, canonical and live_out must not be NULL");
@@ -523,7 +541,7 @@ extern "C" int lsf_slavcheva_optimize_logged(const lsf_slavcheva_params* params,
 	if (nd == 2)
 		LSF_TRY(optimize_device<2>(params, g, taps, use_kernel, live_dev, canonical_dev, live_out_dev, warp_out_dev, report,
 				collect_statistics, max_warps, max_warps_capacity, capture, capture_dev, arena, stream, iteration_statistics,
-				iteration_statistics_capacity));
+				iteration_statistics_capacity, iteration_energies, iteration_energies_capacity));
 	else
 		LSF_TRY(optimize_device<3>(params, g, taps, use_kernel, live_dev, canonical_dev, live_out_dev, warp_out_dev, report,
 				collect_statistics, max_warps, max_warps_capacity, capture, capture_dev, arena, stream, iteration_statistics,
@@ -544,7 +562,7 @@ extern "C" int lsf_slavcheva_optimize(const lsf_slavcheva_params* params, const 
 		int collect_statistics, float* max_warps, int max_warps_capacity, lsf_iteration_capture* capture,
 		void* stream_handle) {
 	return lsf_slavcheva_optimize_logged(params, live, canonical, nd, dims, live_out, warp_out, memory_kind, report,
-			collect_statistics, max_warps, max_warps_capacity, capture, nullptr, 0, stream_handle);
+			collect_statistics, max_warps, max_warps_capacity, capture, nullptr, 0, nullptr, 0, stream_handle);
 }
 
 extern "C" int lsf_warp_advanced(const float* live, const float* canonical, float* warp, int nd, const int* dims,

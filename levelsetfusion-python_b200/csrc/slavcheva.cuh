@@ -583,6 +583,85 @@ static __global__ void __launch_bounds__(256) k_slav_gradient_cpp3_band(SlavGrad
 	}
 }
 
+// ---------------------------------------------------------------------------------------------- energy log (2D, Python)
+// The {data, smoothing, level set} energy aggregates the reference's Python optimizer appends to its OptimizationLog
+// every iteration (slavcheva_optimizer2d.py:370-374), for the state the iteration starts from: DIRECT :236-300 with the
+// local energies of data_term.py:185,225, level_set_term.py:63, smoothing_term.py:97-98,137-138; VECTORIZED :163-175 with
+// data_term.py:352-358 and smoothing_term.py:162-177 (np.gradient of the warp components). Evaluated in double from the
+// float32 fields (like oracle slavcheva_energies); out[0..2] += this block's sums (double atomics: the order of the block
+// sums is not fixed, the result is compared at 1e-9). C++ semantics keep no log: nothing is added.
+static __global__ void __launch_bounds__(256) k_slav_energies2d(SlavGradientArgs a, double* __restrict__ out) {
+	if (a.status[a.iteration]) return;
+	const SlavGeom& g = a.g;
+	const SlavParams& p = a.p;
+	const int N = (int) g.N, H = g.n[0], W = g.n[1];
+	double sums[3] = { 0.0, 0.0, 0.0 };
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx < N && p.semantics != LSF_SEMANTICS_CPP) {
+		const float live_value = a.live[idx], canonical_value = a.canonical[idx];
+		if (!(slav_truncated(live_value) && slav_truncated(canonical_value))) {
+			const int row = idx / W, col = idx - row * W;
+			const double diff = (double) live_value - (double) canonical_value;
+			sums[0] = 0.5 * diff * diff;
+			const float* u = a.warp;       // component 0 displaces along the columns ("x"), component 1 along the rows ("y")
+			const float* v = a.warp + N;
+			if (p.semantics == LSF_SEMANTICS_PY_DIRECT) {
+				if (p.level_set && !slav_truncated(live_value)) {
+					const double xp = col + 1 < W ? a.live[idx + 1] : 1.0f, xm = col >= 1 ? a.live[idx - 1] : 1.0f;
+					const double yp = row + 1 < H ? a.live[idx + W] : 1.0f, ym = row >= 1 ? a.live[idx - W] : 1.0f;
+					const double gx = 0.5 * (xp - xm) * 10.0, gy = 0.5 * (yp - ym) * 10.0;
+					const double length = sqrt(gx * gx + gy * gy);
+					sums[2] = 0.5 * (length - 1.0) * (length - 1.0);
+				}
+				// neighbours outside the field = the centre value (utils/sampling.py:84-88)
+				const int xp = col + 1 < W ? idx + 1 : idx, xm = col >= 1 ? idx - 1 : idx;
+				const int yp = row + 1 < H ? idx + W : idx, ym = row >= 1 ? idx - W : idx;
+				const double ux = 0.5 * ((double) u[xp] - (double) u[xm]), vx = 0.5 * ((double) v[xp] - (double) v[xm]);
+				const double uy = 0.5 * ((double) u[yp] - (double) u[ym]), vy = 0.5 * ((double) v[yp] - (double) v[ym]);
+				if (p.smoothing_term_method == LSF_SMOOTHING_KILLING) {
+					const double jj = ux * ux + vx * vx + uy * uy + vy * vy;
+					const double jtj = ux * ux + uy * vx + vx * uy + vy * vy;
+					sums[1] = jj + (double) p.lambda * jtj;
+				} else {
+					sums[1] = 0.5 * ((ux * ux + vx * vx) + (uy * uy + vy * vy));
+				}
+			} else {
+				double aggregate = 0.0;
+#pragma unroll
+				for (int c = 0; c < 2; c++) {
+					const float* w = c == 0 ? u : v;
+					double d;
+					if (row == 0) d = (double) w[idx + W] - (double) w[idx];
+					else if (row == H - 1) d = (double) w[idx] - (double) w[idx - W];
+					else d = 0.5 * ((double) w[idx + W] - (double) w[idx - W]);
+					aggregate += d * d;
+					if (col == 0) d = (double) w[idx + 1] - (double) w[idx];
+					else if (col == W - 1) d = (double) w[idx] - (double) w[idx - 1];
+					else d = 0.5 * ((double) w[idx + 1] - (double) w[idx - 1]);
+					aggregate += d * d;
+				}
+				sums[1] = 0.5 * aggregate;
+			}
+		}
+	}
+	__shared__ double block_sums[8][3];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		double value = sums[k];
+#pragma unroll
+		for (int offset = 16; offset > 0; offset >>= 1) value += __shfl_xor_sync(0xffffffffu, value, offset);
+		if (lane == 0) block_sums[warp][k] = value;
+	}
+	__syncthreads();
+	if (threadIdx.x < 3) {
+		double total = 0.0;
+		for (int w = 0; w < 8; w++) total += block_sums[w][threadIdx.x];
+		const double weight = threadIdx.x == 0 ? p.data_weight : (threadIdx.x == 1 ? p.smoothing_weight : p.level_set_weight);
+		if (total != 0.0) atomicAdd(out + threadIdx.x, total * weight);
+	}
+}
+
 // ---------------------------------------------------------------------------------------------- Sobolev filter pass
 // reference convolve_with_kernel_preserve_zeros, cpp/src/math/convolution.cpp:23-67,69-145 (C++ rule) and
 // math_utils/convolution.py:114-132 (Python rule)

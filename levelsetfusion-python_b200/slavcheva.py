@@ -114,9 +114,10 @@ def _run(nd, live_field, canonical_field, semantics, data_term_method, smoothing
          sobolev_smoothing_enabled, gradient_descent_rate, data_term_weight, smoothing_term_weight,
          isomorphic_enforcement_factor, level_set_term_weight, lower, upper, maximum_iteration_count,
          minimum_iteration_count, sobolev_kernel, collect_statistics=False, capture_iterations=0,
-         log_iteration_statistics=False):
-    """One lsf_slavcheva_optimize[_logged] call. Returns an object with live, warp, report, max_warps, captured and
-    iteration_statistics (one WarpDeltaStatistics per iteration when log_iteration_statistics is set)."""
+         log_iteration_statistics=False, log_energies=False):
+    """One lsf_slavcheva_optimize[_logged] call. Returns an object with live, warp, report, max_warps, captured,
+    iteration_statistics (one WarpDeltaStatistics per iteration when log_iteration_statistics is set) and energies
+    ([iterations][3] float64: data, smoothing, level-set energy of every iteration when log_energies is set)."""
     on_device = _lib.is_torch_cuda(live_field) or _lib.is_torch_cuda(canonical_field)
     if on_device:
         import torch
@@ -180,11 +181,15 @@ def _run(nd, live_field, canonical_field, semantics, data_term_method, smoothing
     report = _lib.SlavchevaReport()
     dims = (ctypes.c_int * nd)(*shape)
     iteration_statistics = (_lib.WarpDeltaStatisticsRaw * capacity)() if log_iteration_statistics else None
+    energies = np.zeros((capacity, 3), dtype=np.float64) if log_energies else None
     _lib.check(_lib.load().lsf_slavcheva_optimize_logged(
         ctypes.byref(params), _pointer(live), _pointer(canonical), nd, dims, _pointer(live_out), _pointer(warp_out), kind,
         ctypes.byref(report), int(bool(collect_statistics)), _lib.fptr(max_warps), capacity, ctypes.byref(capture),
-        iteration_statistics, capacity if log_iteration_statistics else 0, stream))
+        iteration_statistics, capacity if log_iteration_statistics else 0,
+        None if energies is None else energies.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+        capacity if log_energies else 0, stream))
     result = _Result()
+    result.energies = None if energies is None else energies[:int(report.iteration_count)].copy()
     statistics_class = telemetry.WarpDeltaStatistics2d if nd == 2 else telemetry.WarpDeltaStatistics3d
     result.iteration_statistics = [] if iteration_statistics is None else \
         [statistics_class._from_raw(iteration_statistics[i]) for i in range(int(report.iteration_count))]
@@ -263,7 +268,8 @@ class SobolevOptimizer2d:
 
 
 class OptimizationLog:
-    """reference slavcheva_optimizer2d.py:58-64 (energies are not computed by this implementation)"""
+    """reference slavcheva_optimizer2d.py:58-64: per-iteration maximum warp lengths and the data / smoothing / level-set
+    energy aggregates (:370-374; GPU reductions, lsf_slavcheva_optimize_logged)"""
 
     def __init__(self):
         self.data_energies = []
@@ -288,7 +294,10 @@ class SlavchevaOptimizer2d:
                  data_term_weight=1.0, smoothing_term_weight=0.2, isomorphic_enforcement_factor=0.1,
                  level_set_term_weight=0.2, maximum_warp_length_lower_threshold=0.1,
                  maximum_warp_length_upper_threshold=10000, max_iterations=100, min_iterations=1, sobolev_kernel=None,
-                 visualization_settings=None, enable_convergence_status_logging=True):
+                 visualization_settings=None, enable_convergence_status_logging=True, log_energies=True):
+        # log_energies (extension): the reference always fills OptimizationLog's energy lists; False skips the per-iteration
+        # energy reductions and lets small fields take the single-launch path
+        self.log_energies = bool(log_energies)
         self.out_path = out_path
         self.field_size = field_size
         self.default_value = default_value
@@ -332,9 +341,14 @@ class SlavchevaOptimizer2d:
                       self.data_term_weight, self.smoothing_term_weight, self.isomorphic_enforcement_factor,
                       self.level_set_term_weight, self.maximum_warp_length_lower_threshold,
                       self.maximum_warp_length_upper_threshold, self.max_iterations, self.min_iterations, kernel,
-                      collect_statistics=self.enable_convergence_status_logging, capture_iterations=capture_iterations)
+                      collect_statistics=self.enable_convergence_status_logging, capture_iterations=capture_iterations,
+                      log_energies=self.log_energies)
         self.log = OptimizationLog()
         self.log.max_warps = [float(v) for v in result.max_warps]
+        if result.energies is not None:  # reference :370-374
+            self.log.data_energies = [float(v) for v in result.energies[:, 0]]
+            self.log.smoothing_energies = [float(v) for v in result.energies[:, 1]]
+            self.log.level_set_energies = [float(v) for v in result.energies[:, 2]]
         if self.enable_convergence_status_logging:
             self.log.convergence_report = result.report
         self._last = result

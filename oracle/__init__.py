@@ -313,7 +313,9 @@ def _dims(shape):
 
 def slavcheva_optimize(live, canonical, dump_iterations=0, **kwargs):
     """reference SobolevOptimizer2d.optimize(live, canonical) / SlavchevaOptimizer2d.optimize (+ 3D generalisation).
-    Returns dict(live, warp, iterations, max_warps, dump)."""
+    Returns dict(live, warp, iterations, max_warps, dump, energies); energies [iterations][3] = the {data, smoothing,
+    level set} energy aggregates the reference's Python optimizer appends to its log every iteration (2D, Python semantics;
+    zeros otherwise)."""
     live, canonical = _f32(live), _f32(canonical)
     assert live.shape == canonical.shape
     nd = live.ndim
@@ -330,14 +332,28 @@ def slavcheva_optimize(live, canonical, dump_iterations=0, **kwargs):
     if dump_iterations > 0:
         dump_buffer = np.zeros((dump_iterations,) + live.shape + (nd,), dtype=np.float32)
         dump.buffer = _p(dump_buffer)
-    status = lib().orc_slavcheva_optimize(ctypes.byref(p), _p(live), _p(canonical), nd, _dims(live.shape), _p(live_out),
-                                          _p(warp_out), ctypes.byref(iterations), _p(max_warps), capacity,
-                                          ctypes.byref(dump))
+    energies = np.zeros((capacity, 3), dtype=np.float64)
+    status = lib().orc_slavcheva_optimize_energies(ctypes.byref(p), _p(live), _p(canonical), nd, _dims(live.shape),
+                                                   _p(live_out), _p(warp_out), ctypes.byref(iterations), _p(max_warps),
+                                                   capacity, ctypes.byref(dump),
+                                                   energies.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), capacity)
     if status != 0:
         raise RuntimeError("oracle slavcheva optimizer precondition failed (status %d)" % status)
     return dict(live=live_out, warp=warp_out, iterations=int(iterations.value),
                 max_warps=max_warps[:iterations.value].copy(),
-                dump=None if dump_buffer is None else dump_buffer[:dump.count])
+                dump=None if dump_buffer is None else dump_buffer[:dump.count],
+                energies=energies[:iterations.value].copy())
+
+
+def slavcheva_energies(live, canonical, warp, **kwargs):
+    """{data, smoothing, level set} energy aggregates the reference's Python optimizer logs for an iteration that starts
+    from (live, warp) (slavcheva_optimizer2d.py:163-175,236-300); float64 array of 3."""
+    live, canonical, warp = _f32(live), _f32(canonical), _f32(warp)
+    p = make_slavcheva_params(**kwargs)
+    out = np.zeros(3, dtype=np.float64)
+    lib().orc_slavcheva_energies(ctypes.byref(p), _p(live), _p(canonical), _p(warp), live.ndim, _dims(live.shape),
+                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return out
 
 
 def slavcheva_data_term(live, canonical, band_union_only=False, **kwargs):

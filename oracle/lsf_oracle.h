@@ -127,6 +127,14 @@ typedef struct {
 int orc_slavcheva_optimize(const orc_slavcheva_params* p, const float* live, const float* canonical, int nd,
 		const int* dims, float* live_out, float* warp_out, int* iteration_count, float* max_warps, int max_warps_capacity,
 		orc_iteration_dump* dump);
+/* the same; energies [energies_capacity][3] (or NULL) receives the {data, smoothing, level set} energy aggregates the
+ * reference's Python optimizer logs for every iteration (2D, Python semantics; zeros otherwise) */
+int orc_slavcheva_optimize_energies(const orc_slavcheva_params* p, const float* live, const float* canonical, int nd,
+		const int* dims, float* live_out, float* warp_out, int* iteration_count, float* max_warps, int max_warps_capacity,
+		orc_iteration_dump* dump, double* energies, int energies_capacity);
+/* {data, smoothing, level set} energy aggregates of one state (live = warped live field, warp [dims][nd]) */
+void orc_slavcheva_energies(const orc_slavcheva_params* p, const float* live, const float* canonical, const float* warp,
+		int nd, const int* dims, double* out);
 void orc_slavcheva_data_term(const orc_slavcheva_params* p, const float* live, const float* canonical, int nd,
 		const int* dims, int band_union_only, float* out);
 void orc_slavcheva_smoothing_term(const orc_slavcheva_params* p, const float* warp, const float* live,

@@ -538,11 +538,106 @@ float slavcheva_iteration(const orc_slavcheva_params* p, const Geometry& g, cons
 
 }  // namespace
 
+namespace {
+
+// Energy aggregates of the reference's Python optimizer for the state an iteration starts from: what
+// SlavchevaOptimizer2d.total_data_energy / total_smoothing_energy / total_level_set_energy hold after the gradient pass
+// (appended to OptimizationLog every iteration, slavcheva_optimizer2d.py:370-374). 2D, Python semantics only:
+//   DIRECT     slavcheva_optimizer2d.py:236-300 with the local energies of data_term.py:185,225 (0.5 diff^2),
+//              level_set_term.py:63 (0.5 (|10 grad live| - 1)^2), smoothing_term.py:97-98 (Killing: J.J + lambda J^T.J) and
+//              :137-138 (Tikhonov: 0.5 (|w_x|^2 + |w_y|^2)), summed over the band union, each times its weight;
+//   VECTORIZED :163-175 with data_term.py:352-358 and smoothing_term.py:162-177 (np.gradient of the warp components).
+// Evaluated in double from the float32 fields (the reference mixes float32 locals and Python floats; compared at 1e-5).
+void slavcheva_energies(const orc_slavcheva_params* p, const Geometry& g, const float* live, const float* canonical,
+		const float* warp, double* out) {
+	out[0] = out[1] = out[2] = 0.0;
+	if (g.nd != 2 || p->semantics == ORC_SEMANTICS_CPP) return;
+	const Terms terms(p, g, live, canonical, warp);
+	const int ax_x = g.comp_axis[0], ax_y = g.comp_axis[1];
+	double data = 0.0, smoothing = 0.0, level_set = 0.0;
+	for (long idx = 0; idx < g.N; idx++) {
+		if (both_truncated(live[idx], canonical[idx])) continue;
+		int pos[3] = { 0, 0, 0 };
+		g.coords(idx, pos);
+		const double diff = (double) live[idx] - (double) canonical[idx];
+		data += 0.5 * diff * diff;
+		if (p->semantics == ORC_SEMANTICS_PY_DIRECT) {
+			if (p->level_set_term_enabled && !truncated(live[idx])) {
+				double grad[2];
+				for (int c = 0; c < 2; c++) {
+					int q[3] = { pos[0], pos[1], pos[2] };
+					const int a = g.comp_axis[c];
+					q[a] = pos[a] + 1;
+					const double plus = sample_or_one(g, live, q);
+					q[a] = pos[a] - 1;
+					const double minus = sample_or_one(g, live, q);
+					grad[c] = 0.5 * (plus - minus) * 10.0;
+				}
+				const double length = std::sqrt(grad[0] * grad[0] + grad[1] * grad[1]);
+				level_set += 0.5 * (length - 1.0) * (length - 1.0);
+			}
+			double wx[2], wy[2];  // d(u, v)/dx, d(u, v)/dy; neighbours outside the field = the centre value
+			for (int c = 0; c < 2; c++) {
+				int q[3] = { pos[0], pos[1], pos[2] };
+				q[ax_x] = pos[ax_x] + 1;
+				const double xp = terms.warp_or_centre(q, c, idx);
+				q[ax_x] = pos[ax_x] - 1;
+				const double xm = terms.warp_or_centre(q, c, idx);
+				q[ax_x] = pos[ax_x];
+				q[ax_y] = pos[ax_y] + 1;
+				const double yp = terms.warp_or_centre(q, c, idx);
+				q[ax_y] = pos[ax_y] - 1;
+				const double ym = terms.warp_or_centre(q, c, idx);
+				wx[c] = 0.5 * (xp - xm);
+				wy[c] = 0.5 * (yp - ym);
+			}
+			if (p->smoothing_term_method == ORC_SMOOTHING_KILLING) {
+				const double jj = wx[0] * wx[0] + wx[1] * wx[1] + wy[0] * wy[0] + wy[1] * wy[1];
+				const double jtj = wx[0] * wx[0] + wy[0] * wx[1] + wx[1] * wy[0] + wy[1] * wy[1];
+				smoothing += jj + (double) p->isomorphic_enforcement_factor * jtj;
+			} else {
+				smoothing += 0.5 * ((wx[0] * wx[0] + wx[1] * wx[1]) + (wy[0] * wy[0] + wy[1] * wy[1]));
+			}
+		} else {
+			double aggregate = 0.0;
+			for (int c = 0; c < 2; c++)
+				for (int a = 0; a < 2; a++) {
+					const long s = g.stride[a] * 2;
+					const float* w = warp + idx * 2 + c;
+					const int i = pos[a], n = g.n[a];
+					double d;
+					if (i == 0) d = (double) w[s] - (double) w[0];
+					else if (i == n - 1) d = (double) w[0] - (double) w[-s];
+					else d = 0.5 * ((double) w[s] - (double) w[-s]);
+					aggregate += d * d;
+				}
+			smoothing += 0.5 * aggregate;
+		}
+	}
+	out[0] = data * (double) p->data_term_weight;
+	out[1] = smoothing * (double) p->smoothing_term_weight;
+	out[2] = level_set * (double) p->level_set_term_weight;
+}
+
+}  // namespace
+
 extern "C" {
+
+int orc_slavcheva_optimize_energies(const orc_slavcheva_params* p, const float* live, const float* canonical, int nd,
+		const int* dims, float* live_out, float* warp_out, int* iteration_count, float* max_warps, int max_warps_capacity,
+		orc_iteration_dump* dump, double* energies, int energies_capacity);
 
 int orc_slavcheva_optimize(const orc_slavcheva_params* p, const float* live, const float* canonical, int nd,
 		const int* dims, float* live_out, float* warp_out, int* iteration_count, float* max_warps, int max_warps_capacity,
 		orc_iteration_dump* dump) {
+	return orc_slavcheva_optimize_energies(p, live, canonical, nd, dims, live_out, warp_out, iteration_count, max_warps,
+			max_warps_capacity, dump, nullptr, 0);
+}
+
+/* the same; energies [energies_capacity][3] (or NULL) receives {data, smoothing, level set} energy of every iteration */
+int orc_slavcheva_optimize_energies(const orc_slavcheva_params* p, const float* live, const float* canonical, int nd,
+		const int* dims, float* live_out, float* warp_out, int* iteration_count, float* max_warps, int max_warps_capacity,
+		orc_iteration_dump* dump, double* energies, int energies_capacity) {
 	if (nd != 2 && nd != 3) return -1;
 	for (int a = 0; a < nd; a++)
 		if (dims[a] < 2) return -2;
@@ -564,6 +659,8 @@ int orc_slavcheva_optimize(const orc_slavcheva_params* p, const float* live, con
 	};
 	max_warp = p->semantics == ORC_SEMANTICS_CPP ? upper - 1.0f : INFINITY;  // sobolev_optimizer2d.cpp:77; .py:339
 	while (!finished()) {
+		if (energies && iteration < energies_capacity)
+			slavcheva_energies(p, g, s.live.data(), canonical, s.warp.data(), energies + 3 * (size_t) iteration);
 		max_warp = slavcheva_iteration(p, g, canonical, s);
 		if (max_warps && iteration < max_warps_capacity) max_warps[iteration] = max_warp;
 		if (dump && dump->buffer && iteration < dump->max_iterations) {
@@ -579,6 +676,12 @@ int orc_slavcheva_optimize(const orc_slavcheva_params* p, const float* live, con
 }
 
 /* single steps, exposed so the golden vectors of the reference's unit tests can pin them */
+void orc_slavcheva_energies(const orc_slavcheva_params* p, const float* live, const float* canonical, const float* warp,
+		int nd, const int* dims, double* out) {
+	const Geometry g(nd, dims);
+	slavcheva_energies(p, g, live, canonical, warp, out);
+}
+
 void orc_slavcheva_data_term(const orc_slavcheva_params* p, const float* live, const float* canonical, int nd,
 		const int* dims, int band_union_only, float* out) {
 	const Geometry g(nd, dims);

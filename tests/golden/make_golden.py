@@ -300,6 +300,10 @@ def collect_slavcheva_runs():
             fdm[y, x] = dt.compute_local_data_term_gradient_thresholded_fdm(live, canonical, x, y, gx, gy)[0]
     out["terms/data_basic"] = basic
     out["terms/data_thresholded_fdm"] = fdm
+    # energy aggregates of ComputeMethod.VECTORIZED (slavcheva_optimizer2d.py:169-175; the run itself needs the C++ extension)
+    # on the same random fields: [data energy, smoothing energy] before the weights
+    out["terms/vectorized_energies"] = np.array([dt.compute_data_term_energy_contribution(live.copy(), canonical),
+                                                 st.compute_smoothing_term_energy(warp, live, canonical)], dtype=np.float64)
 
     # ---- optimizer runs (32x32 synthetic pair, 7-tap Sobolev kernel of the reference)
     import math_utils.convolution as mc
@@ -337,6 +341,10 @@ def collect_slavcheva_runs():
                     optimizer.optimize(field, canonical.copy())
                 out["runs/%s/live_after_%d" % (tag, iterations)] = field.astype(np.float32)
                 out["runs/%s/max_warps_%d" % (tag, iterations)] = np.array(optimizer.log.max_warps, dtype=np.float32)
+                # OptimizationLog energies (slavcheva_optimizer2d.py:370-374): one row per iteration
+                out["runs/%s/energies_%d" % (tag, iterations)] = np.array(
+                    [optimizer.log.data_energies, optimizer.log.smoothing_energies, optimizer.log.level_set_energies],
+                    dtype=np.float64).T
     return out
 
 

@@ -243,6 +243,15 @@ def test_slavcheva3d_vs_oracle(lsf, terms):
     run_both(lsf, 3, 0, live, canonical, iterations=5, kernel=KERNEL3, **TERM_CASES[terms])
 
 
+ORACLE_RUN_CASES = {
+    "tikhonov_sobolev": dict(smoothing_term_method=0, level_set_term_enabled=False, sobolev_smoothing_enabled=True),
+    "killing_levelset_sobolev": dict(smoothing_term_method=1, level_set_term_enabled=True, sobolev_smoothing_enabled=True),
+    "killing_levelset_plain": dict(smoothing_term_method=1, level_set_term_enabled=True, sobolev_smoothing_enabled=False),
+    "fdm_tikhonov_sobolev": dict(smoothing_term_method=0, data_term_method=1, level_set_term_enabled=False,
+                                 sobolev_smoothing_enabled=True),
+}
+
+
 def test_python_direct_runs(lsf, runs):
     """whole runs of the reference's Python SlavchevaOptimizer2d (DIRECT): tolerance as in tests/test_oracle_slavcheva.py"""
     canonical, live, kernel = runs["runs/canonical"], runs["runs/live"], runs["runs/kernel7"]
@@ -264,6 +273,31 @@ def test_python_direct_runs(lsf, runs):
             assert np.abs(field - runs["runs/%s/live_after_%d" % (tag, iterations)]).max() <= 2e-5
             assert np.allclose(optimizer.log.max_warps, runs["runs/%s/max_warps_%d" % (tag, iterations)], rtol=1e-5,
                                atol=1e-6)
+            # OptimizationLog energies (reference slavcheva_optimizer2d.py:370-374): the reference's log at 3e-5 (it adds
+            # float32 terms up sequentially), the oracle's double sums at 1e-9
+            logged = np.array([optimizer.log.data_energies, optimizer.log.smoothing_energies,
+                               optimizer.log.level_set_energies]).T
+            assert np.allclose(logged, runs["runs/%s/energies_%d" % (tag, iterations)], rtol=3e-5, atol=1e-7)
+            expected = oracle.slavcheva_optimize(live, canonical, semantics=oracle.SEMANTICS_PY_DIRECT,
+                                                 max_iterations=iterations, maximum_warp_length_lower_threshold=0.001,
+                                                 sobolev_kernel=kernel, **ORACLE_RUN_CASES[tag])
+            assert np.allclose(logged, expected["energies"], rtol=1e-9, atol=1e-12)
+            # without the log the run takes the single-launch path: same field
+            quiet = lsf.SlavchevaOptimizer2d(field_size=32, compute_method=lsf.ComputeMethod.DIRECT,
+                                             maximum_warp_length_lower_threshold=0.001, max_iterations=iterations,
+                                             sobolev_kernel=kernel, enable_convergence_status_logging=False,
+                                             log_energies=False, **kwargs)
+            assert np.array_equal(quiet.optimize(live.copy(), canonical), field) and quiet.log.data_energies == []
+    # ComputeMethod.VECTORIZED logs the aggregates of slavcheva_optimizer2d.py:169-175 (level-set energy stays 0)
+    optimizer = lsf.SlavchevaOptimizer2d(field_size=32, compute_method=lsf.ComputeMethod.VECTORIZED,
+                                         maximum_warp_length_lower_threshold=0.001, max_iterations=4, sobolev_kernel=kernel,
+                                         sobolev_smoothing_enabled=True, enable_convergence_status_logging=False)
+    optimizer.optimize(live.copy(), canonical)
+    expected = oracle.slavcheva_optimize(live, canonical, semantics=oracle.SEMANTICS_PY_VECTORIZED, max_iterations=4,
+                                         maximum_warp_length_lower_threshold=0.001, sobolev_kernel=kernel)
+    logged = np.array([optimizer.log.data_energies, optimizer.log.smoothing_energies, optimizer.log.level_set_energies]).T
+    assert logged.shape == (4, 3) and np.allclose(logged, expected["energies"], rtol=1e-9, atol=1e-12)
+    assert logged[1:, 1].min() > 0 and not logged[:, 2].any()
 
 
 def test_degenerate_volume_reproduces_2d(lsf):

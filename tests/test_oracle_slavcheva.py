@@ -150,6 +150,27 @@ def test_python_direct_runs(runs, tag):
         assert result["iterations"] == iterations
         assert np.abs(result["live"] - runs["runs/%s/live_after_%d" % (tag, iterations)]).max() <= 2e-5
         assert np.allclose(result["max_warps"], runs["runs/%s/max_warps_%d" % (tag, iterations)], rtol=1e-5, atol=1e-6)
+        # OptimizationLog.data_energies / smoothing_energies / level_set_energies (slavcheva_optimizer2d.py:370-374): the
+        # reference adds float32 terms up sequentially (1.2e-5 off the exact sum at iteration 0), the oracle in double
+        expected = runs["runs/%s/energies_%d" % (tag, iterations)]
+        assert result["energies"].shape == expected.shape == (iterations, 3)
+        assert np.allclose(result["energies"], expected, rtol=3e-5, atol=1e-7)
+        assert (expected[:, 2] > 0).all() == bool(PYTHON_RUN_CASES[tag]["level_set_term_enabled"])
+
+
+def test_vectorized_energy_aggregates(runs):
+    """ComputeMethod.VECTORIZED (slavcheva_optimizer2d.py:169-175): data_term.py:352-358 and smoothing_term.py:162-177
+    (np.gradient of the warp components over the band union) evaluated by the reference on random 9 x 9 fields"""
+    warp, live, canonical = runs["terms/warp"], runs["terms/live"], runs["terms/canonical"]
+    energies = oracle.slavcheva_energies(live, canonical, warp, semantics=oracle.SEMANTICS_PY_VECTORIZED,
+                                         data_term_weight=1.0, smoothing_term_weight=1.0)
+    assert np.allclose(energies[:2], runs["terms/vectorized_energies"], rtol=1e-6)
+    assert energies[2] == 0.0
+    weighted = oracle.slavcheva_energies(live, canonical, warp, semantics=oracle.SEMANTICS_PY_VECTORIZED,
+                                         data_term_weight=2.0, smoothing_term_weight=0.25)
+    assert np.allclose(weighted[:2], runs["terms/vectorized_energies"] * [2.0, 0.25], rtol=1e-6)
+    # the C++ optimizer keeps no energy log (sobolev_optimizer2d.cpp:121-138 drops them): zeros
+    assert not oracle.slavcheva_energies(live, canonical, warp, semantics=oracle.SEMANTICS_CPP).any()
 
 
 # ----------------------------------------------------------------------------- 3D generalisation
