@@ -602,7 +602,8 @@ class SlabHierarchicalOptimizer3d:
         """Runs `world_size` virtual ranks on the current GPU and returns the assembled warp field [X, Y, Z, 3] (numpy).
         Verifies the decomposition without a multi-GPU box. exchange="local": one stream, halos copied between the ranks'
         tensors; "peer": one stream per rank and the peer-memory exchange kernel (PeerExchange) -- the ranks wait for each
-        other on the device exactly like the GPUs of a box do."""
+        other on the device exactly like the GPUs of a box do. (The virtual ranks need their kernels to run concurrently on
+        the one GPU: under tools that serialise kernels, e.g. compute-sanitizer, the waits time out and the call raises.)"""
         import torch
         canonical = torch.as_tensor(np.ascontiguousarray(canonical_field, dtype=np.float32))
         live = torch.as_tensor(np.ascontiguousarray(live_field, dtype=np.float32))
