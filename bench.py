@@ -447,9 +447,21 @@ def killingfusion_iteration(lsf_b200, canonical, live, size, peak, iterations=10
     per_iteration = (run(3 * iterations) - run(iterations)) / (2 * iterations)
     updates = size ** 3 / (per_iteration * 1e-3)
     achieved = 36 * updates / 1e9
-    return {"ms_per_iteration": round(per_iteration, 4), "value": updates, "unit": UNIT,
-            "terms": "data + Killing + level set, 7-tap Sobolev filter, masked re-warp",
-            "algorithmic_bytes_per_voxel_update": 36, "achieved": round(achieved, 1), "frac": round(achieved / peak, 4)}
+    # the default path iterates over the narrow band only: the compulsory bytes of a band-only iteration beside the dense
+    # 36 B definition of SURVEY.md 8(d), and the DRAM traffic ncu measured for the four brick kernels of one iteration
+    band_fraction = float((~((live.abs() == 1.0) & (canonical.abs() == 1.0))).float().mean())
+    band_bytes = 36 * band_fraction * size ** 3
+    out = {"ms_per_iteration": round(per_iteration, 4), "value": updates, "unit": UNIT,
+           "terms": "data + Killing + level set, 7-tap Sobolev filter, masked re-warp",
+           "algorithmic_bytes_per_voxel_update": 36, "achieved": round(achieved, 1), "frac": round(achieved / peak, 4),
+           "band_fraction": round(band_fraction, 4), "band_only_compulsory_bytes": int(band_bytes),
+           "achieved_band_only": round(band_bytes / (per_iteration * 1e-3) / 1e9, 1),
+           "frac_band_only": round(band_bytes / (per_iteration * 1e-3) / 1e9 / peak, 4)}
+    if size == 256:
+        out["traffic"] = 504100000
+        out["traffic_source"] = ("profiles/r2_ncu_headline.md, gpurun_out/r2f/killing.ncu-rep: terms 166.6 + filter passes 85.3 + "
+                                 "81.9 + axis 2 / re-warp 170.3 MB of DRAM reads + writes per iteration")
+    return out
 
 
 def tsdf_generation(lsf_b200, size, peak, repeats=20):

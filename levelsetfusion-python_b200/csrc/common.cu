@@ -4,6 +4,9 @@
 #include <algorithm>
 #include <cstring>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <unistd.h>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -26,6 +29,26 @@ void set_error(const char* fmt, ...) {
 	g_last_error = buffer;
 	// the reference prints assertion messages to stderr as well (error_handling/throw_assert.hpp:67-74)
 	fprintf(stderr, "[lsf_b200] %s\n", buffer);
+}
+
+// ---------------------------------------------------------------------------------------------- host-side trace
+// LSF_TRACE=1: host time between labelled points of a call, printed to stderr at the point named "end" (where does a
+// launch-bound call spend its time: allocation, staging, enqueueing or waiting)
+void trace_point(const char* label) {
+	static const bool enabled = []() {
+		const char* e = getenv("LSF_TRACE");
+		return e && e[0] == '1';
+	}();
+	if (!enabled) return;
+	static thread_local std::vector<std::pair<const char*, std::chrono::steady_clock::time_point>> points;
+	points.emplace_back(label, std::chrono::steady_clock::now());
+	if (std::strcmp(label, "end") != 0) return;
+	fprintf(stderr, "[lsf_b200 trace]");
+	for (size_t i = 1; i < points.size(); i++)
+		fprintf(stderr, " %s %.1f us |", points[i].first,
+				std::chrono::duration<double, std::micro>(points[i].second - points[i - 1].second).count());
+	fprintf(stderr, " total %.1f us\n", std::chrono::duration<double, std::micro>(points.back().second - points.front().second).count());
+	points.clear();
 }
 
 // ---------------------------------------------------------------------------------------------- scratch memory
@@ -119,35 +142,82 @@ bool is_pageable(const void* host) {
 	return attributes.type == cudaMemoryTypeUnregistered;
 }
 
-// memcpy on several threads (first-touch page faults of a fresh destination array are spread over the threads too)
-void parallel_copy(void* dst, const void* src, size_t bytes) {
-	// up to 8 threads; with several ranks on the host (torchrun exports LOCAL_WORLD_SIZE) each rank takes its share of the
-	// cores -- all ranks stage their inputs at the same time; LSF_COPY_THREADS overrides
-	static const unsigned workers = []() {
+// memcpy on several threads (first-touch page faults of a fresh destination array are spread over the threads too).
+// The workers are started once and sleep between copies: spawning threads per 32 MB chunk cost ~1 ms per optimize().
+class CopyPool {
+public:
+	static CopyPool& instance() {
+		static CopyPool* pool = new CopyPool();  // never destroyed: the workers may outlive static destruction
+		return *pool;
+	}
+	// the worker threads live in the process that created the pool: a forked child copies on its own thread
+	unsigned workers() const {
+		return getpid() == owner_ ? worker_count_ : 1;
+	}
+	// copies [0, bytes) in `worker_count_` slices; the caller takes slice 0
+	void copy(void* dst, const void* src, size_t bytes) {
+		std::lock_guard<std::mutex> serialise(callers_);  // one copy at a time (callers of different threads queue up)
+		const size_t slice = ((bytes / worker_count_) + 4095) & ~(size_t) 4095;
+		{
+			std::lock_guard<std::mutex> lock(mutex_);
+			dst_ = static_cast<unsigned char*>(dst);
+			src_ = static_cast<const unsigned char*>(src);
+			bytes_ = bytes;
+			slice_ = slice;
+			pending_ = worker_count_ - 1;
+			generation_++;
+		}
+		wake_.notify_all();
+		std::memcpy(dst, src, std::min(slice, bytes));
+		std::unique_lock<std::mutex> lock(mutex_);
+		done_.wait(lock, [&]() { return pending_ == 0; });
+	}
+
+private:
+	CopyPool() {
 		unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+		// with several ranks on the host (torchrun exports LOCAL_WORLD_SIZE) each rank takes its share of the cores -- all
+		// ranks stage their inputs at the same time; LSF_COPY_THREADS overrides
 		const char* local_world = getenv("LOCAL_WORLD_SIZE");
 		if (local_world && atoi(local_world) > 1) cores = std::max(1u, cores / (unsigned) atoi(local_world));
-		unsigned n = std::min(8u, cores);
+		worker_count_ = std::min(8u, cores);
 		const char* fixed = getenv("LSF_COPY_THREADS");
-		if (fixed && atoi(fixed) >= 1) n = std::min(64u, (unsigned) atoi(fixed));
-		return n;
-	}();
-	if (bytes < (4u << 20) || workers == 1) {
+		if (fixed && atoi(fixed) >= 1) worker_count_ = std::min(64u, (unsigned) atoi(fixed));
+		for (unsigned w = 1; w < worker_count_; w++) std::thread([this, w]() { run(w); }).detach();
+	}
+	void run(unsigned w) {
+		unsigned long long seen = 0;
+		for (;;) {
+			std::unique_lock<std::mutex> lock(mutex_);
+			wake_.wait(lock, [&]() { return generation_ != seen; });
+			seen = generation_;
+			unsigned char* dst = dst_;
+			const unsigned char* src = src_;
+			const size_t begin = w * slice_, bytes = bytes_, slice = slice_;
+			lock.unlock();
+			if (begin < bytes) std::memcpy(dst + begin, src + begin, std::min(slice, bytes - begin));
+			lock.lock();
+			if (--pending_ == 0) done_.notify_one();
+		}
+	}
+	std::mutex callers_, mutex_;
+	std::condition_variable wake_, done_;
+	unsigned worker_count_ = 1;
+	const pid_t owner_ = getpid();
+	unsigned char* dst_ = nullptr;
+	const unsigned char* src_ = nullptr;
+	size_t bytes_ = 0, slice_ = 0;
+	unsigned pending_ = 0;
+	unsigned long long generation_ = 0;
+};
+
+void parallel_copy(void* dst, const void* src, size_t bytes) {
+	CopyPool& pool = CopyPool::instance();
+	if (bytes < (4u << 20) || pool.workers() == 1) {
 		std::memcpy(dst, src, bytes);
 		return;
 	}
-	const size_t slice = ((bytes / workers) + 4095) & ~(size_t) 4095;
-	std::vector<std::thread> threads;
-	for (unsigned w = 1; w < workers; w++) {
-		const size_t begin = w * slice;
-		if (begin >= bytes) break;
-		const size_t length = std::min(slice, bytes - begin);
-		threads.emplace_back([=]() {
-			std::memcpy(static_cast<unsigned char*>(dst) + begin, static_cast<const unsigned char*>(src) + begin, length);
-		});
-	}
-	std::memcpy(dst, src, std::min(slice, bytes));
-	for (auto& t : threads) t.join();
+	pool.copy(dst, src, bytes);
 }
 
 }  // namespace

@@ -19,6 +19,9 @@ namespace lsf {
 // ---------------------------------------------------------------------------------------------- errors
 void set_error(const char* fmt, ...);
 
+// LSF_TRACE=1: host time between labelled points of a call (printed at the point named "end")
+void trace_point(const char* label);
+
 // Kernel-launch accounting (bench.py's `gpu_launches`): every launch site reports how many kernels it enqueued.
 void count_launches(int n);
 // wraps the grid argument of every <<<...>>> launch: counts the launch and passes the grid through

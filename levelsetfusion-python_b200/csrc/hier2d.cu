@@ -230,6 +230,7 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 	Plan2 plan;
 	LSF_TRY(make_plan(params, H, W, &plan));
 	LSF_REQUIRE(canonical && live && warp_out, "canonical, live and warp_out must not be NULL");
+	trace_point("begin");
 	const int L = plan.level_count;
 	const Grid2 finest = plan.level_grid[L - 1];
 	const size_t N = (size_t) finest.N;
@@ -239,6 +240,7 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 	LSF_TRY(to_device(arena, live, N, memory_kind, stream, &live_dev));
 	float* out_dev = warp_out;
 	if (memory_kind == LSF_HOST) LSF_TRY(arena.alloc(&out_dev, N * 2));
+	trace_point("inputs");
 
 	// pyramids (reference pyramid.tpp:51-74): live + its full-resolution gradient restricted together
 	std::vector<float4*> packs(L, nullptr);
@@ -270,6 +272,7 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 		}
 	}
 	LSF_CUDA(cudaGetLastError());
+	trace_point("pyramid");
 
 	float *warp_current, *warp_next, *g_post, *scratch_a;
 	unsigned* max_sq_bits;
@@ -331,10 +334,12 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 			LSF_CUDA(cudaGetLastError());
 			LSF_CUDA(cudaMemcpyAsync(host_bits.data() + enqueued, max_sq_bits + enqueued,
 					(size_t) (chunk_end - enqueued) * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+			trace_point("enqueued");
 			LSF_CUDA(cudaStreamSynchronize(stream));
 			for (int it = enqueued; it < chunk_end; it++) {
 				float sq;
 				std::memcpy(&sq, &host_bits[it], sizeof(float));
+				if (it == enqueued) trace_point("level waited");
 				last_max = std::sqrt(sq);
 				executed = it + 1;
 				if (last_max < plan.threshold) {
@@ -388,6 +393,7 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 	}
 	k_planes_to_aos<<<counted(div_up(finest.N, 256)), 256, 0, stream>>>(warp_current, out_dev, finest.N, 2);
 	LSF_CUDA(cudaGetLastError());
+	trace_point("levels done");
 	if (memory_kind == LSF_HOST) {
 		if (capture_dev)
 			LSF_CUDA(cudaMemcpyAsync(capture->buffer, capture_dev,
@@ -395,6 +401,8 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 					cudaMemcpyDeviceToHost, stream));
 		LSF_TRY(from_device(out_dev, warp_out, N * 2, LSF_HOST, stream));
 	}
+	trace_point("result");
+	trace_point("end");
 	return L;
 }
 

@@ -153,6 +153,7 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 	std::vector<unsigned> host_bits((size_t) bound + 1, 0);
 	bool finished = host_finished(p, 0, max_iterations, initial_max) || bound == 0;
 	int enqueued = 0;
+	trace_point("buffers");
 	const unsigned blocks = blocks_for(g.N);
 	unsigned char* band_dead = nullptr;
 	int *band_list = nullptr, *band_positions = nullptr, *band_counts = nullptr, *leave_list = nullptr, *leave_counts = nullptr;
@@ -431,11 +432,13 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 					stream));
 		}
 		LSF_CUDA(cudaGetLastError());
+		trace_point("chunk enqueued");
 		LSF_CUDA(cudaMemcpyAsync(host_status.data() + enqueued + 1, status + enqueued + 1,
 				(size_t) (chunk_end - enqueued) * sizeof(int), cudaMemcpyDeviceToHost, stream));
 		LSF_CUDA(cudaMemcpyAsync(host_bits.data() + enqueued, max_sq_bits + enqueued,
 				(size_t) (chunk_end - enqueued) * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
 		LSF_CUDA(cudaStreamSynchronize(stream));
+		trace_point("chunk waited");
 		for (int it = enqueued; it < chunk_end && !finished; it++) {
 			float sq;
 			std::memcpy(&sq, &host_bits[it], sizeof(float));
@@ -524,10 +527,12 @@ extern "C" int lsf_slavcheva_optimize_logged(const lsf_slavcheva_params* params,
 	const bool use_kernel = params->sobolev_smoothing_enabled && params->sobolev_kernel && params->sobolev_kernel_size > 0;
 	if (use_kernel) LSF_TRY(make_taps(params->sobolev_kernel, params->sobolev_kernel_size, &taps));
 	const size_t N = (size_t) g.N;
+	trace_point("begin");
 	Arena arena(stream);
 	const float *live_dev, *canonical_dev;
 	LSF_TRY(to_device(arena, live, N, memory_kind, stream, &live_dev));
 	LSF_TRY(to_device(arena, canonical, N, memory_kind, stream, &canonical_dev));
+	trace_point("inputs");
 	float *live_out_dev = live_out, *warp_out_dev = warp_out, *capture_dev = nullptr;
 	if (memory_kind == LSF_HOST) {
 		LSF_TRY(arena.alloc(&live_out_dev, N));
@@ -546,6 +551,7 @@ extern "C" int lsf_slavcheva_optimize_logged(const lsf_slavcheva_params* params,
 		LSF_TRY(optimize_device<3>(params, g, taps, use_kernel, live_dev, canonical_dev, live_out_dev, warp_out_dev, report,
 				collect_statistics, max_warps, max_warps_capacity, capture, capture_dev, arena, stream, iteration_statistics,
 				iteration_statistics_capacity));
+	trace_point("optimized");
 	if (memory_kind == LSF_HOST) {
 		if (capture_dev && capture->count > 0)
 			LSF_CUDA(cudaMemcpyAsync(capture->buffer, capture_dev, (size_t) capture->count * N * nd * sizeof(float),
@@ -554,6 +560,8 @@ extern "C" int lsf_slavcheva_optimize_logged(const lsf_slavcheva_params* params,
 			LSF_CUDA(cudaMemcpyAsync(warp_out, warp_out_dev, N * nd * sizeof(float), cudaMemcpyDeviceToHost, stream));
 		LSF_TRY(from_device(live_out_dev, live_out, N, LSF_HOST, stream));
 	}
+	trace_point("result");
+	trace_point("end");
 	return LSF_OK;
 }
 

@@ -258,6 +258,15 @@ def test_hier2d_single_launch_levels_vs_oracle(lsf, mode):
         assert np.array_equal(plain, warp)
         assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
         assert launches < plain_launches / 2, (launches, plain_launches)
+        # levels of up to 16 K pixels run in one thread-block cluster (cluster barrier); LSF_HIER2D_CLUSTER=0 = the same
+        # kernel as a cooperative grid (grid barrier)
+        os.environ["LSF_HIER2D_CLUSTER"] = "0"
+        try:
+            cooperative = optimizer.optimize(c, l)
+        finally:
+            del os.environ["LSF_HIER2D_CLUSTER"]
+        assert np.array_equal(cooperative, warp)
+        assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
 
 
 def test_hier2d_python_reference_runs(lsf, python_runs):

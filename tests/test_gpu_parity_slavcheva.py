@@ -197,6 +197,15 @@ def run_single_launch(lsf, semantics, live, canonical, iterations=12, lower=0.01
         del os.environ["LSF_SLAV_PERSISTENT"]
     assert plain.iteration_count == result.iteration_count
     assert np.array_equal(plain.live, result.live) and np.array_equal(plain.warp, result.warp)
+    # fields of up to 16 K voxels run in one thread-block cluster (cluster barrier); LSF_SLAV_CLUSTER=0 = the same kernel
+    # as a cooperative grid (grid barrier)
+    os.environ["LSF_SLAV_CLUSTER"] = "0"
+    try:
+        cooperative, _ = run()
+    finally:
+        del os.environ["LSF_SLAV_CLUSTER"]
+    assert cooperative.iteration_count == result.iteration_count
+    assert np.array_equal(cooperative.live, result.live) and np.array_equal(cooperative.warp, result.warp)
     if result.iteration_count >= 4:
         assert launches < plain_launches / 2, (launches, plain_launches)
     return result
