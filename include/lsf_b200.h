@@ -289,6 +289,11 @@ int lsf_upsample_2d(const float* field, int channels, int H, int W, int linear, 
 /* reference: math::locate_max_norm, cpp/src/math/statistics.tpp:57-100 */
 int lsf_max_norm(const float* vfield, int channels, long long count, float* max_norm_out, int memory_kind,
 		void* stream);
+/* the same with the location of the longest vector. vfield: [H][W][channels] (nd 2) or [X][Y][Z][channels] (nd 3);
+ * coordinates_out[3]: nd 2 -> (x, y) as statistics.tpp:70-71 decodes them (column, row of a square field), nd 3 -> (x, y, z);
+ * among equal maxima the element the reference's traversal order meets first */
+int lsf_locate_max_norm(const float* vfield, int channels, int nd, const int* dims, float* max_norm_out,
+		int* coordinates_out, int memory_kind, void* stream);
 
 /* ---------------------------------------------------------------- SobolevFusion / KillingFusion ("slavcheva") optimizers
  * reference: SobolevOptimizer2d::optimize(live_field, canonical_field) -> warped live field,

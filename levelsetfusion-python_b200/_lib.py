@@ -216,7 +216,7 @@ EXPORTED_SYMBOLS = [
     "lsf_hier_optimize_3d", "lsf_hier_optimize_2d", "lsf_hier_optimize_3d_batch", "lsf_hier_iterate_3d",
     "lsf_warp_3d", "lsf_warp_2d", "lsf_gradient_3d", "lsf_gradient_2d", "lsf_laplacian_3d", "lsf_laplacian_2d",
     "lsf_convolve_3d", "lsf_convolve_2d", "lsf_downsample_3d", "lsf_upsample_3d", "lsf_downsample_2d",
-    "lsf_upsample_2d", "lsf_max_norm",
+    "lsf_upsample_2d", "lsf_max_norm", "lsf_locate_max_norm",
     "lsf_hier_slab_iteration", "lsf_slab_pack_finest", "lsf_slab_restrict", "lsf_slab_prolong_nearest",
     "lsf_debug_last_path", "lsf_hier_optimize_3d_telemetry", "lsf_hier_optimize_2d_telemetry",
     "lsf_slavcheva_optimize", "lsf_slavcheva_optimize_logged", "lsf_warp_advanced", "lsf_warp_delta_statistics", "lsf_tsdf_difference_statistics",

@@ -341,3 +341,74 @@ extern "C" int lsf_max_norm(const float* vfield, int channels, long long count, 
 	*max_norm_out = sqrtf(sq);
 	return LSF_OK;
 }
+
+// maximum vector length WITH its location (reference math::locate_max_norm, cpp/src/math/statistics.tpp:57-100): the key
+// (bits of the squared length << 32 | ~order) makes one atomicMax return the maximum and, among equal maxima, the element
+// the reference's traversal meets first (its strict `>` keeps the first one). order = index in the reference's
+// column-major element order: 2D [H][W] field c * H + r, 3D [X][Y][Z] field x + X * (y + Y * z).
+namespace lsf {
+namespace {
+
+__global__ void __launch_bounds__(256) k_locate_max_norm(const float* __restrict__ vfield, int channels, int nd, int d0, int d1,
+		int d2, unsigned long long* __restrict__ best_key) {
+	const long long n = (long long) d0 * d1 * d2;
+	unsigned long long best = 0;
+	for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+		float sq = 0.0f;
+		for (int c = 0; c < channels; c++) sq += vfield[i * channels + c] * vfield[i * channels + c];
+		if (!(sq >= 0.0f)) continue;  // NaN: never greater than the running maximum
+		unsigned order;
+		if (nd == 2) order = (unsigned) ((i % d1) * d0 + i / d1);
+		else {
+			const long long z = i % d2, y = (i / d2) % d1, x = i / ((long long) d1 * d2);
+			order = (unsigned) (x + (long long) d0 * (y + (long long) d1 * z));
+		}
+		const unsigned long long key = ((unsigned long long) __float_as_uint(sq) << 32) | (0xffffffffu - order);
+		best = key > best ? key : best;
+	}
+#pragma unroll
+	for (int offset = 16; offset > 0; offset >>= 1) {
+		const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, offset);
+		best = other > best ? other : best;
+	}
+	if ((threadIdx.x & 31) == 0) atomicMax(best_key, best);
+}
+
+}  // namespace
+}  // namespace lsf
+
+extern "C" int lsf_locate_max_norm(const float* vfield, int channels, int nd, const int* dims, float* max_norm_out,
+		int* coordinates_out, int memory_kind, void* stream_handle) {
+	LSF_REQUIRE(channels > 0 && (nd == 2 || nd == 3) && dims && vfield && max_norm_out && coordinates_out, "invalid arguments");
+	const int d0 = dims[0], d1 = dims[1], d2 = nd == 3 ? dims[2] : 1;
+	LSF_REQUIRE(d0 > 0 && d1 > 0 && d2 > 0 && (long long) d0 * d1 * d2 < (1ll << 32), "invalid field dimensions");
+	const long long count = (long long) d0 * d1 * d2;
+	Staged st(stream_handle, memory_kind);
+	const float* in_dev;
+	unsigned long long* key;
+	LSF_TRY(st.in(vfield, (size_t) count * channels, &in_dev));
+	LSF_TRY(st.arena.alloc(&key, 1));
+	LSF_CUDA(cudaMemsetAsync(key, 0, sizeof(unsigned long long), st.stream));
+	const unsigned blocks = (unsigned) std::min<long long>(blocks_for(count), 148 * 8);
+	k_locate_max_norm<<<counted(blocks), 256, 0, st.stream>>>(in_dev, channels, nd, d0, d1, d2, key);
+	LSF_CUDA(cudaGetLastError());
+	unsigned long long host_key = 0;
+	LSF_CUDA(cudaMemcpyAsync(&host_key, key, sizeof(host_key), cudaMemcpyDeviceToHost, st.stream));
+	LSF_CUDA(cudaStreamSynchronize(st.stream));
+	const unsigned bits = (unsigned) (host_key >> 32);
+	float sq;
+	memcpy(&sq, &bits, sizeof(float));
+	*max_norm_out = sqrtf(sq);
+	const unsigned order = 0xffffffffu - (unsigned) (host_key & 0xffffffffull);
+	if (nd == 2) {
+		// statistics.tpp:70-71: x = i_element / column_count, y = i_element % column_count (= column, row of a square field)
+		coordinates_out[0] = (int) (order / (unsigned) d1);
+		coordinates_out[1] = (int) (order % (unsigned) d1);
+		coordinates_out[2] = 0;
+	} else {
+		coordinates_out[0] = (int) (order % (unsigned) d0);
+		coordinates_out[1] = (int) ((order / (unsigned) d0) % (unsigned) d1);
+		coordinates_out[2] = (int) (order / ((unsigned) d0 * (unsigned) d1));
+	}
+	return LSF_OK;
+}

@@ -103,16 +103,17 @@ def get_mean_iteration_count_for_level(data_frame, level):
 
 
 def analyze_convergence_data(data_frame, out_path):
-    """reference :164-175: analysis.txt with the per-level convergence ratios and mean iteration counts"""
+    """reference :164-185: analysis.txt with the per-level convergence ratios and mean iteration counts; the file has the
+    reference's layout byte for byte (all levels of a statistic on ONE line, each as "  level <i>: <value>")"""
     log_path = os.path.join(out_path, "analysis.txt")
+    levels = range(infer_level_count(data_frame))
+    lines = ["Per-level convergence ratios:",
+             "".join("  level {:d}: {:.2%}".format(level, get_converged_ratio_for_level(data_frame, level)) for level in levels),
+             "Per-level mean iteration counts:",
+             "".join("  level {:d}: {:.2f}".format(level, get_mean_iteration_count_for_level(data_frame, level))
+                     for level in levels)]
     with open(log_path, "w") as log_file:
-        print("Per-level convergence ratios:", file=log_file)
-        for level in range(infer_level_count(data_frame)):
-            print("  level {:d}: {:.2%}".format(level, get_converged_ratio_for_level(data_frame, level)), file=log_file)
-        print("Per-level mean iteration counts:", file=log_file)
-        for level in range(infer_level_count(data_frame)):
-            print("  level {:d}: {:.2f}".format(level, get_mean_iteration_count_for_level(data_frame, level)),
-                  file=log_file)
+        log_file.write("\n".join(lines) + "\n")
     return log_path
 
 

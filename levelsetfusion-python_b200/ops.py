@@ -133,3 +133,19 @@ def max_norm(vector_field):
     _lib.check(_lib.load().lsf_max_norm(_ptr(vector_field), channels, ctypes.c_longlong(count), ctypes.byref(out),
                                         kind, stream))
     return float(out.value)
+
+
+def locate_max_norm(vector_field):
+    """(max_norm, coordinates) of a [H][W][C] or [X][Y][Z][C] vector field (reference math::locate_max_norm,
+    cpp/src/math/statistics.tpp:57-100): coordinates = (x, y) = (column, row) for a 2D field, (x, y, z) for a 3D field; among
+    equal maxima the element the reference's column-major traversal meets first"""
+    kind, stream, (vector_field,), _ = _prepare(vector_field)
+    nd = len(vector_field.shape) - 1
+    if nd not in (2, 3):
+        raise ValueError("expected a [H][W][C] or [X][Y][Z][C] vector field, got shape %s" % (tuple(vector_field.shape),))
+    dims = (ctypes.c_int * 3)(*[int(d) for d in vector_field.shape[:nd]])
+    out = ctypes.c_float(0.0)
+    coordinates = (ctypes.c_int * 3)()
+    _lib.check(_lib.load().lsf_locate_max_norm(_ptr(vector_field), int(vector_field.shape[-1]), nd, dims, ctypes.byref(out),
+                                               coordinates, kind, stream))
+    return float(out.value), tuple(int(c) for c in coordinates[:nd])

@@ -173,6 +173,26 @@ def max_norm(vfield):
     return float(lib().orc_max_norm2d(_p(vfield), C, ctypes.c_long(vfield.size // C)))
 
 
+def locate_max_norm(vfield):
+    """reference math::locate_max_norm (cpp/src/math/statistics.tpp:57-100) on a [H][W][C] / [X][Y][Z][C] array:
+    (max_norm, coordinates). Squared lengths summed component by component in float32; the traversal is column-major over the
+    elements with a strict `>` (the first maximum stays); 2D coordinates decoded like statistics.tpp:70-71
+    (x = i / column_count, y = i % column_count), 3D ones by unravel_3d_index (x fastest)."""
+    vfield = _f32(vfield)
+    nd = vfield.ndim - 1
+    sq = np.zeros(vfield.shape[:-1], np.float32)
+    for c in range(vfield.shape[-1]):
+        sq = sq + vfield[..., c] * vfield[..., c]
+    order = sq.ravel(order="F")  # the reference's element order
+    best = int(np.argmax(order)) if order.max() > 0 else 0  # np.argmax: first occurrence
+    value = float(np.sqrt(np.float32(order[best]) if order.max() > 0 else np.float32(0)))
+    if nd == 2:
+        columns = vfield.shape[1]
+        return value, (best // columns, best % columns)
+    X, Y = vfield.shape[0], vfield.shape[1]
+    return value, (best % X, (best // X) % Y, best // (X * Y))
+
+
 # ------------------------------------------------------------------ hierarchical optimizer
 def make_hier_params(tikhonov_term_enabled=True, gradient_kernel_enabled=True, maximum_chunk_size=8, rate=0.1,
                      maximum_iteration_count=100, maximum_warp_update_threshold=0.001, data_term_amplifier=1.0,

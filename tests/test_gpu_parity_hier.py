@@ -142,6 +142,28 @@ def test_max_norm(lsf):
     assert lsf.ops.max_norm(vec) == oracle.max_norm(vec)
 
 
+def test_locate_max_norm(lsf, literals):
+    """reference math::locate_max_norm (statistics.tpp:57-100): value and location, the reference's test literals
+    (cpp/tests/test_math.cpp:67-71,110-113,124-127), ties, all-zero fields, host arrays and device tensors"""
+    import torch
+    for key, expected in (("test_math/max_norm_test01/vector_field", (1, 2)), ("test_data_math/min_max_vector_field_2d/a", (0, 0)),
+                          ("test_data_math/min_max_vector_field_3d/a", (0, 6, 8))):
+        assert lsf.ops.locate_max_norm(literals[key]) == oracle.locate_max_norm(literals[key])
+        assert lsf.ops.locate_max_norm(literals[key])[1] == expected
+    rng = np.random.default_rng(11)
+    for shape in ((64, 64, 2), (33, 47, 2), (16, 20, 24, 3), (128, 128, 128, 3)):
+        field = rng.standard_normal(shape).astype(np.float32)
+        assert lsf.ops.locate_max_norm(field) == oracle.locate_max_norm(field)
+        assert lsf.ops.locate_max_norm(torch.from_numpy(field).cuda()) == oracle.locate_max_norm(field)
+        assert lsf.ops.locate_max_norm(field)[0] == lsf.ops.max_norm(field)
+        # equal maxima
+        flat = field.reshape(-1, shape[-1])
+        for i in rng.integers(0, flat.shape[0], 5):
+            flat[i] = 100.0
+        assert lsf.ops.locate_max_norm(field) == oracle.locate_max_norm(field)
+    assert lsf.ops.locate_max_norm(np.zeros((8, 8, 2), np.float32)) == (0.0, (0, 0))
+
+
 # ----------------------------------------------------------------------------- hierarchical optimizer
 def test_hier2d_golden(lsf, literals):
     """reference cpp/tests/test_hierarchical_optimizer.cpp:161-205, tests/test_hierarchical_optimizer2d.py:39-101"""

@@ -258,6 +258,22 @@ def test_max_norm(literals):
     assert oracle.max_norm(v3) == pytest.approx(float(np.linalg.norm(v3, axis=-1).max()), rel=1e-6)
 
 
+def test_locate_max_norm(literals):
+    """the reference's expectations: cpp/tests/test_math.cpp:67-71 (0.7614307 at (1, 2)), :110-113 (1.25495625 at (0, 0)),
+    :124-127 (1.5980518 at (0, 6, 8))"""
+    norm, at = oracle.locate_max_norm(literals["test_math/max_norm_test01/vector_field"])
+    assert norm == pytest.approx(0.7614307, rel=1e-6) and at == (1, 2)
+    norm, at = oracle.locate_max_norm(literals["test_data_math/min_max_vector_field_2d/a"])
+    assert norm == pytest.approx(1.25495625, rel=1e-6) and at == (0, 0)
+    norm, at = oracle.locate_max_norm(literals["test_data_math/min_max_vector_field_3d/a"])
+    assert norm == pytest.approx(1.5980518, rel=1e-6) and at == (0, 6, 8)
+    # equal maxima: the first one in the reference's column-major traversal stays
+    field = np.zeros((4, 4, 2), np.float32)
+    field[3, 0] = field[0, 2] = (3.0, 4.0)
+    assert oracle.locate_max_norm(field) == (5.0, (0, 3))  # order index 3 (row 3 of column 0) -> x = 3 // 4, y = 3 % 4
+    assert oracle.locate_max_norm(np.zeros((4, 4, 2), np.float32)) == (0.0, (0, 0))
+
+
 # ----------------------------------------------------------------------------- 3D consistency (no reference fixture)
 def test_3d_optimizer_reduces_to_2d_planewise():
     """a 3D pair constant along axis 0 must reproduce the 2D result away from that axis'
