@@ -40,7 +40,7 @@ __device__ __forceinline__ void phase_barrier() {
 }
 
 template<bool TIKHONOV, bool CLUSTER>
-__global__ void __launch_bounds__(CLUSTER ? CLUSTER_THREADS : THREADS) k_hier_level2d(HierIterArgs2 a, ConvArgs2 c, int use_kernel,
+__global__ void __launch_bounds__(CLUSTER ? CLUSTER_THREADS : THREADS, 1) k_hier_level2d(HierIterArgs2 a, ConvArgs2 c, int use_kernel,
 		float* g_post, float* scratch, int first_iteration, int count) {
 	const Grid2 g = a.g;
 	const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x, stride = (long long) gridDim.x * blockDim.x;

@@ -428,8 +428,10 @@ int optimize_device(const lsf_slavcheva_params* params, const SlavGeom& g, const
 			// pageable source: the driver has copied it out when the call returns, `commands` is free for the next chunk
 			LSF_CUDA(cudaMemcpyAsync(commands_dev, commands.data(), (size_t) (chunk_end - enqueued) * sizeof(SlavIterationCommand),
 					cudaMemcpyHostToDevice, stream));
+			SlavOptimizerBuffers buffers = { { warp, field_a, field_b, field_f }, { live_a, live_b, const_cast<float*>(canonical) },
+					g.n[0], g.n[1], use_kernel ? taps.radius : 0 };
 			LSF_TRY(launch_slav_persistent2d(commands_dev, chunk_end - enqueued, p, g.N, max_sq_bits, status, enqueued, max_iterations,
-					stream));
+					stream, D == 2 ? &buffers : nullptr));
 		}
 		LSF_CUDA(cudaGetLastError());
 		trace_point("chunk enqueued");

@@ -112,8 +112,16 @@ struct SlavIterationCommand {
 // largest field (voxels) the single-launch path takes: all blocks must be resident at once
 long long slav_persistent_capacity();
 // iterations [first_iteration, first_iteration + count) from `commands_dev`; the termination test (k_slav_decide) runs inside
+// `buffers` (optional): every buffer the command records name -- fields of up to ~16 K voxels are then kept in the shared
+// memory of one thread-block cluster for the whole launch (k_slav_strips)
+struct SlavOptimizerBuffers {
+	float* vector_fields[4];  // warp and the three update fields (planes)
+	float* scalar_fields[3];  // the two live buffers and the canonical field (last: never written)
+	int H, W, radius;         // field shape, filter radius (0: no filter)
+};
 int launch_slav_persistent2d(const SlavIterationCommand* commands_dev, int count, const SlavParams& p, long long N,
-		const unsigned* max_sq_bits, int* status, int first_iteration, int max_iterations, cudaStream_t stream);
+		unsigned* max_sq_bits, int* status, int first_iteration, int max_iterations, cudaStream_t stream,
+		const SlavOptimizerBuffers* buffers = nullptr);
 
 // Band-union warp statistics and TSDF difference statistics of device-resident fields (defined in slavcheva.cu; also
 // used by the hierarchical optimizers for their per-level convergence reports). `field` element (voxel i,
@@ -714,6 +722,12 @@ struct SlavLiveTile {
 	int lo[3], ext[3];
 };
 
+// a tap of the re-warp's gather (live field at voxel q, row q[0], linear index): a plain load; the single-cluster optimizer of
+// small 2D fields (slavcheva_persistent.cu) keeps the field in distributed shared memory and defines its own look-up
+#ifndef SLAV_LIVE_TAP
+#define SLAV_LIVE_TAP(live, row, index) __ldg((live) + (index))
+#endif
+
 // TILE: the eight taps are read from `tile` when the whole 2 x 2 x 2 cell lies inside it and inside the field (3D,
 // float32 semantics only); other voxels take the global path
 template<int D, bool TILE = false>
@@ -760,7 +774,7 @@ __device__ __forceinline__ void slav_resample_voxel(const SlavResampleArgs& a, i
 				int q[3] = { 0, 0, 0 };
 #pragma unroll
 				for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
-				value[corner] = (double) (slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob);
+				value[corner] = (double) (slav_inside<D>(g, q) ? SLAV_LIVE_TAP(a.live, q[0], (slav_index<D>(g, q))) : oob);
 			}
 #pragma unroll
 			for (int c = D - 1; c >= 0; c--) {
@@ -803,7 +817,7 @@ __device__ __forceinline__ void slav_resample_voxel(const SlavResampleArgs& a, i
 					int q[3] = { 0, 0, 0 };
 #pragma unroll
 					for (int ax = 0; ax < D; ax++) q[ax] = base[ax] + ((corner >> ax) & 1);
-					value[corner] = slav_inside<D>(g, q) ? __ldg(a.live + slav_index<D>(g, q)) : oob;
+					value[corner] = slav_inside<D>(g, q) ? SLAV_LIVE_TAP(a.live, q[0], (slav_index<D>(g, q))) : oob;
 				}
 			}
 			// interpolation along the last component's axis first (reference field_warping.tpp:126-134,187-189)

@@ -17,7 +17,34 @@
 
 #include <cooperative_groups.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #define __ldg(pointer) (*(pointer))
+
+namespace lsf {
+namespace {
+// the strip of rows a block of the distributed-shared-memory optimizer (k_slav_strips, below) holds: rows [row_lo, row_hi) of
+// every field are in this block's shared memory, row r of the field belongs to block r / rows_per
+struct SlavStrip {
+	int enabled;  // 0: the fields live in global memory (k_slav_persistent)
+	int rank, blocks, rows_per, row_lo, row_hi, W;
+};
+__shared__ SlavStrip slav_strip;
+
+// a tap of the re-warp's gather: rows outside the block's strip + halo are read from the shared memory of the block that
+// owns them (every block lays its fields out the same way, so the slot of a voxel in the owner's shared memory is this
+// block's slot shifted by the distance of the two strips)
+__device__ __forceinline__ float slav_strip_live_tap(const float* live, int row, int index) {
+	if (!slav_strip.enabled || (row >= slav_strip.row_lo && row < slav_strip.row_hi)) return live[index];
+	const int owner = min(row / slav_strip.rows_per, slav_strip.blocks - 1);
+	const float* slot = live + index + (slav_strip.rank - owner) * slav_strip.rows_per * slav_strip.W;
+	return *cooperative_groups::this_cluster().map_shared_rank(slot, owner);
+}
+}  // namespace
+}  // namespace lsf
+#define SLAV_LIVE_TAP(live, row, index) lsf::slav_strip_live_tap(live, row, index)
 #include "slavcheva.cuh"
 
 namespace cg = cooperative_groups;
@@ -29,6 +56,7 @@ constexpr int PERSISTENT_THREADS = 256;
 // Fields of up to 16 K voxels (128 x 128, BASELINE.json configs[0]) run in ONE thread-block cluster of up to 16 blocks: the
 // hardware cluster barrier (~0.2 us) replaces the grid barrier through L2 (~1 us), which is most of such an iteration.
 constexpr int CLUSTER_THREADS = 1024, CLUSTER_BLOCKS = 16;
+constexpr int PHASE_CLOCK_ITERATIONS = 8;
 
 // barrier between two phases: grid-wide (cooperative launch) or cluster-wide (the whole grid is one cluster)
 template<bool CLUSTER>
@@ -38,13 +66,24 @@ __device__ __forceinline__ void phase_barrier() {
 }
 
 template<int D, bool CLUSTER>
-__global__ void __launch_bounds__(CLUSTER ? CLUSTER_THREADS : PERSISTENT_THREADS) k_slav_persistent(const SlavIterationCommand* commands,
-		int count, SlavParams p, int N, const unsigned* max_sq_bits, int* status, int first_iteration, int max_iterations) {
+__global__ void __launch_bounds__(CLUSTER ? CLUSTER_THREADS : PERSISTENT_THREADS, 1) k_slav_persistent(const SlavIterationCommand* commands,
+		int count, SlavParams p, int N, const unsigned* max_sq_bits, int* status, int first_iteration, int max_iterations,
+		unsigned long long* phase_clock) {
 	__shared__ SlavIterationCommand command;
 	static_assert(sizeof(SlavIterationCommand) % 4 == 0, "copied word by word");
+	if (threadIdx.x == 0) slav_strip.enabled = 0;  // the fields are in global memory (read after the barrier below)
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
 	// status[first_iteration] comes from the previous launch; later decisions are taken by every thread itself
 	bool finished = *reinterpret_cast<volatile int*>(status + first_iteration) != 0;
+	// LSF_TRACE=2: thread 0 stamps the nanosecond clock at the phase boundaries of the first iterations (8 stamps each)
+	const bool stamping = phase_clock != nullptr && tid == 0;
+	auto stamp = [&](int j, int slot) {
+		if (stamping && j < PHASE_CLOCK_ITERATIONS) {
+			unsigned long long now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			phase_clock[j * 8 + slot] = now;
+		}
+	};
 	for (int j = 0; j < count; j++) {
 		const int it = first_iteration + j;
 		if (finished) {
@@ -56,29 +95,232 @@ __global__ void __launch_bounds__(CLUSTER ? CLUSTER_THREADS : PERSISTENT_THREADS
 		for (int w = threadIdx.x; w < (int) (sizeof(SlavIterationCommand) / 4); w += blockDim.x)
 			reinterpret_cast<int*>(&command)[w] = reinterpret_cast<const int*>(commands + j)[w];
 		__syncthreads();
+		stamp(j, 0);
 		// Grid barriers stand only where a phase reads what OTHER threads wrote in the phase before: a filter pass reads its
 		// input along the pass axis. The re-warp needs the filtered update of its own voxel only (and the old live field),
 		// so the last pass and the re-warp of a voxel run back to back in the thread that owns it.
 		for (int idx = tid; idx < N; idx += stride) slav_gradient_at<D>(command.gradient, idx);
+		stamp(j, 1);
 		for (int pass = 0; pass + 1 < command.passes; pass++) {
 			phase_barrier<CLUSTER>();
+			if (pass == 0) stamp(j, 2);
 			for (int idx = tid; idx < N; idx += stride) slav_filter_axis_at<D>(command.pass[pass], idx);
+			if (pass == 0) stamp(j, 3);
 		}
 		// also without a filter: the re-warp stores the new warp vector of its voxel, which the smoothing terms of the
 		// neighbouring voxels (gradient phase of this iteration, other threads) still read
 		phase_barrier<CLUSTER>();
+		stamp(j, 4);
 		float sq_report = 0.0f;
 		for (int idx = tid; idx < N; idx += stride) {
 			if (command.passes > 0) slav_filter_axis_at<D>(command.pass[command.passes - 1], idx);
 			slav_resample_at<D>(command.resample, idx, sq_report);
 		}
+		stamp(j, 5);
 		if (command.resample.max_sq_bits != nullptr) block_atomic_max(sq_report, command.resample.max_sq_bits);
 		phase_barrier<CLUSTER>();
+		stamp(j, 6);
 		// k_slav_decide, evaluated by every thread (one barrier less); thread 0 records it for the host
 		const float max_warp = sqrtf(__uint_as_float(*reinterpret_cast<const volatile unsigned*>(max_sq_bits + it)));
 		finished = slav_finished(p, it + 1, max_iterations, max_warp);
 		if (tid == 0) status[it + 1] = finished ? 1 : 0;
+		stamp(j, 7);
 	}
+}
+
+
+// ---------------------------------------------------------------------------------------------- fields in distributed shared memory
+// The phases of k_slav_persistent cost ~1 us each, the barriers between them 2.3 us each (LSF_TRACE=2 phase clock, 128 x 128:
+// 13.2 us per iteration): what a barrier waits for is the round trip of the phase's stores to L2 and of the next phase's loads
+// from it. k_slav_strips keeps every field of the optimizer in the shared memory of ONE cluster instead: block k owns the rows
+// [k * rows_per, (k + 1) * rows_per) of all seven buffers (live x 2, canonical, warp, three update fields) plus `halo` rows on
+// either side (halo = filter radius; the term stencils need one row). A phase reads only this block's shared memory, writes
+// its own rows and stores the rows its neighbours keep as halo into THEIR shared memory (distributed shared memory); a cluster
+// barrier separates the phases; the re-warp's gather reads rows outside strip + halo from their owner's shared memory
+// (slav_strip_live_tap); the maximum warp length travels through a slot per block in every block's shared memory. No global
+// memory access is left inside an iteration apart from the command record (prefetched one iteration ahead) and thread 0's
+// status / maximum stores. The per-voxel functions are the kernels' own (slav_gradient_at, slav_filter_axis_at,
+// slav_resample_at): they address voxel idx of a field as base[component * N + idx], so each field gets a VIRTUAL base
+// pointer into shared memory (slot of voxel 0 of the field, were the whole field there) and component 1 of a vector field
+// sits N floats after component 0 (the four vector fields' component-0 tiles must fit in N floats: slav_strips_shape).
+constexpr int STRIP_FIELDS = 7, STRIP_VECTOR_FIELDS = 4;
+struct SlavStripFields {
+	float* base[STRIP_FIELDS];  // global buffers: the vector fields (planes) first, then the scalar ones; the last is read-only
+};
+
+__device__ __forceinline__ float block_max(float value, float* warp_max) {
+	if (!(value >= 0.0f)) value = 0.0f;  // NaN -> ignored, like block_atomic_max
+#pragma unroll
+	for (int offset = 16; offset > 0; offset >>= 1) value = fmaxf(value, __shfl_xor_sync(0xffffffffu, value, offset));
+	if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = value;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		value = threadIdx.x < ((blockDim.x + 31) >> 5) ? warp_max[threadIdx.x] : 0.0f;
+#pragma unroll
+		for (int offset = 16; offset > 0; offset >>= 1) value = fmaxf(value, __shfl_xor_sync(0xffffffffu, value, offset));
+	}
+	return value;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIterationCommand* commands, int count, SlavParams p,
+		int H, int W, int rows_per, int halo, SlavStripFields fields, unsigned* max_sq_bits, int* status, int first_iteration,
+		int max_iterations, unsigned long long* phase_clock) {
+	constexpr int D = 2;
+	constexpr int WORDS = (int) (sizeof(SlavIterationCommand) / 4), PREFETCH = (WORDS + 127) / 128;  // >= 128 threads per block
+	extern __shared__ __align__(16) float strip_tiles[];
+	__shared__ SlavIterationCommand command;
+	__shared__ float* virtual_base[STRIP_FIELDS];
+	__shared__ float block_maxima[CLUSTER_BLOCKS], warp_max[32];
+	cg::cluster_group cluster = cg::this_cluster();
+	const int rank = (int) cluster.block_rank(), blocks = (int) cluster.num_blocks();
+	const int N = H * W, tile = (rows_per + 2 * halo) * W;
+	const int r0 = rank * rows_per, r1 = min(r0 + rows_per, H);
+	const int row_lo = max(r0 - halo, 0), row_hi = min(r1 + halo, H);
+	if (threadIdx.x == 0) {
+		slav_strip.enabled = 1;
+		slav_strip.rank = rank;
+		slav_strip.blocks = blocks;
+		slav_strip.rows_per = rows_per;
+		slav_strip.row_lo = row_lo;
+		slav_strip.row_hi = row_hi;
+		slav_strip.W = W;
+		for (int f = 0; f < STRIP_FIELDS; f++) {
+			const int offset = f < STRIP_VECTOR_FIELDS ? f * tile : N + f * tile;
+			virtual_base[f] = strip_tiles + offset - (r0 - halo) * W;
+		}
+	}
+	__syncthreads();
+	// the block's rows (and halo rows) of every field
+	for (int f = 0; f < STRIP_FIELDS; f++)
+		for (int c = 0; c < (f < STRIP_VECTOR_FIELDS ? D : 1); c++)
+			for (int idx = row_lo * W + threadIdx.x; idx < row_hi * W; idx += blockDim.x)
+				virtual_base[f][c * N + idx] = fields.base[f][c * N + idx];
+	// a command record names the global buffers: translated to the virtual bases when it is staged
+	int prefetched[PREFETCH];
+	auto prefetch = [&](int j) {
+#pragma unroll
+		for (int k = 0; k < PREFETCH; k++) {
+			const int w = threadIdx.x + k * 128;
+			if (threadIdx.x < 128 && w < WORDS && j < count) prefetched[k] = reinterpret_cast<const int*>(commands + j)[w];
+		}
+	};
+	auto translate = [&](const float* pointer) -> float* {
+		if (pointer == nullptr) return nullptr;
+		for (int f = 0; f < STRIP_FIELDS; f++)
+			if (pointer == fields.base[f]) return virtual_base[f];
+		__trap();  // a buffer the host did not announce
+		return nullptr;
+	};
+	auto stage_command = [&]() {
+		__syncthreads();  // the previous iteration's readers of `command` are done
+#pragma unroll
+		for (int k = 0; k < PREFETCH; k++) {
+			const int w = threadIdx.x + k * 128;
+			if (threadIdx.x < 128 && w < WORDS) reinterpret_cast<int*>(&command)[w] = prefetched[k];
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			SlavGradientArgs& ga = command.gradient;
+			ga.live = translate(ga.live);
+			ga.canonical = translate(ga.canonical);
+			ga.warp = translate(ga.warp);
+			ga.stale = translate(ga.stale);
+			ga.out = translate(ga.out);
+		} else if (threadIdx.x >= 32 && threadIdx.x < 35) {
+			SlavFilterArgs& fa = command.pass[threadIdx.x - 32];
+			if ((int) threadIdx.x - 32 < command.passes) {
+				fa.in = translate(fa.in);
+				fa.out = translate(fa.out);
+				fa.original = translate(fa.original);
+			}
+		} else if (threadIdx.x == 64) {
+			SlavResampleArgs& ra = command.resample;
+			ra.live = translate(ra.live);
+			ra.canonical = translate(ra.canonical);
+			ra.update = translate(ra.update);
+			ra.gradient_field = translate(ra.gradient_field);
+			ra.warp = translate(ra.warp);
+			ra.new_live = translate(ra.new_live);
+		}
+		__syncthreads();
+	};
+	// the rows the neighbours keep as halo: stored into their shared memory (slot = this block's slot shifted by a strip)
+	auto push = [&](float* base, int components, int idx) {
+		const int row = idx / W;
+		const bool up = rank > 0 && row - r0 < halo, down = rank + 1 < blocks && r1 - 1 - row < halo;
+		if (!up && !down) return;
+		for (int c = 0; c < components; c++) {
+			float* mine = base + c * N + idx;
+			const float value = *mine;
+			if (up) *cluster.map_shared_rank(mine + rows_per * W, rank - 1) = value;
+			if (down) *cluster.map_shared_rank(mine - rows_per * W, rank + 1) = value;
+		}
+	};
+	const bool stamping = phase_clock != nullptr && rank == 0 && threadIdx.x == 0;
+	auto stamp = [&](int j, int slot) {
+		if (stamping && j < PHASE_CLOCK_ITERATIONS) {
+			unsigned long long now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			phase_clock[j * 8 + slot] = now;
+		}
+	};
+	const int first = r0 * W + threadIdx.x, last = r1 * W;
+	bool finished = *reinterpret_cast<volatile int*>(status + first_iteration) != 0;
+	prefetch(0);
+	cluster.sync();  // every block has loaded its tiles: halo stores may arrive from now on
+	int j = 0;
+	for (; j < count; j++) {
+		const int it = first_iteration + j;
+		if (finished) break;
+		stage_command();
+		prefetch(j + 1);
+		stamp(j, 0);
+		const int passes = command.passes;
+		for (int idx = first; idx < last; idx += blockDim.x) {
+			slav_gradient_at<D>(command.gradient, idx);
+			push(command.gradient.out, D, idx);
+		}
+		stamp(j, 1);
+		for (int pass = 0; pass + 1 < passes; pass++) {
+			cluster.sync();
+			if (pass == 0) stamp(j, 2);
+			for (int idx = first; idx < last; idx += blockDim.x) {
+				slav_filter_axis_at<D>(command.pass[pass], idx);
+				push(command.pass[pass].out, D, idx);
+			}
+			if (pass == 0) stamp(j, 3);
+		}
+		// also without a filter: the re-warp overwrites the warp vectors the neighbours' smoothing terms read
+		cluster.sync();
+		stamp(j, 4);
+		float sq_report = 0.0f;
+		for (int idx = first; idx < last; idx += blockDim.x) {
+			if (passes > 0) slav_filter_axis_at<D>(command.pass[passes - 1], idx);
+			slav_resample_at<D>(command.resample, idx, sq_report);
+			push(command.resample.new_live, 1, idx);
+			push(command.resample.warp, D, idx);
+		}
+		stamp(j, 5);
+		// maximum warp length: every block's maximum into every block's slot array
+		const float mine = block_max(sq_report, warp_max);
+		if (threadIdx.x < blocks) *cluster.map_shared_rank(&block_maxima[rank], threadIdx.x) = mine;
+		cluster.sync();
+		stamp(j, 6);
+		float max_sq = 0.0f;
+		for (int k = 0; k < blocks; k++) max_sq = fmaxf(max_sq, block_maxima[k]);
+		finished = slav_finished(p, it + 1, max_iterations, sqrtf(max_sq));
+		if (rank == 0 && threadIdx.x == 0) {
+			max_sq_bits[it] = __float_as_uint(max_sq);
+			status[it + 1] = finished ? 1 : 0;
+		}
+		stamp(j, 7);
+	}
+	if (finished && rank == 0 && threadIdx.x == 0)
+		for (int k = j; k < count; k++) status[first_iteration + k + 1] = 1;  // sticky, like k_slav_decide
+	// the block's rows of every buffer back to global memory (the host reads the results there; the next launch reloads them)
+	for (int f = 0; f + 1 < STRIP_FIELDS; f++)
+		for (int c = 0; c < (f < STRIP_VECTOR_FIELDS ? D : 1); c++)
+			for (int idx = first; idx < last; idx += blockDim.x) fields.base[f][c * N + idx] = virtual_base[f][c * N + idx];
 }
 
 int resident_blocks() {
@@ -125,6 +367,61 @@ int cluster_blocks() {
 	return blocks;
 }
 
+// strips of the distributed-shared-memory kernel for this field, if it takes it: every block at least `halo` rows (its halo
+// comes from the direct neighbours only), the vector fields' component-0 tiles inside the first N floats, the cluster
+// schedulable with that much shared memory. LSF_SLAV_CLUSTER=1 keeps the fields in global memory (A/B tests).
+struct StripShape {
+	unsigned blocks, threads;
+	int rows_per, halo;
+	size_t shared_bytes;
+};
+bool slav_strips_shape(const SlavOptimizerBuffers& b, StripShape* shape) {
+	const char* env = getenv("LSF_SLAV_CLUSTER");
+	if (env && (env[0] == '0' || env[0] == '1')) return false;
+	const int most = cluster_blocks();
+	if (most <= 0 || b.H < 2 || b.W < 1) return false;
+	const int halo = std::max(b.radius, 1);
+	const int rows_per = std::max((b.H + most - 1) / most, halo);
+	const int blocks = (b.H + rows_per - 1) / rows_per;
+	const long long N = (long long) b.H * b.W, tile = (long long) (rows_per + 2 * halo) * b.W;
+	if (blocks < 1 || blocks > most || STRIP_VECTOR_FIELDS * tile > N) return false;
+	const size_t bytes = (size_t) (N + STRIP_FIELDS * tile) * sizeof(float);
+	if (bytes > 200u * 1024u) return false;
+	unsigned threads = 128;
+	while (threads < (unsigned) CLUSTER_THREADS && (long long) threads < (long long) rows_per * b.W) threads *= 2;
+	// schedulable? (asked once per shape)
+	static std::mutex mutex;
+	static std::map<std::tuple<int, unsigned, size_t>, bool> known;
+	std::lock_guard<std::mutex> lock(mutex);
+	const auto key = std::make_tuple(blocks, threads, bytes);
+	auto found = known.find(key);
+	if (found == known.end()) {
+		bool ok = cudaFuncSetAttribute(k_slav_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess
+				&& (blocks <= 8 || cudaFuncSetAttribute(k_slav_strips, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess);
+		cudaLaunchConfig_t config = {};
+		config.gridDim = dim3(blocks);
+		config.blockDim = dim3(threads);
+		config.dynamicSmemBytes = bytes;
+		cudaLaunchAttribute attribute;
+		attribute.id = cudaLaunchAttributeClusterDimension;
+		attribute.val.clusterDim.x = blocks;
+		attribute.val.clusterDim.y = attribute.val.clusterDim.z = 1;
+		config.attrs = &attribute;
+		config.numAttrs = 1;
+		int clusters = 0;
+		ok = ok && cudaOccupancyMaxActiveClusters(&clusters, k_slav_strips, &config) == cudaSuccess && clusters >= 1;
+		cudaGetLastError();
+		found = known.emplace(key, ok).first;
+	}
+	if (!found->second) return false;
+	shape->blocks = (unsigned) blocks;
+	shape->threads = threads;
+	shape->rows_per = rows_per;
+	shape->halo = halo;
+	shape->shared_bytes = bytes;
+	return true;
+}
+
 }  // namespace
 
 long long slav_persistent_capacity() {
@@ -134,10 +431,62 @@ long long slav_persistent_capacity() {
 }
 
 int launch_slav_persistent2d(const SlavIterationCommand* commands_dev, int count, const SlavParams& p, long long N,
-		const unsigned* max_sq_bits, int* status, int first_iteration, int max_iterations, cudaStream_t stream) {
+		unsigned* max_sq_bits, int* status, int first_iteration, int max_iterations, cudaStream_t stream,
+		const SlavOptimizerBuffers* buffers) {
+	// LSF_TRACE=2: phase clock of the first chunk's first iterations, printed when the launch has finished (debugging aid:
+	// synchronises the stream)
+	static const bool clocked = []() {
+		const char* e = getenv("LSF_TRACE");
+		return e && e[0] == '2';
+	}();
+	unsigned long long* phase_clock = nullptr;
+	if (clocked && first_iteration == 0) {
+		LSF_CUDA(cudaMalloc(&phase_clock, PHASE_CLOCK_ITERATIONS * 8 * sizeof(unsigned long long)));
+		LSF_CUDA(cudaMemsetAsync(phase_clock, 0, PHASE_CLOCK_ITERATIONS * 8 * sizeof(unsigned long long), stream));
+	}
+	auto report = [&]() {
+		if (phase_clock == nullptr) return;
+		unsigned long long host[PHASE_CLOCK_ITERATIONS * 8];
+		cudaStreamSynchronize(stream);
+		cudaMemcpy(host, phase_clock, sizeof(host), cudaMemcpyDeviceToHost);
+		cudaFree(phase_clock);
+		static const char* names[8] = { "command", "gradient", "barrier", "pass 0", "barrier", "pass 1 + re-warp", "max + barrier", "decide" };
+		fprintf(stderr, "[lsf_b200 phase clock] largest cluster %d blocks, %lld voxels\n", cluster_blocks(), N);
+		for (int j = 1; j < PHASE_CLOCK_ITERATIONS && j < count; j++) {
+			fprintf(stderr, "[lsf_b200 phase clock] iteration %d:", j);
+			unsigned long long previous = host[(j - 1) * 8 + 7];
+			for (int slot = 0; slot < 8; slot++) {
+				if (host[j * 8 + slot] == 0) continue;
+				fprintf(stderr, " %s %llu ns |", names[slot], host[j * 8 + slot] - previous);
+				previous = host[j * 8 + slot];
+			}
+			fprintf(stderr, " total %llu ns\n", host[j * 8 + 7] - host[(j - 1) * 8 + 7]);
+		}
+	};
 	LSF_REQUIRE(N > 0 && N <= slav_persistent_capacity(), "field of %lld voxels does not fit the single-launch path", N);
 	int n = (int) N;
 	SlavParams params = p;
+	StripShape shape;
+	if (buffers != nullptr && slav_strips_shape(*buffers, &shape)) {
+		SlavStripFields fields;
+		for (int f = 0; f < STRIP_VECTOR_FIELDS; f++) fields.base[f] = buffers->vector_fields[f];
+		for (int f = STRIP_VECTOR_FIELDS; f < STRIP_FIELDS; f++) fields.base[f] = buffers->scalar_fields[f - STRIP_VECTOR_FIELDS];
+		cudaLaunchConfig_t config = {};
+		config.gridDim = dim3(counted(shape.blocks));
+		config.blockDim = dim3(shape.threads);
+		config.dynamicSmemBytes = shape.shared_bytes;
+		config.stream = stream;
+		cudaLaunchAttribute attribute;
+		attribute.id = cudaLaunchAttributeClusterDimension;
+		attribute.val.clusterDim.x = shape.blocks;
+		attribute.val.clusterDim.y = attribute.val.clusterDim.z = 1;
+		config.attrs = &attribute;
+		config.numAttrs = 1;
+		LSF_CUDA(cudaLaunchKernelEx(&config, k_slav_strips, commands_dev, count, params, buffers->H, buffers->W, shape.rows_per,
+				shape.halo, fields, max_sq_bits, status, first_iteration, max_iterations, phase_clock));
+		report();
+		return LSF_OK;
+	}
 	if (cluster_blocks() > 0 && N <= (long long) cluster_blocks() * CLUSTER_THREADS) {
 		// one voxel per thread where the cluster has the threads; small fields spread over all SMs of the cluster
 		unsigned threads = 128;
@@ -154,14 +503,16 @@ int launch_slav_persistent2d(const SlavIterationCommand* commands_dev, int count
 		config.attrs = &attribute;
 		config.numAttrs = 1;
 		LSF_CUDA(cudaLaunchKernelEx(&config, k_slav_persistent<2, true>, commands_dev, count, params, n, max_sq_bits, status, first_iteration,
-				max_iterations));
+				max_iterations, phase_clock));
+		report();
 		return LSF_OK;
 	}
 	const unsigned blocks = (unsigned) std::min<long long>(div_up(N, PERSISTENT_THREADS), resident_blocks());
 	void* arguments[] = { (void*) &commands_dev, (void*) &count, (void*) &params, (void*) &n, (void*) &max_sq_bits, (void*) &status,
-			(void*) &first_iteration, (void*) &max_iterations };
+			(void*) &first_iteration, (void*) &max_iterations, (void*) &phase_clock };
 	LSF_CUDA(cudaLaunchCooperativeKernel((const void*) k_slav_persistent<2, false>, dim3(counted(blocks)), dim3(PERSISTENT_THREADS), arguments,
 			0, stream));
+	report();
 	return LSF_OK;
 }
 

@@ -167,7 +167,7 @@ def test_slavcheva2d_vs_oracle(lsf, semantics, terms):
     run_both(lsf, 2, semantics, live, canonical, sobolev=False, iterations=6, **TERM_CASES[terms])
 
 
-def run_single_launch(lsf, semantics, live, canonical, iterations=12, lower=0.01, sobolev=True, **terms):
+def run_single_launch(lsf, semantics, live, canonical, iterations=12, lower=0.01, sobolev=True, rate=0.1, **terms):
     """2D runs WITHOUT a per-iteration capture take the single-launch path (csrc/slavcheva_persistent.cu: all iterations of
     a polling chunk in one cooperative kernel); compared with the oracle bit for bit and, through LSF_SLAV_PERSISTENT=0, with
     the one-launch-per-kernel path, whose launch count it must undercut"""
@@ -175,13 +175,13 @@ def run_single_launch(lsf, semantics, live, canonical, iterations=12, lower=0.01
     kernel = synthetic.sobolev_kernel_1d()
     expected = oracle.slavcheva_optimize(live, canonical, semantics=semantics, max_iterations=iterations,
                                          maximum_warp_length_lower_threshold=lower, sobolev_smoothing_enabled=sobolev,
-                                         sobolev_kernel=kernel, **terms)
+                                         sobolev_kernel=kernel, gradient_descent_rate=rate, **terms)
 
     def run():
         before = _lib.load().lsf_launch_count()
         result = slavcheva._run(2, live, canonical, semantics, terms.get("data_term_method", 0),
                                 terms.get("smoothing_term_method", 0), terms.get("level_set_term_enabled", False), sobolev,
-                                0.1, 1.0, 0.2, 0.1, terms.get("level_set_term_weight", 0.2), lower, 10000.0, iterations, 1,
+                                rate, 1.0, 0.2, 0.1, terms.get("level_set_term_weight", 0.2), lower, 10000.0, iterations, 1,
                                 kernel, collect_statistics=False, capture_iterations=0)
         return result, _lib.load().lsf_launch_count() - before
 
@@ -197,15 +197,17 @@ def run_single_launch(lsf, semantics, live, canonical, iterations=12, lower=0.01
         del os.environ["LSF_SLAV_PERSISTENT"]
     assert plain.iteration_count == result.iteration_count
     assert np.array_equal(plain.live, result.live) and np.array_equal(plain.warp, result.warp)
-    # fields of up to 16 K voxels run in one thread-block cluster (cluster barrier); LSF_SLAV_CLUSTER=0 = the same kernel
-    # as a cooperative grid (grid barrier)
-    os.environ["LSF_SLAV_CLUSTER"] = "0"
-    try:
-        cooperative, _ = run()
-    finally:
-        del os.environ["LSF_SLAV_CLUSTER"]
-    assert cooperative.iteration_count == result.iteration_count
-    assert np.array_equal(cooperative.live, result.live) and np.array_equal(cooperative.warp, result.warp)
+    # fields of up to 16 K voxels live in the shared memory of one thread-block cluster (k_slav_strips); LSF_SLAV_CLUSTER=1
+    # keeps them in global memory (k_slav_persistent in one cluster), LSF_SLAV_CLUSTER=0 runs that kernel as a cooperative grid
+    for variant in ("1", "0"):
+        os.environ["LSF_SLAV_CLUSTER"] = variant
+        try:
+            other, _ = run()
+        finally:
+            del os.environ["LSF_SLAV_CLUSTER"]
+        assert other.iteration_count == result.iteration_count
+        assert np.array_equal(other.max_warps, result.max_warps)
+        assert np.array_equal(other.live, result.live) and np.array_equal(other.warp, result.warp)
     if result.iteration_count >= 4:
         assert launches < plain_launches / 2, (launches, plain_launches)
     return result
@@ -230,6 +232,21 @@ def test_single_launch_2d_config1_and_odd_shape(lsf):
     assert result.iteration_count == 52
     result = run_single_launch(lsf, 0, live[:90, :90].copy(), canonical[:90, :90].copy(), iterations=150, lower=0.0)
     assert result.iteration_count == 150  # more iterations than one launch takes (chunks of 128)
+
+
+@pytest.mark.parametrize("semantics", [0, 1, 2])
+def test_single_launch_2d_long_warps(lsf, semantics):
+    """a gradient-descent rate of 3 moves voxels by 14 - 65 rows within six iterations (unstable, but finite): the re-warp's taps then lie outside the rows
+    a block of the cluster keeps in its own shared memory and are read from the owner's (distributed shared memory); still
+    bit-identical to the oracle and to the other paths. 64 x 64 = 16 strips of 4 rows, 128 x 128 = 16 strips of 8 rows,
+    48 x 48 = 16 strips of 3 rows, the 7-tap filter's halo is 3 rows"""
+    from lsf_b200 import synthetic
+    for size in (64, 128, 48):
+        canonical, live = synthetic.circle_line_pair_2d(size, shift=(5.0, -3.0), line_shift=-4.0)
+        result = run_single_launch(lsf, semantics, live, canonical, iterations=6, lower=0.0, rate=3.0)
+        assert result.iteration_count == 6
+        assert float(result.max_warps.max()) > 10.0  # the updates really are longer than the halo
+        run_single_launch(lsf, semantics, live, canonical, iterations=6, lower=0.0, rate=3.0, sobolev=False)
 
 
 def test_slavcheva2d_128_config1(lsf):
