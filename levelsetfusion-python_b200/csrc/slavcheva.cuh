@@ -387,10 +387,15 @@ __device__ __forceinline__ void slav_level_set(const SlavGradientArgs& a, int id
 
 // the gradient terms at voxel idx (body of k_slav_gradient; also called by the single-launch optimizer of small fields,
 // slavcheva_persistent.cu)
+// known_pos (optional): the voxel's coordinates, if the caller has them (saves the integer divisions of slav_coords)
 template<int D>
-__device__ __forceinline__ void slav_gradient_at(const SlavGradientArgs& a, int idx) {
+__device__ __forceinline__ void slav_gradient_at(const SlavGradientArgs& a, int idx, const int* known_pos = nullptr) {
 	int pos[3];
-	slav_coords<D>(a.g, idx, pos);
+	if (known_pos != nullptr) {
+#pragma unroll
+		for (int ax = 0; ax < 3; ax++) pos[ax] = known_pos[ax];
+	} else
+		slav_coords<D>(a.g, idx, pos);
 	const float live_value = __ldg(a.live + idx);
 	const bool outside = slav_truncated(live_value) && slav_truncated(__ldg(a.canonical + idx));
 	const SlavParams& p = a.p;
@@ -674,10 +679,14 @@ static __global__ void __launch_bounds__(256) k_slav_energies2d(SlavGradientArgs
 // reference convolve_with_kernel_preserve_zeros, cpp/src/math/convolution.cpp:23-67,69-145 (C++ rule) and
 // math_utils/convolution.py:114-132 (Python rule)
 template<int D>
-__device__ __forceinline__ void slav_filter_axis_at(const SlavFilterArgs& a, int idx) {
+__device__ __forceinline__ void slav_filter_axis_at(const SlavFilterArgs& a, int idx, const int* known_pos = nullptr) {
 	int pos[3];
-	slav_coords<D>(a.g, idx, pos);
-	const int i = pos[a.axis], n = a.g.n[a.axis], s = a.g.stride[a.axis];
+	if (known_pos != nullptr) {
+#pragma unroll
+		for (int ax = 0; ax < 3; ax++) pos[ax] = known_pos[ax];
+	} else
+		slav_coords<D>(a.g, idx, pos);
+	const int i = a.axis == 0 ? pos[0] : (a.axis == 1 ? pos[1] : pos[2]), n = a.g.n[a.axis], s = a.g.stride[a.axis];
 	if (a.zero_rule == 1) {
 		bool all_zero = true;
 #pragma unroll
@@ -856,14 +865,15 @@ __device__ __forceinline__ void slav_resample_voxel(const SlavResampleArgs& a, i
 }
 
 template<int D>
-__device__ __forceinline__ void slav_resample_at(const SlavResampleArgs& a, int idx, float& sq_report) {
+__device__ __forceinline__ void slav_resample_at(const SlavResampleArgs& a, int idx, float& sq_report,
+		const int* known_pos = nullptr) {
 	const SlavGeom& g = a.g;
 	float update[3] = { 0.f, 0.f, 0.f }, w[3], new_value;
 #pragma unroll
 	for (int c = 0; c < D; c++) update[c] = __ldg(a.update + c * g.N + idx);
 	const float live_value = __ldg(a.live + idx);
 	const float canonical_value = a.band_union_only ? __ldg(a.canonical + idx) : 0.0f;
-	slav_resample_voxel<D>(a, idx, update, live_value, canonical_value, new_value, w, sq_report);
+	slav_resample_voxel<D>(a, idx, update, live_value, canonical_value, new_value, w, sq_report, nullptr, known_pos);
 	a.new_live[idx] = new_value;
 	if (a.warp != nullptr) {
 #pragma unroll

@@ -17,6 +17,7 @@
 
 #include <cooperative_groups.h>
 
+#include <cstddef>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -162,6 +163,34 @@ __device__ __forceinline__ float block_max(float value, float* warp_max) {
 	return value;  // valid in warp 0
 }
 
+// the pointer fields of a command record that name optimizer buffers: byte offset and the filter pass the field belongs to
+// (-1: always used)
+constexpr int COMMAND_POINTERS = 20;
+__device__ __forceinline__ int command_pointer_pass(int t) {
+	return t >= 5 && t < 14 ? (t - 5) / 3 : -1;
+}
+__device__ __forceinline__ size_t command_pointer_offset(int t) {
+	switch (t) {
+	case 0: return offsetof(SlavIterationCommand, gradient) + offsetof(SlavGradientArgs, live);
+	case 1: return offsetof(SlavIterationCommand, gradient) + offsetof(SlavGradientArgs, canonical);
+	case 2: return offsetof(SlavIterationCommand, gradient) + offsetof(SlavGradientArgs, warp);
+	case 3: return offsetof(SlavIterationCommand, gradient) + offsetof(SlavGradientArgs, stale);
+	case 4: return offsetof(SlavIterationCommand, gradient) + offsetof(SlavGradientArgs, out);
+	case 5: case 8: case 11:
+		return offsetof(SlavIterationCommand, pass) + (size_t) ((t - 5) / 3) * sizeof(SlavFilterArgs) + offsetof(SlavFilterArgs, in);
+	case 6: case 9: case 12:
+		return offsetof(SlavIterationCommand, pass) + (size_t) ((t - 5) / 3) * sizeof(SlavFilterArgs) + offsetof(SlavFilterArgs, out);
+	case 7: case 10: case 13:
+		return offsetof(SlavIterationCommand, pass) + (size_t) ((t - 5) / 3) * sizeof(SlavFilterArgs) + offsetof(SlavFilterArgs, original);
+	case 14: return offsetof(SlavIterationCommand, resample) + offsetof(SlavResampleArgs, live);
+	case 15: return offsetof(SlavIterationCommand, resample) + offsetof(SlavResampleArgs, canonical);
+	case 16: return offsetof(SlavIterationCommand, resample) + offsetof(SlavResampleArgs, update);
+	case 17: return offsetof(SlavIterationCommand, resample) + offsetof(SlavResampleArgs, gradient_field);
+	case 18: return offsetof(SlavIterationCommand, resample) + offsetof(SlavResampleArgs, warp);
+	default: return offsetof(SlavIterationCommand, resample) + offsetof(SlavResampleArgs, new_live);
+	}
+}
+
 __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIterationCommand* commands, int count, SlavParams p,
 		int H, int W, int rows_per, int halo, SlavStripFields fields, unsigned* max_sq_bits, int* status, int first_iteration,
 		int max_iterations, unsigned long long* phase_clock) {
@@ -204,51 +233,35 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 			if (threadIdx.x < 128 && w < WORDS && j < count) prefetched[k] = reinterpret_cast<const int*>(commands + j)[w];
 		}
 	};
-	auto translate = [&](const float* pointer) -> float* {
-		if (pointer == nullptr) return nullptr;
-		for (int f = 0; f < STRIP_FIELDS; f++)
-			if (pointer == fields.base[f]) return virtual_base[f];
-		__trap();  // a buffer the host did not announce
-		return nullptr;
-	};
+	// thread t < COMMAND_POINTERS translates pointer field t of the staged record (the fields of passes that do not run are
+	// left alone: they hold whatever the host's record held)
 	auto stage_command = [&]() {
-		__syncthreads();  // the previous iteration's readers of `command` are done
+		// (the cluster barrier at the end of the previous iteration stands between that iteration's readers of `command`
+		// and these stores)
 #pragma unroll
 		for (int k = 0; k < PREFETCH; k++) {
 			const int w = threadIdx.x + k * 128;
 			if (threadIdx.x < 128 && w < WORDS) reinterpret_cast<int*>(&command)[w] = prefetched[k];
 		}
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			SlavGradientArgs& ga = command.gradient;
-			ga.live = translate(ga.live);
-			ga.canonical = translate(ga.canonical);
-			ga.warp = translate(ga.warp);
-			ga.stale = translate(ga.stale);
-			ga.out = translate(ga.out);
-		} else if (threadIdx.x >= 32 && threadIdx.x < 35) {
-			SlavFilterArgs& fa = command.pass[threadIdx.x - 32];
-			if ((int) threadIdx.x - 32 < command.passes) {
-				fa.in = translate(fa.in);
-				fa.out = translate(fa.out);
-				fa.original = translate(fa.original);
+		if (threadIdx.x < COMMAND_POINTERS && command_pointer_pass(threadIdx.x) < command.passes) {
+			float** field = reinterpret_cast<float**>(reinterpret_cast<unsigned char*>(&command) + command_pointer_offset(threadIdx.x));
+			const float* pointer = *field;
+			if (pointer != nullptr) {
+				float* translated = nullptr;
+				for (int f = 0; f < STRIP_FIELDS; f++)
+					if (pointer == fields.base[f]) translated = virtual_base[f];
+				if (translated == nullptr) __trap();  // a buffer the host did not announce
+				*field = translated;
 			}
-		} else if (threadIdx.x == 64) {
-			SlavResampleArgs& ra = command.resample;
-			ra.live = translate(ra.live);
-			ra.canonical = translate(ra.canonical);
-			ra.update = translate(ra.update);
-			ra.gradient_field = translate(ra.gradient_field);
-			ra.warp = translate(ra.warp);
-			ra.new_live = translate(ra.new_live);
 		}
 		__syncthreads();
 	};
 	// the rows the neighbours keep as halo: stored into their shared memory (slot = this block's slot shifted by a strip)
-	auto push = [&](float* base, int components, int idx) {
-		const int row = idx / W;
-		const bool up = rank > 0 && row - r0 < halo, down = rank + 1 < blocks && r1 - 1 - row < halo;
-		if (!up && !down) return;
+	// (edges: bit 0 = the upper neighbour keeps the voxel's row as halo, bit 1 = the lower one)
+	auto push = [&](float* base, int components, int idx, int edges) {
+		const bool up = edges & 1, down = edges & 2;
+		if (edges == 0) return;
 		for (int c = 0; c < components; c++) {
 			float* mine = base + c * N + idx;
 			const float value = *mine;
@@ -265,6 +278,16 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 		}
 	};
 	const int first = r0 * W + threadIdx.x, last = r1 * W;
+	// coordinates of a thread's voxels: the first one's are computed once per launch (blocks usually have a thread per voxel)
+	const int first_pos[3] = { first / W, first % W, 0 };
+	auto row_edges = [&](int row) { return (rank > 0 && row - r0 < halo ? 1 : 0) | (rank + 1 < blocks && r1 - 1 - row < halo ? 2 : 0); };
+	const int first_edges = row_edges(first_pos[0]);
+	auto coordinates = [&](int idx, int (&pos)[3]) {
+		pos[0] = idx == first ? first_pos[0] : idx / W;
+		pos[1] = idx == first ? first_pos[1] : idx - pos[0] * W;
+		pos[2] = 0;
+		return idx == first ? first_edges : row_edges(pos[0]);
+	};
 	bool finished = *reinterpret_cast<volatile int*>(status + first_iteration) != 0;
 	prefetch(0);
 	cluster.sync();  // every block has loaded its tiles: halo stores may arrive from now on
@@ -277,16 +300,20 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 		stamp(j, 0);
 		const int passes = command.passes;
 		for (int idx = first; idx < last; idx += blockDim.x) {
-			slav_gradient_at<D>(command.gradient, idx);
-			push(command.gradient.out, D, idx);
+			int pos[3];
+			const int edges = coordinates(idx, pos);
+			slav_gradient_at<D>(command.gradient, idx, pos);
+			push(command.gradient.out, D, idx, edges);
 		}
 		stamp(j, 1);
 		for (int pass = 0; pass + 1 < passes; pass++) {
 			cluster.sync();
 			if (pass == 0) stamp(j, 2);
 			for (int idx = first; idx < last; idx += blockDim.x) {
-				slav_filter_axis_at<D>(command.pass[pass], idx);
-				push(command.pass[pass].out, D, idx);
+				int pos[3];
+				const int edges = coordinates(idx, pos);
+				slav_filter_axis_at<D>(command.pass[pass], idx, pos);
+				push(command.pass[pass].out, D, idx, edges);
 			}
 			if (pass == 0) stamp(j, 3);
 		}
@@ -295,10 +322,12 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 		stamp(j, 4);
 		float sq_report = 0.0f;
 		for (int idx = first; idx < last; idx += blockDim.x) {
-			if (passes > 0) slav_filter_axis_at<D>(command.pass[passes - 1], idx);
-			slav_resample_at<D>(command.resample, idx, sq_report);
-			push(command.resample.new_live, 1, idx);
-			push(command.resample.warp, D, idx);
+			int pos[3];
+			const int edges = coordinates(idx, pos);
+			if (passes > 0) slav_filter_axis_at<D>(command.pass[passes - 1], idx, pos);
+			slav_resample_at<D>(command.resample, idx, sq_report, pos);
+			push(command.resample.new_live, 1, idx, edges);
+			push(command.resample.warp, D, idx, edges);
 		}
 		stamp(j, 5);
 		// maximum warp length: every block's maximum into every block's slot array
