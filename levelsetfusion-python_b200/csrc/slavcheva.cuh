@@ -678,7 +678,9 @@ static __global__ void __launch_bounds__(256) k_slav_energies2d(SlavGradientArgs
 // ---------------------------------------------------------------------------------------------- Sobolev filter pass
 // reference convolve_with_kernel_preserve_zeros, cpp/src/math/convolution.cpp:23-67,69-145 (C++ rule) and
 // math_utils/convolution.py:114-132 (Python rule)
-template<int D>
+// R > 0: the caller knows the filter radius (a.radius == R, a.size == 2R + 1): the tap loop unrolls and voxels at least R
+// from both ends of their line skip the bounds tests (same taps, same order)
+template<int D, int R = 0>
 __device__ __forceinline__ void slav_filter_axis_at(const SlavFilterArgs& a, int idx, const int* known_pos = nullptr) {
 	int pos[3];
 	if (known_pos != nullptr) {
@@ -701,10 +703,22 @@ __device__ __forceinline__ void slav_filter_axis_at(const SlavFilterArgs& a, int
 	for (int c = 0; c < D; c++) {
 		const float* line = a.in + c * a.g.N + idx;
 		float acc = 0.0f;
-		for (int j = 0; j < a.size; j++) {
-			const int src = i - a.radius + j;
-			const float value = (src >= 0 && src < n) ? __ldg(line + (j - a.radius) * s) : 0.0f;
-			acc += value * a.k[j];
+		if (R > 0 && i >= R && i + R < n) {
+#pragma unroll
+			for (int j = 0; j < 2 * R + 1; j++) acc += __ldg(line + (j - R) * s) * a.k[j];
+		} else if (R > 0) {
+#pragma unroll
+			for (int j = 0; j < 2 * R + 1; j++) {
+				const int src = i - R + j;
+				const float value = (src >= 0 && src < n) ? __ldg(line + (j - R) * s) : 0.0f;
+				acc += value * a.k[j];
+			}
+		} else {
+			for (int j = 0; j < a.size; j++) {
+				const int src = i - a.radius + j;
+				const float value = (src >= 0 && src < n) ? __ldg(line + (j - a.radius) * s) : 0.0f;
+				acc += value * a.k[j];
+			}
 		}
 		if (a.zero_rule == 2 && fabsf(__ldg(a.original + c * a.g.N + idx)) < 1e-6f) acc = 0.0f;
 		a.out[c * a.g.N + idx] = acc;

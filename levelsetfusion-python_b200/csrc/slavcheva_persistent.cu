@@ -269,6 +269,13 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 			if (down) *cluster.map_shared_rank(mine - rows_per * W, rank + 1) = value;
 		}
 	};
+	// the tap loop unrolled for the usual radii (the launch's filter radius = halo, when there is a filter)
+	auto filter_pass = [&](const SlavFilterArgs& fa, int idx, const int (&pos)[3]) {
+		if (fa.radius == 3) slav_filter_axis_at<D, 3>(fa, idx, pos);
+		else if (fa.radius == 1) slav_filter_axis_at<D, 1>(fa, idx, pos);
+		else if (fa.radius == 2) slav_filter_axis_at<D, 2>(fa, idx, pos);
+		else slav_filter_axis_at<D>(fa, idx, pos);
+	};
 	const bool stamping = phase_clock != nullptr && rank == 0 && threadIdx.x == 0;
 	auto stamp = [&](int j, int slot) {
 		if (stamping && j < PHASE_CLOCK_ITERATIONS) {
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 			for (int idx = first; idx < last; idx += blockDim.x) {
 				int pos[3];
 				const int edges = coordinates(idx, pos);
-				slav_filter_axis_at<D>(command.pass[pass], idx, pos);
+				filter_pass(command.pass[pass], idx, pos);
 				push(command.pass[pass].out, D, idx, edges);
 			}
 			if (pass == 0) stamp(j, 3);
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 		for (int idx = first; idx < last; idx += blockDim.x) {
 			int pos[3];
 			const int edges = coordinates(idx, pos);
-			if (passes > 0) slav_filter_axis_at<D>(command.pass[passes - 1], idx, pos);
+			if (passes > 0) filter_pass(command.pass[passes - 1], idx, pos);
 			slav_resample_at<D>(command.resample, idx, sq_report, pos);
 			push(command.resample.new_live, 1, idx, edges);
 			push(command.resample.warp, D, idx, edges);
