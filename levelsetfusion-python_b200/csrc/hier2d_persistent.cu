@@ -16,9 +16,37 @@
 #include <cooperative_groups.h>
 
 #define __ldg(pointer) (*(pointer))
+
+#include <cuda_runtime.h>
+
+namespace lsf {
+namespace {
+// the strip of the padded live pack a block of the distributed-shared-memory level kernel (k_hier_level2d_strips, below)
+// holds: padded rows [pack_lo, pack_hi) are in this block's shared memory; padded row p belongs to block (p - 2) / rows_per
+struct HierStrip {
+	int enabled;  // 0: the fields live in global memory (k_hier_level2d)
+	int rank, blocks, rows_per, pack_lo, pack_hi, PW;
+};
+__shared__ HierStrip hier_strip;
+
+// a tap of the gather: padded rows outside the block's strip + halo are read from the shared memory of the block that owns
+// them (all blocks lay their tiles out the same way: the owner's slot of an element is this block's slot shifted by the
+// distance of the two strips)
+__device__ __forceinline__ float4 hier_strip_pack_tap(const float4* pack, int padded_row, long long index) {
+	if (!hier_strip.enabled || (padded_row >= hier_strip.pack_lo && padded_row < hier_strip.pack_hi)) return pack[index];
+	const int owner = min(max((padded_row - 2) / hier_strip.rows_per, 0), hier_strip.blocks - 1);
+	const float4* slot = pack + index + (long long) (hier_strip.rank - owner) * hier_strip.rows_per * hier_strip.PW;
+	return *cooperative_groups::this_cluster().map_shared_rank(slot, owner);
+}
+}  // namespace
+}  // namespace lsf
+#define HIER_PACK_TAP(pack, padded_row, index) lsf::hier_strip_pack_tap(pack, padded_row, index)
 #include "kernels2d.cuh"
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 namespace cg = cooperative_groups;
 
@@ -43,6 +71,8 @@ template<bool TIKHONOV, bool CLUSTER>
 __global__ void __launch_bounds__(CLUSTER ? CLUSTER_THREADS : THREADS, 1) k_hier_level2d(HierIterArgs2 a, ConvArgs2 c, int use_kernel,
 		float* g_post, float* scratch, int first_iteration, int count) {
 	const Grid2 g = a.g;
+	if (threadIdx.x == 0) hier_strip.enabled = 0;  // the fields are in global memory
+	__syncthreads();
 	const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x, stride = (long long) gridDim.x * blockDim.x;
 	for (int it = first_iteration; it < first_iteration + count; it++) {
 		// level_converged(): the slot of the previous iteration is complete (grid barrier / previous launch)
@@ -94,6 +124,183 @@ __global__ void __launch_bounds__(CLUSTER ? CLUSTER_THREADS : THREADS, 1) k_hier
 		block_atomic_max(sq, a.max_sq_bits + it);
 		phase_barrier<CLUSTER>();
 	}
+}
+
+
+// ---------------------------------------------------------------------------------------------- fields in distributed shared memory
+// The small pyramid levels are bound by latency: an iteration of k_hier_level2d costs 2.2 us per phase whatever the level's
+// size (one barrier + one chain of dependent L2 loads; tools/overhead2d.py). k_hier_level2d_strips keeps the level in the
+// shared memory of ONE cluster: block k owns the rows [k * rows_per, (k + 1) * rows_per) of the warp field, the canonical
+// field and the two gradient fields (these with `halo` rows either side: filter radius / 1 for the Laplacian) and the
+// matching rows of the padded live pack (PACK_HALO rows either side). A phase reads this block's shared memory only, writes
+// its rows and stores the rows its neighbours keep as halo into THEIR shared memory; cluster barriers separate the phases;
+// gather taps outside the block's pack rows are read from their owner's shared memory (hier_strip_pack_tap); the maximum of
+// an iteration travels through a slot per block in every block's shared memory. Per-pixel functions = the kernels' own
+// (hier_gradient2d_at, convolve_axis2d_at): every field gets a virtual base pointer into shared memory, the component
+// stride of the two-plane fields (Grid2::N in the argument blocks) is the tile size. Only the warp field is written back.
+constexpr int PACK_HALO = 4;
+
+__device__ __forceinline__ float strip_block_max(float value, float* warp_max) {
+	if (!(value >= 0.0f)) value = 0.0f;  // NaN -> ignored, like block_atomic_max
+#pragma unroll
+	for (int offset = 16; offset > 0; offset >>= 1) value = fmaxf(value, __shfl_xor_sync(0xffffffffu, value, offset));
+	if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = value;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		value = threadIdx.x < ((blockDim.x + 31) >> 5) ? warp_max[threadIdx.x] : 0.0f;
+#pragma unroll
+		for (int offset = 16; offset > 0; offset >>= 1) value = fmaxf(value, __shfl_xor_sync(0xffffffffu, value, offset));
+	}
+	return value;  // valid in warp 0
+}
+
+template<bool TIKHONOV, int R>
+__global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_hier_level2d_strips(HierIterArgs2 a, ConvArgs2 c, int use_kernel,
+		float* g_post_global, float* scratch_global, int rows_per, int halo, int first_iteration, int count) {
+	extern __shared__ __align__(16) unsigned char strip_memory[];
+	__shared__ float block_maxima[CLUSTER_BLOCKS], warp_max[32];
+	cg::cluster_group cluster = cg::this_cluster();
+	const int rank = (int) cluster.block_rank(), blocks = (int) cluster.num_blocks();
+	const Grid2 g = a.g;
+	const int H = g.H, W = g.W, PW = g.PW();
+	const int r0 = rank * rows_per, r1 = min(r0 + rows_per, H);
+	const int tile = (rows_per + 2 * halo) * W;                      // floats per plane
+	const int pack_rows = rows_per + 2 * PACK_HALO + 1;              // padded rows r0 + 2 - PACK_HALO ... (unclipped)
+	const int pack_first = r0 + 2 - PACK_HALO;
+	const int pack_lo = max(pack_first, 0), pack_hi = min(pack_first + pack_rows, H + 4);
+	if (threadIdx.x == 0) {
+		hier_strip.enabled = 1;
+		hier_strip.rank = rank;
+		hier_strip.blocks = blocks;
+		hier_strip.rows_per = rows_per;
+		hier_strip.pack_lo = pack_lo;
+		hier_strip.pack_hi = pack_hi;
+		hier_strip.PW = PW;
+	}
+	// tiles: pack | warp (2 planes) | g_post (2) | scratch (2) | canonical; virtual base = slot of element 0 of the field
+	float4* pack_tile = reinterpret_cast<float4*>(strip_memory);
+	float* planes = reinterpret_cast<float*>(pack_tile + (size_t) pack_rows * PW);
+	const long long shift = (long long) (r0 - halo) * W;
+	float4* pack = pack_tile - (long long) pack_first * PW;
+	float* warp = planes - shift;
+	float* g_post = planes + 2 * tile - shift;
+	float* scratch = planes + 4 * tile - shift;
+	float* canonical = planes + 6 * tile - shift;
+	const long long N = g.N;
+	const int row_lo = max(r0 - halo, 0), row_hi = min(r1 + halo, H);
+	for (long long i = (long long) pack_lo * PW + threadIdx.x; i < (long long) pack_hi * PW; i += blockDim.x) pack[i] = a.pack[i];
+	for (long long idx = (long long) row_lo * W + threadIdx.x; idx < (long long) row_hi * W; idx += blockDim.x) {
+		for (int k = 0; k < 2; k++) {
+			warp[k * tile + idx] = a.warp[k * N + idx];
+			g_post[k * tile + idx] = g_post_global[k * N + idx];
+			scratch[k * tile + idx] = scratch_global[k * N + idx];
+		}
+		canonical[idx] = a.canonical[idx];
+	}
+	const float* warp_global_in = a.warp;
+	float* warp_global = a.warp_out;
+	unsigned* max_sq_bits = a.max_sq_bits;
+	// the argument blocks now name the tiles; the component stride of the two-plane fields is the tile size
+	a.pack = pack;
+	a.canonical = canonical;
+	a.warp = warp;
+	a.warp_out = warp;
+	a.g.N = tile;
+	c.warp = warp;
+	c.g.N = tile;
+	(void) warp_global_in;
+	// rows the neighbours keep as halo go into their shared memory (slot = this block's slot shifted by a strip)
+	auto push = [&](float* base, long long idx, int edges) {
+		if (edges == 0) return;
+		for (int k = 0; k < 2; k++) {
+			float* mine = base + k * tile + idx;
+			const float value = *mine;
+			if (edges & 1) *cluster.map_shared_rank(mine + rows_per * W, rank - 1) = value;
+			if (edges & 2) *cluster.map_shared_rank(mine - rows_per * W, rank + 1) = value;
+		}
+	};
+	auto row_edges = [&](int row) { return (rank > 0 && row - r0 < halo ? 1 : 0) | (rank + 1 < blocks && r1 - 1 - row < halo ? 2 : 0); };
+	const long long first = (long long) r0 * W + threadIdx.x, last = (long long) r1 * W;
+	// row, column and halo flags of a thread's pixels: the first one's are computed once per launch (blocks usually have a
+	// thread per pixel)
+	const int first_row = (int) (first / W), first_col = (int) (first - (long long) first_row * W), first_edges = row_edges(first_row);
+	auto coordinates = [&](long long idx, int& row, int& col) {
+		if (idx == first) {
+			row = first_row;
+			col = first_col;
+			return first_edges;
+		}
+		row = (int) (idx / W);
+		col = (int) (idx - (long long) row * W);
+		return row_edges(row);
+	};
+	float previous_max_sq = 0.0f;
+	if (first_iteration > 0) previous_max_sq = __uint_as_float(*reinterpret_cast<const volatile unsigned*>(max_sq_bits + first_iteration - 1));
+	__syncthreads();
+	cluster.sync();  // every block has loaded its tiles: halo stores may arrive from now on
+	for (int it = first_iteration; it < first_iteration + count; it++) {
+		if (it > 0 && sqrtf(previous_max_sq) < a.threshold) break;  // level_converged()
+		a.g_prev = g_post;
+		float sq = 0.0f;
+		if (!use_kernel) {
+			a.g_out = TIKHONOV ? scratch : nullptr;
+			for (long long idx = first; idx < last; idx += blockDim.x) {
+				int row, col;
+				const int edges = coordinates(idx, row, col);
+				float mine = 0.0f;
+				hier_gradient2d_at<TIKHONOV, true>(a, row, col, idx, mine);
+				sq = fmaxf(sq, mine);
+				if (TIKHONOV) push(scratch, idx, edges);
+			}
+			if (TIKHONOV) {
+				float* t = g_post;
+				g_post = scratch;
+				scratch = t;
+			}
+		} else {
+			a.g_out = scratch;
+			for (long long idx = first; idx < last; idx += blockDim.x) {
+				int row, col;
+				const int edges = coordinates(idx, row, col);
+				float unused = 0.0f;
+				hier_gradient2d_at<TIKHONOV, false>(a, row, col, idx, unused);
+				push(scratch, idx, edges);
+			}
+			cluster.sync();
+			c.in = scratch;
+			c.out = g_post;
+			for (long long idx = first; idx < last; idx += blockDim.x) {
+				int row, col;
+				const int edges = coordinates(idx, row, col);
+				float unused = 0.0f;
+				convolve_axis2d_at<0, false, R>(c, row, col, idx, unused);
+				push(g_post, idx, edges);
+			}
+			cluster.sync();
+			c.in = g_post;
+			c.out = scratch;
+			for (long long idx = first; idx < last; idx += blockDim.x) {
+				int row, col;
+				const int edges = coordinates(idx, row, col);
+				float mine = 0.0f;
+				convolve_axis2d_at<1, true, R>(c, row, col, idx, mine);
+				sq = fmaxf(sq, mine);
+				push(scratch, idx, edges);
+			}
+			float* t = g_post;
+			g_post = scratch;
+			scratch = t;
+		}
+		// the iteration's maximum: every block's maximum into every block's slot array
+		const float mine = strip_block_max(sq, warp_max);
+		if (threadIdx.x < blocks) *cluster.map_shared_rank(&block_maxima[rank], threadIdx.x) = mine;
+		cluster.sync();
+		previous_max_sq = 0.0f;
+		for (int k = 0; k < blocks; k++) previous_max_sq = fmaxf(previous_max_sq, block_maxima[k]);
+		if (rank == 0 && threadIdx.x == 0) max_sq_bits[it] = __float_as_uint(previous_max_sq);
+	}
+	for (long long idx = first; idx < last; idx += blockDim.x)
+		for (int k = 0; k < 2; k++) warp_global[k * N + idx] = warp[k * tile + idx];
 }
 
 int resident_blocks() {
@@ -151,6 +358,72 @@ void cluster_shape(long long N, unsigned& blocks, unsigned& threads) {
 	blocks = (unsigned) std::min<long long>(most, div_up(N, (long long) threads));
 }
 
+// strips of the distributed-shared-memory level kernel for this level, if it takes it: every block at least `halo` rows (its
+// halo comes from the direct neighbours only), the tiles within the shared memory of a block, the cluster schedulable.
+// LSF_HIER2D_CLUSTER=1 keeps the fields in global memory (A/B tests).
+struct StripShape {
+	unsigned blocks, threads;
+	int rows_per, halo;
+	size_t shared_bytes;
+};
+// the tap loops are unrolled for the usual filter radii (0 = any / no filter: runtime loop)
+typedef void (*StripsKernel)(HierIterArgs2, ConvArgs2, int, float*, float*, int, int, int, int);
+StripsKernel strips_kernel(bool tikhonov, int radius) {
+	switch (radius) {
+	case 1: return tikhonov ? k_hier_level2d_strips<true, 1> : k_hier_level2d_strips<false, 1>;
+	case 2: return tikhonov ? k_hier_level2d_strips<true, 2> : k_hier_level2d_strips<false, 2>;
+	case 3: return tikhonov ? k_hier_level2d_strips<true, 3> : k_hier_level2d_strips<false, 3>;
+	default: return tikhonov ? k_hier_level2d_strips<true, 0> : k_hier_level2d_strips<false, 0>;
+	}
+}
+bool hier2d_strips_shape(const Grid2& g, bool tikhonov, int radius, StripShape* shape) {
+	const char* env = getenv("LSF_HIER2D_CLUSTER");
+	if (env && (env[0] == '0' || env[0] == '1')) return false;
+	const int most = cluster_blocks();
+	if (most <= 0 || g.H < 1 || g.W < 1) return false;
+	const int halo = std::max(radius, 1);
+	const int rows_per = std::max((g.H + most - 1) / most, halo);
+	const int blocks = (g.H + rows_per - 1) / rows_per;
+	if (blocks < 1 || blocks > most) return false;
+	const size_t tile = (size_t) (rows_per + 2 * halo) * g.W;
+	const size_t bytes = (size_t) (rows_per + 2 * PACK_HALO + 1) * g.PW() * sizeof(float4) + 7 * tile * sizeof(float);
+	if (bytes > 200u * 1024u) return false;
+	unsigned threads = 128;
+	while (threads < (unsigned) CLUSTER_THREADS && (long long) threads < (long long) rows_per * g.W) threads *= 2;
+	// schedulable? (asked once per shape and kernel)
+	static std::mutex mutex;
+	static std::map<std::tuple<int, unsigned, size_t, int>, bool> known;
+	std::lock_guard<std::mutex> lock(mutex);
+	const auto key = std::make_tuple(blocks, threads, bytes, (tikhonov ? 8 : 0) + std::min(radius, 4));
+	auto found = known.find(key);
+	if (found == known.end()) {
+		const void* kernel = reinterpret_cast<const void*>(strips_kernel(tikhonov, radius));
+		bool ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess
+				&& (blocks <= 8 || cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess);
+		cudaLaunchConfig_t config = {};
+		config.gridDim = dim3(blocks);
+		config.blockDim = dim3(threads);
+		config.dynamicSmemBytes = bytes;
+		cudaLaunchAttribute attribute;
+		attribute.id = cudaLaunchAttributeClusterDimension;
+		attribute.val.clusterDim.x = blocks;
+		attribute.val.clusterDim.y = attribute.val.clusterDim.z = 1;
+		config.attrs = &attribute;
+		config.numAttrs = 1;
+		int clusters = 0;
+		ok = ok && cudaOccupancyMaxActiveClusters(&clusters, kernel, &config) == cudaSuccess && clusters >= 1;
+		cudaGetLastError();
+		found = known.emplace(key, ok).first;
+	}
+	if (!found->second) return false;
+	shape->blocks = (unsigned) blocks;
+	shape->threads = threads;
+	shape->rows_per = rows_per;
+	shape->halo = halo;
+	shape->shared_bytes = bytes;
+	return true;
+}
+
 }  // namespace
 
 long long hier2d_persistent_capacity() {
@@ -166,6 +439,24 @@ int launch_hier2d_persistent(const HierIterArgs2& gradient, const ConvArgs2& fil
 	HierIterArgs2 a = gradient;
 	ConvArgs2 c = filter;
 	int kernel_flag = use_kernel ? 1 : 0;
+	StripShape shape;
+	// (a level is one launch: the strips kernel does not write its gradient fields back for a later chunk)
+	if (first_iteration == 0 && hier2d_strips_shape(gradient.g, tikhonov, use_kernel ? filter.taps.radius : 0, &shape)) {
+		cudaLaunchConfig_t config = {};
+		config.gridDim = dim3(counted(shape.blocks));
+		config.blockDim = dim3(shape.threads);
+		config.dynamicSmemBytes = shape.shared_bytes;
+		config.stream = stream;
+		cudaLaunchAttribute attribute;
+		attribute.id = cudaLaunchAttributeClusterDimension;
+		attribute.val.clusterDim.x = shape.blocks;
+		attribute.val.clusterDim.y = attribute.val.clusterDim.z = 1;
+		config.attrs = &attribute;
+		config.numAttrs = 1;
+		LSF_CUDA(cudaLaunchKernelEx(&config, strips_kernel(tikhonov, use_kernel ? filter.taps.radius : 0), a, c, kernel_flag, g_post, scratch,
+				shape.rows_per, shape.halo, first_iteration, count));
+		return LSF_OK;
+	}
 	if (cluster_blocks() > 0 && N <= (long long) cluster_blocks() * CLUSTER_THREADS) {
 		unsigned blocks = 0, threads = 0;
 		cluster_shape(N, blocks, threads);

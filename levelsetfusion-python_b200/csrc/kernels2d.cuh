@@ -42,6 +42,12 @@ inline dim3 grid2(const Grid2& g) {
 	const bool in_grid = (col < (g).W) && (row < (g).H);       \
 	const long long idx = (long long) row * (g).W + col
 
+// a tap of the gather (element `index` of the padded live pack, in padded row `padded_row`): a plain load; the single-cluster
+// level kernel of small fields (hier2d_persistent.cu) keeps the pack in distributed shared memory and defines its own look-up
+#ifndef HIER_PACK_TAP
+#define HIER_PACK_TAP(pack, padded_row, index) __ldg((pack) + (index))
+#endif
+
 // bilinear gather: reference field_warping.tpp:159-189 -- interpolation along y (rows) first, then x
 __device__ __forceinline__ float4 gather4_2d(const float4* __restrict__ pack, const Grid2& g, int row, int col,
 		float u, float v) {
@@ -53,9 +59,9 @@ __device__ __forceinline__ float4 gather4_2d(const float4* __restrict__ pack, co
 	const float ix = 1.0f - rx, iy = 1.0f - ry;
 	bx = min(max(bx, -2), g.W);
 	by = min(max(by, -2), g.H);
-	const float4* p = pack + g.padded_index(by, bx);
-	const float4 v00 = __ldg(p), v01 = __ldg(p + g.PW());       // (x, y), (x, y+1)
-	const float4 v10 = __ldg(p + 1), v11 = __ldg(p + g.PW() + 1);  // (x+1, y), (x+1, y+1)
+	const long long at = g.padded_index(by, bx);
+	const float4 v00 = HIER_PACK_TAP(pack, by + 2, at), v01 = HIER_PACK_TAP(pack, by + 3, at + g.PW());  // (x, y), (x, y+1)
+	const float4 v10 = HIER_PACK_TAP(pack, by + 2, at + 1), v11 = HIER_PACK_TAP(pack, by + 3, at + g.PW() + 1);  // (x+1, ..)
 	const float4 i0 = v00 * iy + v01 * ry;
 	const float4 i1 = v10 * iy + v11 * ry;
 	return i0 * ix + i1 * rx;
@@ -187,8 +193,11 @@ struct ConvArgs2 {
 	int preserve_zeros;
 };
 
-// one pixel of a filter pass (body of k_convolve_axis2d); sq accumulates the pixel's ||out||^2 when FINAL
-template<int AXIS, bool FINAL>
+// one pixel of a filter pass (body of k_convolve_axis2d); sq accumulates the pixel's ||out||^2 when FINAL.
+// R > 0: the caller knows the filter radius (a.taps.radius == R): the tap loop unrolls (the taps are then read at
+// compile-time offsets of the argument block instead of from a stack copy of it) and pixels at least R from both ends of
+// their line skip the bounds tests (same taps, same order)
+template<int AXIS, bool FINAL, int R = 0>
 __device__ __forceinline__ void convolve_axis2d_at(const ConvArgs2& a, int row, int col, long long idx, float& sq) {
 	const Grid2& g = a.g;
 	const int i = AXIS == 0 ? row : col;
@@ -204,10 +213,22 @@ __device__ __forceinline__ void convolve_axis2d_at(const ConvArgs2& a, int row, 
 		float acc = 0.0f;
 		if (!keep_zero) {
 			const float* line = a.in + c * g.N + idx;
-			for (int j = 0; j < a.taps.size; j++) {
-				const int src = i - r + j;
-				const float value = (src >= 0 && src < n) ? __ldg(line + (long long) (j - r) * stride) : 0.0f;
-				acc += value * a.taps.k[j];
+			if (R > 0 && i >= R && i + R < n) {
+#pragma unroll
+				for (int j = 0; j < 2 * R + 1; j++) acc += __ldg(line + (long long) (j - R) * stride) * a.taps.k[j];
+			} else if (R > 0) {
+#pragma unroll
+				for (int j = 0; j < 2 * R + 1; j++) {
+					const int src = i - R + j;
+					const float value = (src >= 0 && src < n) ? __ldg(line + (long long) (j - R) * stride) : 0.0f;
+					acc += value * a.taps.k[j];
+				}
+			} else {
+				for (int j = 0; j < a.taps.size; j++) {
+					const int src = i - r + j;
+					const float value = (src >= 0 && src < n) ? __ldg(line + (long long) (j - r) * stride) : 0.0f;
+					acc += value * a.taps.k[j];
+				}
 			}
 		}
 		a.out[c * g.N + idx] = acc;

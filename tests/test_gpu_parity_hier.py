@@ -280,15 +280,43 @@ def test_hier2d_single_launch_levels_vs_oracle(lsf, mode):
         assert np.array_equal(plain, warp)
         assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
         assert launches < plain_launches / 2, (launches, plain_launches)
-        # levels of up to 16 K pixels run in one thread-block cluster (cluster barrier); LSF_HIER2D_CLUSTER=0 = the same
-        # kernel as a cooperative grid (grid barrier)
-        os.environ["LSF_HIER2D_CLUSTER"] = "0"
+        # small levels live in the shared memory of one thread-block cluster (k_hier_level2d_strips); LSF_HIER2D_CLUSTER=1
+        # keeps them in global memory (k_hier_level2d in one cluster), LSF_HIER2D_CLUSTER=0 runs that kernel as a cooperative grid
+        for variant in ("1", "0"):
+            os.environ["LSF_HIER2D_CLUSTER"] = variant
+            try:
+                other = optimizer.optimize(c, l)
+            finally:
+                del os.environ["LSF_HIER2D_CLUSTER"]
+            assert np.array_equal(other, warp)
+            assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
+
+
+@pytest.mark.parametrize("mode", sorted(HIER_MODES))
+def test_hier2d_single_launch_long_warps(lsf, mode):
+    """shapes displaced by 14 / 11 pixels: the warps of the finer levels reach beyond the rows of the live pack a block of the
+    cluster keeps in its own shared memory (strip + 4 rows), so gather taps are read from other blocks' shared memory; also
+    fields whose levels do not divide evenly into strips (96 x 96: 6, 3, 2 rows per block with a 7-tap filter); bit-identical
+    to the oracle and to the global-memory path"""
+    from lsf_b200 import synthetic
+    for size in (128, 96):
+        canonical, live = synthetic.circle_line_pair_2d(size, shift=(14.0, -11.0), line_shift=-9.0)
+        kwargs = dict(HIER_MODES[mode])
+        kwargs.update(maximum_chunk_size=8 if size == 128 else 4, rate=0.5, maximum_iteration_count=60,
+                      maximum_warp_update_threshold=0.0005, data_term_amplifier=1.0, kernel=synthetic.sobolev_kernel_1d(),
+                      resampling_strategy=1 if size == 96 else 0)
+        expected = oracle.hier_optimize(canonical, live, **kwargs)
+        optimizer = lsf.HierarchicalOptimizer2d(**kwargs)
+        warp = optimizer.optimize(canonical, live)
+        assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
+        assert np.array_equal(warp, expected["warp"])
+        assert float(np.abs(warp).max()) > 6.0  # longer than the pack halo
+        os.environ["LSF_HIER2D_CLUSTER"] = "1"
         try:
-            cooperative = optimizer.optimize(c, l)
+            other = optimizer.optimize(canonical, live)
         finally:
             del os.environ["LSF_HIER2D_CLUSTER"]
-        assert np.array_equal(cooperative, warp)
-        assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
+        assert np.array_equal(other, warp)
 
 
 def test_hier2d_python_reference_runs(lsf, python_runs):
