@@ -511,8 +511,9 @@ def optimizers_2d(lsf_b200, size=128, repeats=5):
     """BASELINE.json configs[0] and the reference's 2D class: one size x size pair from numpy arrays (host staging inside),
     ms per optimize() of SobolevOptimizer2d with the reference experiment's parameters (experiment/
     singleframe_experiment.py:91-116) and of HierarchicalOptimizer2d (4 levels x 100 iterations, data term), the CPU
-    oracle beside them, results compared bit for bit. 2D fields are launch-bound: both run one cooperative launch per
-    iteration loop (csrc/slavcheva_persistent.cu, csrc/hier2d_persistent.cu)."""
+    oracle beside them, results compared bit for bit. 2D fields are launch-bound: both run an iteration loop (a polling chunk /
+    a pyramid level) as ONE launch of one thread-block cluster that keeps the fields in distributed shared memory
+    (csrc/slavcheva_persistent.cu k_slav_strips, csrc/hier2d_persistent.cu k_hier_level2d_strips)."""
     import time
     import numpy as np
     import torch

@@ -158,7 +158,9 @@ template<bool TIKHONOV, int R>
 __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_hier_level2d_strips(HierIterArgs2 a, ConvArgs2 c, int use_kernel,
 		float* g_post_global, float* scratch_global, int rows_per, int halo, int first_iteration, int count) {
 	extern __shared__ __align__(16) unsigned char strip_memory[];
-	__shared__ float block_maxima[CLUSTER_BLOCKS], warp_max[32];
+	// slots of the blocks' maxima, one set per iteration parity: without a filter nothing but this exchange's own barrier
+	// separates two iterations, and a block that is ahead stores its next maximum while a slower block still reads the last
+	__shared__ float block_maxima[2][CLUSTER_BLOCKS], warp_max[32];
 	cg::cluster_group cluster = cg::this_cluster();
 	const int rank = (int) cluster.block_rank(), blocks = (int) cluster.num_blocks();
 	const Grid2 g = a.g;
@@ -293,10 +295,10 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_hier_level2d_strips(Hier
 		}
 		// the iteration's maximum: every block's maximum into every block's slot array
 		const float mine = strip_block_max(sq, warp_max);
-		if (threadIdx.x < blocks) *cluster.map_shared_rank(&block_maxima[rank], threadIdx.x) = mine;
+		if (threadIdx.x < blocks) *cluster.map_shared_rank(&block_maxima[it & 1][rank], threadIdx.x) = mine;
 		cluster.sync();
 		previous_max_sq = 0.0f;
-		for (int k = 0; k < blocks; k++) previous_max_sq = fmaxf(previous_max_sq, block_maxima[k]);
+		for (int k = 0; k < blocks; k++) previous_max_sq = fmaxf(previous_max_sq, block_maxima[it & 1][k]);
 		if (rank == 0 && threadIdx.x == 0) max_sq_bits[it] = __float_as_uint(previous_max_sq);
 	}
 	for (long long idx = first; idx < last; idx += blockDim.x)

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 	extern __shared__ __align__(16) float strip_tiles[];
 	__shared__ SlavIterationCommand command;
 	__shared__ float* virtual_base[STRIP_FIELDS];
-	__shared__ float block_maxima[CLUSTER_BLOCKS], warp_max[32];
+	__shared__ float block_maxima[2][CLUSTER_BLOCKS], warp_max[32];  // one set of slots per iteration parity
 	cg::cluster_group cluster = cg::this_cluster();
 	const int rank = (int) cluster.block_rank(), blocks = (int) cluster.num_blocks();
 	const int N = H * W, tile = (rows_per + 2 * halo) * W;
@@ -339,11 +339,11 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 		stamp(j, 5);
 		// maximum warp length: every block's maximum into every block's slot array
 		const float mine = block_max(sq_report, warp_max);
-		if (threadIdx.x < blocks) *cluster.map_shared_rank(&block_maxima[rank], threadIdx.x) = mine;
+		if (threadIdx.x < blocks) *cluster.map_shared_rank(&block_maxima[j & 1][rank], threadIdx.x) = mine;
 		cluster.sync();
 		stamp(j, 6);
 		float max_sq = 0.0f;
-		for (int k = 0; k < blocks; k++) max_sq = fmaxf(max_sq, block_maxima[k]);
+		for (int k = 0; k < blocks; k++) max_sq = fmaxf(max_sq, block_maxima[j & 1][k]);
 		finished = slav_finished(p, it + 1, max_iterations, sqrtf(max_sq));
 		if (rank == 0 && threadIdx.x == 0) {
 			max_sq_bits[it] = __float_as_uint(max_sq);
