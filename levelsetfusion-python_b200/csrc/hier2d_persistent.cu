@@ -396,7 +396,9 @@ bool hier2d_strips_shape(const Grid2& g, bool tikhonov, int radius, StripShape* 
 	static std::mutex mutex;
 	static std::map<std::tuple<int, unsigned, size_t, int>, bool> known;
 	std::lock_guard<std::mutex> lock(mutex);
-	const auto key = std::make_tuple(blocks, threads, bytes, (tikhonov ? 8 : 0) + std::min(radius, 4));
+	int device = 0;
+	cudaGetDevice(&device);  // function attributes are per device
+	const auto key = std::make_tuple(blocks, threads, bytes, device * 16 + (tikhonov ? 8 : 0) + std::min(radius, 4));
 	auto found = known.find(key);
 	if (found == known.end()) {
 		const void* kernel = reinterpret_cast<const void*>(strips_kernel(tikhonov, radius));

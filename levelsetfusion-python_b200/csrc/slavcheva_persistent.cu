@@ -429,7 +429,9 @@ bool slav_strips_shape(const SlavOptimizerBuffers& b, StripShape* shape) {
 	static std::mutex mutex;
 	static std::map<std::tuple<int, unsigned, size_t>, bool> known;
 	std::lock_guard<std::mutex> lock(mutex);
-	const auto key = std::make_tuple(blocks, threads, bytes);
+	int device = 0;
+	cudaGetDevice(&device);  // function attributes are per device
+	const auto key = std::make_tuple(blocks * 64 + device, threads, bytes);
 	auto found = known.find(key);
 	if (found == known.end()) {
 		bool ok = cudaFuncSetAttribute(k_slav_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess
