@@ -280,9 +280,13 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 	LSF_TRY(arena.alloc(&warp_next, N * 2));
 	LSF_TRY(arena.alloc(&g_post, N * 2));
 	LSF_TRY(arena.alloc(&scratch_a, N * 2));
+	// one row of maximum slots per level: levels that run as ONE launch (termination test inside) are enqueued back to
+	// back and the host reads all their slots at the end instead of waiting for every level
 	const int slot_count = std::max(plan.max_iterations, 1);
-	LSF_TRY(arena.alloc(&max_sq_bits, (size_t) slot_count));
-	std::vector<unsigned> host_bits((size_t) slot_count);
+	LSF_TRY(arena.alloc(&max_sq_bits, (size_t) slot_count * L));
+	LSF_CUDA(cudaMemsetAsync(max_sq_bits, 0, (size_t) slot_count * L * sizeof(unsigned), stream));
+	std::vector<unsigned> host_bits((size_t) slot_count * L);
+	std::vector<char> deferred((size_t) L, 0);
 	LSF_CUDA(cudaMemsetAsync(warp_current, 0, (size_t) plan.level_grid[0].N * 2 * sizeof(float), stream));
 	TelemetryScratch telemetry;
 	if (sink != nullptr) LSF_TRY(telemetry.allocate(arena, N, 2, plan.tikhonov, sink->want_fields != 0));
@@ -305,9 +309,9 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 		s.warp = warp_current;
 		s.g_post = g_post;
 		s.scratch_a = scratch_a;
-		s.max_sq_bits = max_sq_bits;
+		s.max_sq_bits = max_sq_bits + (size_t) level * slot_count;
+		unsigned* level_bits = host_bits.data() + (size_t) level * slot_count;
 		LSF_CUDA(cudaMemsetAsync(s.g_post, 0, (size_t) s.g.N * 2 * sizeof(float), stream));
-		LSF_CUDA(cudaMemsetAsync(max_sq_bits, 0, (size_t) slot_count * sizeof(unsigned), stream));
 		const bool capturing = capture_dev != nullptr && capture->level == level;
 		int executed = 0, enqueued = 0;
 		bool converged = false;
@@ -321,6 +325,14 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 		const char* persistent_env = getenv("LSF_HIER2D_PERSISTENT");
 		const bool persistent = !capturing && sink == nullptr && !(persistent_env && persistent_env[0] == '0')
 				&& s.g.N <= hier2d_persistent_capacity();
+		// nothing the host does before the next level depends on this level's iteration count: look at the end
+		const char* defer_env = getenv("LSF_HIER2D_DEFER_POLL");
+		deferred[level] = persistent && !collect_reports && plan.max_iterations > 0 && !(defer_env && defer_env[0] == '0');
+		if (deferred[level]) {
+			LSF_TRY(enqueue_level_persistent(plan, s, 0, plan.max_iterations, stream));
+			trace_point("enqueued");
+			converged = true;  // (skips the polling loop)
+		}
 		while (!converged && enqueued < plan.max_iterations) {
 			// the launch ends by itself at the first converged iteration: the host looks once per level
 			const int chunk_end = persistent ? plan.max_iterations : std::min(plan.max_iterations, enqueued + POLL_CHUNK);
@@ -332,13 +344,13 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 							s.g.N, 2);
 			}
 			LSF_CUDA(cudaGetLastError());
-			LSF_CUDA(cudaMemcpyAsync(host_bits.data() + enqueued, max_sq_bits + enqueued,
+			LSF_CUDA(cudaMemcpyAsync(level_bits + enqueued, s.max_sq_bits + enqueued,
 					(size_t) (chunk_end - enqueued) * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
 			trace_point("enqueued");
 			LSF_CUDA(cudaStreamSynchronize(stream));
 			for (int it = enqueued; it < chunk_end; it++) {
 				float sq;
-				std::memcpy(&sq, &host_bits[it], sizeof(float));
+				std::memcpy(&sq, &level_bits[it], sizeof(float));
 				if (it == enqueued) trace_point("level waited");
 				last_max = std::sqrt(sq);
 				executed = it + 1;
@@ -394,6 +406,30 @@ int hier_optimize_2d(const lsf_hier_params* params, const float* canonical, cons
 	k_planes_to_aos<<<counted(div_up(finest.N, 256)), 256, 0, stream>>>(warp_current, out_dev, finest.N, 2);
 	LSF_CUDA(cudaGetLastError());
 	trace_point("levels done");
+	// the levels whose slots the host has not looked at yet: iteration counts and last maxima for the reports
+	bool any_deferred = false;
+	for (int level = 0; level < L; level++) any_deferred = any_deferred || deferred[level];
+	if (any_deferred) {
+		LSF_CUDA(cudaMemcpyAsync(host_bits.data(), max_sq_bits, (size_t) slot_count * L * sizeof(unsigned), cudaMemcpyDeviceToHost,
+				stream));
+		LSF_CUDA(cudaStreamSynchronize(stream));
+		for (int level = 0; level < L && reports != nullptr; level++) {
+			if (!deferred[level]) continue;
+			int executed = 0;
+			float last_max = FLT_MAX;
+			for (int it = 0; it < plan.max_iterations; it++) {
+				float sq;
+				std::memcpy(&sq, &host_bits[(size_t) level * slot_count + it], sizeof(float));
+				last_max = std::sqrt(sq);
+				executed = it + 1;
+				if (last_max < plan.threshold) break;  // reference optimizer.tpp:149,166-171
+			}
+			reports[level].iteration_count = executed;
+			reports[level].iteration_limit_reached = executed >= plan.max_iterations;
+			reports[level].max_update_length = last_max;
+		}
+		trace_point("slots read");
+	}
 	if (memory_kind == LSF_HOST) {
 		if (capture_dev)
 			LSF_CUDA(cudaMemcpyAsync(capture->buffer, capture_dev,

@@ -553,6 +553,9 @@ class SlabHierarchicalOptimizer3d:
                         converged = True
                         break
                 enqueued = chunk_end
+            # iterations enqueued behind the convergence point are no-ops on the device (at most two polling chunks); their
+            # exchange rounds still run but move nothing the result depends on: counted as executed iterations only
+            self.exchanged_bytes -= (enqueued - executed) * per_iteration_bytes
             self.iteration_counts.append(executed)
             self.max_update_lengths.append(last_max)
             if level != plan0.level_count - 1:
