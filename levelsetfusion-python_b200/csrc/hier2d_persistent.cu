@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_hier_level2d_strips(Hier
 	extern __shared__ __align__(16) unsigned char strip_memory[];
 	// slots of the blocks' maxima, one set per iteration parity: without a filter nothing but this exchange's own barrier
 	// separates two iterations, and a block that is ahead stores its next maximum while a slower block still reads the last
-	__shared__ float block_maxima[2][CLUSTER_BLOCKS], warp_max[32];
+	__shared__ float block_maxima[3][CLUSTER_BLOCKS], warp_max[2][32];  // (three / two sets: the data-term-only loop below)
 	cg::cluster_group cluster = cg::this_cluster();
 	const int rank = (int) cluster.block_rank(), blocks = (int) cluster.num_blocks();
 	const Grid2 g = a.g;
@@ -240,6 +240,60 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_hier_level2d_strips(Hier
 	if (first_iteration > 0) previous_max_sq = __uint_as_float(*reinterpret_cast<const volatile unsigned*>(max_sq_bits + first_iteration - 1));
 	__syncthreads();
 	cluster.sync();  // every block has loaded its tiles: halo stores may arrive from now on
+	if (!use_kernel && !TIKHONOV) {
+		// Data term only: a pixel's iteration reads and writes that pixel's warp vector alone, so nothing but the termination
+		// test (optimizer.tpp:166-171: stop after the first iteration whose maximum is below the threshold) connects the
+		// blocks. The test runs one iteration late: iteration `it` is computed while the maxima of iteration it - 1 travel
+		// (split cluster barrier: arrive after storing the maximum, wait after the next iteration's work), into the OTHER of
+		// two warp tiles (the unused gradient tile), so that an iteration computed past the stopping point is simply dropped.
+		// Slot sets: a block that is ahead stores the maximum of it + 1 while a slower one still reads it - 1 -> three sets.
+		float* tiles[2] = { warp, g_post };
+		int current = 0;  // tiles[current] = the warp field before iteration `it`
+		bool pending = false;
+		a.g_prev = nullptr;
+		a.g_out = nullptr;
+		int it = first_iteration;
+		if (it > 0 && sqrtf(previous_max_sq) < a.threshold) it = first_iteration + count;  // nothing left to do
+		for (; it < first_iteration + count; it++) {
+			a.warp = tiles[current];
+			a.warp_out = tiles[current ^ 1];
+			float sq = 0.0f;
+			for (long long idx = first; idx < last; idx += blockDim.x) {
+				int row, col;
+				coordinates(idx, row, col);
+				float mine = 0.0f;
+				hier_gradient2d_at<false, true>(a, row, col, idx, mine);
+				sq = fmaxf(sq, mine);
+			}
+			// (no block-wide barrier follows the reduction in this loop: its scratch alternates, a warp cannot be two iterations ahead)
+			const float mine = strip_block_max(sq, warp_max[it & 1]);
+			if (threadIdx.x < blocks) *cluster.map_shared_rank(&block_maxima[it % 3][rank], threadIdx.x) = mine;
+			current ^= 1;
+			if (pending) {
+				cluster.barrier_wait();  // the maxima of iteration it - 1 have arrived
+				float before = 0.0f;
+				for (int k = 0; k < blocks; k++) before = fmaxf(before, block_maxima[(it - 1) % 3][k]);
+				if (rank == 0 && threadIdx.x == 0) max_sq_bits[it - 1] = __float_as_uint(before);
+				if (sqrtf(before) < a.threshold) {
+					current ^= 1;  // iteration `it` ran past the stopping point: dropped
+					pending = false;
+					break;
+				}
+			}
+			cluster.barrier_arrive();
+			pending = true;
+		}
+		if (pending) {
+			cluster.barrier_wait();
+			float before = 0.0f;
+			for (int k = 0; k < blocks; k++) before = fmaxf(before, block_maxima[(it - 1) % 3][k]);
+			if (rank == 0 && threadIdx.x == 0) max_sq_bits[it - 1] = __float_as_uint(before);
+		}
+		cluster.sync();  // no block leaves while maxima of a dropped iteration may still be on their way into its slots
+		for (long long idx = first; idx < last; idx += blockDim.x)
+			for (int k = 0; k < 2; k++) warp_global[k * N + idx] = tiles[current][k * tile + idx];
+		return;
+	}
 	for (int it = first_iteration; it < first_iteration + count; it++) {
 		if (it > 0 && sqrtf(previous_max_sq) < a.threshold) break;  // level_converged()
 		a.g_prev = g_post;
@@ -294,7 +348,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_hier_level2d_strips(Hier
 			scratch = t;
 		}
 		// the iteration's maximum: every block's maximum into every block's slot array
-		const float mine = strip_block_max(sq, warp_max);
+		const float mine = strip_block_max(sq, warp_max[0]);
 		if (threadIdx.x < blocks) *cluster.map_shared_rank(&block_maxima[it & 1][rank], threadIdx.x) = mine;
 		cluster.sync();
 		previous_max_sq = 0.0f;
