@@ -290,6 +290,17 @@ def test_hier2d_single_launch_levels_vs_oracle(lsf, mode):
                 del os.environ["LSF_HIER2D_CLUSTER"]
             assert np.array_equal(other, warp)
             assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
+        # the levels are enqueued back to back and their maximum slots read once at the end; LSF_HIER2D_DEFER_POLL=0 waits
+        # for every level as the one-launch-per-kernel path does
+        os.environ["LSF_HIER2D_DEFER_POLL"] = "0"
+        try:
+            other = optimizer.optimize(c, l)
+        finally:
+            del os.environ["LSF_HIER2D_DEFER_POLL"]
+        assert np.array_equal(other, warp)
+        assert optimizer.get_per_level_iteration_counts() == expected["iterations"]
+        reports = optimizer.get_per_level_convergence_reports()
+        assert np.allclose([r.max_update_length for r in reports], expected["max_updates"], rtol=0, atol=0)
 
 
 @pytest.mark.parametrize("mode", sorted(HIER_MODES))
