@@ -306,26 +306,34 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_slav_strips(const SlavIt
 		prefetch(j + 1);
 		stamp(j, 0);
 		const int passes = command.passes;
+		// Only a pass along axis 0 (rows) reads rows of other blocks: its input is pushed into the neighbours' halo and a
+		// cluster barrier stands in front of it. A pass along axis 1 reads its own rows: nothing is pushed for it and a
+		// block-wide barrier is enough (the blocks drift apart there and meet again at the end of the iteration).
+		const bool first_pass_crosses = passes > 0 && command.pass[0].axis == 0;
 		for (int idx = first; idx < last; idx += blockDim.x) {
 			int pos[3];
 			const int edges = coordinates(idx, pos);
 			slav_gradient_at<D>(command.gradient, idx, pos);
-			push(command.gradient.out, D, idx, edges);
+			if (first_pass_crosses) push(command.gradient.out, D, idx, edges);
 		}
 		stamp(j, 1);
 		for (int pass = 0; pass + 1 < passes; pass++) {
-			cluster.sync();
+			if (command.pass[pass].axis == 0) cluster.sync();
+			else __syncthreads();
 			if (pass == 0) stamp(j, 2);
+			const bool next_crosses = command.pass[pass + 1].axis == 0;
 			for (int idx = first; idx < last; idx += blockDim.x) {
 				int pos[3];
 				const int edges = coordinates(idx, pos);
 				filter_pass(command.pass[pass], idx, pos);
-				push(command.pass[pass].out, D, idx, edges);
+				if (next_crosses) push(command.pass[pass].out, D, idx, edges);
 			}
 			if (pass == 0) stamp(j, 3);
 		}
-		// also without a filter: the re-warp overwrites the warp vectors the neighbours' smoothing terms read
-		cluster.sync();
+		// without a filter the cluster barrier stands between the neighbours' smoothing terms (gradient phase), which read
+		// this block's warp vectors in their halo, and the re-warp that overwrites them; with a filter an earlier one does
+		if (passes == 0 || command.pass[passes - 1].axis == 0) cluster.sync();
+		else __syncthreads();
 		stamp(j, 4);
 		float sq_report = 0.0f;
 		for (int idx = first; idx < last; idx += blockDim.x) {
