@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_hier_level2d_strips(Hier
 		hier_strip.pack_hi = pack_hi;
 		hier_strip.PW = PW;
 	}
-	// tiles: pack | warp (2 planes) | g_post (2) | scratch (2) | canonical; virtual base = slot of element 0 of the field
+	// tiles: pack | warp (2 planes) | g_post (2) | scratch (2) | canonical | between (2); virtual base = slot of element 0 of the field
 	float4* pack_tile = reinterpret_cast<float4*>(strip_memory);
 	float* planes = reinterpret_cast<float*>(pack_tile + (size_t) pack_rows * PW);
 	const long long shift = (long long) (r0 - halo) * W;
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_hier_level2d_strips(Hier
 	float* g_post = planes + 2 * tile - shift;
 	float* scratch = planes + 4 * tile - shift;
 	float* canonical = planes + 6 * tile - shift;
+	float* between = planes + 7 * tile - shift;  // output of the rows pass (two planes, never leaves the block)
 	const long long N = g.N;
 	const int row_lo = max(r0 - halo, 0), row_hi = min(r1 + halo, H);
 	for (long long i = (long long) pack_lo * PW + threadIdx.x; i < (long long) pack_hi * PW; i += blockDim.x) pack[i] = a.pack[i];
@@ -322,30 +323,31 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, 1) k_hier_level2d_strips(Hier
 				hier_gradient2d_at<TIKHONOV, false>(a, row, col, idx, unused);
 				push(scratch, idx, edges);
 			}
+			// Only the rows pass reads rows of other blocks (its input was pushed above, a cluster barrier in front of it);
+			// the columns pass reads its own rows of the rows pass's output, which stays in the block (block barrier), and
+			// writes the filtered gradient back into g_post -- every reader of the old one (stage 1 above, any block) is
+			// behind the cluster barrier -- so the two fields keep their roles; its rows go to the neighbours' halo for
+			// the next iteration's Laplacian.
 			cluster.sync();
 			c.in = scratch;
-			c.out = g_post;
+			c.out = between;
 			for (long long idx = first; idx < last; idx += blockDim.x) {
 				int row, col;
-				const int edges = coordinates(idx, row, col);
+				coordinates(idx, row, col);
 				float unused = 0.0f;
 				convolve_axis2d_at<0, false, R>(c, row, col, idx, unused);
-				push(g_post, idx, edges);
 			}
-			cluster.sync();
-			c.in = g_post;
-			c.out = scratch;
+			__syncthreads();
+			c.in = between;
+			c.out = g_post;
 			for (long long idx = first; idx < last; idx += blockDim.x) {
 				int row, col;
 				const int edges = coordinates(idx, row, col);
 				float mine = 0.0f;
 				convolve_axis2d_at<1, true, R>(c, row, col, idx, mine);
 				sq = fmaxf(sq, mine);
-				push(scratch, idx, edges);
+				if (TIKHONOV) push(g_post, idx, edges);
 			}
-			float* t = g_post;
-			g_post = scratch;
-			scratch = t;
 		}
 		// the iteration's maximum: every block's maximum into every block's slot array
 		const float mine = strip_block_max(sq, warp_max[0]);
@@ -442,7 +444,7 @@ bool hier2d_strips_shape(const Grid2& g, bool tikhonov, int radius, StripShape* 
 	const int blocks = (g.H + rows_per - 1) / rows_per;
 	if (blocks < 1 || blocks > most) return false;
 	const size_t tile = (size_t) (rows_per + 2 * halo) * g.W;
-	const size_t bytes = (size_t) (rows_per + 2 * PACK_HALO + 1) * g.PW() * sizeof(float4) + 7 * tile * sizeof(float);
+	const size_t bytes = (size_t) (rows_per + 2 * PACK_HALO + 1) * g.PW() * sizeof(float4) + 9 * tile * sizeof(float);
 	if (bytes > 200u * 1024u) return false;
 	unsigned threads = 128;
 	while (threads < (unsigned) CLUSTER_THREADS && (long long) threads < (long long) rows_per * g.W) threads *= 2;
